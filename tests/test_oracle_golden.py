@@ -1,0 +1,360 @@
+"""Pins the CPU oracle (oracle/) against every golden vector the reference's own
+tests hold for the PS hot path.  Paths in comments are
+relative to /root/reference/elasticdl/.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ps_oracle as O
+
+F = np.float32
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_python_vectors.json")
+
+
+def rel_close(a, b, tol):
+    """go/pkg/common/util.go:22-41 CompareFloatArray."""
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    diff = np.abs(a - b)
+    mean = np.abs(a + b) / 2.0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        r = diff / mean
+    return bool(np.all(np.isnan(r) | (r < tol)))
+
+
+def c_dense(fn, *arrs_and_scalars):
+    return fn(*arrs_and_scalars)
+
+
+# ---------------------------------------------------------------- kernel_test.go
+def test_sgd_kernel_test_go_25():
+    rng = np.random.RandomState(0)
+    a = rng.rand(10).astype(F)
+    b = rng.rand(10).astype(F)
+    expected = b - F(0.1) * a  # kernel_test.go:41-43, assert.Equal (exact)
+    p = b.copy()
+    O.lib.oracle_sgd(O._f32(a), O._f32(p), 0.1, 10)
+    assert np.array_equal(p, expected)
+    q = b.copy()
+    O.np_sgd(a, q, 0.1)
+    assert np.array_equal(q, p)
+
+
+def test_sparse_sgd_kernel_test_go_49():
+    # grad -1 rows for ids [1,3,3], dim 2, "zero" table, lr .1 -> id1=.1, id3=.2, size 2
+    t = O.OracleTable(2, "zero")
+    ids = np.array([1, 3, 3], dtype=np.int64)
+    g = -np.ones((3, 2), dtype=F)
+    O.lib.oracle_sparse_sgd(t._h, O._i64(ids), O._f32(g), 3, 0.1)
+    assert len(t) == 2
+    assert np.array_equal(t.get([1])[0], np.array([0.1, 0.1], dtype=F))
+    assert np.array_equal(t.get([3])[0], np.array([0.2, 0.2], dtype=F))
+
+
+def _adam_expected(g, p, m, v, ms, lr, step, b1, b2, eps):
+    """Closed form written in kernel_test.go:97-110 / 155-170 (float32 steps)."""
+    lr, b1, b2, eps = F(lr), F(b1), F(b2), F(eps)
+    em = b1 * m + (F(1) - b1) * g
+    ev = b2 * v + (F(1) - b2) * g * g
+    ems = None
+    den = ev
+    if ms is not None:
+        ems = np.where(ms < ev, ev, ms)
+        den = ems
+    c1 = F(1) - F(np.power(np.float64(b1), np.float64(step)))
+    c2 = F(1) - F(np.power(np.float64(b2), np.float64(step)))
+    ep = p - lr * em / c1 / (np.sqrt((den / c2).astype(np.float64)).astype(F) + eps)
+    return ep, em, ev, ems
+
+
+@pytest.mark.parametrize("amsgrad", [False, True])
+def test_adam_kernel_test_go_69_120(amsgrad):
+    rng = np.random.RandomState(1)
+    g, p, m, v, ms = [rng.rand(10).astype(F) for _ in range(5)]
+    ep, em, ev, ems = _adam_expected(g, p, m, v, ms if amsgrad else None, 0.1, 5, 0.9, 0.999, 1e-8)
+    cp, cm, cv, cms = p.copy(), m.copy(), v.copy(), ms.copy()
+    O.lib.oracle_adam(O._f32(g), O._f32(cp), O._f32(cm), O._f32(cv), 0.1, 10, 5, 0.9, 0.999, 1e-8,
+                      O._f32(cms) if amsgrad else O._null_f32())
+    assert rel_close(em, cm, 1e-4) and rel_close(ev, cv, 1e-5) and rel_close(ep, cp, 1e-5)
+    if amsgrad:
+        assert rel_close(ems, cms, 1e-5)
+    # numpy twin is bit-identical to the C restatement
+    np_p, np_m, np_v, np_ms = p.copy(), m.copy(), v.copy(), ms.copy()
+    O.np_adam(g, np_p, np_m, np_v, 0.1, 5, 0.9, 0.999, 1e-8, np_ms if amsgrad else None)
+    assert np.array_equal(np_p, cp) and np.array_equal(np_m, cm) and np.array_equal(np_v, cv)
+
+
+def test_sparse_adam_amsgrad_kernel_test_go_182():
+    rng = np.random.RandomState(2)
+    g, p, m, v, ms = [rng.rand(10).astype(F) for _ in range(5)]
+    tabs = [O.OracleTable(10, "zero") for _ in range(4)]
+    for t, x in zip(tabs, (p, m, v, ms)):
+        t.set([1], x[None, :])
+    ids = np.array([1], dtype=np.int64)
+    O.lib.oracle_sparse_adam(tabs[0]._h, tabs[1]._h, tabs[2]._h, tabs[3]._h, O._i64(ids),
+                             O._f32(g.reshape(1, 10).copy()), 1, 0.1, 5, 0.9, 0.999, 1e-8)
+    ep, em, ev, ems = _adam_expected(g, p, m, v, ms, 0.1, 5, 0.9, 0.999, 1e-8)
+    assert rel_close(em, tabs[1].get([1]), 1e-5) and rel_close(ev, tabs[2].get([1]), 1e-5)
+    assert rel_close(ep, tabs[0].get([1]), 1e-5) and rel_close(ems, tabs[3].get([1]), 1e-5)
+
+
+def test_dense_kernels_numpy_twin_bit_identical():
+    rng = np.random.RandomState(3)
+    n = 1001
+    g, p, s0, s1 = [rng.randn(n).astype(F) for _ in range(4)]
+    s0, s1 = np.abs(s0), np.abs(s1)
+    for nesterov in (0, 1):
+        a, b = p.copy(), s0.copy()
+        O.lib.oracle_momentum(O._f32(g), O._f32(a), O._f32(b), 0.9, nesterov, 0.05, n)
+        c, d = p.copy(), s0.copy()
+        O.np_momentum(g, c, d, 0.9, bool(nesterov), 0.05)
+        assert np.array_equal(a, c) and np.array_equal(b, d)
+    a, b = p.copy(), s0.copy()
+    O.lib.oracle_adagrad(O._f32(g), O._f32(a), O._f32(b), 0.05, n, 1e-7)
+    c, d = p.copy(), s0.copy()
+    O.np_adagrad(g, c, d, 0.05, 1e-7)
+    assert np.array_equal(a, c) and np.array_equal(b, d)
+    for l1, l2, l2s in [(0.0, 0.0, 0.0), (0.01, 0.02, 0.0), (0.01, 0.0, 0.05)]:
+        a, b, e = p.copy(), s0.copy() + F(0.1), s1.copy()
+        O.lib.oracle_ftrl(O._f32(g), O._f32(a), O._f32(b), O._f32(e), 0.1, n, l1, l2, l2s)
+        c, d, f = p.copy(), s0.copy() + F(0.1), s1.copy()
+        O.np_ftrl(g, c, d, f, 0.1, l1, l2, l2s)
+        assert np.array_equal(a, c) and np.array_equal(b, d) and np.array_equal(e, f)
+
+
+# ------------------------------------------------------------- optimizer_test.go
+def _model_t1_t2(server):
+    server.push_model(dense={"t1": np.array([[1, 2, 3], [4, 5, 6]], dtype=F),
+                             "t2": np.array([[1, 2], [1.1, 2.2]], dtype=F)})
+
+
+def test_sgd_optimizer_optimizer_test_go_25():
+    s = O.OracleServer(0, "SGD", "learning_rate=0.1;momentum=0.0;nesterov=false;")
+    _model_t1_t2(s)
+    g1, g2 = np.ones((2, 3), dtype=F), np.ones((2, 2), dtype=F)
+    s._apply_gradients({"t1": g1, "t2": g2}, {}, F(0.5) * s.opt.lr)
+    assert s.opt.lr == F(0.1)
+    assert rel_close(s.dense["t1"], [0.95, 1.95, 2.95, 3.95, 4.95, 5.95], 1e-4)
+    assert rel_close(s.dense["t2"], [0.95, 1.95, 1.05, 2.15], 1e-4)
+    with pytest.raises(KeyError):  # optimizer_test.go:67-72 unknown grad name
+        s._apply_gradients({"t3": g2}, {}, s.opt.lr)
+    s.push_embedding_table_infos([O.EmbeddingTableInfo("t3", 2, "zero", 1)])
+    i3 = np.array([1, 3], dtype=np.int64)
+    s._apply_gradients({"t1": g1, "t2": g2}, {"t3": (i3, np.ones((2, 2), dtype=F))}, s.opt.lr)
+    assert rel_close(s.dense["t1"], [0.85, 1.85, 2.85, 3.85, 4.85, 5.85], 1e-4)
+    assert rel_close(s.dense["t2"], [0.85, 1.85, 0.95, 2.05], 1e-4)
+    assert rel_close(s.tables["t3"].get(i3), [-0.1] * 4, 1e-4)
+    i3 = np.array([1, 3, 3, 5], dtype=np.int64)  # sequential duplicates
+    s._apply_gradients({}, {"t3": (i3, np.ones((4, 2), dtype=F))}, s.opt.lr)
+    assert rel_close(s.tables["t3"].get([1, 3, 5]), [-0.2, -0.2, -0.3, -0.3, -0.1, -0.1], 1e-4)
+
+
+def test_adam_optimizer_global_step_optimizer_test_go_118():
+    s = O.OracleServer(0, "Adam", "learning_rate=0.1;beta_1=0.9;beta_2=0.999;epsilon=1e-08;amsgrad=false;")
+    _model_t1_t2(s)
+    s.push_embedding_table_infos([O.EmbeddingTableInfo("t3", 2, "zero", 1)])
+    s.opt.step = 1  # optimizer_test.go:150
+    g1, g2 = np.ones((2, 3), dtype=F), np.ones((2, 2), dtype=F)
+    s._apply_gradients({"t1": g1, "t2": g2}, {}, s.opt.lr)  # step -> 2
+    off1 = np.array([0, 1, 2, 3, 4, 5])
+    assert rel_close(s.dense["t1"], 0.9255863187 + off1, 1e-4)
+    assert rel_close(s.dense["t2"], [0.9255863187, 1.9255863187, 1.0255863187, 2.1255863187], 1e-4)
+    with pytest.raises(KeyError):  # failed call still bumps step (quirk Q2) -> 3
+        s._apply_gradients({"t3": g2}, {}, s.opt.lr)
+    i3 = np.array([1, 3], dtype=np.int64)
+    s._apply_gradients({"t1": g1, "t2": g2}, {"t3": (i3, np.ones((2, 2), dtype=F))}, s.opt.lr)  # 4
+    assert s.opt.step == 4
+    assert rel_close(s.dense["t1"], 0.8474920307 + off1, 1e-4)
+    assert rel_close(s.dense["t2"], [0.8474920307, 1.8474920307, 0.9474920307, 2.0474920307], 1e-4)
+    assert rel_close(s.tables["t3"].get(i3), [-0.058112835] * 4, 1e-4)
+    i3 = np.array([1, 3, 5], dtype=np.int64)
+    s._apply_gradients({}, {"t3": (i3, np.ones((3, 2), dtype=F))}, s.opt.lr)  # 5
+    assert rel_close(s.tables["t3"].get(i3),
+                     [-0.1314178004] * 4 + [-0.0545489238] * 2, 1e-4)
+
+
+def test_parse_opt_args_optimizer_test_go_221():
+    a = O.parse_opt_args("SGD", "learning_rate=0.1;momentum=0.0;nesterov=true;")
+    assert a == {"learning_rate": "0.1", "momentum": "0.0", "nesterov": "true"}
+    with pytest.raises(ValueError):
+        O.parse_opt_args("SGD", "learning_rate=0.1;momentum=0.0;nesterov=true;redundant_arg=1;")
+    with pytest.raises(ValueError):
+        O.parse_opt_args("SGD", "momentum=0.0;nesterov=true;redundant_arg=1;")
+    a = O.parse_opt_args("Adam", "learning_rate=0.2;beta_1=0.5;beta_2=0.3;epsilon=0.005;amsgrad=false;")
+    assert len(a) == 5 and a["beta_2"] == "0.3"
+    o = O.OracleOptimizer("SGD", "learning_rate=0.1;momentum=0.0;nesterov=False;")
+    assert o.lr == F(0.1) and o.kind == "sgd"
+    o = O.OracleOptimizer("Adam", "learning_rate=0.2;beta_1=0.5;beta_2=0.3;epsilon=0.005;amsgrad=false;")
+    assert (o.lr, o.beta1, o.beta2, o.epsilon, o.amsgrad) == (F(0.2), F(0.5), F(0.3), F(0.005), False)
+    o = O.OracleOptimizer("Adagrad", "learning_rate=0.2;epsilon=0.005;")
+    assert (o.lr, o.epsilon) == (F(0.2), F(0.005))
+    o = O.OracleOptimizer("SGD", "learning_rate=0.1;momentum=0.9;nesterov=true;")  # quirk Q5
+    assert o.kind == "momentum" and o.nesterov
+
+
+# ---------------------------------------------------------------- server_test.go
+def test_server_push_pull_server_test_go_107_333():
+    rng = np.random.RandomState(4)
+    a, b, c = [rng.rand(10).astype(F) for _ in range(3)]
+    s = O.OracleServer(0, "SGD", "learning_rate=0.1;momentum=0.0;nesterov=false;")
+    assert s.pull_dense_parameters(0)[0] is False
+    info = O.EmbeddingTableInfo("e1", 10, "zero", 1)
+    s.push_model(dense={"t1": a.reshape(2, 5), "t2": b.reshape(2, 5)}, infos=[info],
+                 tables={"e1": (np.array([1]), c.reshape(1, 10))})
+    assert s.initialized and set(s.dense) == {"t1", "t2"} and s.tables["e1"].dim == 10
+    assert rel_close(s.pull_embedding_vectors("e1", [1]), c, 1e-4)
+    ok, ver, params = s.pull_dense_parameters(0)
+    assert ok and ver == 0 and rel_close(params["t1"], a, 1e-4) and rel_close(params["t2"], b, 1e-4)
+    # PushGradients{LearningRate: 0.2}, grads == params (server_test.go:305-331)
+    acc, ver = s.push_gradients({"t1": a.reshape(2, 5), "t2": b.reshape(2, 5)},
+                                {"e1": (np.array([1], dtype=np.int64), c.reshape(1, 10))}, 0.2, 0)
+    assert acc and ver == 1
+    assert rel_close(s.dense["t1"], a - F(0.2) * a, 1e-4)
+    assert rel_close(s.dense["t2"], b - F(0.2) * b, 1e-4)
+    assert rel_close(s.tables["e1"].get([1]), c - F(0.2) * c, 1e-4)
+    # first-writer-wins re-push is ignored (server.go:209-221)
+    s.push_model(dense={"t1": np.zeros((2, 5), dtype=F)})
+    assert rel_close(s.dense["t1"], a - F(0.2) * a, 1e-4)
+    with pytest.raises(KeyError):
+        s.pull_embedding_vectors("nope", [1])
+
+
+def test_staleness_modulation_server_go_178():
+    s = O.OracleServer(0, "SGD", "learning_rate=0.1;momentum=0.0;nesterov=false;",
+                       lr_staleness_modulation=True)
+    s.push_model(dense={"w": np.ones(4, dtype=F)})
+    s.version = 5
+    s.push_gradients({"w": np.ones(4, dtype=F)}, {}, 0.1, 1)  # staleness 4 -> lr .025
+    assert np.allclose(s.dense["w"], 1 - 0.025)
+    s.push_gradients({"w": np.ones(4, dtype=F)}, {}, 0.0, 6)  # lr<=0 -> opt lr, no staleness
+    assert np.allclose(s.dense["w"], 1 - 0.025 - 0.1)
+
+
+# ------------------------------------------------------- embedding_table_test.go
+def test_embedding_table_embedding_table_test_go_21():
+    t = O.OracleTable(2, "zero")
+    t.set([1], np.array([[1, 2]], dtype=F))
+    out = t.get([1, 3, 5, 7, 9])
+    assert np.array_equal(out.reshape(-1), np.array([1, 2] + [0] * 8, dtype=F))
+    assert len(t) == 5
+    u = O.OracleTable(3, "uniform", seed=7)
+    r = u.get([11, 12])
+    assert np.all(r >= -0.05) and np.all(r < 0.05) and not np.array_equal(r[0], r[1])
+    assert np.array_equal(u.get([11]), r[:1])  # stable once created
+
+
+def test_model_roundtrip_model_test_go_46():
+    s = O.OracleServer(0, "SGD", "learning_rate=0.1;momentum=0.0;nesterov=false;")
+    s.push_model(infos=[O.EmbeddingTableInfo("e1", 2, "zero", 1)],
+                 tables={"e1": (np.array([1, 3, 5]), np.array([[1, 2], [3, 4], [5, 6]], dtype=F))},
+                 version=3)
+    assert s.version == 3
+    keys = np.sort(s.tables["e1"].keys())
+    assert keys.tolist() == [1, 3, 5]
+    assert np.array_equal(s.tables["e1"].get(keys), np.array([[1, 2], [3, 4], [5, 6]], dtype=F))
+
+
+def test_checkpoint_resharding_checkpoint_test_go_25():
+    # ids {0,2,4} U {1,3,5} re-hashed 2 -> 3 shards: {0,3} {1,4} {2,5}
+    ids = [0, 2, 4, 1, 3, 5]
+    shards = {}
+    for i in ids:
+        shards.setdefault(O.int_to_id(i, 3), []).append(i)
+    assert {k: sorted(v) for k, v in shards.items()} == {0: [0, 3], 1: [1, 4], 2: [2, 5]}
+
+
+# --------------------------------------------------------------- python vectors
+def test_string_to_id_pserver_servicer_test_py_509():
+    assert O.string_to_id("dense/kernel:0", 2) == 0
+    assert O.string_to_id("dense/bias:0", 2) == 1
+
+
+def test_reference_python_vectors():
+    gold = json.load(open(GOLD))
+    for c in gold["string_to_id"]:
+        assert O.string_to_id(c["name"], c["buckets"]) == c["id"]
+    for c in gold["int_to_id"]:
+        assert O.int_to_id(c["id"], c["buckets"]) == c["ps"]
+    for c in gold["scatter_embedding_vector"]:
+        res = O.scatter_embedding_vector(np.array(c["values"], dtype=F), np.array(c["ids"]), c["buckets"])
+        assert {str(k) for k in res} == set(c["result"])
+        for k, (v, i) in res.items():
+            assert list(i) == c["result"][str(k)]["ids"]
+            assert np.array_equal(v, np.array(c["result"][str(k)]["values"], dtype=F))
+    for c in gold["deduplicate_indexed_slices"]:
+        vals, ids = np.array(c["values"], dtype=F), np.array(c["ids"], dtype=np.int64)
+        v, i = O.deduplicate_indexed_slices(vals, ids)
+        assert i.tolist() == c["out_ids"]
+        assert np.array_equal(v, np.array(c["out_values"], dtype=F))  # bit-exact sums
+        v2, i2 = O.np_deduplicate_indexed_slices(vals, ids)
+        assert np.array_equal(v2, v) and np.array_equal(i2, i)
+
+
+def test_hash_utils_test_py_26():
+    # 5 ids, N=2, order-preserving groups
+    ids = np.array([8, 1, 7, 2, 3])
+    vals = np.arange(10, dtype=F).reshape(5, 2)
+    res = O.scatter_embedding_vector(vals, ids, 2)
+    assert res[0][1] == [8, 2] and res[1][1] == [1, 7, 3]
+    assert np.array_equal(res[0][0], vals[[0, 3]]) and np.array_equal(res[1][0], vals[[1, 2, 4]])
+
+
+def test_unique_first_occurrence_layer_test_py_135():
+    u, idx = O.unique_first_occurrence([0, 1, 3, 8, 3, 2, 3])
+    assert u.tolist() == [0, 1, 3, 8, 2] and idx.tolist() == [0, 1, 2, 3, 2, 4, 2]
+
+
+# -------------------------------------------- worker_ps_interaction / servicer py
+def _client(n, opt="SGD", args="learning_rate=0.1;momentum=0.0;nesterov=false;"):
+    return O.OraclePSClient([O.OracleServer(i, opt, args, num_ps=n) for i in range(n)])
+
+
+def test_pull_ordering_across_shards_worker_ps_interaction_test_py_153():
+    c = _client(2)
+    c.push_embedding_table_infos([O.EmbeddingTableInfo("emb", 8, "zero", 1)])
+    all_ids = np.arange(0, 11)
+    for s in c.servers:
+        mine = all_ids[all_ids % 2 == s.id]
+        s.tables["emb"].set(mine, np.repeat(mine[:, None], 8, 1).astype(F))
+    ids = [3, 5, 1, 6, 10, 2, 1, 2, 4, 7, 9]
+    out = c.pull_embedding_vectors("emb", ids)
+    assert np.array_equal(out, np.repeat(np.array(ids)[:, None], 8, 1).astype(F))
+
+
+def test_async_push_versions_pserver_servicer_test_py_305():
+    c = _client(1)
+    c.push_embedding_table_infos([O.EmbeddingTableInfo("emb", 2, "zero", 1)])
+    c.partition_dense_parameters(["w"])
+    c.push_dense_parameters([O.Tensor("w", np.ones(3, dtype=F), None)], 0, 0)
+    g = np.array([[1, 1], [2, 2], [3, 3]], dtype=F)
+    versions = [0]
+    acc, v = c.push_gradients([O.Tensor("w", np.ones(3, dtype=F), None)],
+                              [O.Tensor("emb", g.copy(), np.array([3, 1, 3]))], 0.1, versions)
+    assert acc and v == 1
+    # table[id] -= lr*g per occurrence (client dedup-sum == per-occurrence for SGD)
+    assert np.allclose(c.servers[0].tables["emb"].get([3]), -0.1 * (g[0] + g[2]))
+    assert np.allclose(c.servers[0].tables["emb"].get([1]), -0.1 * g[1])
+    acc, v = c.push_gradients([O.Tensor("w", np.ones(3, dtype=F), None)], [], 0.1, versions)
+    assert acc and v == 2
+    assert np.allclose(c.servers[0].dense["w"], 0.8)
+
+
+def test_every_shard_advances_quirk_q7():
+    c = _client(3, "Adam", "learning_rate=0.1;beta_1=0.9;beta_2=0.999;epsilon=1e-07;amsgrad=false;")
+    c.push_embedding_table_infos([O.EmbeddingTableInfo("emb", 2, "zero", 1)])
+    acc, v = c.push_gradients([], [O.Tensor("emb", np.ones((1, 2), dtype=F), np.array([3]))], 0.1, [0, 0, 0])
+    assert acc and v == 1
+    assert [s.version for s in c.servers] == [1, 1, 1]
+    assert [s.opt.step for s in c.servers] == [1, 1, 1]
+
+
+def test_amsgrad_dense_q1_flag():
+    args = "learning_rate=0.1;beta_1=0.9;beta_2=0.999;epsilon=1e-07;amsgrad=true;"
+    a = O.OracleServer(0, "Adam", args)
+    b = O.OracleServer(0, "Adam", args, reproduce_q1=True)
+    for s in (a, b):
+        s.push_model(dense={"w": np.ones(4, dtype=F)})
+        s.push_gradients({"w": np.ones(4, dtype=F)}, {}, 0.1, 0)
+    assert not np.allclose(a.dense["w"], b.dense["w"])  # the reference applies twice
