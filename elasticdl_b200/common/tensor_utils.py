@@ -1,0 +1,14 @@
+"""Value types of the PS boundary (elasticdl/python/common/tensor_utils.py:25-28)."""
+from collections import namedtuple
+
+Tensor = namedtuple("Tensor", ("name", "values", "indices"))
+
+# The reference's EmbeddingTableInfo is (name, dim, initializer, dtype).  The HBM
+# tables are direct-indexed, so the number of ids (the layer's input_dim) travels
+# with it as an optional fifth field.
+EmbeddingTableInfo = namedtuple(
+    "EmbeddingTableInfo", ("name", "dim", "initializer", "dtype", "capacity"),
+    defaults=(None,),
+)
+
+DT_FLOAT = 1  # tensorflow types_pb2.DT_FLOAT, the only dtype the PS stores (ps_trainer.py:187)

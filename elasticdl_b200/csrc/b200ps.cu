@@ -1,0 +1,952 @@
+// libb200ps.so -- host side of the C ABI declared in include/b200ps.h.
+// State a Go PS keeps in maps (go/pkg/ps/model.go:25-31) lives here as HBM
+// allocations on the owning shard's GPU plus a small directory (TableView[])
+// mirrored to the client device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ps_kernels.cuh"
+
+using namespace b200ps_impl;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_OK(expr)                                                                 \
+  do {                                                                                \
+    cudaError_t e_ = (expr);                                                          \
+    if (e_ != cudaSuccess)                                                            \
+      return fail(B200PS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+struct Alloc {  // one cudaMalloc on a shard, exported / imported as a CUDA-IPC handle
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  bool imported = false;
+};
+
+struct Table {
+  std::string name;
+  int dim = 0;
+  int n_slots = 0;
+  bool is_dense = false;
+  int owner = -1;
+  int64_t rows = 0;  // per shard (striped) or total (dense)
+  int64_t row_stride = 0;
+  int64_t slot_off[kMaxSlots + 1] = {0, 0, 0, 0};
+  size_t present_off = 0;  // byte offset of the bitmap inside the allocation
+  size_t bytes = 0;
+  bool uniform = false;
+  uint64_t seed = 0;
+  Alloc alloc[kMaxShards];
+};
+
+struct Shard {
+  bool local = false;
+  bool attached = false;
+  int device = -1;
+  Alloc ctl;
+};
+
+// Blob layout for export / import.
+struct BlobHeader {
+  uint32_t magic;
+  int32_t shard;
+  int32_t n_entries;
+  int32_t pad;
+};
+struct BlobEntry {
+  int32_t table;  // -1: control block
+  int32_t pad;
+  uint64_t bytes;
+  cudaIpcMemHandle_t handle;
+};
+constexpr uint32_t kBlobMagic = 0xB200F5A1u;
+
+}  // namespace
+
+struct b200ps {
+  int n_shards = 0;
+  int client_device = 0;
+  OptParams opt{};
+  int staleness = 0;
+  unsigned flags = 0;
+  Shard shard[kMaxShards];
+  std::vector<Table> tables;
+  std::unordered_map<std::string, int> by_name;
+  TableView* d_tables = nullptr;
+  int d_tables_cap = 0;
+  bool dirty = true;
+  PushRt* d_rt = nullptr;
+  unsigned* d_err = nullptr;
+  int* d_versions = nullptr;
+  unsigned long long* d_count = nullptr;
+  long long* d_state = nullptr;
+  long long launches = 0;
+  int n_sm = 148;
+  std::mutex mu;
+};
+
+namespace {
+
+// ---- optimizer argument grammar: go/pkg/ps/optimizer.go:284-390 -------------
+int parse_bool(const std::string& s, bool* out) {  // strconv.ParseBool
+  static const char* t[] = {"1", "t", "T", "TRUE", "true", "True"};
+  static const char* f[] = {"0", "f", "F", "FALSE", "false", "False"};
+  for (auto x : t) if (s == x) { *out = true; return 0; }
+  for (auto x : f) if (s == x) { *out = false; return 0; }
+  return -1;
+}
+
+int parse_float(const std::string& s, float* out) {
+  char* end = nullptr;
+  double v = strtod(s.c_str(), &end);
+  if (end == s.c_str() || *end != '\0') return -1;
+  *out = (float)v;  // strconv.ParseFloat(s, 32) then float32()
+  return 0;
+}
+
+int parse_optimizer(const char* type_c, const char* args_c, OptParams* o) {
+  std::string type = type_c ? type_c : "", args = args_c ? args_c : "";
+  static const std::map<std::string, std::vector<std::string>> want = {
+      {"SGD", {"learning_rate", "momentum", "nesterov"}},
+      {"Adam", {"learning_rate", "beta_1", "beta_2", "epsilon", "amsgrad"}},
+      {"Adagrad", {"learning_rate", "epsilon"}},
+      {"Ftrl", {"learning_rate", "initial_accumulator_value", "l1_regularization_strength",
+                "l2_regularization_strength", "l2_shrinkage_regularization_strength", "beta"}},
+  };
+  auto it = want.find(type);
+  if (it == want.end()) return fail(B200PS_EINVAL, "Unknown optimizer type " + type);
+  std::map<std::string, std::string> kv;
+  size_t pos = 0;
+  while (pos <= args.size()) {  // strings.Split(optArgs, ";")
+    size_t semi = args.find(';', pos);
+    std::string item = args.substr(pos, semi == std::string::npos ? std::string::npos : semi - pos);
+    if (!item.empty()) {
+      size_t eq = item.find('=');
+      if (eq == std::string::npos) return fail(B200PS_EINVAL, "malformed optimizer argument " + item);
+      kv[item.substr(0, eq)] = item.substr(eq + 1);
+    }
+    if (semi == std::string::npos) break;
+    pos = semi + 1;
+  }
+  for (auto& k : it->second)
+    if (!kv.count(k)) return fail(B200PS_EINVAL, "Args passed to ps should contain " + k);
+  if (kv.size() != it->second.size()) return fail(B200PS_EINVAL, "Args passed to ps contain redundant items");
+  memset(o, 0, sizeof(*o));
+  if (parse_float(kv["learning_rate"], &o->lr)) return fail(B200PS_EINVAL, "Having error converting learning rate to number");
+  if (type == "SGD") {
+    bool nes;
+    if (parse_float(kv["momentum"], &o->mu) || parse_bool(kv["nesterov"], &nes)) return fail(B200PS_EINVAL, "bad SGD argument");
+    o->nesterov = nes;
+    o->kind = o->mu > 0.0f ? kMomentum : kSGD;  // optimizer.go:353-356
+  } else if (type == "Adam") {
+    bool ams;
+    if (parse_float(kv["beta_1"], &o->beta1) || parse_float(kv["beta_2"], &o->beta2) ||
+        parse_float(kv["epsilon"], &o->epsilon) || parse_bool(kv["amsgrad"], &ams))
+      return fail(B200PS_EINVAL, "bad Adam argument");
+    o->kind = ams ? kAMSGrad : kAdam;
+    o->c1 = (float)(1.0 - (double)o->beta1);
+    o->c2 = (float)(1.0 - (double)o->beta2);
+  } else if (type == "Adagrad") {
+    if (parse_float(kv["epsilon"], &o->epsilon)) return fail(B200PS_EINVAL, "bad Adagrad argument");
+    o->kind = kAdagrad;
+  } else {
+    if (parse_float(kv["initial_accumulator_value"], &o->init_accum) ||
+        parse_float(kv["l1_regularization_strength"], &o->l1) ||
+        parse_float(kv["l2_regularization_strength"], &o->l2) ||
+        parse_float(kv["l2_shrinkage_regularization_strength"], &o->l2s) || parse_float(kv["beta"], &o->beta))
+      return fail(B200PS_EINVAL, "bad Ftrl argument");
+    o->kind = kFTRL;
+  }
+  return B200PS_OK;
+}
+
+GroupView group_view(b200ps_t* ps) {
+  GroupView gv{};
+  gv.tables = ps->d_tables;
+  for (int s = 0; s < ps->n_shards; ++s) gv.ctl[s] = (ShardCtl*)ps->shard[s].ctl.ptr;
+  gv.rt = ps->d_rt;
+  gv.err = ps->d_err;
+  gv.n_shards = ps->n_shards;
+  gv.shard_shift = -1;
+  if ((ps->n_shards & (ps->n_shards - 1)) == 0) {
+    int sh = 0;
+    while ((1 << sh) < ps->n_shards) ++sh;
+    gv.shard_shift = sh;
+  }
+  return gv;
+}
+
+int grid_for(b200ps_t* ps, long long work_items, int per_block = 256) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)ps->n_sm * 16;  // 16 CTAs of 256 threads per SM keep ~2 waves resident
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int ready(b200ps_t* ps) {
+  if (!ps) return fail(B200PS_EINVAL, "null group");
+  for (int s = 0; s < ps->n_shards; ++s)
+    if (!ps->shard[s].attached) return fail(B200PS_ESTATE, "shard " + std::to_string(s) + " is not attached");
+  if (ps->dirty) return fail(B200PS_ESTATE, "b200ps_commit() not called after the last registration/import");
+  return B200PS_OK;
+}
+
+void fill_view(b200ps_t* ps, const Table& t, TableView* v) {
+  memset(v, 0, sizeof(*v));
+  for (int s = 0; s < ps->n_shards; ++s) {
+    v->base[s] = (float*)t.alloc[s].ptr;
+    v->present[s] = (t.present_off && t.alloc[s].ptr) ? (uint32_t*)((char*)t.alloc[s].ptr + t.present_off) : nullptr;
+  }
+  v->rows = t.rows;
+  v->row_stride = t.row_stride;
+  for (int k = 0; k <= kMaxSlots; ++k) v->slot_off[k] = t.slot_off[k];
+  v->dim = t.dim;
+  v->n_slots = t.n_slots;
+  v->owner = t.owner;
+  v->is_dense = t.is_dense;
+}
+
+int alloc_table_on_shard(b200ps_t* ps, Table& t, int s, int table_id) {
+  Shard& sh = ps->shard[s];
+  DeviceGuard g(sh.device);
+  void* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, t.bytes));
+  t.alloc[s].ptr = p;
+  t.alloc[s].bytes = t.bytes;
+  InitArgs a{};
+  a.base = (float*)p;
+  a.rows = t.rows;
+  a.row_stride = t.row_stride;
+  for (int k = 0; k <= kMaxSlots; ++k) { a.slot_off[k] = t.slot_off[k]; a.slot_init[k] = 0.f; }
+  if (ps->opt.kind == kFTRL) a.slot_init[1] = ps->opt.init_accum;  // "accumulator" slot
+  a.dim = t.dim;
+  a.n_slots = t.n_slots;
+  a.uniform = t.uniform;
+  a.shard = s;
+  a.n_shards = ps->n_shards;
+  a.is_dense = t.is_dense;
+  a.seed = t.seed;
+  bool need_kernel = t.uniform || (ps->opt.kind == kFTRL && ps->opt.init_accum != 0.0f);
+  if (need_kernel) {
+    if (t.bytes > t.present_off && t.present_off) CUDA_OK(cudaMemsetAsync((char*)p + t.present_off, 0, t.bytes - t.present_off, 0));
+    long long work = t.rows * (long long)t.dim * (t.n_slots + 1);
+    k_init_rows<<<grid_for(ps, work), 256>>>(a);
+    ps->launches++;
+    CUDA_OK(cudaGetLastError());
+  } else {
+    CUDA_OK(cudaMemsetAsync(p, 0, t.bytes, 0));
+  }
+  CUDA_OK(cudaDeviceSynchronize());
+  (void)table_id;
+  return B200PS_OK;
+}
+
+// Splits a batch by vector class so that each launch is homogeneous:
+// class 2: dim % 8 == 0 (32 B sector per thread), 1: dim % 4 == 0, 0: scalar.
+int vec_class(const Table& t) {
+  // record slabs are 256 B aligned and row_stride is a multiple of 4 floats for vector classes
+  if (t.dim % 8 == 0 && t.row_stride % 4 == 0) return 2;
+  if (t.dim % 4 == 0 && t.row_stride % 4 == 0) return 1;
+  return 0;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+struct Split {
+  SegBatch b[3];
+  long long max_work[3] = {0, 0, 0};
+};
+
+int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense, Split* out) {
+  if (nseg < 0 || nseg > kMaxSegs) return fail(B200PS_EINVAL, "nseg out of range (max " + std::to_string(kMaxSegs) + ")");
+  for (int c = 0; c < 3; ++c) out->b[c].nseg = 0;
+  for (int i = 0; i < nseg; ++i) {
+    const b200ps_seg_t& sg = segs[i];
+    if (sg.table < 0 || sg.table >= (int)ps->tables.size()) return fail(B200PS_ENOTFOUND, "unknown table id " + std::to_string(sg.table));
+    const Table& t = ps->tables[sg.table];
+    if (want_dense && !t.is_dense) return fail(B200PS_EINVAL, t.name + " is not a dense parameter");
+    if (sg.n < 0) return fail(B200PS_EINVAL, "negative segment length");
+    if (sg.n == 0 && !want_dense) continue;
+    int c = vec_class(t);
+    if (c > 0 && !aligned16(sg.rows_dev)) c = 0;
+    long long work;
+    if (want_dense) {
+      long long numel = t.rows * t.dim;
+      c = (numel % 4 == 0 && aligned16(sg.rows_dev)) ? 1 : 0;
+      work = c ? numel / 4 : numel;
+    } else {
+      int W = c == 0 ? 1 : 4 * c;
+      work = (long long)sg.n * (t.dim / W);
+    }
+    SegBatch& b = out->b[c];
+    b.seg[b.nseg++] = sg;
+    if (work > out->max_work[c]) out->max_work[c] = work;
+  }
+  return B200PS_OK;
+}
+
+template <typename F>
+int for_each_class(b200ps_t* ps, Split& sp, F&& launch) {
+  for (int c = 0; c < 3; ++c) {
+    if (sp.b[c].nseg == 0) continue;
+    dim3 grid(grid_for(ps, sp.max_work[c]), sp.b[c].nseg);
+    launch(c, grid, sp.b[c]);
+    ps->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
+  return B200PS_OK;
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+const char* b200ps_last_error(void) { return g_err.c_str(); }
+int b200ps_abi_version(void) { return B200PS_ABI_VERSION; }
+
+int b200ps_create(int n_shards, int client_device, const char* opt_type, const char* opt_args,
+                  int lr_staleness_modulation, unsigned flags, b200ps_t** out) {
+  if (!out) return fail(B200PS_EINVAL, "out is null");
+  if (n_shards < 1 || n_shards > kMaxShards) return fail(B200PS_EINVAL, "n_shards must be in [1, 16]");
+  OptParams o;
+  int rc = parse_optimizer(opt_type, opt_args, &o);
+  if (rc) return rc;
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (client_device < 0 || client_device >= ndev) return fail(B200PS_ECUDA, "client device " + std::to_string(client_device) + " not present");
+  b200ps_t* ps = new b200ps();
+  ps->n_shards = n_shards;
+  ps->client_device = client_device;
+  ps->opt = o;
+  ps->staleness = lr_staleness_modulation;
+  ps->flags = flags;
+  DeviceGuard g(client_device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, client_device) == cudaSuccess) ps->n_sm = prop.multiProcessorCount;
+  cudaError_t e = cudaMalloc(&ps->d_rt, sizeof(PushRt));
+  if (e == cudaSuccess) e = cudaMemset(ps->d_rt, 0, sizeof(PushRt));
+  if (e == cudaSuccess) e = cudaMalloc(&ps->d_err, 64);
+  if (e == cudaSuccess) e = cudaMemset(ps->d_err, 0, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&ps->d_versions, sizeof(int) * kMaxShards);
+  if (e == cudaSuccess) e = cudaMalloc(&ps->d_count, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&ps->d_state, sizeof(long long) * 3 * kMaxShards);
+  if (e != cudaSuccess) {
+    delete ps;
+    return fail(B200PS_ECUDA, std::string("b200ps_create: ") + cudaGetErrorString(e));
+  }
+  *out = ps;
+  return B200PS_OK;
+}
+
+int b200ps_destroy(b200ps_t* ps) {
+  if (!ps) return B200PS_OK;
+  cudaSetDevice(ps->client_device);
+  cudaDeviceSynchronize();
+  for (auto& t : ps->tables)
+    for (int s = 0; s < ps->n_shards; ++s) {
+      if (!t.alloc[s].ptr) continue;
+      if (t.alloc[s].imported) cudaIpcCloseMemHandle(t.alloc[s].ptr);
+      else { DeviceGuard g(ps->shard[s].device); cudaFree(t.alloc[s].ptr); }
+    }
+  for (int s = 0; s < ps->n_shards; ++s) {
+    Alloc& a = ps->shard[s].ctl;
+    if (!a.ptr) continue;
+    if (a.imported) cudaIpcCloseMemHandle(a.ptr);
+    else { DeviceGuard g(ps->shard[s].device); cudaFree(a.ptr); }
+  }
+  cudaFree(ps->d_tables);
+  cudaFree(ps->d_rt);
+  cudaFree(ps->d_err);
+  cudaFree(ps->d_versions);
+  cudaFree(ps->d_count);
+  cudaFree(ps->d_state);
+  delete ps;
+  return B200PS_OK;
+}
+
+int b200ps_shard_create_local(b200ps_t* ps, int shard_id, int device) {
+  if (!ps || shard_id < 0 || shard_id >= ps->n_shards) return fail(B200PS_EINVAL, "bad shard id");
+  Shard& sh = ps->shard[shard_id];
+  if (sh.attached) return fail(B200PS_ESTATE, "shard already attached");
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(B200PS_ECUDA, "shard device not present");
+  if (device != ps->client_device) {
+    int can = 0;
+    CUDA_OK(cudaDeviceCanAccessPeer(&can, ps->client_device, device));
+    if (!can) return fail(B200PS_ECUDA, "no peer access from client device to shard device");
+    DeviceGuard g(ps->client_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_OK(e);
+    cudaGetLastError();
+  }
+  DeviceGuard g(device);
+  CUDA_OK(cudaMalloc(&sh.ctl.ptr, sizeof(ShardCtl)));
+  CUDA_OK(cudaMemset(sh.ctl.ptr, 0, sizeof(ShardCtl)));
+  sh.ctl.bytes = sizeof(ShardCtl);
+  sh.local = true;
+  sh.attached = true;
+  sh.device = device;
+  // tables registered before this shard existed
+  for (size_t i = 0; i < ps->tables.size(); ++i) {
+    Table& t = ps->tables[i];
+    if ((t.owner < 0 || t.owner == shard_id) && !t.alloc[shard_id].ptr) {
+      int rc = alloc_table_on_shard(ps, t, shard_id, (int)i);
+      if (rc) return rc;
+    }
+  }
+  ps->dirty = true;
+  return B200PS_OK;
+}
+
+int b200ps_shard_export(b200ps_t* ps, int shard_id, void* blob, size_t cap, size_t* size) {
+  if (!ps || shard_id < 0 || shard_id >= ps->n_shards || !size) return fail(B200PS_EINVAL, "bad argument");
+  Shard& sh = ps->shard[shard_id];
+  if (!sh.local) return fail(B200PS_ESTATE, "only a local shard can be exported");
+  std::vector<BlobEntry> entries;
+  DeviceGuard g(sh.device);
+  BlobEntry ce{};
+  ce.table = -1;
+  ce.bytes = sh.ctl.bytes;
+  CUDA_OK(cudaIpcGetMemHandle(&ce.handle, sh.ctl.ptr));
+  entries.push_back(ce);
+  for (size_t i = 0; i < ps->tables.size(); ++i) {
+    Table& t = ps->tables[i];
+    if (!t.alloc[shard_id].ptr) continue;
+    BlobEntry e{};
+    e.table = (int)i;
+    e.bytes = t.alloc[shard_id].bytes;
+    CUDA_OK(cudaIpcGetMemHandle(&e.handle, t.alloc[shard_id].ptr));
+    entries.push_back(e);
+  }
+  size_t need = sizeof(BlobHeader) + entries.size() * sizeof(BlobEntry);
+  *size = need;
+  if (!blob || cap < need) return blob ? fail(B200PS_EINVAL, "blob buffer too small") : B200PS_OK;
+  BlobHeader h{kBlobMagic, shard_id, (int)entries.size(), 0};
+  memcpy(blob, &h, sizeof(h));
+  memcpy((char*)blob + sizeof(h), entries.data(), entries.size() * sizeof(BlobEntry));
+  return B200PS_OK;
+}
+
+int b200ps_shard_import(b200ps_t* ps, int shard_id, const void* blob, size_t size) {
+  if (!ps || shard_id < 0 || shard_id >= ps->n_shards || !blob || size < sizeof(BlobHeader)) return fail(B200PS_EINVAL, "bad argument");
+  Shard& sh = ps->shard[shard_id];
+  if (sh.local) return fail(B200PS_ESTATE, "shard is local to this process");
+  BlobHeader h;
+  memcpy(&h, blob, sizeof(h));
+  if (h.magic != kBlobMagic || h.shard != shard_id) return fail(B200PS_EINVAL, "blob does not describe this shard");
+  if (size < sizeof(h) + (size_t)h.n_entries * sizeof(BlobEntry)) return fail(B200PS_EINVAL, "truncated blob");
+  DeviceGuard g(ps->client_device);
+  const BlobEntry* e = (const BlobEntry*)((const char*)blob + sizeof(h));
+  for (int i = 0; i < h.n_entries; ++i) {
+    Alloc* a = nullptr;
+    if (e[i].table < 0) a = &sh.ctl;
+    else {
+      if (e[i].table >= (int)ps->tables.size()) return fail(B200PS_ESTATE, "peer registered a table this process has not (register on every process first)");
+      a = &ps->tables[e[i].table].alloc[shard_id];
+    }
+    if (a->ptr) continue;  // already mapped
+    void* p = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&p, e[i].handle, cudaIpcMemLazyEnablePeerAccess));
+    a->ptr = p;
+    a->bytes = e[i].bytes;
+    a->imported = true;
+  }
+  sh.attached = true;
+  ps->dirty = true;
+  return B200PS_OK;
+}
+
+int b200ps_lookup(b200ps_t* ps, const char* name) {
+  if (!ps || !name) return fail(B200PS_EINVAL, "bad argument");
+  auto it = ps->by_name.find(name);
+  if (it == ps->by_name.end()) return fail(B200PS_ENOTFOUND, std::string(name) + " not in Parameter");
+  return it->second;
+}
+
+static int register_common(b200ps_t* ps, Table&& t) {
+  t.n_slots = opt_slots(ps->opt.kind);
+  int id = (int)ps->tables.size();
+  ps->tables.push_back(std::move(t));
+  Table& tt = ps->tables.back();
+  ps->by_name[tt.name] = id;
+  for (int s = 0; s < ps->n_shards; ++s) {
+    if (!ps->shard[s].local) continue;
+    if (tt.owner >= 0 && tt.owner != s) continue;
+    int rc = alloc_table_on_shard(ps, tt, s, id);
+    if (rc) return rc;
+  }
+  ps->dirty = true;
+  return id;
+}
+
+int b200ps_table_register(b200ps_t* ps, const char* name, int dim, const char* initializer, int64_t capacity,
+                          uint64_t seed) {
+  if (!ps || !name || dim < 1 || capacity < 1) return fail(B200PS_EINVAL, "bad table definition");
+  std::lock_guard<std::mutex> lk(ps->mu);
+  auto it = ps->by_name.find(name);
+  if (it != ps->by_name.end()) return it->second;  // model.go:57-63 idempotent
+  Table t;
+  t.name = name;
+  t.dim = dim;
+  t.owner = -1;
+  t.is_dense = false;
+  t.rows = (capacity + ps->n_shards - 1) / ps->n_shards;
+  int slots = opt_slots(ps->opt.kind);
+  int64_t rec = (int64_t)dim * (slots + 1);
+  rec = (rec + 3) / 4 * 4;  // 16 B aligned records
+  t.row_stride = rec;
+  for (int k = 0; k <= kMaxSlots; ++k) t.slot_off[k] = (int64_t)k * dim;
+  size_t rec_bytes = (size_t)t.rows * rec * sizeof(float);
+  rec_bytes = (rec_bytes + 255) / 256 * 256;
+  size_t bitmap = (ps->flags & 2u) ? 0 : (((size_t)t.rows + 31) / 32 * 4 + 255) / 256 * 256;
+  t.present_off = bitmap ? rec_bytes : 0;
+  t.bytes = rec_bytes + bitmap;
+  t.uniform = initializer && strcmp(initializer, "uniform") == 0;  // embedding_table.go:51 (quirk Q6)
+  t.seed = seed;
+  return register_common(ps, std::move(t));
+}
+
+int b200ps_dense_register(b200ps_t* ps, const char* name, int shard, int64_t rows, int dim) {
+  if (!ps || !name || dim < 1 || rows < 1 || shard < 0 || shard >= ps->n_shards) return fail(B200PS_EINVAL, "bad dense parameter definition");
+  std::lock_guard<std::mutex> lk(ps->mu);
+  auto it = ps->by_name.find(name);
+  if (it != ps->by_name.end()) return it->second;
+  Table t;
+  t.name = name;
+  t.dim = dim;
+  t.owner = shard;
+  t.is_dense = true;
+  t.rows = rows;
+  t.row_stride = dim;
+  int64_t numel = rows * dim;
+  int64_t padded = (numel + 63) / 64 * 64;  // every slot array starts 256 B aligned
+  for (int k = 0; k <= kMaxSlots; ++k) t.slot_off[k] = (int64_t)k * padded;
+  int slots = opt_slots(ps->opt.kind);
+  t.present_off = 0;
+  t.bytes = (size_t)padded * (slots + 1) * sizeof(float);
+  t.uniform = false;
+  return register_common(ps, std::move(t));
+}
+
+int b200ps_commit(b200ps_t* ps) {
+  if (!ps) return fail(B200PS_EINVAL, "null group");
+  std::lock_guard<std::mutex> lk(ps->mu);
+  DeviceGuard g(ps->client_device);
+  int n = (int)ps->tables.size();
+  if (n > ps->d_tables_cap) {
+    // the old directory may still be read by in-flight kernels
+    CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(ps->d_tables);
+    int cap = n < 64 ? 64 : n * 2;
+    CUDA_OK(cudaMalloc(&ps->d_tables, sizeof(TableView) * cap));
+    ps->d_tables_cap = cap;
+  }
+  if (n) {
+    std::vector<TableView> host(n);
+    for (int i = 0; i < n; ++i) fill_view(ps, ps->tables[i], &host[i]);
+    CUDA_OK(cudaMemcpy(ps->d_tables, host.data(), sizeof(TableView) * n, cudaMemcpyHostToDevice));
+  }
+  ps->dirty = false;
+  return B200PS_OK;
+}
+
+// ---- data path ---------------------------------------------------------------
+
+static int rows_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream, bool write, int slot = 0) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  if (slot < 0 || slot > opt_slots(ps->opt.kind)) return fail(B200PS_EINVAL, "optimizer has no such slot");
+  DeviceGuard g(ps->client_device);
+  Split sp;
+  rc = split_segs(ps, segs, nseg, false, &sp);
+  if (rc) return rc;
+  GroupView gv = group_view(ps);
+  cudaStream_t st = (cudaStream_t)stream;
+  return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
+    if (write) {
+      if (c == 2) k_rows_copy<2, true><<<grid, 256, 0, st>>>(gv, b, slot);
+      else if (c == 1) k_rows_copy<1, true><<<grid, 256, 0, st>>>(gv, b, slot);
+      else k_rows_copy<0, true><<<grid, 256, 0, st>>>(gv, b, slot);
+    } else {
+      if (c == 2) k_rows_copy<2, false><<<grid, 256, 0, st>>>(gv, b, slot);
+      else if (c == 1) k_rows_copy<1, false><<<grid, 256, 0, st>>>(gv, b, slot);
+      else k_rows_copy<0, false><<<grid, 256, 0, st>>>(gv, b, slot);
+    }
+  });
+}
+
+int b200ps_pull_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream) {
+  return rows_copy(ps, segs, nseg, stream, false);
+}
+int b200ps_set_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream) {
+  return rows_copy(ps, segs, nseg, stream, true);
+}
+
+static int dense_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream, bool write, int slot = 0) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  if (slot < 0 || slot > opt_slots(ps->opt.kind)) return fail(B200PS_EINVAL, "optimizer has no such slot");
+  DeviceGuard g(ps->client_device);
+  Split sp;
+  rc = split_segs(ps, segs, nseg, true, &sp);
+  if (rc) return rc;
+  GroupView gv = group_view(ps);
+  cudaStream_t st = (cudaStream_t)stream;
+  return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
+    if (write) {
+      if (c) k_dense_copy<4, true><<<grid, 256, 0, st>>>(gv, b, slot);
+      else k_dense_copy<1, true><<<grid, 256, 0, st>>>(gv, b, slot);
+    } else {
+      if (c) k_dense_copy<4, false><<<grid, 256, 0, st>>>(gv, b, slot);
+      else k_dense_copy<1, false><<<grid, 256, 0, st>>>(gv, b, slot);
+    }
+  });
+}
+
+int b200ps_pull_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream) {
+  return dense_copy(ps, segs, nseg, stream, false);
+}
+int b200ps_set_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream) {
+  return dense_copy(ps, segs, nseg, stream, true);
+}
+
+int b200ps_slot_rows(b200ps_t* ps, int slot, int write, const b200ps_seg_t* segs, int nseg, void* stream) {
+  return rows_copy(ps, segs, nseg, stream, write != 0, slot);
+}
+int b200ps_slot_dense(b200ps_t* ps, int slot, int write, const b200ps_seg_t* segs, int nseg, void* stream) {
+  return dense_copy(ps, segs, nseg, stream, write != 0, slot);
+}
+
+static int push_begin_impl(b200ps_t* ps, float lr, const int32_t* mv, void* stream, int bump_only) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  DeviceGuard g(ps->client_device);
+  VersionsIn v{};
+  for (int s = 0; s < ps->n_shards; ++s) v.v[s] = mv ? mv[s] : 0;
+  k_push_begin<<<1, 32, 0, (cudaStream_t)stream>>>(group_view(ps), ps->opt, lr, v, ps->staleness, bump_only);
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
+int b200ps_push_begin(b200ps_t* ps, float learning_rate, const int32_t* model_versions, void* stream) {
+  return push_begin_impl(ps, learning_rate, model_versions, stream, 0);
+}
+int b200ps_bump_step(b200ps_t* ps, void* stream) { return push_begin_impl(ps, 0.f, nullptr, stream, 1); }
+
+#define DISPATCH_OPT(KIND, ...)                        \
+  switch (KIND) {                                       \
+    case kSGD: { constexpr int OPT = kSGD; __VA_ARGS__; } break;           \
+    case kMomentum: { constexpr int OPT = kMomentum; __VA_ARGS__; } break; \
+    case kAdam: { constexpr int OPT = kAdam; __VA_ARGS__; } break;         \
+    case kAMSGrad: { constexpr int OPT = kAMSGrad; __VA_ARGS__; } break;   \
+    case kAdagrad: { constexpr int OPT = kAdagrad; __VA_ARGS__; } break;   \
+    default: { constexpr int OPT = kFTRL; __VA_ARGS__; } break;            \
+  }
+
+int b200ps_push_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  DeviceGuard g(ps->client_device);
+  Split sp;
+  rc = split_segs(ps, segs, nseg, false, &sp);
+  if (rc) return rc;
+  GroupView gv = group_view(ps);
+  cudaStream_t st = (cudaStream_t)stream;
+  OptParams o = ps->opt;
+  return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
+    DISPATCH_OPT(o.kind, {
+      if (c == 2) k_push_rows<OPT, 2><<<grid, 256, 0, st>>>(gv, b, o);
+      else if (c == 1) k_push_rows<OPT, 1><<<grid, 256, 0, st>>>(gv, b, o);
+      else k_push_rows<OPT, 0><<<grid, 256, 0, st>>>(gv, b, o);
+    });
+  });
+}
+
+int b200ps_push_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  DeviceGuard g(ps->client_device);
+  Split sp;
+  rc = split_segs(ps, segs, nseg, true, &sp);
+  if (rc) return rc;
+  GroupView gv = group_view(ps);
+  cudaStream_t st = (cudaStream_t)stream;
+  OptParams o = ps->opt;
+  const bool twice = (ps->flags & 1u) && o.kind == kAMSGrad;
+  return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
+    if (twice) {
+      if (c) k_push_dense<kAMSGrad, 4, true><<<grid, 256, 0, st>>>(gv, b, o);
+      else k_push_dense<kAMSGrad, 1, true><<<grid, 256, 0, st>>>(gv, b, o);
+      return;
+    }
+    DISPATCH_OPT(o.kind, {
+      if (c) k_push_dense<OPT, 4, false><<<grid, 256, 0, st>>>(gv, b, o);
+      else k_push_dense<OPT, 1, false><<<grid, 256, 0, st>>>(gv, b, o);
+    });
+  });
+}
+
+int b200ps_push_dense_reduce(b200ps_t* ps, int dense_id, const float* const* grads_dev, int n_replicas, float scale,
+                             void* stream) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  if (dense_id < 0 || dense_id >= (int)ps->tables.size() || !ps->tables[dense_id].is_dense) return fail(B200PS_ENOTFOUND, "not a dense parameter");
+  if (n_replicas < 1 || n_replicas > kMaxShards || !grads_dev) return fail(B200PS_EINVAL, "n_replicas out of range");
+  DeviceGuard g(ps->client_device);
+  const Table& t = ps->tables[dense_id];
+  ReplicaGrads rg{};
+  bool vec = (t.rows * t.dim) % 4 == 0;
+  for (int r = 0; r < n_replicas; ++r) {
+    rg.g[r] = grads_dev[r];
+    vec = vec && aligned16(grads_dev[r]);
+  }
+  rg.n = n_replicas;
+  rg.scale = scale;
+  long long numel = t.rows * t.dim;
+  GroupView gv = group_view(ps);
+  cudaStream_t st = (cudaStream_t)stream;
+  OptParams o = ps->opt;
+  const bool twice = (ps->flags & 1u) && o.kind == kAMSGrad;
+  int grid = grid_for(ps, vec ? numel / 4 : numel);
+  if (twice) {
+    if (vec) k_push_dense_reduce<kAMSGrad, 4, true><<<grid, 256, 0, st>>>(gv, dense_id, rg, o);
+    else k_push_dense_reduce<kAMSGrad, 1, true><<<grid, 256, 0, st>>>(gv, dense_id, rg, o);
+  } else {
+    DISPATCH_OPT(o.kind, {
+      if (vec) k_push_dense_reduce<OPT, 4, false><<<grid, 256, 0, st>>>(gv, dense_id, rg, o);
+      else k_push_dense_reduce<OPT, 1, false><<<grid, 256, 0, st>>>(gv, dense_id, rg, o);
+    });
+  }
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
+int b200ps_push_end(b200ps_t* ps, int32_t* versions_out_host, void* stream) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  DeviceGuard g(ps->client_device);
+  cudaStream_t st = (cudaStream_t)stream;
+  k_push_end<<<1, 32, 0, st>>>(group_view(ps), ps->d_versions);
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  if (versions_out_host)
+    CUDA_OK(cudaMemcpyAsync(versions_out_host, ps->d_versions, sizeof(int) * ps->n_shards, cudaMemcpyDeviceToHost, st));
+  return B200PS_OK;
+}
+
+// ---- unique / segment sum ------------------------------------------------------
+
+static int uniq_cap(int64_t k) {
+  int cap = 64;
+  while ((int64_t)cap < 2 * k) cap <<= 1;
+  return cap;
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+size_t b200ps_unique_workspace(int T, int64_t k) {
+  if (T < 1 || k < 1) return 256;
+  size_t cap = (size_t)uniq_cap(k);
+  size_t ntiles = (size_t)((k + kTile - 1) / kTile);
+  return align256((size_t)T * cap * 8) + align256((size_t)T * cap * 4) + 2 * align256((size_t)T * k * 4) +
+         align256((size_t)T * ntiles * 4) + 256;
+}
+
+int b200ps_unique(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, int64_t* uniq_dev, int32_t* inv_dev,
+                  int32_t* n_unique_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!ps || T < 1 || T > 65535 || k < 1 || k > (1LL << 30)) return fail(B200PS_EINVAL, "bad unique shape");
+  if (workspace_bytes < b200ps_unique_workspace(T, k)) return fail(B200PS_EINVAL, "unique workspace too small");
+  DeviceGuard g(ps->client_device);
+  cudaStream_t st = (cudaStream_t)stream;
+  UniqueWs ws;
+  ws.cap = uniq_cap(k);
+  ws.ntiles = (int)((k + kTile - 1) / kTile);
+  char* p = (char*)workspace_dev;
+  ws.keys = (long long*)p; p += align256((size_t)T * ws.cap * 8);
+  ws.minpos = (int*)p; p += align256((size_t)T * ws.cap * 4);
+  ws.fp = (int*)p; p += align256((size_t)T * k * 4);
+  ws.rank_at = (int*)p; p += align256((size_t)T * k * 4);
+  ws.tile_cnt = (int*)p;
+  k_uniq_clear<<<grid_for(ps, (long long)T * ws.cap), 256, 0, st>>>(ws, T);
+  dim3 gk((unsigned)((k + 255) / 256), T), gt(ws.ntiles, T);
+  k_uniq_insert<<<gk, 256, 0, st>>>(ids_dev, k, ws);
+  k_uniq_flag<<<gt, 256, 0, st>>>(k, ws);
+  k_uniq_scan_tiles<<<T, 1024, 0, st>>>(ws, n_unique_dev);
+  k_uniq_rank<<<gt, 256, 0, st>>>(ids_dev, k, ws, uniq_dev);
+  k_uniq_inverse<<<gk, 256, 0, st>>>(k, ws, inv_dev);
+  ps->launches += 6;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
+static int dim_class(int dim, const void* a, const void* b) {
+  if (!aligned16(a) || !aligned16(b)) return 0;
+  return dim % 8 == 0 ? 2 : dim % 4 == 0 ? 1 : 0;
+}
+
+int b200ps_segment_sum(b200ps_t* ps, const float* values_dev, const int32_t* inv_dev, int T, int64_t k, int dim,
+                       float* out_dev, void* stream) {
+  if (!ps || T < 1 || T > 65535 || k < 1 || dim < 1) return fail(B200PS_EINVAL, "bad segment_sum shape");
+  DeviceGuard g(ps->client_device);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaMemsetAsync(out_dev, 0, (size_t)T * k * dim * sizeof(float), st));
+  int c = dim_class(dim, values_dev, out_dev);
+  int W = c == 0 ? 1 : 4 * c;
+  dim3 grid(grid_for(ps, k * (dim / W)), T);
+  if (c == 2) k_segment_sum<2><<<grid, 256, 0, st>>>(values_dev, inv_dev, k, dim, out_dev);
+  else if (c == 1) k_segment_sum<1><<<grid, 256, 0, st>>>(values_dev, inv_dev, k, dim, out_dev);
+  else k_segment_sum<0><<<grid, 256, 0, st>>>(values_dev, inv_dev, k, dim, out_dev);
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
+int b200ps_gather_rows(b200ps_t* ps, const float* bet_dev, const int32_t* inv_dev, int T, int64_t k, int dim,
+                       float* out_dev, void* stream) {
+  if (!ps || T < 1 || T > 65535 || k < 1 || dim < 1) return fail(B200PS_EINVAL, "bad gather shape");
+  DeviceGuard g(ps->client_device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int c = dim_class(dim, bet_dev, out_dev);
+  int W = c == 0 ? 1 : 4 * c;
+  dim3 grid(grid_for(ps, k * (dim / W)), T);
+  if (c == 2) k_gather_rows<2><<<grid, 256, 0, st>>>(bet_dev, inv_dev, k, dim, out_dev);
+  else if (c == 1) k_gather_rows<1><<<grid, 256, 0, st>>>(bet_dev, inv_dev, k, dim, out_dev);
+  else k_gather_rows<0><<<grid, 256, 0, st>>>(bet_dev, inv_dev, k, dim, out_dev);
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
+// ---- state ---------------------------------------------------------------------
+
+int b200ps_shard_state(b200ps_t* ps, int shard, int32_t* version, int64_t* step, int32_t* initialized) {
+  if (!ps || shard < 0 || shard >= ps->n_shards || !ps->shard[shard].attached) return fail(B200PS_EINVAL, "bad shard");
+  DeviceGuard g(ps->client_device);
+  CUDA_OK(cudaDeviceSynchronize());
+  ShardCtl c;
+  CUDA_OK(cudaMemcpy(&c, ps->shard[shard].ctl.ptr, sizeof(c), cudaMemcpyDefault));
+  if (version) *version = c.version;
+  if (step) *step = c.step;
+  if (initialized) *initialized = c.initialized;
+  return B200PS_OK;
+}
+
+int b200ps_set_shard_state(b200ps_t* ps, int shard, int32_t version, int64_t step, int32_t initialized) {
+  if (!ps || shard < 0 || shard >= ps->n_shards || !ps->shard[shard].attached) return fail(B200PS_EINVAL, "bad shard");
+  DeviceGuard g(ps->client_device);
+  CUDA_OK(cudaDeviceSynchronize());
+  ShardCtl c;
+  CUDA_OK(cudaMemcpy(&c, ps->shard[shard].ctl.ptr, sizeof(c), cudaMemcpyDefault));
+  if (version >= 0) c.version = version;
+  if (step >= 0) c.step = step;
+  if (initialized >= 0) c.initialized = initialized;
+  CUDA_OK(cudaMemcpy(ps->shard[shard].ctl.ptr, &c, sizeof(c), cudaMemcpyDefault));
+  return B200PS_OK;
+}
+
+int b200ps_snapshot_state(b200ps_t* ps, int64_t* out_host, void* stream) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  if (!out_host) return fail(B200PS_EINVAL, "out_host is null");
+  DeviceGuard g(ps->client_device);
+  cudaStream_t st = (cudaStream_t)stream;
+  k_snapshot<<<1, 32, 0, st>>>(group_view(ps), (long long*)ps->d_state);
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(out_host, ps->d_state, sizeof(int64_t) * 3 * ps->n_shards, cudaMemcpyDeviceToHost, st));
+  return B200PS_OK;
+}
+
+int b200ps_try_init(b200ps_t* ps, int shard, int* won) {
+  if (!ps || shard < 0 || shard >= ps->n_shards || !ps->shard[shard].attached || !won) return fail(B200PS_EINVAL, "bad shard");
+  DeviceGuard g(ps->client_device);
+  k_try_init<<<1, 1>>>((ShardCtl*)ps->shard[shard].ctl.ptr, (int*)ps->d_count);
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  int w = 0;
+  CUDA_OK(cudaMemcpy(&w, ps->d_count, sizeof(int), cudaMemcpyDeviceToHost));
+  *won = w;
+  return B200PS_OK;
+}
+
+int b200ps_finish_init(b200ps_t* ps, int shard, int32_t version, void* stream) {
+  if (!ps || shard < 0 || shard >= ps->n_shards || !ps->shard[shard].attached) return fail(B200PS_EINVAL, "bad shard");
+  DeviceGuard g(ps->client_device);
+  k_finish_init<<<1, 1, 0, (cudaStream_t)stream>>>((ShardCtl*)ps->shard[shard].ctl.ptr, version);
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
+static int present_scan(b200ps_t* ps, int table, int shard, int64_t* ids_dev, int64_t cap, int64_t* n) {
+  if (!ps || table < 0 || table >= (int)ps->tables.size() || shard < 0 || shard >= ps->n_shards || !n) return fail(B200PS_EINVAL, "bad argument");
+  const Table& t = ps->tables[table];
+  if (t.is_dense || !t.present_off) return fail(B200PS_ESTATE, "created rows are not tracked for " + t.name);
+  if (!t.alloc[shard].ptr) return fail(B200PS_ESTATE, "shard not attached");
+  DeviceGuard g(ps->client_device);
+  CUDA_OK(cudaMemsetAsync(ps->d_count, 0, 8, 0));
+  k_present_ids<<<grid_for(ps, t.rows), 256>>>((const uint32_t*)((const char*)t.alloc[shard].ptr + t.present_off), t.rows,
+                                                shard, ps->n_shards, ids_dev, cap, ps->d_count);
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  unsigned long long c = 0;
+  CUDA_OK(cudaMemcpy(&c, ps->d_count, 8, cudaMemcpyDeviceToHost));
+  *n = (int64_t)c;
+  return B200PS_OK;
+}
+
+int b200ps_table_size(b200ps_t* ps, int table, int shard, int64_t* rows) { return present_scan(ps, table, shard, nullptr, 0, rows); }
+int b200ps_table_ids(b200ps_t* ps, int table, int shard, int64_t* ids_dev, int64_t cap, int64_t* n) {
+  return present_scan(ps, table, shard, ids_dev, cap, n);
+}
+
+int b200ps_check(b200ps_t* ps) {
+  if (!ps) return fail(B200PS_EINVAL, "null group");
+  DeviceGuard g(ps->client_device);
+  CUDA_OK(cudaDeviceSynchronize());
+  unsigned e = 0;
+  CUDA_OK(cudaMemcpy(&e, ps->d_err, 4, cudaMemcpyDeviceToHost));
+  if (e) {
+    CUDA_OK(cudaMemset(ps->d_err, 0, 4));
+    if (e & kErrRange) return fail(B200PS_ERANGE, "embedding id outside the registered table capacity (or negative)");
+    return fail(B200PS_EINVAL, "device-side error word " + std::to_string(e));
+  }
+  return B200PS_OK;
+}
+
+int64_t b200ps_launch_count(b200ps_t* ps) { return ps ? ps->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+"""PSClient: the worker-side boundary of the parameter-server path.
+
+Same class name, attributes, method names, argument order and return
+conventions as elasticdl/python/worker/ps_client.py:87-301, so the trainer and
+the Embedding layer call it unchanged.  What is different is underneath: the
+"channels" are the HBM shards of a PSGroup, the per-shard request fan-out
+(ps_client.py:105-120, 243-277) is the `id % N` addressing inside one CUDA
+launch, and nothing is serialised.
+
+Array types: numpy arrays / lists in -> numpy arrays out (the reference's
+contract); torch CUDA tensors in -> torch CUDA tensors out (no host hop).
+"""
+import numpy as np
+import torch
+
+from elasticdl_b200 import _lib
+from elasticdl_b200.common.hash_utils import string_to_id
+from elasticdl_b200.common.tensor_utils import Tensor  # noqa: F401  (re-export, as the reference module does)
+from elasticdl_b200.ps.group import PSGroup
+
+
+def build_ps_client(ps_group, logger=None):
+    """≙ build_ps_client(ps_addrs, logger) (ps_client.py:37-84): there are no
+    addresses to dial -- the group's shards are already attached -- so this only
+    wraps the group.  Returns None for a falsy group like the reference does for
+    an empty address list."""
+    if not ps_group:
+        return None
+    return PSClient(ps_group)
+
+
+def _is_torch(x):
+    return isinstance(x, torch.Tensor)
+
+
+class PSClient(object):
+    def __init__(self, ps_group):
+        if not isinstance(ps_group, PSGroup):
+            raise TypeError("PSClient needs a PSGroup (the HBM shards); got %r" % type(ps_group))
+        self.group = ps_group
+        self.ps_num = ps_group.n_shards
+        self.parameter_to_ps = {}
+        self.ps_to_parameter = {}
+        self.dense_output = "numpy"  # or "torch": keep pulled dense parameters on the device
+
+    # ------------------------------------------------------------------ embeddings
+    def pull_embedding_vectors(self, layer_name, embedding_ids):
+        """Pulls and returns embedding vectors ordered by the embedding ids
+        (ps_client.py:96-130)."""
+        as_torch = _is_torch(embedding_ids)
+        n = embedding_ids.numel() if as_torch else len(embedding_ids)
+        if n == 0:
+            # the reference np.concatenate()s an empty list here
+            raise ValueError("need at least one array to concatenate")
+        (out,) = self.group.pull_rows([(layer_name, embedding_ids)])
+        if as_torch:
+            return out
+        self.group.check()  # device sync + out-of-range ids -> exception
+        return out.cpu().numpy()
+
+    def pull_embedding_vectors_batch(self, requests):
+        """[(layer_name, ids)] -> [rows] with one launch per vector class (device
+        tensors in, device tensors out).  No reference counterpart: the reference
+        issues one RPC per (layer, shard)."""
+        return self.group.pull_rows(requests)
+
+    def push_embedding_table_infos(self, infos):
+        """ps_client.py:289-301 -> every shard creates the tables + slot tables."""
+        for info in infos:
+            cap = getattr(info, "capacity", None)
+            self.group.register_table(info.name, info.dim, info.initializer, cap)
+        self.group.commit()
+
+    # ------------------------------------------------------------------ dense
+    def partition_dense_parameters(self, param_names, shapes=None):
+        """ps_id = string_to_id(param_name) (ps_client.py:132-144).  `shapes`
+        (optional, name -> shape) lets every process of a multi-process group
+        register the parameters collectively up front."""
+        registered = False
+        for name in param_names:
+            if name not in self.parameter_to_ps:
+                self.parameter_to_ps[name] = string_to_id(name, self.ps_num)
+                ps_id = self.parameter_to_ps[name]
+                if ps_id not in self.ps_to_parameter:
+                    self.ps_to_parameter[ps_id] = [name]
+                else:
+                    self.ps_to_parameter[ps_id].append(name)
+            if shapes is not None and name not in self.group.tables:
+                self.group.register_dense(name, shapes[name], self.parameter_to_ps[name])
+                registered = True
+        if registered:
+            self.group.commit()
+
+    def push_dense_parameters(self, parameters, ps_id, version):
+        """Push dense parameters to one shard (ps_client.py:146-159 -> PushModel,
+        server.go:209-221: first writer wins, later pushes are ignored)."""
+        mine = [p for p in parameters if self.parameter_to_ps[p.name] == ps_id]
+        registered = False
+        for p in mine:
+            if p.name not in self.group.tables:
+                if len(self.group.local_shards) != self.group.n_shards:
+                    raise RuntimeError(
+                        "dense parameter %s was not registered collectively; call "
+                        "partition_dense_parameters(names, shapes=...) on every rank first" % p.name)
+                self.group.register_dense(p.name, tuple(np.shape(p.values)), ps_id)
+                registered = True
+        if registered:
+            self.group.commit()
+        if self.group.try_init(ps_id):
+            self.group.set_dense([(p.name, p.values) for p in mine])
+            self.group.finish_init(ps_id, version)
+
+    def pull_dense_parameters(self, ps_ids, model_versions):
+        """Pull dense parameters (ps_client.py:161-188).  Mutates model_versions in
+        place.  Go semantics: parameters are sent when Version >= requested
+        (server.go:150, quirk Q8)."""
+        wanted = [ps_id for ps_id in ps_ids if ps_id in self.ps_to_parameter]
+        dense_params = {}
+        uninit_ps = []
+        if not wanted:
+            return dense_params, uninit_ps
+        state = self.group.snapshot()
+        names = []
+        for ps_id in wanted:
+            version, _, initialized = state[ps_id]
+            if not initialized:
+                uninit_ps.append(ps_id)
+                continue
+            if version >= model_versions[ps_id]:
+                names.extend(n for n in self.ps_to_parameter[ps_id] if n in self.group.tables)
+            model_versions[ps_id] = version
+        if names:
+            pulled = self.group.pull_dense(names)
+            if self.dense_output == "torch":
+                dense_params.update(pulled)
+            else:
+                for k, v in pulled.items():
+                    dense_params[k] = v.cpu().numpy()
+        return dense_params, uninit_ps
+
+    # ------------------------------------------------------------------ gradients
+    def _dedup(self, name, values_list, indices_list, dim):
+        """merge_indexed_slices + deduplicate_indexed_slices (tensor_utils.py:31-60)
+        on the device: concatenate, unique ids in first-occurrence order, summed rows."""
+        g = self.group
+        vals = [g._f32(v).reshape(-1, dim) for v in values_list]
+        ids = [g._ids(i) for i in indices_list]
+        v = vals[0] if len(vals) == 1 else torch.cat(vals, 0)
+        i = ids[0] if len(ids) == 1 else torch.cat(ids, 0)
+        k = i.numel()
+        if v.shape[0] != k:
+            raise ValueError("gradient rows (%d) and indices (%d) differ for %s" % (v.shape[0], k, name))
+        uniq, inv, n_unique = g.unique(i, 1)
+        gsum = g.segment_sum(v, inv, 1, k, dim)
+        return uniq, n_unique, gsum, k
+
+    def push_gradients(self, grads, edl_grads, learning_rate, model_versions):
+        """Push gradients to the PS (ps_client.py:190-287).  Two kinds:
+         - gradients of normal layers (dense, or IndexedSlices of a dense parameter)
+         - sparse gradients of ElasticDL embedding layers
+        Every shard applies exactly one ApplyGradients and bumps its version
+        (quirk Q7).  Returns (accepted, max_version)."""
+        g = self.group
+        # 1. group by name; same-name merge (ps_client.py:203-217)
+        dense, indexed = {}, {}
+        for grad in grads:
+            if grad.name not in self.parameter_to_ps:
+                raise KeyError(grad.name)  # the reference indexes parameter_to_ps[grad.name]
+            if grad.indices is not None:
+                indexed.setdefault(grad.name, ([], []))
+                indexed[grad.name][0].append(grad.values)
+                indexed[grad.name][1].append(grad.indices)
+            elif grad.name in dense:
+                dense[grad.name] = g._f32(dense[grad.name]) + g._f32(grad.values)
+            else:
+                dense[grad.name] = grad.values
+        edl = {}
+        for grad in edl_grads:  # ps_client.py:243-251
+            edl.setdefault(grad.name, ([], []))
+            edl[grad.name][0].append(grad.values)
+            edl[grad.name][1].append(grad.indices)
+
+        # validate before launching: the Go PS fails the whole ApplyGradients
+        # ("grad %s not in Parameter", optimizer.go:49,59; width check kernel.go:36-38)
+        # after step++ (quirk Q2)
+        try:
+            dense_items, row_items = [], []
+            for name, v in dense.items():
+                tid, _, is_dense, shape = g.lookup(name)
+                t = g._f32(v)
+                if t.numel() != int(np.prod(shape)):
+                    raise ValueError("grad size mismatch for %s" % name)
+                dense_items.append((tid, 0, None, None, t))
+            for group_, is_edl in ((indexed, False), (edl, True)):
+                for name, (vl, il) in group_.items():
+                    tid, dim, is_dense, shape = g.lookup(name)
+                    width = int(np.prod(np.shape(vl[0])[1:])) if np.ndim(vl[0]) > 1 else 1
+                    if width != dim:
+                        raise ValueError("grad width is not equal to embedding dim")
+                    uniq, n_unique, gsum, k = self._dedup(name, vl, il, dim)
+                    row_items.append((tid, k, uniq, n_unique, gsum))
+        except (_lib.PSNotFound, ValueError):
+            g.bump_step()
+            raise
+
+        # 2. one ApplyGradients per shard: begin (step++, lr), kernels, end (version++)
+        g.push_begin(learning_rate, model_versions)
+        if dense_items:
+            g.push_dense(dense_items)
+        if row_items:
+            g.push_rows(row_items)
+        versions = g.push_end(sync=True)
+        g.check()
+        return True, max(versions)

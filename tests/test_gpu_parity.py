@@ -1,0 +1,443 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via PSGroup/PSClient)
+against the CPU oracle on the same seeded inputs.  Bit-exact for ids / gathers /
+integer work; fp32 optimizer state within 1e-5 relative (BASELINE.json
+north_star), and bit-exact where no duplicate-id summation is involved."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ps_oracle as O
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+OPTS = {
+    "sgd": ("SGD", "learning_rate=0.1;momentum=0.0;nesterov=false;"),
+    "momentum": ("SGD", "learning_rate=0.1;momentum=0.9;nesterov=false;"),
+    "nesterov": ("SGD", "learning_rate=0.1;momentum=0.9;nesterov=true;"),
+    "adam": ("Adam", "learning_rate=0.001;beta_1=0.9;beta_2=0.999;epsilon=1e-07;amsgrad=false;"),
+    "amsgrad": ("Adam", "learning_rate=0.001;beta_1=0.9;beta_2=0.999;epsilon=1e-07;amsgrad=true;"),
+    "adagrad": ("Adagrad", "learning_rate=0.1;epsilon=1e-07;"),
+    "ftrl": ("Ftrl", "learning_rate=0.1;initial_accumulator_value=0.1;l1_regularization_strength=0.01;"
+                     "l2_regularization_strength=0.02;l2_shrinkage_regularization_strength=0.0;beta=0.0;"),
+    "ftrl_shrink": ("Ftrl", "learning_rate=0.05;initial_accumulator_value=0.1;l1_regularization_strength=0.0;"
+                            "l2_regularization_strength=0.0;l2_shrinkage_regularization_strength=0.1;beta=0.5;"),
+}
+
+
+def make_pair(n_shards, opt="sgd", **kw):
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+
+    ot, oa = OPTS[opt]
+    group = PSGroup(n_shards, ot, oa, device=0, **kw)
+    client = PSClient(group)
+    servers = [O.OracleServer(i, ot, oa, num_ps=n_shards,
+                              lr_staleness_modulation=kw.get("lr_staleness_modulation", False),
+                              reproduce_q1=kw.get("reproduce_q1", False)) for i in range(n_shards)]
+    return group, client, O.OraclePSClient(servers)
+
+
+def info(name, dim, init="zero", capacity=1000):
+    from elasticdl_b200.common.tensor_utils import EmbeddingTableInfo
+
+    return EmbeddingTableInfo(name, dim, init, 1, capacity)
+
+
+def oinfo(name, dim, init="zero"):
+    return O.EmbeddingTableInfo(name, dim, init, 1)
+
+
+def close(a, b, rtol=1e-5, atol=1e-7):
+    return np.allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol, atol=atol)
+
+
+# ------------------------------------------------------------------ pull (bit exact)
+@pytest.mark.parametrize("n_shards", [1, 2, 3, 8])
+@pytest.mark.parametrize("dim", [1, 4, 8, 10, 64])
+def test_pull_bit_exact(n_shards, dim):
+    group, client, oc = make_pair(n_shards)
+    rng = np.random.RandomState(n_shards * 100 + dim)
+    cap = 5000
+    client.push_embedding_table_infos([info("emb", dim, capacity=cap)])
+    oc.push_embedding_table_infos([oinfo("emb", dim)])
+    ids = rng.permutation(cap)[:3000].astype(np.int64)
+    vals = rng.randn(3000, dim).astype(F)
+    group.set_rows([("emb", ids, vals)])
+    for s in oc.servers:
+        m = ids % n_shards == s.id
+        s.tables["emb"].set(ids[m], vals[m])
+    q = rng.choice(ids, size=4096).astype(np.int64)  # with repeats, arbitrary order
+    got = client.pull_embedding_vectors("emb", q)
+    want = oc.pull_embedding_vectors("emb", q)
+    assert got.dtype == np.float32 and got.shape == (4096, dim)
+    assert np.array_equal(got, want)
+    # never-written rows of a "zero" table read back as zeros and become created rows
+    fresh = np.setdiff1d(np.arange(cap), ids)[:50].astype(np.int64)
+    assert np.array_equal(client.pull_embedding_vectors("emb", fresh), np.zeros((50, dim), dtype=F))
+    assert group.table_size("emb") == len(np.unique(np.concatenate([ids, fresh])))
+    # torch in -> torch out, same bits
+    tq = torch.from_numpy(q).cuda()
+    assert np.array_equal(client.pull_embedding_vectors("emb", tq).cpu().numpy(), want)
+    group.close()
+
+
+def test_pull_ordering_worker_ps_interaction_test_py_153():
+    group, client, _ = make_pair(2)
+    client.push_embedding_table_infos([info("emb", 8, capacity=16)])
+    all_ids = np.arange(11, dtype=np.int64)
+    group.set_rows([("emb", all_ids, np.repeat(all_ids[:, None], 8, 1).astype(F))])
+    ids = [3, 5, 1, 6, 10, 2, 1, 2, 4, 7, 9]
+    out = client.pull_embedding_vectors("emb", ids)
+    assert np.array_equal(out, np.repeat(np.array(ids)[:, None], 8, 1).astype(F))
+    group.close()
+
+
+def test_uniform_initializer_matches_oracle_generator():
+    from elasticdl_b200.ps.group import table_seed
+
+    group, client, _ = make_pair(3, seed=11)
+    client.push_embedding_table_infos([info("u", 8, "uniform", capacity=999), info("RandomUniform", 8, "RandomUniform")])
+    ids = np.array([0, 1, 2, 500, 998, 7], dtype=np.int64)
+    got = client.pull_embedding_vectors("u", ids)
+    seed = table_seed(11, "u")
+    want = np.array([[O.lib.oracle_uniform_init(seed, int(i), c) for c in range(8)] for i in ids], dtype=F)
+    assert np.array_equal(got, want)
+    assert got.min() >= -0.05 and got.max() < 0.05
+    # quirk Q6: any initializer string other than the literal "uniform" zero-fills
+    assert not client.pull_embedding_vectors("RandomUniform", ids).any()
+    group.close()
+
+
+# ------------------------------------------------------------------ unique / dedup
+@pytest.mark.parametrize("k,hi,T", [(7, 9, 1), (1000, 50, 1), (4096, 100000, 3), (100000, 3000, 2), (1, 5, 4)])
+def test_unique_first_occurrence(k, hi, T):
+    group, _, _ = make_pair(1)
+    rng = np.random.RandomState(k + hi)
+    ids = rng.randint(0, hi, size=(T, k)).astype(np.int64)
+    if k == 7:
+        ids[0] = [0, 1, 3, 8, 3, 2, 3]  # layer_test.py:135 vector
+    uniq, inv, n = group.unique(torch.from_numpy(ids).cuda().view(-1), T)
+    uniq, inv, n = uniq.cpu().numpy().reshape(T, k), inv.cpu().numpy().reshape(T, k), n.cpu().numpy()
+    for t in range(T):
+        wu, wi = O.unique_first_occurrence(ids[t])
+        assert n[t] == len(wu)
+        assert np.array_equal(uniq[t, : n[t]], wu)
+        assert np.array_equal(inv[t], wi)
+    group.close()
+
+
+@pytest.mark.parametrize("dim", [1, 4, 8, 10])
+def test_segment_sum_matches_dedup(dim):
+    group, _, _ = make_pair(1)
+    rng = np.random.RandomState(dim)
+    k = 20000
+    ids = rng.zipf(1.3, size=k).astype(np.int64) % 4000
+    vals = rng.randn(k, dim).astype(F)
+    uniq, inv, n = group.unique(torch.from_numpy(ids).cuda(), 1)
+    out = group.segment_sum(torch.from_numpy(vals).cuda(), inv, 1, k, dim).cpu().numpy().reshape(k, dim)
+    wv, wi = O.deduplicate_indexed_slices(vals, ids)
+    u = int(n.item())
+    assert u == len(wi) and np.array_equal(uniq.cpu().numpy()[:u], wi)
+    assert np.allclose(out[:u], wv, rtol=1e-5, atol=1e-5)  # atomics: summation order differs
+    assert not out[u:].any()
+    # no duplicates -> bit exact
+    ids2 = rng.permutation(50000)[:k].astype(np.int64)
+    uniq, inv, n = group.unique(torch.from_numpy(ids2).cuda(), 1)
+    out = group.segment_sum(torch.from_numpy(vals).cuda(), inv, 1, k, dim).cpu().numpy().reshape(k, dim)
+    assert np.array_equal(out, vals)
+    g = group.gather_rows(torch.from_numpy(vals).cuda(), inv, 1, k, dim).cpu().numpy().reshape(k, dim)
+    assert np.array_equal(g, vals)
+    group.close()
+
+
+# ------------------------------------------------------------------ push: all optimizers
+def _setup_model(client, oc, rng, dims=(1, 8, 10)):
+    from elasticdl_b200.common.tensor_utils import Tensor
+
+    client.push_embedding_table_infos([info("e%d" % d, d, capacity=500) for d in dims])
+    oc.push_embedding_table_infos([oinfo("e%d" % d, d) for d in dims])
+    dense = {"t1": rng.randn(2, 3).astype(F), "t2": rng.randn(64, 8).astype(F), "bias": rng.randn(7).astype(F),
+             "big": rng.randn(1000, 16).astype(F)}
+    for c in (client, oc):
+        c.partition_dense_parameters(dense.keys())
+        for ps_id in range(c.ps_num):
+            params = [(Tensor if c is client else O.Tensor)(n, v.copy(), None) for n, v in dense.items()]
+            if any(c.parameter_to_ps[n] == ps_id for n in dense):
+                c.push_dense_parameters(params, ps_id, 0)
+            else:
+                # shards without dense params still need Initialized for parity of pull
+                pass
+    return dense
+
+
+def _grads(rng, dims, step, dup):
+    from elasticdl_b200.common.tensor_utils import Tensor
+
+    dense = [("t1", rng.randn(2, 3).astype(F)), ("t2", rng.randn(64, 8).astype(F) if step % 2 else None),
+             ("bias", rng.randn(7).astype(F)), ("big", rng.randn(1000, 16).astype(F))]
+    sparse_dense = ("t2", rng.randn(20, 8).astype(F),
+                    (rng.randint(0, 64, 20) if dup else rng.permutation(64)[:20]).astype(np.int64))
+    edl = []
+    for d in dims:
+        k = 300
+        ids = (rng.randint(0, 200, k) if dup else rng.permutation(500)[:k]).astype(np.int64)
+        edl.append(("e%d" % d, rng.randn(k, d).astype(F), ids))
+    def build(T):
+        grads = [T(n, v.copy(), None) for n, v in dense if v is not None]
+        if not step % 2:
+            grads.append(T(sparse_dense[0], sparse_dense[1].copy(), sparse_dense[2].copy()))
+        return grads, [T(n, v.copy(), i.copy()) for n, v, i in edl]
+    return build(Tensor), build(O.Tensor)
+
+
+@pytest.mark.parametrize("opt", list(OPTS))
+@pytest.mark.parametrize("n_shards", [1, 3])
+@pytest.mark.parametrize("dup", [False, True])
+def test_push_gradients_all_optimizers(opt, n_shards, dup):
+    group, client, oc = make_pair(n_shards, opt)
+    import zlib
+    rng = np.random.RandomState(zlib.crc32(repr((opt, n_shards, dup)).encode()))
+    dims = (1, 8, 10)
+    dense = _setup_model(client, oc, rng, dims)
+    versions, oversions = [0] * n_shards, [0] * n_shards
+    for step in range(4):
+        (grads, edl), (ograds, oedl) = _grads(rng, dims, step, dup)
+        lr = 0.05 if step == 2 else 0.0  # 0 -> optimizer's own lr (server.go:183-187)
+        acc, v = client.push_gradients(grads, edl, lr, versions)
+        oacc, ov = oc.push_gradients(ograds, oedl, lr, oversions)
+        assert (acc, v) == (oacc, ov) == (True, step + 1)
+        versions = [v] * n_shards
+        oversions = [ov] * n_shards
+    state = group.snapshot()
+    assert [s[0] for s in state] == [4] * n_shards and [s[1] for s in state] == [4] * n_shards
+    exact = not dup
+    cmp = (lambda a, b: np.array_equal(a, b)) if exact else (lambda a, b: close(a, b, 1e-5, 1e-6))
+    n_slots = len(oc.servers[0].opt.slot_names)
+    for name in dense:
+        ps = oc.parameter_to_ps[name]
+        assert client.parameter_to_ps[name] == ps
+        srv = oc.servers[ps]
+        got = group.pull_dense([name])[name].cpu().numpy()
+        assert cmp(got, srv.dense[name]), name
+        for k, sn in enumerate(srv.opt.slot_names):
+            gs = group.slot_dense(name, k + 1).cpu().numpy()
+            assert cmp(gs, srv.opt.dense_slots[sn][name]), (name, sn)
+    all_ids = np.arange(500, dtype=np.int64)
+    for d in dims:
+        name = "e%d" % d
+        got = client.pull_embedding_vectors(name, all_ids)
+        for s in oc.servers:
+            m = all_ids % n_shards == s.id
+            touched = np.isin(all_ids[m], s.tables[name].keys())
+            ids_t = all_ids[m][touched]
+            assert cmp(got[m][touched], s.tables[name].get(ids_t)), name
+            assert not got[m][~touched].any()
+            for k, sn in enumerate(s.opt.slot_names):
+                gs = group.slot_rows(name, ids_t, k + 1).cpu().numpy()
+                assert cmp(gs, s.opt.table_slots[sn][name].get(ids_t)), (name, sn)
+    assert n_slots == {"sgd": 0, "momentum": 1, "nesterov": 1, "adam": 2, "amsgrad": 3, "adagrad": 1,
+                       "ftrl": 2, "ftrl_shrink": 2}[opt]
+    group.close()
+
+
+# ------------------------------------------------------------------ reference golden vectors on the GPU path
+def test_gpu_sgd_optimizer_test_go_25():
+    from elasticdl_b200.common.tensor_utils import Tensor
+
+    group, client, _ = make_pair(1, "sgd")
+    client.partition_dense_parameters(["t1", "t2"])
+    client.push_dense_parameters([Tensor("t1", np.array([[1, 2, 3], [4, 5, 6]], dtype=F), None),
+                                  Tensor("t2", np.array([[1, 2], [1.1, 2.2]], dtype=F), None)], 0, 0)
+    g1, g2 = np.ones((2, 3), dtype=F), np.ones((2, 2), dtype=F)
+    client.push_gradients([Tensor("t1", g1, None), Tensor("t2", g2, None)], [], 0.05, [0])
+    d = group.pull_dense(["t1", "t2"])
+    assert close(d["t1"].cpu().numpy().ravel(), [0.95, 1.95, 2.95, 3.95, 4.95, 5.95], 1e-4)
+    assert close(d["t2"].cpu().numpy().ravel(), [0.95, 1.95, 1.05, 2.15], 1e-4)
+    with pytest.raises(KeyError):
+        client.push_gradients([Tensor("t3", g2, None)], [], 0.1, [1])
+    client.push_embedding_table_infos([info("t3", 2, capacity=16)])
+    client.push_gradients([Tensor("t1", g1, None), Tensor("t2", g2, None)],
+                          [Tensor("t3", np.ones((2, 2), dtype=F), np.array([1, 3]))], 0.1, [1])
+    d = group.pull_dense(["t1", "t2"])
+    assert close(d["t1"].cpu().numpy().ravel(), [0.85, 1.85, 2.85, 3.85, 4.85, 5.85], 1e-4)
+    assert close(client.pull_embedding_vectors("t3", [1, 3]).ravel(), [-0.1] * 4, 1e-4)
+    # ids [1,3,3,5]: the raw Go kernel applies duplicates sequentially, the PSClient sums
+    # them first (ps_client.py:255-257) -- identical for SGD: -0.2, -0.3, -0.1
+    client.push_gradients([], [Tensor("t3", np.ones((4, 2), dtype=F), np.array([1, 3, 3, 5]))], 0.1, [2])
+    assert close(client.pull_embedding_vectors("t3", [1, 3, 5]).ravel(), [-0.2, -0.2, -0.3, -0.3, -0.1, -0.1], 1e-4)
+    group.close()
+
+
+def test_gpu_adam_global_step_optimizer_test_go_118():
+    from elasticdl_b200.common.tensor_utils import Tensor
+
+    ot, oa = "Adam", "learning_rate=0.1;beta_1=0.9;beta_2=0.999;epsilon=1e-08;amsgrad=false;"
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+
+    group = PSGroup(1, ot, oa, device=0)
+    client = PSClient(group)
+    client.partition_dense_parameters(["t1", "t2"])
+    client.push_dense_parameters([Tensor("t1", np.array([[1, 2, 3], [4, 5, 6]], dtype=F), None),
+                                  Tensor("t2", np.array([[1, 2], [1.1, 2.2]], dtype=F), None)], 0, 0)
+    client.push_embedding_table_infos([info("t3", 2, capacity=16)])
+    group.set_shard_state(0, step=1)  # optimizer_test.go:150 opt.step = 1
+    g1, g2 = np.ones((2, 3), dtype=F), np.ones((2, 2), dtype=F)
+    client.push_gradients([Tensor("t1", g1, None), Tensor("t2", g2, None)], [], 0.0, [0])  # step 2
+    off = np.arange(6)
+    assert close(group.pull_dense(["t1"])["t1"].cpu().numpy().ravel(), 0.9255863187 + off, 1e-4)
+    with pytest.raises(KeyError):  # failed call still bumps the step (quirk Q2) -> 3
+        client.push_gradients([], [Tensor("nope", g2, np.array([0, 1]))], 0.0, [1])
+    client.push_gradients([Tensor("t1", g1, None), Tensor("t2", g2, None)],
+                          [Tensor("t3", np.ones((2, 2), dtype=F), np.array([1, 3]))], 0.0, [1])  # step 4
+    assert group.snapshot()[0][1] == 4
+    assert close(group.pull_dense(["t1"])["t1"].cpu().numpy().ravel(), 0.8474920307 + off, 1e-4)
+    assert close(group.pull_dense(["t2"])["t2"].cpu().numpy().ravel(),
+                 [0.8474920307, 1.8474920307, 0.9474920307, 2.0474920307], 1e-4)
+    assert close(client.pull_embedding_vectors("t3", [1, 3]).ravel(), [-0.058112835] * 4, 1e-4)
+    client.push_gradients([], [Tensor("t3", np.ones((3, 2), dtype=F), np.array([1, 3, 5]))], 0.0, [2])  # step 5
+    assert close(client.pull_embedding_vectors("t3", [1, 3, 5]).ravel(),
+                 [-0.1314178004] * 4 + [-0.0545489238] * 2, 1e-4)
+    group.close()
+
+
+def test_gpu_push_model_handshake_server_test_go_107():
+    from elasticdl_b200.common.tensor_utils import Tensor
+
+    group, client, _ = make_pair(2, "sgd")
+    rng = np.random.RandomState(9)
+    a, b = rng.rand(2, 5).astype(F), rng.rand(2, 5).astype(F)
+    client.partition_dense_parameters(["t1", "t2"])
+    versions = [-1, -1]
+    params, uninit = client.pull_dense_parameters([0, 1], versions)
+    assert params == {} and sorted(uninit) == sorted(client.ps_to_parameter.keys())
+    for ps_id in uninit:
+        client.push_dense_parameters([Tensor("t1", a, None), Tensor("t2", b, None)], ps_id, 0)
+    params, uninit = client.pull_dense_parameters([0, 1], versions)
+    assert uninit == [] and np.array_equal(params["t1"], a) and np.array_equal(params["t2"], b)
+    assert all(versions[p] == 0 for p in client.ps_to_parameter)
+    # first writer wins: a second push_model is ignored
+    for ps_id in client.ps_to_parameter:
+        client.push_dense_parameters([Tensor("t1", a * 0, None), Tensor("t2", b * 0, None)], ps_id, 0)
+    params, _ = client.pull_dense_parameters([0, 1], versions)
+    assert np.array_equal(params["t1"], a)
+    # PushGradients{LearningRate: 0.2} with grads == params (server_test.go:305-331)
+    client.push_embedding_table_infos([info("e1", 10, capacity=8)])
+    c = rng.rand(1, 10).astype(F)
+    group.set_rows([("e1", [1], c)])
+    acc, ver = client.push_gradients([Tensor("t1", a, None), Tensor("t2", b, None)],
+                                     [Tensor("e1", c, np.array([1]))], 0.2, versions)
+    assert acc and ver == 1
+    params, _ = client.pull_dense_parameters([0, 1], versions)
+    assert np.array_equal(params["t1"], a - F(0.2) * a) and np.array_equal(params["t2"], b - F(0.2) * b)
+    assert np.array_equal(client.pull_embedding_vectors("e1", [1]), c - F(0.2) * c)
+    assert versions == [1, 1] or all(versions[p] == 1 for p in client.ps_to_parameter)
+    group.close()
+
+
+def test_gpu_staleness_modulation_server_go_178():
+    from elasticdl_b200.common.tensor_utils import Tensor
+
+    group, client, oc = make_pair(1, "sgd", lr_staleness_modulation=True)
+    for c, T in ((client, Tensor), (oc, O.Tensor)):
+        c.partition_dense_parameters(["w"])
+        c.push_dense_parameters([T("w", np.ones(4, dtype=F), None)], 0, 0)
+    group.set_shard_state(0, version=5)
+    oc.servers[0].version = 5
+    for lr, ver in ((0.1, 1), (0.0, 6), (0.3, 2)):
+        client.push_gradients([Tensor("w", np.ones(4, dtype=F), None)], [], lr, [ver])
+        oc.push_gradients([O.Tensor("w", np.ones(4, dtype=F), None)], [], lr, [ver])
+        assert np.array_equal(group.pull_dense(["w"])["w"].cpu().numpy(), oc.servers[0].dense["w"])
+    group.close()
+
+
+def test_gpu_amsgrad_dense_quirk_q1():
+    from elasticdl_b200.common.tensor_utils import Tensor
+
+    for q1 in (False, True):
+        group, client, oc = make_pair(1, "amsgrad", reproduce_q1=q1)
+        for c, T in ((client, Tensor), (oc, O.Tensor)):
+            c.partition_dense_parameters(["w"])
+            c.push_dense_parameters([T("w", np.linspace(-1, 1, 12).astype(F), None)], 0, 0)
+        for _ in range(3):
+            g = np.linspace(0.5, -0.5, 12).astype(F)
+            client.push_gradients([Tensor("w", g, None)], [], 0.0, [0])
+            oc.push_gradients([O.Tensor("w", g, None)], [], 0.0, [0])
+        assert np.array_equal(group.pull_dense(["w"])["w"].cpu().numpy(), oc.servers[0].dense["w"])
+        group.close()
+
+
+def test_gpu_errors():
+    from elasticdl_b200._lib import PSNotFound, PSRangeError
+    from elasticdl_b200.common.tensor_utils import Tensor
+
+    group, client, _ = make_pair(2, "sgd")
+    client.push_embedding_table_infos([info("e", 4, capacity=100)])
+    with pytest.raises(KeyError):
+        client.pull_embedding_vectors("missing", [1])
+    with pytest.raises(ValueError):
+        client.pull_embedding_vectors("e", [])
+    with pytest.raises(ValueError):  # id beyond capacity (embedding_delegate.py:254-264)
+        client.pull_embedding_vectors("e", [5, 100000])
+    with pytest.raises(ValueError):  # width mismatch (kernel.go:36-38)
+        client.push_gradients([], [Tensor("e", np.ones((2, 3), dtype=F), np.array([1, 2]))], 0.1, [0, 0])
+    assert [s[1] for s in group.snapshot()] == [1, 1]  # the failed ApplyGradients bumped step (Q2)
+    assert [s[0] for s in group.snapshot()] == [0, 0]  # ... but not the version
+    with pytest.raises(ValueError):
+        from elasticdl_b200.ps import PSGroup
+
+        PSGroup(1, "SGD", "learning_rate=0.1;momentum=0.0;nesterov=true;redundant_arg=1;", device=0)
+    with pytest.raises(ValueError):
+        PSGroup(1, "RMSprop", "learning_rate=0.1;", device=0)
+    group.close()
+
+
+def test_gpu_table_ids_and_len():
+    group, client, _ = make_pair(3, "sgd")
+    client.push_embedding_table_infos([info("e", 2, capacity=64)])
+    client.pull_embedding_vectors("e", [1, 3, 5, 7, 9, 3])
+    assert group.table_size("e") == 5
+    got = sorted(sum((group.table_ids("e", s).cpu().tolist() for s in range(3)), []))
+    assert got == [1, 3, 5, 7, 9]
+    for s in range(3):
+        assert all(i % 3 == s for i in group.table_ids("e", s).cpu().tolist())
+    group.close()
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE config 2 sizes)
+def test_full_size_roundtrip_and_linearity():
+    """5.5 M-row deep table (dac_ctr C3+C4+... after the 1e6 cap), 8 shards:
+    set -> pull round trip, SGD push(+g) then push(-g) returns bit-exactly (values on a
+    binary grid), pulls are idempotent, checksum of checksums."""
+    from elasticdl_b200.common.tensor_utils import Tensor
+
+    group, client, _ = make_pair(8, "sgd")
+    rows = 5_549_416
+    client.push_embedding_table_infos([info("deep", 8, capacity=rows), info("wide", 1, capacity=rows)])
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    k = 1 << 20
+    ids = torch.randperm(rows, device="cuda", generator=gen)[:k]
+    vals = torch.randint(-64, 64, (k, 8), device="cuda", generator=gen).float() / 8
+    group.set_rows([("deep", ids, vals)])
+    (got,) = group.pull_rows([("deep", ids)])
+    assert torch.equal(got, vals)
+    (again,) = group.pull_rows([("deep", ids)])
+    assert torch.equal(again, got)
+    g = torch.randint(-8, 8, (k, 8), device="cuda", generator=gen).float()
+    client.push_gradients([], [Tensor("deep", g, ids)], 0.5, [0] * 8)
+    (mid,) = group.pull_rows([("deep", ids)])
+    assert torch.equal(mid, vals - 0.5 * g)
+    client.push_gradients([], [Tensor("deep", -g, ids)], 0.5, [1] * 8)
+    (back,) = group.pull_rows([("deep", ids)])
+    assert torch.equal(back, vals)
+    assert float(back.double().sum()) == float(vals.double().sum())
+    assert group.table_size("deep") == k
+    # duplicates: pushing each id twice with g/2 equals pushing g once (exact on the grid)
+    ids2 = torch.cat([ids, ids])
+    g2 = torch.cat([g / 2, g / 2])
+    client.push_gradients([], [Tensor("deep", g2, ids2)], 0.5, [2] * 8)
+    (dup,) = group.pull_rows([("deep", ids)])
+    assert torch.equal(dup, vals - 0.5 * g)
+    assert [s[0] for s in group.snapshot()] == [3] * 8
+    group.close()
