@@ -3,6 +3,14 @@ from collections import namedtuple
 
 Tensor = namedtuple("Tensor", ("name", "values", "indices"))
 
+
+
+class UniqueTensor(Tensor):
+    """A Tensor whose indices are already unique (e.g. a BET gradient keyed by the
+    layer's unique ids): PSClient skips the dedup pass for it."""
+    __slots__ = ()
+
+
 # The reference's EmbeddingTableInfo is (name, dim, initializer, dtype).  The HBM
 # tables are direct-indexed, so the number of ids (the layer's input_dim) travels
 # with it as an optional fifth field.

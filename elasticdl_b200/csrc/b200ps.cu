@@ -204,9 +204,22 @@ GroupView group_view(b200ps_t* ps) {
   return gv;
 }
 
+long long g_free_launches = 0;  // launches of the group-less primitives (ps == NULL)
+
+int client_dev(b200ps_t* ps) {
+  if (ps) return ps->client_device;
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+
+void count_launch(b200ps_t* ps, int n) {
+  if (ps) ps->launches += n; else g_free_launches += n;
+}
+
 int grid_for(b200ps_t* ps, long long work_items, int per_block = 256) {
   long long blocks = (work_items + per_block - 1) / per_block;
-  long long cap = (long long)ps->n_sm * 16;  // 16 CTAs of 256 threads per SM keep ~2 waves resident
+  long long cap = (long long)(ps ? ps->n_sm : 148) * 16;  // 16 CTAs of 256 threads per SM keep ~2 waves resident
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -787,9 +800,9 @@ size_t b200ps_unique_workspace(int T, int64_t k) {
 
 int b200ps_unique(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, int64_t* uniq_dev, int32_t* inv_dev,
                   int32_t* n_unique_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
-  if (!ps || T < 1 || T > 65535 || k < 1 || k > (1LL << 30)) return fail(B200PS_EINVAL, "bad unique shape");
+  if (T < 1 || T > 65535 || k < 1 || k > (1LL << 30)) return fail(B200PS_EINVAL, "bad unique shape");
   if (workspace_bytes < b200ps_unique_workspace(T, k)) return fail(B200PS_EINVAL, "unique workspace too small");
-  DeviceGuard g(ps->client_device);
+  DeviceGuard g(client_dev(ps));
   cudaStream_t st = (cudaStream_t)stream;
   UniqueWs ws;
   ws.cap = uniq_cap(k);
@@ -807,7 +820,7 @@ int b200ps_unique(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, int64_
   k_uniq_scan_tiles<<<T, 1024, 0, st>>>(ws, n_unique_dev);
   k_uniq_rank<<<gt, 256, 0, st>>>(ids_dev, k, ws, uniq_dev);
   k_uniq_inverse<<<gk, 256, 0, st>>>(k, ws, inv_dev);
-  ps->launches += 6;
+  count_launch(ps, 6);
   CUDA_OK(cudaGetLastError());
   return B200PS_OK;
 }
@@ -819,8 +832,8 @@ static int dim_class(int dim, const void* a, const void* b) {
 
 int b200ps_segment_sum(b200ps_t* ps, const float* values_dev, const int32_t* inv_dev, int T, int64_t k, int dim,
                        float* out_dev, void* stream) {
-  if (!ps || T < 1 || T > 65535 || k < 1 || dim < 1) return fail(B200PS_EINVAL, "bad segment_sum shape");
-  DeviceGuard g(ps->client_device);
+  if (T < 1 || T > 65535 || k < 1 || dim < 1) return fail(B200PS_EINVAL, "bad segment_sum shape");
+  DeviceGuard g(client_dev(ps));
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_OK(cudaMemsetAsync(out_dev, 0, (size_t)T * k * dim * sizeof(float), st));
   int c = dim_class(dim, values_dev, out_dev);
@@ -829,15 +842,15 @@ int b200ps_segment_sum(b200ps_t* ps, const float* values_dev, const int32_t* inv
   if (c == 2) k_segment_sum<2><<<grid, 256, 0, st>>>(values_dev, inv_dev, k, dim, out_dev);
   else if (c == 1) k_segment_sum<1><<<grid, 256, 0, st>>>(values_dev, inv_dev, k, dim, out_dev);
   else k_segment_sum<0><<<grid, 256, 0, st>>>(values_dev, inv_dev, k, dim, out_dev);
-  ps->launches++;
+  count_launch(ps, 1);
   CUDA_OK(cudaGetLastError());
   return B200PS_OK;
 }
 
 int b200ps_gather_rows(b200ps_t* ps, const float* bet_dev, const int32_t* inv_dev, int T, int64_t k, int dim,
                        float* out_dev, void* stream) {
-  if (!ps || T < 1 || T > 65535 || k < 1 || dim < 1) return fail(B200PS_EINVAL, "bad gather shape");
-  DeviceGuard g(ps->client_device);
+  if (T < 1 || T > 65535 || k < 1 || dim < 1) return fail(B200PS_EINVAL, "bad gather shape");
+  DeviceGuard g(client_dev(ps));
   cudaStream_t st = (cudaStream_t)stream;
   int c = dim_class(dim, bet_dev, out_dev);
   int W = c == 0 ? 1 : 4 * c;
@@ -845,7 +858,7 @@ int b200ps_gather_rows(b200ps_t* ps, const float* bet_dev, const int32_t* inv_de
   if (c == 2) k_gather_rows<2><<<grid, 256, 0, st>>>(bet_dev, inv_dev, k, dim, out_dev);
   else if (c == 1) k_gather_rows<1><<<grid, 256, 0, st>>>(bet_dev, inv_dev, k, dim, out_dev);
   else k_gather_rows<0><<<grid, 256, 0, st>>>(bet_dev, inv_dev, k, dim, out_dev);
-  ps->launches++;
+  count_launch(ps, 1);
   CUDA_OK(cudaGetLastError());
   return B200PS_OK;
 }
@@ -947,6 +960,6 @@ int b200ps_check(b200ps_t* ps) {
   return B200PS_OK;
 }
 
-int64_t b200ps_launch_count(b200ps_t* ps) { return ps ? ps->launches : 0; }
+int64_t b200ps_launch_count(b200ps_t* ps) { return ps ? ps->launches : g_free_launches; }
 
 }  // extern "C"

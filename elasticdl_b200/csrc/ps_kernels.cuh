@@ -46,7 +46,7 @@ __device__ __forceinline__ void opt_update(float g, float& p, float& s0, float& 
     float a = add(s0, mul(g, g));
     s0 = a;
     p = sub(p, fdiv(mul(lr, g), add(fsqrt(a), o.epsilon)));
-  } else {  // FTRL -- see oracle/ps_oracle.c oracle_ftrl (parity unpinned)
+  } else {  // FTRL: TF ApplyFtrl, lr_power = -0.5 (restated in DESIGN.md; parity unpinned)
     float gs = add(g, mul(mul(2.0f, o.l2s), p));
     float a_new = add(s0, mul(g, g));
     float sigma = fdiv(sub(fsqrt(a_new), fsqrt(s0)), lr);

@@ -15,7 +15,7 @@ import torch
 
 from elasticdl_b200 import _lib
 from elasticdl_b200.common.hash_utils import string_to_id
-from elasticdl_b200.common.tensor_utils import Tensor  # noqa: F401  (re-export, as the reference module does)
+from elasticdl_b200.common.tensor_utils import Tensor, UniqueTensor  # noqa: F401  (Tensor re-exported as the reference module does)
 from elasticdl_b200.ps.group import PSGroup
 
 
@@ -174,11 +174,12 @@ class PSClient(object):
                 dense[grad.name] = g._f32(dense[grad.name]) + g._f32(grad.values)
             else:
                 dense[grad.name] = grad.values
-        edl = {}
+        edl, already_unique = {}, {}
         for grad in edl_grads:  # ps_client.py:243-251
             edl.setdefault(grad.name, ([], []))
             edl[grad.name][0].append(grad.values)
             edl[grad.name][1].append(grad.indices)
+            already_unique[grad.name] = isinstance(grad, UniqueTensor) and grad.name not in already_unique
 
         # validate before launching: the Go PS fails the whole ApplyGradients
         # ("grad %s not in Parameter", optimizer.go:49,59; width check kernel.go:36-38)
@@ -197,6 +198,10 @@ class PSClient(object):
                     width = int(np.prod(np.shape(vl[0])[1:])) if np.ndim(vl[0]) > 1 else 1
                     if width != dim:
                         raise ValueError("grad width is not equal to embedding dim")
+                    if is_edl and already_unique.get(name) and len(vl) == 1:
+                        ids_t = g._ids(il[0])
+                        row_items.append((tid, ids_t.numel(), ids_t, None, g._f32(vl[0]).reshape(-1, dim)))
+                        continue
                     uniq, n_unique, gsum, k = self._dedup(name, vl, il, dim)
                     row_items.append((tid, k, uniq, n_unique, gsum))
         except (_lib.PSNotFound, ValueError):

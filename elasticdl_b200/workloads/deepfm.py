@@ -1,0 +1,257 @@
+"""DeepFM on Criteo-shaped data over the HBM parameter server: the workload of
+BASELINE.json configs[1] (model_zoo/dac_ctr/deepfm_model.py:20-109, utils.py:17-41,
+feature_config.py:61-195, feature_transform.py:33,102-110).
+
+38 id groups (12 bucketised integer features + 26 hashed categorical features
+capped at 1e6 buckets), one id per group per sample, two embedding tables per
+group (wide dim 1, deep dim 8) -> 76 PS tables, 5 549 416 rows per family; dense
+tower DNN[16,4] over 13 + 38*8 inputs, FM over the 38x8 deep embeddings, linear
+part = sum of wide embeddings + Dense(1)(dense features); Adam lr 1e-3.
+
+`DeepFMPSEngine.step` is one pass of the hot path: pull dense -> unique ids
+(first-occurrence) -> pull rows (one launch per vector class for all 76 tables) ->
+gather -> tower fwd/bwd (torch, library GEMMs) -> segment-sum of per-occurrence
+gradients -> push (dense + 76 tables, fused Adam) -> version++.  No host sync
+inside the step; nothing but ids/features/labels comes from the host.
+"""
+import math
+
+import torch
+
+from elasticdl_b200._lib import check
+
+# model_zoo/dac_ctr/feature_config.py:61-75 (len(boundaries)+1 buckets; I4 is not in FEATURE_GROUPS)
+INT_BUCKETS = [5, 10, 9, 10, 9, 9, 10, 10, 3, 6, 2, 9]
+# feature_config.py:123-150 distinct counts, capped by MAX_HASHING_BUCKET_SIZE = 1e6 (feature_transform.py:33)
+CAT_COUNTS = [1460, 582, 9264260, 2046299, 305, 24, 12506, 633, 3, 91211, 5670, 7659856, 3194, 27, 14876,
+              5031503, 10, 5624, 2171, 4, 6477624, 18, 15, 272811, 105, 138075]
+GROUP_ROWS = INT_BUCKETS + [min(c, 1000000) for c in CAT_COUNTS]
+N_GROUPS = len(GROUP_ROWS)  # 38
+N_DENSE = 13
+DEEP_DIM = 8
+assert N_GROUPS == 38 and sum(GROUP_ROWS) == 5549416
+
+
+class DeepFMTower(torch.nn.Module):
+    """deepfm_model.py:61-109 without the embedding lookups."""
+
+    def __init__(self, n_groups=N_GROUPS, deep_dim=DEEP_DIM, n_dense=N_DENSE, hidden=(16, 4)):
+        super().__init__()
+        self.n_groups, self.deep_dim = n_groups, deep_dim
+        self.dense_linear = torch.nn.Linear(n_dense, 1, bias=False)
+        dims = [n_dense + n_groups * deep_dim] + list(hidden)
+        self.dnn = torch.nn.ModuleList([torch.nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:])])
+        self.dnn_logit = torch.nn.Linear(dims[-1], 1, bias=False)
+
+    def forward(self, dense, wide, deep):
+        """dense [B,13], wide [B,G], deep [B,G,D] -> logits [B]."""
+        B = dense.shape[0]
+        x = torch.cat([dense, deep.reshape(B, -1)], 1)
+        for layer in self.dnn:
+            x = torch.relu(layer(x))
+        dnn_logit = self.dnn_logit(x).squeeze(1)
+        linear_logit = wide.sum(1) + self.dense_linear(dense).squeeze(1)
+        s = deep.sum(1)  # FM: 0.5 * sum_d[(sum_f e)^2 - sum_f e^2]  (deepfm_edl_embedding.py:50-56)
+        fm = 0.5 * (s * s - (deep * deep).sum(1)).sum(1)
+        return linear_logit + dnn_logit + fm
+
+
+def synthetic_batch(batch, seed, device, dist="zipf", zipf_s=1.05, group_rows=GROUP_ROWS):
+    """bucket ids uniform, categorical ids Zipf(s) over the
+    table's rows (or uniform), dense features N(0,1), labels Bernoulli(0.25).
+    Returns ids [G, B] int64 (group-major, like the reference's per-group id tensors)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    G = len(group_rows)
+    u = torch.rand((G, batch), generator=g, device=device, dtype=torch.float64)
+    rows = torch.tensor(group_rows, device=device, dtype=torch.float64).unsqueeze(1)
+    if dist == "zipf":
+        # bounded-Pareto inverse CDF: rank in [1, N], P(rank) ~ rank^-s
+        a = 1.0 - zipf_s
+        rank = torch.floor(((rows.pow(a) - 1.0) * u + 1.0).pow(1.0 / a))
+        ids = (rank - 1.0).clamp_(min=0)
+        ids = torch.minimum(ids, rows - 1)
+        small = rows < 64  # the bucketised integer groups are uniform
+        ids = torch.where(small.expand_as(ids), torch.floor(u * rows), ids)
+    else:
+        ids = torch.floor(u * rows)
+    ids = ids.to(torch.int64)
+    dense = torch.randn((batch, N_DENSE), generator=g, device=device)
+    labels = (torch.rand(batch, generator=g, device=device) < 0.25).float()
+    return ids, dense, labels
+
+
+class DeepFMPSEngine:
+    def __init__(self, group, batch, lr=1e-3, init_std=0.01, seed=7, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM,
+                 init_rows=True):
+        self.group = group
+        self.B = int(batch)
+        self.G = len(group_rows)
+        self.D = deep_dim
+        self.lr = lr
+        dev = group.device
+        self.device = dev
+        G, B, D = self.G, self.B, self.D
+        self.wide_names = ["group_%d_wide/embeddings:0" % i for i in range(G)]
+        self.deep_names = ["group_%d_deep/embeddings:0" % i for i in range(G)]
+        self.wide_ids = [group.register_table(n, 1, "zero", r) for n, r in zip(self.wide_names, group_rows)]
+        self.deep_ids = [group.register_table(n, D, "zero", r) for n, r in zip(self.deep_names, group_rows)]
+        torch.manual_seed(seed)
+        self.tower = DeepFMTower(G, D).to(dev)
+        self.params = [(n, p) for n, p in self.tower.named_parameters()]
+        from elasticdl_b200.common.hash_utils import string_to_id
+
+        self.dense_ids = []
+        for n, p in self.params:
+            self.dense_ids.append(group.register_dense(n, tuple(p.shape), string_to_id(n, group.n_shards)))
+        group.commit()
+        # explicit N(0, init_std) initial rows, seed 7: set through the PS (set_rows)
+        if init_rows and init_std > 0:
+            gen = torch.Generator(device=dev).manual_seed(seed)
+            for names, dim in ((self.wide_names, 1), (self.deep_names, D)):
+                for n, r in zip(names, group_rows):
+                    if r % group.n_shards and group.n_shards > 1:
+                        pass
+                    ids = torch.arange(r, device=dev)
+                    if len(group.local_shards) != group.n_shards:
+                        # multi-process: every rank initialises the rows it owns
+                        mine = torch.zeros(r, dtype=torch.bool, device=dev)
+                        for s in group.local_shards:
+                            mine |= (ids % group.n_shards) == s
+                        vals = torch.randn((r, dim), generator=gen, device=dev) * init_std
+                        ids, vals = ids[mine], vals[mine]
+                    else:
+                        vals = torch.randn((r, dim), generator=gen, device=dev) * init_std
+                    if ids.numel():
+                        group.set_rows([(n, ids, vals)])
+        # first-writer-wins dense init (PushModel)
+        for s in range(group.n_shards):
+            if s in group.local_shards and group.try_init(s):
+                mine = [(n, p.detach()) for (n, p) in self.params if string_to_id(n, group.n_shards) == s]
+                if mine:
+                    group.set_dense(mine)
+                group.finish_init(s, 0)
+        # persistent buffers
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.uniq = torch.empty(G * B, dtype=torch.int64, device=dev)
+        self.inv = torch.empty(G * B, dtype=torch.int32, device=dev)
+        self.n_unique = torch.empty(G, dtype=torch.int32, device=dev)
+        self.ws = torch.empty(group.lib.b200ps_unique_workspace(G, B), dtype=torch.uint8, device=dev)
+        self.bet_w = torch.zeros((G * B, 1), **f32)
+        self.bet_d = torch.zeros((G * B, D), **f32)
+        self.act_w = torch.empty((G * B, 1), **f32)
+        self.act_d = torch.empty((G * B, D), **f32)
+        self.gsum_w = torch.empty((G * B, 1), **f32)
+        self.gsum_d = torch.empty((G * B, D), **f32)
+        self.zero_versions = [0] * group.n_shards
+        self.loss_fn = torch.nn.BCEWithLogitsLoss()
+        self._build_segs()
+        self.steps = 0
+
+    def _seg_items(self, ids_tab, rows, dim):
+        B = self.B
+        return [(ids_tab[t], B, self.uniq[t * B:(t + 1) * B], self.n_unique[t:t + 1], rows[t * B:(t + 1) * B])
+                for t in range(self.G)]
+
+    def _build_segs(self):
+        g = self.group
+        self.pull_segs = [g.make_segs(self._seg_items(self.wide_ids, self.bet_w, 1)),
+                          g.make_segs(self._seg_items(self.deep_ids, self.bet_d, self.D))]
+        self.push_segs = [g.make_segs(self._seg_items(self.wide_ids, self.gsum_w, 1)),
+                          g.make_segs(self._seg_items(self.deep_ids, self.gsum_d, self.D))]
+        self.pull_dense_segs = g.make_segs([(tid, 0, None, None, p) for tid, (_, p) in zip(self.dense_ids, self.params)])
+
+    def step(self, ids, dense, labels, ev=None):
+        """ids int64 [G, B] (group-major), dense fp32 [B, 13], labels fp32 [B] -- all on the device.
+        Returns the loss (device scalar).  ev: optional dict name -> list; CUDA-event pairs are
+        recorded around the named PS kernels on the launching stream."""
+        g, lib, h = self.group, self.group.lib, self.group._h
+        G, B, D = self.G, self.B, self.D
+        st = g._stream()
+
+        def mark(name):
+            if ev is None:
+                return None
+            e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev.setdefault(name, []).append(e)
+            e[0].record()
+            return e
+
+        def done(e):
+            if e is not None:
+                e[1].record()
+        # (1) pull dense parameters straight into the tower's tensors
+        arr, n = self.pull_dense_segs
+        check(lib.b200ps_pull_dense(h, arr, n, st))
+        # (2) unique ids per group; wide and deep tables of a group share them
+        e = mark("unique")
+        check(lib.b200ps_unique(h, ids.data_ptr(), G, B, self.uniq.data_ptr(), self.inv.data_ptr(),
+                                self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st))
+        done(e)
+        # (3) pull the unique rows of all 76 tables
+        for name, (arr, n) in zip(("pull_wide", "pull_deep"), self.pull_segs):
+            e = mark(name)
+            check(lib.b200ps_pull_rows(h, arr, n, st))
+            done(e)
+        # (4) BET -> per-occurrence activations
+        check(lib.b200ps_gather_rows(h, self.bet_w.data_ptr(), self.inv.data_ptr(), G, B, 1, self.act_w.data_ptr(), st))
+        check(lib.b200ps_gather_rows(h, self.bet_d.data_ptr(), self.inv.data_ptr(), G, B, D, self.act_d.data_ptr(), st))
+        # (5) tower forward / backward
+        e_t = mark("tower_fwd_bwd")
+        act_w = self.act_w.detach().requires_grad_(True)
+        act_d = self.act_d.detach().requires_grad_(True)
+        wide = act_w.view(G, B).t()
+        deep = act_d.view(G, B, D).permute(1, 0, 2)
+        logits = self.tower(dense, wide, deep)
+        loss = self.loss_fn(logits, labels)
+        plist = [p for _, p in self.params]
+        grads = torch.autograd.grad(loss, plist + [act_w, act_d])
+        gw, gd = grads[-2].contiguous(), grads[-1].contiguous()
+        done(e_t)
+        # (6) per-occurrence gradients -> per-unique-id sums (deduplicate_indexed_slices)
+        check(lib.b200ps_segment_sum(h, gw.data_ptr(), self.inv.data_ptr(), G, B, 1, self.gsum_w.data_ptr(), st))
+        e = mark("segment_sum_deep")
+        check(lib.b200ps_segment_sum(h, gd.data_ptr(), self.inv.data_ptr(), G, B, D, self.gsum_d.data_ptr(), st))
+        done(e)
+        # (7) push: one ApplyGradients per shard
+        g.push_begin(self.lr, self.zero_versions)
+        dense_grads = [gr.contiguous() for gr in grads[:-2]]
+        arr, n = g.make_segs([(tid, 0, None, None, gr) for tid, gr in zip(self.dense_ids, dense_grads)])
+        check(lib.b200ps_push_dense(h, arr, n, st))
+        for name, (arr, n) in zip(("push_wide", "push_deep"), self.push_segs):
+            e = mark(name)
+            check(lib.b200ps_push_rows(h, arr, n, st))
+            done(e)
+        g.push_end(sync=False)
+        self.steps += 1
+        return loss.detach()
+
+    def kernel_report(self, ev, uniq_per_step, opt_slots=2):
+        """Average CUDA-event duration and algorithmic GB/s per named PS kernel.
+        Algorithmic bytes: pull U*(8+8D); push U*(8+4D+(1+S)*8D); segment_sum
+        k*(4+4D)+U*4D; unique k*(8+4)+U*8 (ids in, inverse out, unique ids out)."""
+        D, k = self.D, self.G * self.B
+        out = {}
+        for name, pairs in ev.items():
+            ms = [a.elapsed_time(b) for a, b in pairs]
+            U = sum(uniq_per_step) / max(len(uniq_per_step), 1)
+            nbytes = {
+                "pull_wide": U * (8 + 8 * 1), "pull_deep": U * (8 + 8 * D),
+                "push_wide": U * (8 + 4 * 1 + (1 + opt_slots) * 8 * 1),
+                "push_deep": U * (8 + 4 * D + (1 + opt_slots) * 8 * D),
+                "segment_sum_deep": k * (4 + 4 * D) + U * 4 * D,
+                "unique": k * 12 + U * 8,
+            }.get(name)
+            avg = sum(ms) / len(ms)
+            out[name] = {"ms": avg, "launches": len(ms)}
+            if nbytes:
+                out[name]["bytes"] = nbytes
+                out[name]["gbs"] = nbytes / (avg * 1e-3) / 1e9
+        return out
+
+    @staticmethod
+    def algorithmic_bytes(n_unique_total, opt_slots=2, deep_dim=DEEP_DIM):
+        """SURVEY.md section 8d per-unit figures, fp32 rows, int64 ids:
+        pull U*(8 + 4D + 4D); sparse push U*(8 + 4D + (1+S)*8D), for D in {1, deep_dim}."""
+        pull = sum(n_unique_total * (8 + 8 * d) for d in (1, deep_dim))
+        push = sum(n_unique_total * (8 + 4 * d + (1 + opt_slots) * 8 * d) for d in (1, deep_dim))
+        return pull, push

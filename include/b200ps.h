@@ -155,7 +155,9 @@ int b200ps_bump_step(b200ps_t* ps, void* stream);
 
 /* ---- id dedup (client side of the exchange) -------------------------- */
 
-/* tf.unique (embedding_delegate.py:85) for T equal-length id segments in one
+/* These three take `ps` only for the device and the launch counter; ps may be
+ * NULL (current device).
+ * tf.unique (embedding_delegate.py:85) for T equal-length id segments in one
  * launch set: uniq_dev[t*k + r] = r-th distinct id of segment t in
  * FIRST-OCCURRENCE order, inv_dev[t*k + i] = rank of ids[t*k + i],
  * n_unique_dev[t] = number of distinct ids.  Workspace from
@@ -194,7 +196,8 @@ int b200ps_table_size(b200ps_t* ps, int table, int shard, int64_t* rows);
 int b200ps_table_ids(b200ps_t* ps, int table, int shard, int64_t* ids_dev, int64_t cap, int64_t* n);
 /* Raise and clear the sticky device-side error word (out-of-range ids ...). */
 int b200ps_check(b200ps_t* ps);
-/* Kernels launched so far by this group (bench.py gpu_launches). */
+/* Kernels launched so far by this group (bench.py gpu_launches); ps == NULL:
+ * launches of the group-less primitives. */
 int64_t b200ps_launch_count(b200ps_t* ps);
 
 #ifdef __cplusplus

@@ -1,0 +1,184 @@
+"""GPU tests of the reference-facing layer/trainer mirrors and the fused DeepFM engine.
+Vectors follow elasticdl/python/tests/layer_test.py:135-383 (fake lookup returning
+[id]*dim rows) and worker_ps_interaction_test.py:203-270 (PS training == local training)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ps_oracle as O
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+SGD = ("SGD", "learning_rate=0.1;momentum=0.0;nesterov=false;")
+ADAM = ("Adam", "learning_rate=0.001;beta_1=0.9;beta_2=0.999;epsilon=1e-07;amsgrad=false;")
+
+
+def fake_lookup(dim):
+    def fn(name, ids):  # layer_test.py:71-101 mock_worker.lookup_embedding
+        return ids.to(torch.float32).unsqueeze(1).repeat(1, dim)
+    return fn
+
+
+def test_embedding_layer_forward_and_bet_grads_layer_test_py_135():
+    from elasticdl_b200.layers import Embedding
+
+    layer = Embedding(8, input_dim=10, name="emb_a")
+    layer.set_lookup_embedding_func(fake_lookup(8))
+    ids = torch.tensor([[0, 1, 3], [8, 3, 2], [3, 3, 3]], device="cuda")
+    out = layer(ids)
+    assert out.shape == (3, 3, 8)
+    assert torch.equal(out, ids.float().unsqueeze(-1).expand(3, 3, 8))
+    assert layer.embedding_and_ids == []  # nothing recorded without a tape
+    layer.set_tape(True)
+    out = layer(ids)
+    (bet, batch_ids), = layer.embedding_and_ids
+    assert batch_ids.tolist() == [0, 1, 3, 8, 2]  # tf.unique order
+    up = torch.arange(9 * 8, device="cuda", dtype=torch.float32).reshape(3, 3, 8)
+    (g,) = torch.autograd.grad((out * up).sum(), [bet])
+    flat = ids.reshape(-1).tolist()
+    want = torch.zeros(5, 8, device="cuda")
+    for pos, i in enumerate(flat):
+        want[[0, 1, 3, 8, 2].index(i)] += up.reshape(9, 8)[pos]
+    assert torch.equal(g, want)
+    layer.reset()
+    assert layer.embedding_and_ids == [] and layer.tape is None
+    assert layer.embedding_weight_name == "emb_a/embeddings:0"
+    with pytest.raises(ValueError):  # embedding_delegate.py:254-264
+        layer(torch.tensor([1, 50], device="cuda"))
+
+
+@pytest.mark.parametrize("combiner", ["sum", "mean", "sqrtn"])
+def test_embedding_layer_sparse_combiners_layer_test_py(combiner):
+    from elasticdl_b200.layers import Embedding
+
+    layer = Embedding(4, combiner=combiner, name="emb_s_" + combiner)
+    layer.set_lookup_embedding_func(fake_lookup(4))
+    # rows: [1,2], [], [3,-1(pruned)], [5,5,7]
+    idx = torch.tensor([[0, 0, 2, 2, 3, 3, 3], [0, 1, 0, 1, 0, 1, 2]], device="cuda")
+    val = torch.tensor([1, 2, 3, -1, 5, 5, 7], device="cuda")
+    sp = torch.sparse_coo_tensor(idx, val, (4, 3))
+    out = layer(sp)
+    rows = [[1, 2], [], [3], [5, 5, 7]]
+    want = torch.zeros(4, 4)
+    for r, ids in enumerate(rows):
+        if ids:
+            s = float(sum(ids))
+            want[r] = {"sum": s, "mean": s / len(ids), "sqrtn": s / len(ids) ** 0.5}[combiner]
+    assert torch.allclose(out.cpu(), want, atol=1e-6)
+    with pytest.raises(ValueError):
+        Embedding(4, name="emb_nocomb")(sp)
+
+
+class TinyModel(torch.nn.Module):
+    def __init__(self, dim=8, rows=50):
+        super().__init__()
+        from elasticdl_b200.layers import Embedding
+
+        self.emb = Embedding(dim, input_dim=rows, embeddings_initializer="zero", name="tiny_emb")
+        self.fc = torch.nn.Linear(3 * dim, 1)
+        self.optimizer = torch.optim.SGD(self.fc.parameters(), lr=0.1)
+        self.loss = lambda labels, out: ((out.squeeze(1) - labels) ** 2).mean()
+
+    def forward(self, ids):
+        e = self.emb(ids)
+        return self.fc(e.reshape(ids.shape[0], -1))
+
+
+@pytest.mark.parametrize("n_shards", [1, 2])
+def test_trainer_equals_local_training_worker_ps_interaction_test_py_203(n_shards):
+    """PS training (SGD) == local torch training on the same data."""
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+    from elasticdl_b200.worker.ps_trainer import ParameterServerTrainer
+
+    torch.manual_seed(0)
+    model = TinyModel().cuda()
+    group = PSGroup(n_shards, *SGD, device=0)
+    client = PSClient(group)
+    client.dense_output = "torch"
+    trainer = ParameterServerTrainer(model, client)
+    # local twin: nn.Embedding holding the table, same init
+    rows, dim = 50, 8
+    init = torch.randn(rows, dim, device="cuda") * 0.1
+    group.set_rows([("tiny_emb/embeddings:0", torch.arange(rows), init)])
+    table = init.clone().requires_grad_(True)
+    fc = torch.nn.Linear(3 * dim, 1).cuda()
+    fc.load_state_dict(model.fc.state_dict())
+    opt = torch.optim.SGD([table] + list(fc.parameters()), lr=0.1)
+    gen = torch.Generator().manual_seed(1)
+    for step in range(4):
+        ids = torch.randint(0, rows, (16, 3), generator=gen).cuda()
+        labels = torch.randn(16, generator=gen).cuda()
+        accepted, version, loss = trainer.train_minibatch(ids, labels)
+        assert accepted and version == step + 1
+        opt.zero_grad()
+        l2 = ((fc(table[ids].reshape(16, -1)).squeeze(1) - labels) ** 2).mean()
+        l2.backward()
+        opt.step()
+        assert abs(float(loss) - float(l2)) < 1e-5
+    got = client.pull_embedding_vectors("tiny_emb/embeddings:0", torch.arange(rows).cuda())
+    assert torch.allclose(got, table.detach(), rtol=1e-5, atol=1e-6)
+    versions = [-1] * n_shards
+    params, _ = client.pull_dense_parameters(list(range(n_shards)), versions)
+    assert torch.allclose(params["fc.weight"], fc.weight.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(params["fc.bias"], fc.bias.detach(), rtol=1e-5, atol=1e-6)
+    assert trainer.get_model_version() >= 3
+    group.close()
+
+
+@pytest.mark.parametrize("n_shards", [1, 4])
+def test_deepfm_engine_step_matches_oracle_adam(n_shards):
+    """One fused-engine step == torch autograd gradients applied with the oracle's Adam."""
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.workloads.deepfm import DeepFMPSEngine, synthetic_batch
+
+    rows = [5, 9, 300, 2000, 17]
+    B, D = 256, 8
+    group = PSGroup(n_shards, *ADAM, device=0)
+    eng = DeepFMPSEngine(group, B, group_rows=rows)
+    dev = torch.device("cuda", 0)
+    ids, dense, labels = synthetic_batch(B, 5, dev, "zipf", group_rows=rows)
+    # replica of the state before the step
+    wide0 = [group.pull_rows([(n, torch.arange(r))])[0] for n, r in zip(eng.wide_names, rows)]
+    deep0 = [group.pull_rows([(n, torch.arange(r))])[0] for n, r in zip(eng.deep_names, rows)]
+    import copy
+
+    tower = copy.deepcopy(eng.tower)
+    loss = eng.step(ids, dense, labels)
+    group.check()
+    # reference gradients with plain torch fp32 autograd over dense tables
+    wt = [w.clone().requires_grad_(True) for w in wide0]
+    dt = [d.clone().requires_grad_(True) for d in deep0]
+    wide = torch.stack([wt[g][ids[g]].squeeze(1) for g in range(len(rows))], 1)
+    deep = torch.stack([dt[g][ids[g]] for g in range(len(rows))], 1)
+    l2 = torch.nn.BCEWithLogitsLoss()(tower(dense, wide, deep), labels)
+    grads = torch.autograd.grad(l2, wt + dt + list(tower.parameters()))
+    assert abs(float(loss) - float(l2)) < 1e-6
+    G = len(rows)
+    for fam, (names, t0, gr, dim) in enumerate(((eng.wide_names, wide0, grads[:G], 1),
+                                                 (eng.deep_names, deep0, grads[G:2 * G], D))):
+        for g in range(G):
+            touched = torch.unique(ids[g]).cpu().numpy()
+            p = t0[g].cpu().numpy()[touched].copy()
+            gg = gr[g].cpu().numpy()[touched].copy()
+            m, v = np.zeros_like(p), np.zeros_like(p)
+            O.np_adam(gg, p, m, v, 0.001, 1, 0.9, 0.999, 1e-7)
+            got = group.pull_rows([(names[g], torch.from_numpy(touched))])[0].cpu().numpy()
+            assert np.allclose(got, p, rtol=1e-5, atol=1e-6), (fam, g)
+            gm = group.slot_rows(names[g], touched, 1).cpu().numpy()
+            assert np.allclose(gm, m, rtol=1e-4, atol=1e-8), (fam, g)
+            # untouched rows unchanged, never created
+            assert group.table_size(names[g]) == rows[g]  # all rows were created by the init set_rows
+    for (name, p), gref, pref in zip(eng.params, grads[2 * G:], tower.parameters()):
+        want = pref.detach().cpu().numpy().copy()
+        m, v = np.zeros_like(want), np.zeros_like(want)
+        O.np_adam(gref.cpu().numpy(), want, m, v, 0.001, 1, 0.9, 0.999, 1e-7)
+        got = group.pull_dense([name])[name].cpu().numpy()
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-6), name
+    assert [s[0] for s in group.snapshot()] == [1] * n_shards
+    # training makes progress on a fixed batch
+    l_first = float(loss)
+    for _ in range(30):
+        l_last = float(eng.step(ids, dense, labels))
+    assert l_last < l_first
+    group.close()

@@ -139,7 +139,19 @@ def test_segment_sum_matches_dedup(dim):
     wv, wi = O.deduplicate_indexed_slices(vals, ids)
     u = int(n.item())
     assert u == len(wi) and np.array_equal(uniq.cpu().numpy()[:u], wi)
-    assert np.allclose(out[:u], wv, rtol=1e-5, atol=1e-5)  # atomics: summation order differs
+    # hot ids are summed thousands of times in a different (atomic) order than the oracle's
+    # left-to-right loop: both are within the fp32 accumulation bound of the exact sum
+    exact = np.zeros((u, dim), dtype=np.float64)
+    mag = np.zeros((u, dim), dtype=np.float64)
+    rank = {int(x): r for r, x in enumerate(wi)}
+    r_of = np.array([rank[int(x)] for x in ids])
+    np.add.at(exact, r_of, vals.astype(np.float64))
+    np.add.at(mag, r_of, np.abs(vals).astype(np.float64))
+    bound = 4e-6 * mag + 1e-7
+    assert np.all(np.abs(out[:u] - exact) <= bound)
+    assert np.all(np.abs(wv - exact) <= bound)
+    few = np.bincount(r_of, minlength=u) <= 4  # lightly duplicated ids: 1e-5 relative
+    assert np.allclose(out[:u][few], wv[few], rtol=1e-5, atol=1e-6)
     assert not out[u:].any()
     # no duplicates -> bit exact
     ids2 = rng.permutation(50000)[:k].astype(np.int64)
