@@ -424,9 +424,11 @@ int b200ps_shard_create_local(b200ps_t* ps, int shard_id, int device) {
     cudaGetLastError();
   }
   DeviceGuard g(device);
-  CUDA_OK(cudaMalloc(&sh.ctl.ptr, sizeof(ShardCtl)));
-  CUDA_OK(cudaMemset(sh.ctl.ptr, 0, sizeof(ShardCtl)));
-  sh.ctl.bytes = sizeof(ShardCtl);
+  // a whole 2 MiB block: an IPC export then never exposes unrelated small allocations
+  constexpr size_t kCtlBytes = 2u << 20;
+  CUDA_OK(cudaMalloc(&sh.ctl.ptr, kCtlBytes));
+  CUDA_OK(cudaMemset(sh.ctl.ptr, 0, kCtlBytes));
+  sh.ctl.bytes = kCtlBytes;
   sh.local = true;
   sh.attached = true;
   sh.device = device;
@@ -544,7 +546,7 @@ int b200ps_table_register(b200ps_t* ps, const char* name, int dim, const char* i
   rec_bytes = (rec_bytes + 255) / 256 * 256;
   size_t bitmap = (ps->flags & 2u) ? 0 : (((size_t)t.rows + 31) / 32 * 4 + 255) / 256 * 256;
   t.present_off = bitmap ? rec_bytes : 0;
-  t.bytes = rec_bytes + bitmap;
+  t.bytes = (rec_bytes + bitmap + (2u << 20) - 1) / (2u << 20) * (2u << 20);  // IPC-exportable whole blocks
   t.uniform = initializer && strcmp(initializer, "uniform") == 0;  // embedding_table.go:51 (quirk Q6)
   t.seed = seed;
   return register_common(ps, std::move(t));
@@ -567,7 +569,7 @@ int b200ps_dense_register(b200ps_t* ps, const char* name, int shard, int64_t row
   for (int k = 0; k <= kMaxSlots; ++k) t.slot_off[k] = (int64_t)k * padded;
   int slots = opt_slots(ps->opt.kind);
   t.present_off = 0;
-  t.bytes = (size_t)padded * (slots + 1) * sizeof(float);
+  t.bytes = ((size_t)padded * (slots + 1) * sizeof(float) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
   t.uniform = false;
   return register_common(ps, std::move(t));
 }

@@ -86,7 +86,7 @@ __device__ __forceinline__ RowLoc locate(const GroupView& gv, const TableView& t
   if (r.ok && tv.present[r.shard] != nullptr) {
     uint32_t* w = tv.present[r.shard] + (slot >> 5);
     uint32_t bit = 1u << (slot & 31);
-    if (!(*(volatile uint32_t*)w & bit)) atomicOr(w, bit);
+    if (!(*(volatile uint32_t*)w & bit)) atomicOr_system(w, bit);  // the shard may be a peer GPU
   }
   return r;
 }

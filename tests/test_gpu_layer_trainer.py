@@ -182,3 +182,18 @@ def test_deepfm_engine_step_matches_oracle_adam(n_shards):
         l_last = float(eng.step(ids, dense, labels))
     assert l_last < l_first
     group.close()
+
+
+def test_multi_gpu_peer_shards_via_torchrun():
+    """Rank-per-GPU group with CUDA-IPC peer shards (needs >= 2 GPUs; skipped on 1)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run: gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "mgpu_check ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
