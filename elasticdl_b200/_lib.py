@@ -25,6 +25,18 @@ class Seg(ctypes.Structure):
     ]
 
 
+class DeepFMArgs(ctypes.Structure):  # b200_deepfm_args_t (include/b200_deepfm.h)
+    _fields_ = [
+        ("G", ctypes.c_int32), ("B", ctypes.c_int32),
+        ("inv", ctypes.c_void_p), ("n_unique", ctypes.c_void_p),
+        ("bet_wide", ctypes.c_void_p), ("bet_deep", ctypes.c_void_p),
+        ("dense", ctypes.c_void_p), ("labels", ctypes.c_void_p),
+        ("params", ctypes.c_void_p), ("grads", ctypes.c_void_p),
+        ("gsum_wide", ctypes.c_void_p), ("gsum_deep", ctypes.c_void_p),
+        ("loss", ctypes.c_void_p), ("logits", ctypes.c_void_p), ("scratch", ctypes.c_void_p),
+    ]
+
+
 class PSError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("b200ps error %d: %s" % (code, msg))
@@ -79,6 +91,11 @@ SYMBOLS = {
     "b200ps_table_ids": (_i, [_vp, _i, _i, _vp, _i64, ctypes.POINTER(_i64)]),
     "b200ps_check": (_i, [_vp]),
     "b200ps_launch_count": (_i64, [_vp]),
+    # include/b200_deepfm.h
+    "b200_deepfm_param_count": (_sz, [_i]),
+    "b200_deepfm_fwd_bwd": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
+    "b200_deepfm_forward": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
+    "b200_deepfm_launch_count": (_i64, []),
 }
 
 _lib = None

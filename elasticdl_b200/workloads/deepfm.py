@@ -80,9 +80,29 @@ def synthetic_batch(batch, seed, device, dist="zipf", zipf_s=1.05, group_rows=GR
     return ids, dense, labels
 
 
+def flatten_tower(tower, flat):
+    """Re-point the tower's parameters at views of one flat buffer laid out as
+    include/b200_deepfm.h documents: [w_dense 13 (+3 pad) | w1 | b1 | w2 | b2 | w3]."""
+    order = [(tower.dense_linear.weight, 16), (tower.dnn[0].weight, None), (tower.dnn[0].bias, None),
+             (tower.dnn[1].weight, None), (tower.dnn[1].bias, None), (tower.dnn_logit.weight, None)]
+    off, views = 0, []
+    with torch.no_grad():
+        for p, padded in order:
+            n = p.numel()
+            flat[off:off + n].copy_(p.reshape(-1))
+            p.data = flat[off:off + n].view(p.shape)
+            views.append((off, n))
+            off += padded or n
+    return views
+
+
 class DeepFMPSEngine:
     def __init__(self, group, batch, lr=1e-3, init_std=0.01, seed=7, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM,
-                 init_rows=True):
+                 init_rows=True, tower="fused"):
+        """tower="fused": the hand-written CUDA tower (csrc/deepfm_tower.cu);
+        tower="torch": torch autograd over library kernels (kept for A/B measurements and tests)."""
+        assert tower in ("fused", "torch")
+        self.tower_kind = tower
         self.group = group
         self.B = int(batch)
         self.G = len(group_rows)
@@ -97,7 +117,15 @@ class DeepFMPSEngine:
         self.deep_ids = [group.register_table(n, D, "zero", r) for n, r in zip(self.deep_names, group_rows)]
         torch.manual_seed(seed)
         self.tower = DeepFMTower(G, D).to(dev)
-        self.params = [(n, p) for n, p in self.tower.named_parameters()]
+        n_flat = int(group.lib.b200_deepfm_param_count(G))
+        self.flat_params = torch.zeros(n_flat, dtype=torch.float32, device=dev)
+        self.flat_grads = torch.zeros(n_flat, dtype=torch.float32, device=dev)
+        self.flat_views = flatten_tower(self.tower, self.flat_params)
+        # named_parameters order != flat order: keep both
+        flat_order = [self.tower.dense_linear.weight, self.tower.dnn[0].weight, self.tower.dnn[0].bias,
+                      self.tower.dnn[1].weight, self.tower.dnn[1].bias, self.tower.dnn_logit.weight]
+        names = {id(p): n for n, p in self.tower.named_parameters()}
+        self.params = [(names[id(p)], p) for p in flat_order]
         from elasticdl_b200.common.hash_utils import string_to_id
 
         self.dense_ids = []
@@ -140,8 +168,11 @@ class DeepFMPSEngine:
         self.bet_d = torch.zeros((G * B, D), **f32)
         self.act_w = torch.empty((G * B, 1), **f32)
         self.act_d = torch.empty((G * B, D), **f32)
-        self.gsum_w = torch.empty((G * B, 1), **f32)
-        self.gsum_d = torch.empty((G * B, D), **f32)
+        self.gsum_w = torch.zeros((G * B, 1), **f32)
+        self.gsum_d = torch.zeros((G * B, D), **f32)
+        self.scratch = torch.empty((B, 44), **f32)
+        self.loss_buf = torch.zeros(1, **f32)
+        self.logits_buf = torch.empty(B, **f32)
         self.zero_versions = [0] * group.n_shards
         self.loss_fn = torch.nn.BCEWithLogitsLoss()
         self._build_segs()
@@ -159,6 +190,18 @@ class DeepFMPSEngine:
         self.push_segs = [g.make_segs(self._seg_items(self.wide_ids, self.gsum_w, 1)),
                           g.make_segs(self._seg_items(self.deep_ids, self.gsum_d, self.D))]
         self.pull_dense_segs = g.make_segs([(tid, 0, None, None, p) for tid, (_, p) in zip(self.dense_ids, self.params)])
+        grad_views = [self.flat_grads[off:off + n] for off, n in self.flat_views]
+        self.push_dense_segs = g.make_segs([(tid, 0, None, None, gv) for tid, gv in zip(self.dense_ids, grad_views)])
+        from elasticdl_b200._lib import DeepFMArgs
+
+        a = DeepFMArgs()
+        a.G, a.B = self.G, self.B
+        a.inv, a.n_unique = self.inv.data_ptr(), self.n_unique.data_ptr()
+        a.bet_wide, a.bet_deep = self.bet_w.data_ptr(), self.bet_d.data_ptr()
+        a.params, a.grads = self.flat_params.data_ptr(), self.flat_grads.data_ptr()
+        a.gsum_wide, a.gsum_deep = self.gsum_w.data_ptr(), self.gsum_d.data_ptr()
+        a.loss, a.logits, a.scratch = self.loss_buf.data_ptr(), self.logits_buf.data_ptr(), self.scratch.data_ptr()
+        self.tower_args = a
 
     def step(self, ids, dense, labels, ev=None):
         """ids int64 [G, B] (group-major), dense fp32 [B, 13], labels fp32 [B] -- all on the device.
@@ -192,10 +235,39 @@ class DeepFMPSEngine:
             e = mark(name)
             check(lib.b200ps_pull_rows(h, arr, n, st))
             done(e)
-        # (4) BET -> per-occurrence activations
+        if self.tower_kind == "fused":
+            # (4-6) gather + tower forward/backward + per-unique-id gradient sums: three launches
+            e_t = mark("tower_fwd_bwd")
+            a = self.tower_args
+            a.dense, a.labels = dense.data_ptr(), labels.data_ptr()
+            import ctypes as _ct
+
+            rc = lib.b200_deepfm_fwd_bwd(_ct.byref(a), st)
+            if rc:
+                raise RuntimeError("b200_deepfm_fwd_bwd failed (%d)" % rc)
+            done(e_t)
+            loss = self.loss_buf
+            dense_segs = self.push_dense_segs
+        else:
+            loss, dense_segs = self._torch_tower(dense, labels, mark, done, st)
+        # (7) push: one ApplyGradients per shard
+        g.push_begin(self.lr, self.zero_versions)
+        arr, n = dense_segs
+        check(lib.b200ps_push_dense(h, arr, n, st))
+        for name, (arr, n) in zip(("push_wide", "push_deep"), self.push_segs):
+            e = mark(name)
+            check(lib.b200ps_push_rows(h, arr, n, st))
+            done(e)
+        g.push_end(sync=False)
+        self.steps += 1
+        return loss.detach().reshape(())
+
+    def _torch_tower(self, dense, labels, mark, done, st):
+        """Steps (4)-(6) with torch autograd over library kernels (A/B reference for the fused tower)."""
+        g, lib, h = self.group, self.group.lib, self.group._h
+        G, B, D = self.G, self.B, self.D
         check(lib.b200ps_gather_rows(h, self.bet_w.data_ptr(), self.inv.data_ptr(), G, B, 1, self.act_w.data_ptr(), st))
         check(lib.b200ps_gather_rows(h, self.bet_d.data_ptr(), self.inv.data_ptr(), G, B, D, self.act_d.data_ptr(), st))
-        # (5) tower forward / backward
         e_t = mark("tower_fwd_bwd")
         act_w = self.act_w.detach().requires_grad_(True)
         act_d = self.act_d.detach().requires_grad_(True)
@@ -207,23 +279,30 @@ class DeepFMPSEngine:
         grads = torch.autograd.grad(loss, plist + [act_w, act_d])
         gw, gd = grads[-2].contiguous(), grads[-1].contiguous()
         done(e_t)
-        # (6) per-occurrence gradients -> per-unique-id sums (deduplicate_indexed_slices)
         check(lib.b200ps_segment_sum(h, gw.data_ptr(), self.inv.data_ptr(), G, B, 1, self.gsum_w.data_ptr(), st))
         e = mark("segment_sum_deep")
         check(lib.b200ps_segment_sum(h, gd.data_ptr(), self.inv.data_ptr(), G, B, D, self.gsum_d.data_ptr(), st))
         done(e)
-        # (7) push: one ApplyGradients per shard
-        g.push_begin(self.lr, self.zero_versions)
-        dense_grads = [gr.contiguous() for gr in grads[:-2]]
-        arr, n = g.make_segs([(tid, 0, None, None, gr) for tid, gr in zip(self.dense_ids, dense_grads)])
-        check(lib.b200ps_push_dense(h, arr, n, st))
-        for name, (arr, n) in zip(("push_wide", "push_deep"), self.push_segs):
-            e = mark(name)
-            check(lib.b200ps_push_rows(h, arr, n, st))
-            done(e)
-        g.push_end(sync=False)
-        self.steps += 1
-        return loss.detach()
+        self._dense_grads = [gr.contiguous() for gr in grads[:-2]]
+        return loss, g.make_segs([(tid, 0, None, None, gr) for tid, gr in zip(self.dense_ids, self._dense_grads)])
+
+    def predict(self, ids, dense):
+        """Forward only (logits) through the PS: unique -> pull -> fused tower forward."""
+        g, lib, h = self.group, self.group.lib, self.group._h
+        st = g._stream()
+        arr, n = self.pull_dense_segs
+        check(lib.b200ps_pull_dense(h, arr, n, st))
+        check(lib.b200ps_unique(h, ids.data_ptr(), self.G, self.B, self.uniq.data_ptr(), self.inv.data_ptr(),
+                                self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st))
+        for arr, n in self.pull_segs:
+            check(lib.b200ps_pull_rows(h, arr, n, st))
+        import ctypes as _ct
+
+        a = self.tower_args
+        a.dense = dense.data_ptr()
+        if lib.b200_deepfm_forward(_ct.byref(a), st):
+            raise RuntimeError("b200_deepfm_forward failed")
+        return self.logits_buf
 
     def kernel_report(self, ev, uniq_per_step, opt_slots=2):
         """Average CUDA-event duration and algorithmic GB/s per named PS kernel.
