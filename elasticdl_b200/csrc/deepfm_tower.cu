@@ -116,18 +116,22 @@ __device__ __forceinline__ float dot16(const float (&h)[H1], const float* __rest
   return acc;
 }
 
+constexpr int TA_THREADS = 128;  // samples per block (lane = sample)
+constexpr int GC = 4;            // id groups gathered per batch of loads (memory-level parallelism)
+
 template <bool BACKWARD>
-__global__ void __launch_bounds__(256) k_tower_a(b200_deepfm_args_t a) {
+__global__ void __launch_bounds__(TA_THREADS) k_tower_a(b200_deepfm_args_t a) {
   extern __shared__ __align__(16) float smem[];
   const Layout l = layout(a.G);
   SmemParams sp = carve(smem, l.in);
+  int* sinv = reinterpret_cast<int*>(smem + smem_floats(l.in));  // [G][TA_THREADS] ranks of this block's samples
   load_params(a.params, l, sp);
   const int B = a.B, G = a.G;
   const int lane = threadIdx.x & 31;
   float loss_acc = 0.f;
-  const long long nblk = ((long long)B + blockDim.x - 1) / blockDim.x;
+  const long long nblk = ((long long)B + TA_THREADS - 1) / TA_THREADS;
   for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const long long b = blk * blockDim.x + threadIdx.x;
+    const long long b = blk * TA_THREADS + threadIdx.x;
     const bool live = b < B;
     const long long bb = live ? b : B - 1;  // dead lanes replay the last sample, results discarded
     float h[H1];
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(256) k_tower_a(b200_deepfm_args_t a) {
     float lin = 0.f;
 #pragma unroll
     for (int e = 0; e < ND; ++e) {
-      float x = a.dense[bb * ND + e];
+      const float x = a.dense[bb * ND + e];
       lin = fmaf(sp.wd[e], x, lin);
       axpy16(h, sp.w1t + e * H1, x);
     }
@@ -144,18 +148,35 @@ __global__ void __launch_bounds__(256) k_tower_a(b200_deepfm_args_t a) {
 #pragma unroll
     for (int d = 0; d < D; ++d) s[d] = 0.f;
     float q = 0.f;
-    for (int g = 0; g < G; ++g) {
-      const int r = a.inv[(long long)g * B + bb];
-      const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + r) * D);
-      const float4 e0 = row[0], e1 = row[1];
-      lin += a.bet_wide[(long long)g * B + r];
-      const float ev[D] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-      const float* w = sp.w1t + (ND + g * D) * H1;
+    // pass 1: GC groups per round -- GC rank loads, then 3*GC independent row loads in flight
+    for (int g0 = 0; g0 < G; g0 += GC) {
+      int r[GC];
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        s[d] += ev[d];
-        q = fmaf(ev[d], ev[d], q);
-        axpy16(h, w + d * H1, ev[d]);
+      for (int u = 0; u < GC; ++u) r[u] = (g0 + u < G) ? a.inv[(long long)(g0 + u) * B + bb] : 0;
+      float4 e0[GC], e1[GC];
+      float wv[GC];
+#pragma unroll
+      for (int u = 0; u < GC; ++u) {
+        const int g = (g0 + u < G) ? g0 + u : G - 1;
+        const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + r[u]) * D);
+        e0[u] = row[0];
+        e1[u] = row[1];
+        wv[u] = a.bet_wide[(long long)g * B + r[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < GC; ++u) {
+        if (g0 + u < G) {
+          sinv[(g0 + u) * TA_THREADS + threadIdx.x] = r[u];
+          lin += wv[u];
+          const float ev[D] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
+          const float* w = sp.w1t + (ND + (g0 + u) * D) * H1;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            s[d] += ev[d];
+            q = fmaf(ev[d], ev[d], q);
+            axpy16(h, w + d * H1, ev[d]);
+          }
+        }
       }
     }
     float a1[H1];
@@ -172,64 +193,77 @@ __global__ void __launch_bounds__(256) k_tower_a(b200_deepfm_args_t a) {
     for (int d = 0; d < D; ++d) ss = fmaf(s[d], s[d], ss);
     const float z = lin + dnn + 0.5f * (ss - q);
     if (live && a.logits != nullptr) a.logits[b] = z;
-    if (!BACKWARD) continue;
-    const float y = a.labels[bb];
-    const float lb = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));  // BCE with logits
-    if (live) loss_acc += lb;
-    const float p = 1.f / (1.f + expf(-z));
-    const float dz = live ? (p - y) / (float)B : 0.f;
-    float dh2[H2];
+    if (BACKWARD) {
+      const float y = a.labels[bb];
+      const float lb = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));  // BCE with logits
+      if (live) loss_acc += lb;
+      const float p = 1.f / (1.f + expf(-z));
+      const float dz = live ? (p - y) / (float)B : 0.f;
+      float dh2[H2];
 #pragma unroll
-    for (int k = 0; k < H2; ++k) dh2[k] = h2[k] > 0.f ? dz * sp.w3[k] : 0.f;
-    float dh1[H1];
+      for (int k = 0; k < H2; ++k) dh2[k] = h2[k] > 0.f ? dz * sp.w3[k] : 0.f;
+      float dh1[H1];
 #pragma unroll
-    for (int j = 0; j < H1; ++j) {
-      float acc = 0.f;
+      for (int j = 0; j < H1; ++j) {
+        float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < H2; ++k) acc = fmaf(sp.w2[k * H1 + j], dh2[k], acc);
-      dh1[j] = h[j] > 0.f ? acc : 0.f;
-    }
-    if (live) {  // per-sample backward state for k_tower_b: [dh1 16 | a1 16 | dh2 4 | h2 4 | dz | pad 3]
-      float4* sc = reinterpret_cast<float4*>(a.scratch + b * SCR);
-#pragma unroll
-      for (int qd = 0; qd < 4; ++qd) sc[qd] = make_float4(dh1[4 * qd], dh1[4 * qd + 1], dh1[4 * qd + 2], dh1[4 * qd + 3]);
-#pragma unroll
-      for (int qd = 0; qd < 4; ++qd) sc[4 + qd] = make_float4(a1[4 * qd], a1[4 * qd + 1], a1[4 * qd + 2], a1[4 * qd + 3]);
-      sc[8] = make_float4(dh2[0], dh2[1], dh2[2], dh2[3]);
-      sc[9] = make_float4(h2[0], h2[1], h2[2], h2[3]);
-      sc[10] = make_float4(dz, 0.f, 0.f, 0.f);
-    }
-    // pass 2: d loss / d embedding rows, reduced per unique id (deduplicate_indexed_slices' sum)
-    for (int g = 0; g < G; ++g) {
-      const int r = a.inv[(long long)g * B + bb];
-      const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + r) * D);
-      const float4 e0 = row[0], e1 = row[1];
-      const float ev[D] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-      const float* w = sp.w1t + (ND + g * D) * H1;
-      float x[D + 1];
-#pragma unroll
-      for (int d = 0; d < D; ++d) x[d] = fmaf(dz, s[d] - ev[d], dot16(dh1, w + d * H1));
-      x[D] = dz;  // wide row gradient
-      // warp-level id dedup: lanes hitting the same row combine (lane order), lowest lane writes
-      const int key = live ? r : -1 - lane;
-      const unsigned peers = __match_any_sync(0xffffffffu, key);
-      const bool leader = (__ffs(peers) - 1) == lane;
-      unsigned rest = peers & ~(1u << lane);
-      const int maxn = __reduce_max_sync(0xffffffffu, (unsigned)__popc(peers));
-      for (int it = 1; it < maxn; ++it) {
-        const int src = rest ? __ffs(rest) - 1 : lane;
-#pragma unroll
-        for (int e = 0; e <= D; ++e) {
-          const float yv = __shfl_sync(0xffffffffu, x[e], src);
-          if (leader && rest) x[e] += yv;
-        }
-        rest &= rest - 1;
+        for (int k = 0; k < H2; ++k) acc = fmaf(sp.w2[k * H1 + j], dh2[k], acc);
+        dh1[j] = h[j] > 0.f ? acc : 0.f;
       }
-      if (live && leader) {
-        float* od = a.gsum_deep + ((long long)g * B + r) * D;
-        atomicAdd(reinterpret_cast<float4*>(od), make_float4(x[0], x[1], x[2], x[3]));
-        atomicAdd(reinterpret_cast<float4*>(od + 4), make_float4(x[4], x[5], x[6], x[7]));
-        atomicAdd(a.gsum_wide + (long long)g * B + r, x[D]);
+      if (live) {  // per-sample backward state for k_tower_b: [dh1 16 | a1 16 | dh2 4 | h2 4 | dz | pad 3]
+        float4* sc = reinterpret_cast<float4*>(a.scratch + b * SCR);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) sc[qd] = make_float4(dh1[4 * qd], dh1[4 * qd + 1], dh1[4 * qd + 2], dh1[4 * qd + 3]);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) sc[4 + qd] = make_float4(a1[4 * qd], a1[4 * qd + 1], a1[4 * qd + 2], a1[4 * qd + 3]);
+        sc[8] = make_float4(dh2[0], dh2[1], dh2[2], dh2[3]);
+        sc[9] = make_float4(h2[0], h2[1], h2[2], h2[3]);
+        sc[10] = make_float4(dz, 0.f, 0.f, 0.f);
+      }
+      // pass 2: d loss / d embedding rows, reduced per unique id (deduplicate_indexed_slices' sum)
+      for (int g0 = 0; g0 < G; g0 += GC) {
+        int r[GC];
+        float4 e0[GC], e1[GC];
+#pragma unroll
+        for (int u = 0; u < GC; ++u) {
+          const int g = (g0 + u < G) ? g0 + u : G - 1;
+          r[u] = sinv[g * TA_THREADS + threadIdx.x];
+          const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + r[u]) * D);
+          e0[u] = row[0];
+          e1[u] = row[1];
+        }
+#pragma unroll
+        for (int u = 0; u < GC; ++u) {
+          if (g0 + u >= G) break;  // warp-uniform
+          const int g = g0 + u;
+          const float ev[D] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
+          const float* w = sp.w1t + (ND + g * D) * H1;
+          float x[D + 1];
+#pragma unroll
+          for (int d = 0; d < D; ++d) x[d] = fmaf(dz, s[d] - ev[d], dot16(dh1, w + d * H1));
+          x[D] = dz;  // wide row gradient
+          // warp-level id dedup: lanes hitting the same row combine (lane order), lowest lane writes
+          const int key = live ? r[u] : -1 - lane;
+          const unsigned peers = __match_any_sync(0xffffffffu, key);
+          const bool leader = (__ffs(peers) - 1) == lane;
+          unsigned rest = peers & ~(1u << lane);
+          const int maxn = __reduce_max_sync(0xffffffffu, (unsigned)__popc(peers));
+          for (int it = 1; it < maxn; ++it) {
+            const int src = rest ? __ffs(rest) - 1 : lane;
+#pragma unroll
+            for (int e = 0; e <= D; ++e) {
+              const float yv = __shfl_sync(0xffffffffu, x[e], src);
+              if (leader && rest) x[e] += yv;
+            }
+            rest &= rest - 1;
+          }
+          if (live && leader) {
+            float* od = a.gsum_deep + ((long long)g * B + r[u]) * D;
+            atomicAdd(reinterpret_cast<float4*>(od), make_float4(x[0], x[1], x[2], x[3]));
+            atomicAdd(reinterpret_cast<float4*>(od + 4), make_float4(x[4], x[5], x[6], x[7]));
+            atomicAdd(a.gsum_wide + (long long)g * B + r[u], x[D]);
+          }
+        }
       }
     }
   }
@@ -348,7 +382,7 @@ int b200_deepfm_fwd_bwd(const b200_deepfm_args_t* args, void* stream) {
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const size_t smem = smem_floats(l.in) * sizeof(float);
+  const size_t smem = smem_floats(l.in) * sizeof(float) + (size_t)args->G * TA_THREADS * sizeof(int);
   static bool attr_done[64] = {false};
   if (smem > 48 * 1024 && dev < 64 && !attr_done[dev]) {
     cudaFuncSetAttribute(k_tower_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -357,9 +391,9 @@ int b200_deepfm_fwd_bwd(const b200_deepfm_args_t* args, void* stream) {
   }
   dim3 gp(8, args->G);
   k_tower_prep<<<gp, 256, 0, st>>>(*args, l.total);
-  long long blocks = ((long long)args->B + 255) / 256;
+  long long blocks = ((long long)args->B + TA_THREADS - 1) / TA_THREADS;
   long long cap = (long long)n_sm * 4;
-  k_tower_a<true><<<(unsigned)(blocks < cap ? blocks : cap), 256, smem, st>>>(*args);
+  k_tower_a<true><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
   long long chunks = ((long long)args->B + S_CHUNK - 1) / S_CHUNK;
   cap = (long long)n_sm * 2;
   k_tower_b<<<(unsigned)(chunks < cap ? chunks : cap), TB_THREADS, 0, st>>>(*args);
@@ -376,11 +410,11 @@ int b200_deepfm_forward(const b200_deepfm_args_t* args, void* stream) {
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const size_t smem = smem_floats(l.in) * sizeof(float);
+  const size_t smem = smem_floats(l.in) * sizeof(float) + (size_t)args->G * TA_THREADS * sizeof(int);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_tower_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  long long blocks = ((long long)args->B + 255) / 256;
+  long long blocks = ((long long)args->B + TA_THREADS - 1) / TA_THREADS;
   long long cap = (long long)n_sm * 4;
-  k_tower_a<false><<<(unsigned)(blocks < cap ? blocks : cap), 256, smem, st>>>(*args);
+  k_tower_a<false><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_msg = cudaGetErrorString(e); return -2; }

@@ -64,6 +64,7 @@ __device__ __forceinline__ void opt_update(float g, float& p, float& s0, float& 
 // ---------------------------------------------------------------------------
 struct RowLoc {
   float* rec;
+  int64_t slot;
   int shard;
   bool ok;
 };
@@ -82,13 +83,19 @@ __device__ __forceinline__ RowLoc locate(const GroupView& gv, const TableView& t
     r.shard = (int)(id - slot * gv.n_shards);
   }
   r.ok = (id >= 0) && (slot < tv.rows);
+  r.slot = slot;
   r.rec = tv.base[r.shard] + slot * tv.row_stride;
-  if (r.ok && tv.present[r.shard] != nullptr) {
-    uint32_t* w = tv.present[r.shard] + (slot >> 5);
-    uint32_t bit = 1u << (slot & 31);
-    if (!(*(volatile uint32_t*)w & bit)) atomicOr_system(w, bit);  // the shard may be a peer GPU
-  }
   return r;
+}
+
+// Created-row bitmap (len(EmbeddingVectors) / ToIndexedSlices).  Called AFTER the row loads
+// are issued so that the (possibly remote) bitmap read overlaps them.
+__device__ __forceinline__ void mark_present(const TableView& tv, const RowLoc& r) {
+  uint32_t* bm = tv.present[r.shard];
+  if (bm == nullptr) return;
+  uint32_t* w = bm + (r.slot >> 5);
+  const uint32_t bit = 1u << (r.slot & 31);
+  if (!(*(volatile uint32_t*)w & bit)) atomicOr_system(w, bit);  // the shard may be a peer GPU
 }
 
 __device__ __forceinline__ int seg_count(const b200ps_seg_t& sg) {
@@ -140,13 +147,15 @@ __global__ void __launch_bounds__(256) k_rows_copy(GroupView gv, SegBatch sb, in
     }
     float* rec = loc.rec + tv.slot_off[slot] + c * W;
     if (VPT == 0) {
-      if (WRITE) *rec = *user; else *user = *rec;
+      if (WRITE) { *rec = *user; if (c == 0) mark_present(tv, loc); }
+      else { float x = *rec; if (c == 0) mark_present(tv, loc); *user = x; }
     } else {
+      float4 x[VPT == 0 ? 1 : VPT];
 #pragma unroll
-      for (int v = 0; v < VPT; ++v) {
-        if (WRITE) st_f4(rec + 4 * v, ld_f4(user + 4 * v));
-        else st_f4(user + 4 * v, ld_f4(rec + 4 * v));
-      }
+      for (int v = 0; v < VPT; ++v) x[v] = ld_f4((WRITE ? user : rec) + 4 * v);
+      if (c == 0) mark_present(tv, loc);
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) st_f4((WRITE ? rec : user) + 4 * v, x[v]);
     }
   }
 }
@@ -187,6 +196,7 @@ __global__ void __launch_bounds__(256) k_push_rows(GroupView gv, SegBatch sb, Op
       if (S > 0) s0 = rec[o0];
       if (S > 1) s1 = rec[o1];
       if (S > 2) s2 = rec[o2];
+      if (c == 0) mark_present(tv, loc);
       opt_update<OPT>(g, p, s0, s1, s2, lr, alpha, l2adj, o);
       *rec = p;
       if (S > 0) rec[o0] = s0;
@@ -203,6 +213,7 @@ __global__ void __launch_bounds__(256) k_push_rows(GroupView gv, SegBatch sb, Op
         if (S > 1) s1[v] = ld_f4(rec + o1 + 4 * v);
         if (S > 2) s2[v] = ld_f4(rec + o2 + 4 * v);
       }
+      if (c == 0) mark_present(tv, loc);
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
         float* gf = reinterpret_cast<float*>(&g[v]);
@@ -467,20 +478,30 @@ __global__ void __launch_bounds__(256) k_uniq_clear(UniqueWs ws, int T) {
 __global__ void __launch_bounds__(256) k_uniq_insert(const int64_t* ids, long long k, UniqueWs ws) {
   const int t = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= k) return;
-  const long long id = ids[t * k + i];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws.keys + (long long)t * ws.cap);
-  int* minpos = ws.minpos + (long long)t * ws.cap;
-  const unsigned mask = ws.cap - 1;
-  unsigned s = (unsigned)mix64((uint64_t)id) & mask;
-  while (true) {
-    unsigned long long prev = keys[s];
-    if (prev == (unsigned long long)kEmptyKey) prev = atomicCAS(&keys[s], (unsigned long long)kEmptyKey, (unsigned long long)id);
-    if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)id) break;
-    s = (s + 1) & mask;
+  const bool live = i < k;
+  const int lane = threadIdx.x & 31;
+  // warp-level id dedup: lanes holding the same id elect the lowest lane (= smallest position),
+  // which alone probes the table; Zipf-hot ids then cost one atomic per warp, not one per lane.
+  const long long id = live ? ids[t * k + i] : (long long)(-1 - lane);
+  const unsigned peers = __match_any_sync(0xffffffffu, id);
+  const int leader = __ffs(peers) - 1;
+  unsigned s = 0;
+  if (live && lane == leader) {
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws.keys + (long long)t * ws.cap);
+    int* minpos = ws.minpos + (long long)t * ws.cap;
+    const unsigned mask = ws.cap - 1;
+    s = (unsigned)mix64((uint64_t)id) & mask;
+    while (true) {
+      unsigned long long prev = keys[s];
+      if (prev == (unsigned long long)kEmptyKey) prev = atomicCAS(&keys[s], (unsigned long long)kEmptyKey, (unsigned long long)id);
+      if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)id) break;
+      s = (s + 1) & mask;
+    }
+    // after the first few occurrences the recorded position is already smaller
+    if (*(volatile int*)&minpos[s] > (int)i) atomicMin(&minpos[s], (int)i);
   }
-  atomicMin(&minpos[s], (int)i);
-  ws.fp[t * k + i] = (int)s;
+  s = __shfl_sync(0xffffffffu, s, leader);
+  if (live) ws.fp[t * k + i] = (int)s;
 }
 
 __device__ __forceinline__ int block_sum_256(int v, int* smem) {

@@ -262,6 +262,33 @@ class DeepFMPSEngine:
         self.steps += 1
         return loss.detach().reshape(())
 
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self):
+        """Capture one whole step (19 launches + the versions read-back) into a CUDA graph.
+        Every buffer the step touches is persistent, so the graph replays on new inputs
+        copied into the static input buffers.  lr is baked in: re-capture to change it."""
+        if self.tower_kind != "fused":
+            raise RuntimeError("graph capture needs the fused tower (torch autograd allocates)")
+        dev, G, B = self.device, self.G, self.B
+        self.s_ids = torch.zeros((G, B), dtype=torch.int64, device=dev)
+        self.s_dense = torch.zeros((B, N_DENSE), dtype=torch.float32, device=dev)
+        self.s_labels = torch.zeros(B, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.step(self.s_ids, self.s_dense, self.s_labels)
+        self.steps -= 1  # capture does not execute
+        return self.graph
+
+    def step_graph(self, ids, dense, labels):
+        """Same step through the captured graph; inputs may be pinned-host or device tensors."""
+        self.s_ids.copy_(ids, non_blocking=True)
+        self.s_dense.copy_(dense, non_blocking=True)
+        self.s_labels.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        self.steps += 1
+        return self.loss_buf.reshape(())
+
     def _torch_tower(self, dense, labels, mark, done, st):
         """Steps (4)-(6) with torch autograd over library kernels (A/B reference for the fused tower)."""
         g, lib, h = self.group, self.group.lib, self.group._h
