@@ -268,12 +268,19 @@ def main():
     # ---- end to end: host buffers in, loss out, every step ----------------------------
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    feeder = engine.host_feeder(2) if use_graph else None
     e2.record()
+    if feeder is not None:
+        feeder.submit(*host[0])
     for i in range(args.steps):
-        hi, hd, hl = host[i % args.pool]
-        if use_graph:
-            loss = engine.step_graph(hi, hd, hl)  # H2D copies into the graph's static inputs
+        if feeder is not None:
+            # every step's inputs come from pinned host memory; the copy of batch i+1 (side stream)
+            # overlaps the kernels of batch i, like the reference's dataset.prefetch(1)
+            if i + 1 < args.steps:
+                feeder.submit(*host[(i + 1) % args.pool])
+            loss = feeder.run_next()
         else:
+            hi, hd, hl = host[i % args.pool]
             loss = engine.step(hi.to(dev, non_blocking=True), hd.to(dev, non_blocking=True),
                                hl.to(dev, non_blocking=True))
         loss_pin[i].copy_(loss, non_blocking=True)

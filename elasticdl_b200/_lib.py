@@ -59,6 +59,7 @@ SYMBOLS = {
     "b200ps_abi_version": (_i, []),
     "b200ps_create": (_i, [_i, _i, ctypes.c_char_p, ctypes.c_char_p, _i, ctypes.c_uint, ctypes.POINTER(_vp)]),
     "b200ps_destroy": (_i, [_vp]),
+    "b200ps_clone_view": (_i, [_vp, _i, ctypes.POINTER(_vp)]),
     "b200ps_shard_create_local": (_i, [_vp, _i, _i]),
     "b200ps_shard_export": (_i, [_vp, _i, _vp, _sz, ctypes.POINTER(_sz)]),
     "b200ps_shard_import": (_i, [_vp, _i, _vp, _sz]),

@@ -48,7 +48,8 @@ struct DeviceGuard {
 struct Alloc {  // one cudaMalloc on a shard, exported / imported as a CUDA-IPC handle
   void* ptr = nullptr;
   size_t bytes = 0;
-  bool imported = false;
+  bool imported = false;  // mapped from a peer process (cudaIpcOpenMemHandle)
+  bool borrowed = false;  // owned by another b200ps_t of this process (b200ps_clone_view)
 };
 
 struct Table {
@@ -387,13 +388,13 @@ int b200ps_destroy(b200ps_t* ps) {
   cudaDeviceSynchronize();
   for (auto& t : ps->tables)
     for (int s = 0; s < ps->n_shards; ++s) {
-      if (!t.alloc[s].ptr) continue;
+      if (!t.alloc[s].ptr || t.alloc[s].borrowed) continue;
       if (t.alloc[s].imported) cudaIpcCloseMemHandle(t.alloc[s].ptr);
       else { DeviceGuard g(ps->shard[s].device); cudaFree(t.alloc[s].ptr); }
     }
   for (int s = 0; s < ps->n_shards; ++s) {
     Alloc& a = ps->shard[s].ctl;
-    if (!a.ptr) continue;
+    if (!a.ptr || a.borrowed) continue;
     if (a.imported) cudaIpcCloseMemHandle(a.ptr);
     else { DeviceGuard g(ps->shard[s].device); cudaFree(a.ptr); }
   }
@@ -404,6 +405,52 @@ int b200ps_destroy(b200ps_t* ps) {
   cudaFree(ps->d_count);
   cudaFree(ps->d_state);
   delete ps;
+  return B200PS_OK;
+}
+
+int b200ps_clone_view(b200ps_t* src, int client_device, b200ps_t** out) {
+  if (!src || !out) return fail(B200PS_EINVAL, "bad argument");
+  for (int s = 0; s < src->n_shards; ++s)
+    if (!src->shard[s].attached) return fail(B200PS_ESTATE, "source group has unattached shards");
+  std::lock_guard<std::mutex> lk(src->mu);
+  b200ps_t* ps = new b200ps();
+  ps->n_shards = src->n_shards;
+  ps->client_device = client_device;
+  ps->opt = src->opt;
+  ps->staleness = src->staleness;
+  ps->flags = src->flags;
+  ps->n_sm = src->n_sm;
+  for (int s = 0; s < src->n_shards; ++s) {
+    ps->shard[s] = src->shard[s];
+    ps->shard[s].local = false;  // memory stays owned by `src`
+    ps->shard[s].ctl.borrowed = true;
+  }
+  ps->tables = src->tables;
+  for (auto& t : ps->tables)
+    for (int s = 0; s < src->n_shards; ++s) t.alloc[s].borrowed = true;
+  ps->by_name = src->by_name;
+  DeviceGuard g(client_device);
+  if (client_device != src->client_device) {
+    for (int s = 0; s < src->n_shards; ++s) {
+      if (src->shard[s].device == client_device) continue;
+      cudaError_t e = cudaDeviceEnablePeerAccess(src->shard[s].device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { delete ps; return fail(B200PS_ECUDA, cudaGetErrorString(e)); }
+      cudaGetLastError();
+    }
+  }
+  cudaError_t e = cudaMalloc(&ps->d_rt, sizeof(PushRt));
+  if (e == cudaSuccess) e = cudaMemset(ps->d_rt, 0, sizeof(PushRt));
+  if (e == cudaSuccess) e = cudaMalloc(&ps->d_err, 64);
+  if (e == cudaSuccess) e = cudaMemset(ps->d_err, 0, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&ps->d_versions, sizeof(int) * kMaxShards);
+  if (e == cudaSuccess) e = cudaMalloc(&ps->d_count, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&ps->d_state, sizeof(long long) * 3 * kMaxShards);
+  if (e != cudaSuccess) {
+    delete ps;
+    return fail(B200PS_ECUDA, std::string("b200ps_clone_view: ") + cudaGetErrorString(e));
+  }
+  ps->dirty = true;
+  *out = ps;
   return B200PS_OK;
 }
 
@@ -509,7 +556,14 @@ int b200ps_lookup(b200ps_t* ps, const char* name) {
   return it->second;
 }
 
+static bool is_borrowed_view(b200ps_t* ps) {
+  for (int s = 0; s < ps->n_shards; ++s)
+    if (ps->shard[s].ctl.borrowed) return true;
+  return false;
+}
+
 static int register_common(b200ps_t* ps, Table&& t) {
+  if (is_borrowed_view(ps)) return fail(B200PS_ESTATE, "tables are registered on the owning group, then b200ps_clone_view again");
   t.n_slots = opt_slots(ps->opt.kind);
   int id = (int)ps->tables.size();
   ps->tables.push_back(std::move(t));

@@ -116,48 +116,66 @@ __device__ __forceinline__ float dot16(const float (&h)[H1], const float* __rest
   return acc;
 }
 
-constexpr int TA_THREADS = 128;  // samples per block (lane = sample)
-constexpr int GC = 4;            // id groups gathered per batch of loads (memory-level parallelism)
+// k_tower_a work split: a block = SPB samples x NPART group-parts.  Warp w handles the samples
+// (w / NPART) * 32 + lane and the id groups g = w % NPART, + NPART, ...  (lane = sample keeps every
+// weight read a shared-memory broadcast; splitting the 38 groups over 4 warps quadruples the
+// number of independent gather chains in flight -- the kernel is latency-bound, not math-bound).
+constexpr int NPART = 4;
+constexpr int SPB = 64;                        // samples per block
+constexpr int TA_THREADS = SPB * NPART;        // 256
+constexpr int GC = 3;                          // groups gathered per round per warp
+constexpr int RW = H1 + D + 2;                 // partial-sum record: h[16] | s[8] | q | lin
 
 template <bool BACKWARD>
-__global__ void __launch_bounds__(TA_THREADS) k_tower_a(b200_deepfm_args_t a) {
+__global__ void __launch_bounds__(TA_THREADS, 2) k_tower_a(b200_deepfm_args_t a) {
   extern __shared__ __align__(16) float smem[];
   const Layout l = layout(a.G);
   SmemParams sp = carve(smem, l.in);
-  int* sinv = reinterpret_cast<int*>(smem + smem_floats(l.in));  // [G][TA_THREADS] ranks of this block's samples
+  float* red = smem + smem_floats(l.in);                       // [NPART][RW][SPB]
+  int* sinv = reinterpret_cast<int*>(red + NPART * RW * SPB);  // [G][SPB]
   load_params(a.params, l, sp);
   const int B = a.B, G = a.G;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = warp % NPART;
+  const int sl = (warp / NPART) * 32 + lane;  // sample slot within the block
   float loss_acc = 0.f;
-  const long long nblk = ((long long)B + TA_THREADS - 1) / TA_THREADS;
+  const long long nblk = ((long long)B + SPB - 1) / SPB;
   for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const long long b = blk * TA_THREADS + threadIdx.x;
+    const long long b = blk * SPB + sl;
     const bool live = b < B;
     const long long bb = live ? b : B - 1;  // dead lanes replay the last sample, results discarded
     float h[H1];
-#pragma unroll
-    for (int j = 0; j < H1; ++j) h[j] = sp.b1[j];
     float lin = 0.f;
+    if (part == 0) {
 #pragma unroll
-    for (int e = 0; e < ND; ++e) {
-      const float x = a.dense[bb * ND + e];
-      lin = fmaf(sp.wd[e], x, lin);
-      axpy16(h, sp.w1t + e * H1, x);
+      for (int j = 0; j < H1; ++j) h[j] = sp.b1[j];
+#pragma unroll
+      for (int e = 0; e < ND; ++e) {
+        const float x = a.dense[bb * ND + e];
+        lin = fmaf(sp.wd[e], x, lin);
+        axpy16(h, sp.w1t + e * H1, x);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < H1; ++j) h[j] = 0.f;
     }
     float s[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) s[d] = 0.f;
     float q = 0.f;
-    // pass 1: GC groups per round -- GC rank loads, then 3*GC independent row loads in flight
-    for (int g0 = 0; g0 < G; g0 += GC) {
+    // pass 1 over this warp's groups: GC rank loads, then 3*GC independent row loads in flight
+    for (int g0 = part; g0 < G; g0 += NPART * GC) {
       int r[GC];
 #pragma unroll
-      for (int u = 0; u < GC; ++u) r[u] = (g0 + u < G) ? a.inv[(long long)(g0 + u) * B + bb] : 0;
+      for (int u = 0; u < GC; ++u) {
+        const int g = g0 + u * NPART;
+        r[u] = g < G ? a.inv[(long long)g * B + bb] : 0;
+      }
       float4 e0[GC], e1[GC];
       float wv[GC];
 #pragma unroll
       for (int u = 0; u < GC; ++u) {
-        const int g = (g0 + u < G) ? g0 + u : G - 1;
+        const int g = g0 + u * NPART < G ? g0 + u * NPART : part;
         const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + r[u]) * D);
         e0[u] = row[0];
         e1[u] = row[1];
@@ -165,11 +183,12 @@ __global__ void __launch_bounds__(TA_THREADS) k_tower_a(b200_deepfm_args_t a) {
       }
 #pragma unroll
       for (int u = 0; u < GC; ++u) {
-        if (g0 + u < G) {
-          sinv[(g0 + u) * TA_THREADS + threadIdx.x] = r[u];
+        const int g = g0 + u * NPART;
+        if (g < G) {
+          sinv[g * SPB + sl] = r[u];
           lin += wv[u];
           const float ev[D] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
-          const float* w = sp.w1t + (ND + (g0 + u) * D) * H1;
+          const float* w = sp.w1t + (ND + g * D) * H1;
 #pragma unroll
           for (int d = 0; d < D; ++d) {
             s[d] += ev[d];
@@ -178,6 +197,33 @@ __global__ void __launch_bounds__(TA_THREADS) k_tower_a(b200_deepfm_args_t a) {
           }
         }
       }
+    }
+    // combine the NPART partial sums of each sample through shared memory
+    {
+      float* mine = red + (part * RW) * SPB + sl;
+#pragma unroll
+      for (int j = 0; j < H1; ++j) mine[j * SPB] = h[j];
+#pragma unroll
+      for (int d = 0; d < D; ++d) mine[(H1 + d) * SPB] = s[d];
+      mine[(H1 + D) * SPB] = q;
+      mine[(H1 + D + 1) * SPB] = lin;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < H1; ++j) h[j] = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) s[d] = 0.f;
+    q = 0.f;
+    lin = 0.f;
+#pragma unroll
+    for (int pt = 0; pt < NPART; ++pt) {
+      const float* src = red + (pt * RW) * SPB + sl;
+#pragma unroll
+      for (int j = 0; j < H1; ++j) h[j] += src[j * SPB];
+#pragma unroll
+      for (int d = 0; d < D; ++d) s[d] += src[(H1 + d) * SPB];
+      q += src[(H1 + D) * SPB];
+      lin += src[(H1 + D + 1) * SPB];
     }
     float a1[H1];
 #pragma unroll
@@ -192,11 +238,11 @@ __global__ void __launch_bounds__(TA_THREADS) k_tower_a(b200_deepfm_args_t a) {
 #pragma unroll
     for (int d = 0; d < D; ++d) ss = fmaf(s[d], s[d], ss);
     const float z = lin + dnn + 0.5f * (ss - q);
-    if (live && a.logits != nullptr) a.logits[b] = z;
+    if (part == 0 && live && a.logits != nullptr) a.logits[b] = z;
     if (BACKWARD) {
       const float y = a.labels[bb];
       const float lb = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));  // BCE with logits
-      if (live) loss_acc += lb;
+      if (part == 0 && live) loss_acc += lb;
       const float p = 1.f / (1.f + expf(-z));
       const float dz = live ? (p - y) / (float)B : 0.f;
       float dh2[H2];
@@ -210,7 +256,7 @@ __global__ void __launch_bounds__(TA_THREADS) k_tower_a(b200_deepfm_args_t a) {
         for (int k = 0; k < H2; ++k) acc = fmaf(sp.w2[k * H1 + j], dh2[k], acc);
         dh1[j] = h[j] > 0.f ? acc : 0.f;
       }
-      if (live) {  // per-sample backward state for k_tower_b: [dh1 16 | a1 16 | dh2 4 | h2 4 | dz | pad 3]
+      if (part == 0 && live) {  // per-sample backward state for k_tower_b: [dh1 16 | a1 16 | dh2 4 | h2 4 | dz | pad 3]
         float4* sc = reinterpret_cast<float4*>(a.scratch + b * SCR);
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) sc[qd] = make_float4(dh1[4 * qd], dh1[4 * qd + 1], dh1[4 * qd + 2], dh1[4 * qd + 3]);
@@ -220,22 +266,23 @@ __global__ void __launch_bounds__(TA_THREADS) k_tower_a(b200_deepfm_args_t a) {
         sc[9] = make_float4(h2[0], h2[1], h2[2], h2[3]);
         sc[10] = make_float4(dz, 0.f, 0.f, 0.f);
       }
-      // pass 2: d loss / d embedding rows, reduced per unique id (deduplicate_indexed_slices' sum)
-      for (int g0 = 0; g0 < G; g0 += GC) {
+      // pass 2: d loss / d embedding rows of this warp's groups, reduced per unique id
+      // (deduplicate_indexed_slices' sum)
+      for (int g0 = part; g0 < G; g0 += NPART * GC) {
         int r[GC];
         float4 e0[GC], e1[GC];
 #pragma unroll
         for (int u = 0; u < GC; ++u) {
-          const int g = (g0 + u < G) ? g0 + u : G - 1;
-          r[u] = sinv[g * TA_THREADS + threadIdx.x];
+          const int g = g0 + u * NPART < G ? g0 + u * NPART : part;
+          r[u] = sinv[g * SPB + sl];
           const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + r[u]) * D);
           e0[u] = row[0];
           e1[u] = row[1];
         }
 #pragma unroll
         for (int u = 0; u < GC; ++u) {
-          if (g0 + u >= G) break;  // warp-uniform
-          const int g = g0 + u;
+          const int g = g0 + u * NPART;
+          if (g >= G) break;  // warp-uniform
           const float ev[D] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
           const float* w = sp.w1t + (ND + g * D) * H1;
           float x[D + 1];
@@ -266,31 +313,45 @@ __global__ void __launch_bounds__(TA_THREADS) k_tower_a(b200_deepfm_args_t a) {
         }
       }
     }
+    __syncthreads();  // red / sinv are reused by the next block of samples
   }
   if (BACKWARD) {
     for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, o);
-    if (lane == 0) atomicAdd(a.loss, loss_acc / (float)B);
+    if (lane == 0 && part == 0) atomicAdd(a.loss, loss_acc / (float)B);
   }
 }
 
-// parameter gradients.  Block = 416 threads, chunk of S samples staged in shared memory.
-constexpr int S_CHUNK = 128;
+__host__ inline size_t tower_a_smem(int G) {
+  return (smem_floats(ND + G * D) + (size_t)NPART * RW * SPB) * sizeof(float) + (size_t)G * SPB * sizeof(int);
+}
+
+// parameter gradients.  dW1 = dH1^T [16 x B] . X [B x IN] is a contraction over the batch: a block
+// stages a chunk of S samples in shared memory -- the per-sample backward state written by
+// k_tower_a and the gathered input rows X (cooperative, fully independent 32 B row gathers) --
+// then thread e owns input column e with 16 accumulators; the remaining threads own db1 and
+// the small gradients (dW2, db2, dw3, dw_dense).  One atomicAdd per output per block.
+constexpr int S_CHUNK = 64;
 constexpr int TB_THREADS = 416;
 constexpr int N_SMALL = H2 * H1 + H2 + H2 + ND;  // dW2 64 | db2 4 | dw3 4 | dw_dense 13
 
+__host__ __device__ inline int tb_xpad(int G) { return (G * D + ND + 3) / 4 * 4; }  // tile row: [deep G*8 | dense 13 | pad]
+__host__ inline size_t tower_b_smem(int G) {
+  return ((size_t)S_CHUNK * SCR + (size_t)S_CHUNK * tb_xpad(G)) * sizeof(float) + (size_t)G * S_CHUNK * sizeof(int);
+}
+
 __global__ void __launch_bounds__(TB_THREADS) k_tower_b(b200_deepfm_args_t a) {
-  __shared__ __align__(16) float sc[S_CHUNK * SCR];
-  __shared__ float dn[S_CHUNK * ND];
+  extern __shared__ __align__(16) float smem_b[];
   const Layout l = layout(a.G);
-  const int B = a.B, t = threadIdx.x;
-  const int IN = l.in;
+  const int B = a.B, G = a.G, t = threadIdx.x;
+  const int IN = l.in, XP = tb_xpad(G), NDEEP = G * D;
+  float* sc = smem_b;                                   // [S][SCR]
+  float* xt = sc + S_CHUNK * SCR;                       // [S][XP]
+  int* sinv = reinterpret_cast<int*>(xt + S_CHUNK * XP);  // [G][S]
   // role of this thread
-  const bool is_col = t < IN;         // dW1 column t
-  const bool is_b1 = t == IN;         // db1
-  const int small = t - (IN + 1);     // small outputs
+  const bool is_col = t < IN;      // tile column t -> dW1 column (deep columns first in the tile)
+  const bool is_b1 = t == IN;      // db1
+  const int small = t - (IN + 1);  // small outputs
   const bool is_small = small >= 0 && small < N_SMALL;
-  const int g = is_col && t >= ND ? (t - ND) / D : 0;
-  const int d = is_col && t >= ND ? (t - ND) % D : 0;
   float acc[H1];
 #pragma unroll
   for (int j = 0; j < H1; ++j) acc[j] = 0.f;
@@ -304,46 +365,46 @@ __global__ void __launch_bounds__(TB_THREADS) k_tower_b(b200_deepfm_args_t a) {
       const float4* src = reinterpret_cast<const float4*>(a.scratch + b0 * SCR);
       float4* dst = reinterpret_cast<float4*>(sc);
       for (int i = t; i < n * (SCR / 4); i += TB_THREADS) dst[i] = src[i];
-      for (int i = t; i < n * ND; i += TB_THREADS) dn[i] = a.dense[b0 * ND + i];
+      for (int i = t; i < n * ND; i += TB_THREADS) {
+        const int s_ = i / ND, e = i - s_ * ND;
+        xt[s_ * XP + NDEEP + e] = a.dense[b0 * ND + i];
+      }
+      for (int i = t; i < G * n; i += TB_THREADS) {  // coalesced rank loads
+        const int g = i / n, s_ = i - g * n;
+        sinv[g * S_CHUNK + s_] = a.inv[(long long)g * B + b0 + s_];
+      }
+    }
+    __syncthreads();
+    for (int i = t; i < n * G; i += TB_THREADS) {  // independent 32 B row gathers, group fastest
+      const int s_ = i / G, g = i - s_ * G;
+      const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + sinv[g * S_CHUNK + s_]) * D);
+      const float4 e0 = row[0], e1 = row[1];
+      float4* dst = reinterpret_cast<float4*>(xt + s_ * XP + g * D);
+      dst[0] = e0;
+      dst[1] = e1;
     }
     __syncthreads();
     if (is_col) {
-      constexpr int U = 8;  // samples in flight per thread
-      for (int s0 = 0; s0 < n; s0 += U) {
-        float x[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int s = s0 + u;
-          if (s < n) {
-            if (t < ND) x[u] = dn[s * ND + t];
-            else {
-              const int r = a.inv[(long long)g * B + b0 + s];
-              x[u] = a.bet_deep[((long long)g * B + r) * D + d];
-            }
-          } else x[u] = 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (s0 + u < n) axpy16(acc, sc + (s0 + u) * SCR, x[u]);
-        }
-      }
+#pragma unroll 4
+      for (int s_ = 0; s_ < n; ++s_) axpy16(acc, sc + s_ * SCR, xt[s_ * XP + t]);
     } else if (is_b1) {
-      for (int s = 0; s < n; ++s) axpy16(acc, sc + s * SCR, 1.0f);
+      for (int s_ = 0; s_ < n; ++s_) axpy16(acc, sc + s_ * SCR, 1.0f);
     } else if (is_small) {
-      for (int s = 0; s < n; ++s) {
-        const float* r = sc + s * SCR;
+      for (int s_ = 0; s_ < n; ++s_) {
+        const float* r = sc + s_ * SCR;
         float v;
-        if (small < H2 * H1) v = r[32 + small / H1] * r[16 + small % H1];           // dh2[k] * a1[j]
-        else if (small < H2 * H1 + H2) v = r[32 + small - H2 * H1];                  // dh2[k]
+        if (small < H2 * H1) v = r[32 + small / H1] * r[16 + small % H1];            // dh2[k] * a1[j]
+        else if (small < H2 * H1 + H2) v = r[32 + small - H2 * H1];                   // dh2[k]
         else if (small < H2 * H1 + 2 * H2) v = r[40] * r[36 + small - H2 * H1 - H2];  // dz * h2[k]
-        else v = r[40] * dn[s * ND + small - H2 * H1 - 2 * H2];                       // dz * dense[e]
+        else v = r[40] * xt[s_ * XP + NDEEP + small - H2 * H1 - 2 * H2];              // dz * dense[e]
         sacc += v;
       }
     }
   }
   if (is_col) {
+    const int col = t < NDEEP ? ND + t : t - NDEEP;  // tile column -> W1 input index (dense first)
 #pragma unroll
-    for (int j = 0; j < H1; ++j) atomicAdd(a.grads + l.o_w1 + j * IN + t, acc[j]);
+    for (int j = 0; j < H1; ++j) atomicAdd(a.grads + l.o_w1 + j * IN + col, acc[j]);
   } else if (is_b1) {
 #pragma unroll
     for (int j = 0; j < H1; ++j) atomicAdd(a.grads + l.o_b1 + j, acc[j]);
@@ -382,21 +443,26 @@ int b200_deepfm_fwd_bwd(const b200_deepfm_args_t* args, void* stream) {
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const size_t smem = smem_floats(l.in) * sizeof(float) + (size_t)args->G * TA_THREADS * sizeof(int);
+  const size_t smem = tower_a_smem(args->G);
   static bool attr_done[64] = {false};
-  if (smem > 48 * 1024 && dev < 64 && !attr_done[dev]) {
+  if (dev < 64 && !attr_done[dev]) {
     cudaFuncSetAttribute(k_tower_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_tower_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_done[dev] = true;
   }
   dim3 gp(8, args->G);
   k_tower_prep<<<gp, 256, 0, st>>>(*args, l.total);
-  long long blocks = ((long long)args->B + TA_THREADS - 1) / TA_THREADS;
-  long long cap = (long long)n_sm * 4;
+  long long blocks = ((long long)args->B + SPB - 1) / SPB;
+  long long cap = (long long)n_sm * 8;
   k_tower_a<true><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
   long long chunks = ((long long)args->B + S_CHUNK - 1) / S_CHUNK;
   cap = (long long)n_sm * 2;
-  k_tower_b<<<(unsigned)(chunks < cap ? chunks : cap), TB_THREADS, 0, st>>>(*args);
+  static bool attr_b[64] = {false};
+  if (dev < 64 && !attr_b[dev]) {
+    cudaFuncSetAttribute(k_tower_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    attr_b[dev] = true;
+  }
+  k_tower_b<<<(unsigned)(chunks < cap ? chunks : cap), TB_THREADS, tower_b_smem(args->G), st>>>(*args);
   g_launches += 3;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_msg = cudaGetErrorString(e); return -2; }
@@ -410,10 +476,10 @@ int b200_deepfm_forward(const b200_deepfm_args_t* args, void* stream) {
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const size_t smem = smem_floats(l.in) * sizeof(float) + (size_t)args->G * TA_THREADS * sizeof(int);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_tower_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  long long blocks = ((long long)args->B + TA_THREADS - 1) / TA_THREADS;
-  long long cap = (long long)n_sm * 4;
+  const size_t smem = tower_a_smem(args->G);
+  cudaFuncSetAttribute(k_tower_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  long long blocks = ((long long)args->B + SPB - 1) / SPB;
+  long long cap = (long long)n_sm * 8;
   k_tower_a<false><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();

@@ -107,6 +107,26 @@ class PSGroup:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def clone_view(self, device=None):
+        """A second client view of the same shards for another worker thread / stream of this
+        process (b200ps_clone_view).  Register every table on the owning group first."""
+        view = object.__new__(PSGroup)
+        view.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_h", "_ws")})
+        view._h = None
+        dev = self.device if device is None else torch.device("cuda", device)
+        h = ctypes.c_void_p()
+        check(self.lib.b200ps_clone_view(self._h, dev.index, ctypes.byref(h)))
+        view._h = h
+        view.device = dev
+        view.local_shards = []  # owns no memory
+        view.tables = dict(self.tables)
+        view._owner = self  # keep the owner alive
+        view._pinned_state = torch.empty(3 * _lib.MAX_SHARDS, dtype=torch.int64).pin_memory()
+        view._pinned_versions = torch.empty(_lib.MAX_SHARDS, dtype=torch.int32).pin_memory()
+        view._ws = None
+        check(self.lib.b200ps_commit(view._h))
+        return view
+
     def sync_peers(self):
         """Export local shards, all-gather the CUDA-IPC blobs, import the peers' shards."""
         blobs = {}
@@ -148,7 +168,7 @@ class PSGroup:
         return tid
 
     def commit(self):
-        if len(self.local_shards) == self.n_shards:
+        if len(self.local_shards) == self.n_shards or getattr(self, "_owner", None) is not None:
             check(self.lib.b200ps_commit(self._h))
         else:
             self.sync_peers()

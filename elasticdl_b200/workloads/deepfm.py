@@ -96,6 +96,45 @@ def flatten_tower(tower, flat):
     return views
 
 
+class HostFeeder:
+    def __init__(self, engine, depth=2):
+        if getattr(engine, "graph", None) is None:
+            engine.capture()
+        self.e = engine
+        dev, G, B = engine.device, engine.G, engine.B
+        self.depth = depth
+        self.slots = [(torch.empty((G, B), dtype=torch.int64, device=dev),
+                       torch.empty((B, N_DENSE), dtype=torch.float32, device=dev),
+                       torch.empty(B, dtype=torch.float32, device=dev)) for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [torch.cuda.Event() for _ in range(depth)]
+        self.head = self.tail = 0
+
+    def submit(self, host_ids, host_dense, host_labels):
+        """Enqueue the H2D copies of one batch (pinned host tensors) on the copy stream."""
+        k = self.head % self.depth
+        with torch.cuda.stream(self.copy_stream):
+            if self.head >= self.depth:
+                self.copy_stream.wait_event(self.free[k])
+            ids, dense, labels = self.slots[k]
+            ids.copy_(host_ids, non_blocking=True)
+            dense.copy_(host_dense, non_blocking=True)
+            labels.copy_(host_labels, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        self.head += 1
+
+    def run_next(self):
+        """Run one step on the oldest submitted batch; returns the loss (device scalar)."""
+        k = self.tail % self.depth
+        main = torch.cuda.current_stream(self.e.device)
+        main.wait_event(self.ready[k])
+        loss = self.e.step_graph(*self.slots[k])
+        self.free[k].record(main)
+        self.tail += 1
+        return loss
+
+
 class DeepFMPSEngine:
     def __init__(self, group, batch, lr=1e-3, init_std=0.01, seed=7, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM,
                  init_rows=True, tower="fused"):
@@ -288,6 +327,12 @@ class DeepFMPSEngine:
         self.graph.replay()
         self.steps += 1
         return self.loss_buf.reshape(())
+
+    def host_feeder(self, depth=2):
+        """Input pipeline for host-resident batches: H2D copies run on a side stream into
+        `depth` staging slots and overlap the previous step's kernels (the reference prefetches
+        one batch too: dataset.prefetch(1), elasticdl/python/worker/worker.py:334)."""
+        return HostFeeder(self, depth)
 
     def _torch_tower(self, dense, labels, mark, done, st):
         """Steps (4)-(6) with torch autograd over library kernels (A/B reference for the fused tower)."""

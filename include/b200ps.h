@@ -77,6 +77,13 @@ int b200ps_create(int n_shards, int client_device, const char* opt_type, const c
                   int lr_staleness_modulation, unsigned flags, b200ps_t** out);
 int b200ps_destroy(b200ps_t* ps);
 
+/* A second client view of the SAME shards inside one process (one view per worker thread /
+ * stream: each view has its own per-push scratch, error word and directory copy).  The
+ * reference's tests drive several workers as threads against shared PS instances
+ * (python/tests/worker_ps_interaction_test.py:136-151).  `src` keeps ownership of the memory
+ * and must outlive the view; register tables on `src` first.  Call b200ps_commit on the view. */
+int b200ps_clone_view(b200ps_t* src, int client_device, b200ps_t** out);
+
 /* This process owns shard `shard_id`; its memory is allocated on `device`. */
 int b200ps_shard_create_local(b200ps_t* ps, int shard_id, int device);
 /* Serialise the CUDA-IPC handles of everything allocated so far on a local

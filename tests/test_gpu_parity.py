@@ -453,3 +453,74 @@ def test_full_size_roundtrip_and_linearity():
     assert torch.equal(dup, vals - 0.5 * g)
     assert [s[0] for s in group.snapshot()] == [3] * 8
     group.close()
+
+
+# ------------------------------------------------------------------ config 2: census wide&deep, async SGD, 4 workers
+def test_four_concurrent_workers_async_sgd_census_shapes():
+    """BASELINE.json configs[2]: 3 wide (dim 1) + 3 deep (dim 8) small tables, async SGD, 4 workers,
+    batch 64 (scripts/client_test.sh:38).  Workers are threads with their own view + stream
+    (worker_ps_interaction_test.py:136-151 drives workers as threads against shared PS instances).
+    Sparse ids are disjoint per worker so the racy interleaving cannot change the result."""
+    import threading
+
+    from elasticdl_b200.common.tensor_utils import Tensor
+    from elasticdl_b200.worker.ps_client import PSClient
+
+    n_shards, n_workers, steps, rows = 2, 4, 6, 4000
+    group, client, oc = make_pair(n_shards, "sgd")
+    names = [("wide%d" % i, 1) for i in range(3)] + [("deep%d" % i, 8) for i in range(3)]
+    client.push_embedding_table_infos([info(n, d, capacity=rows) for n, d in names])
+    oc.push_embedding_table_infos([oinfo(n, d) for n, d in names])
+    for c, T in ((client, Tensor), (oc, O.Tensor)):
+        c.partition_dense_parameters(["mlp/w"])
+        for ps_id in set(c.parameter_to_ps.values()):
+            c.push_dense_parameters([T("mlp/w", np.zeros((24, 16), dtype=F), None)], ps_id, 0)
+    plans = []
+    for w in range(n_workers):
+        rng = np.random.RandomState(100 + w)  # seed per worker = 100 + rank (SURVEY 8d config 3)
+        plan = []
+        for s in range(steps):
+            step_grads = []
+            for n, d in names:
+                ids = (rng.randint(0, rows // n_workers, 64) * n_workers + w).astype(np.int64)  # ids == w (mod 4)
+                step_grads.append((n, rng.randn(64, d).astype(F), ids))
+            plan.append(step_grads)
+        plans.append(plan)
+    errors = []
+
+    def worker(w):
+        try:
+            view = group.clone_view()
+            wc = PSClient(view)
+            wc.parameter_to_ps, wc.ps_to_parameter = client.parameter_to_ps, client.ps_to_parameter
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                versions = [0] * n_shards
+                for step_grads in plans[w]:
+                    acc, v = wc.push_gradients([], [Tensor(n, g, i) for n, g, i in step_grads], 0.1, versions)
+                    assert acc
+                    versions = [v] * n_shards
+                    wc.pull_embedding_vectors(names[3][0], step_grads[3][2])
+            stream.synchronize()
+            view.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((w, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(n_workers)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for w in range(n_workers):
+        for step_grads in plans[w]:
+            oc.push_gradients([], [O.Tensor(n, g.copy(), i) for n, g, i in step_grads], 0.1, [0] * n_shards)
+    state = group.snapshot()
+    assert [s[0] for s in state] == [n_workers * steps] * n_shards  # one version per push per worker
+    all_ids = np.arange(rows, dtype=np.int64)
+    for n, d in names:
+        got = client.pull_embedding_vectors(n, all_ids)
+        want = np.zeros_like(got)
+        for s in oc.servers:
+            keys = s.tables[n].keys()
+            want[keys] = s.tables[n].get(keys)
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-6), n
+    group.close()
