@@ -12,6 +12,7 @@
 // gather/scatter of embedding rows, not by math).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/b200_deepfm.h"
@@ -91,17 +92,6 @@ __device__ inline void load_params(const float* __restrict__ p, const Layout& l,
   __syncthreads();
 }
 
-__device__ __forceinline__ void axpy16(float (&h)[H1], const float* __restrict__ w, float x) {
-  const float4* w4 = reinterpret_cast<const float4*>(w);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float4 v = w4[q];
-    h[4 * q + 0] = fmaf(v.x, x, h[4 * q + 0]);
-    h[4 * q + 1] = fmaf(v.y, x, h[4 * q + 1]);
-    h[4 * q + 2] = fmaf(v.z, x, h[4 * q + 2]);
-    h[4 * q + 3] = fmaf(v.w, x, h[4 * q + 3]);
-  }
-}
 __device__ __forceinline__ float dot16(const float (&h)[H1], const float* __restrict__ w) {
   const float4* w4 = reinterpret_cast<const float4*>(w);
   float acc = 0.f;
@@ -116,17 +106,50 @@ __device__ __forceinline__ float dot16(const float (&h)[H1], const float* __rest
   return acc;
 }
 
-// k_tower_a work split: a block = SPB samples x NPART group-parts.  Warp w handles the samples
-// (w / NPART) * 32 + lane and the id groups g = w % NPART, + NPART, ...  (lane = sample keeps every
-// weight read a shared-memory broadcast; splitting the 38 groups over 4 warps quadruples the
-// number of independent gather chains in flight -- the kernel is latency-bound, not math-bound).
+// k_tower_a work split: a block = SPB samples x NPART group-parts.  Warp w handles NS samples per
+// lane (register blocking: every shared-memory weight read feeds NS samples -- the kernel is bound
+// by shared-memory bandwidth for the broadcast weight reads, then by gather latency) and the id
+// groups g = w % NPART, + NPART, ...  (lane = sample keeps every weight read a broadcast;
+// splitting the 38 groups over 4 warps quadruples the independent gather chains in flight).
 constexpr int NPART = 4;
-constexpr int SPB = 64;                        // samples per block
-constexpr int TA_THREADS = SPB * NPART;        // 256
-constexpr int GC = 3;                          // groups gathered per round per warp
+constexpr int NS = 2;                          // samples per lane
+constexpr int SLAB = 32 * NS;                  // samples per warp
+constexpr int SPB = 2 * SLAB;                  // samples per block (2 slabs x NPART warps = 8 warps)
+constexpr int TA_THREADS = (SPB / SLAB) * NPART * 32;  // 256
 constexpr int RW = H1 + D + 2;                 // partial-sum record: h[16] | s[8] | q | lin
 
-template <bool BACKWARD>
+__device__ __forceinline__ void axpy16x(float (&h)[NS][H1], const float* __restrict__ w, const float (&x)[NS]) {
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = w4[q];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      h[n][4 * q + 0] = fmaf(v.x, x[n], h[n][4 * q + 0]);
+      h[n][4 * q + 1] = fmaf(v.y, x[n], h[n][4 * q + 1]);
+      h[n][4 * q + 2] = fmaf(v.z, x[n], h[n][4 * q + 2]);
+      h[n][4 * q + 3] = fmaf(v.w, x[n], h[n][4 * q + 3]);
+    }
+  }
+}
+__device__ __forceinline__ void dot16x(float (&out)[NS], const float (&h)[NS][H1], const float* __restrict__ w) {
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+#pragma unroll
+  for (int n = 0; n < NS; ++n) out[n] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = w4[q];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      out[n] = fmaf(v.x, h[n][4 * q + 0], out[n]);
+      out[n] = fmaf(v.y, h[n][4 * q + 1], out[n]);
+      out[n] = fmaf(v.z, h[n][4 * q + 2], out[n]);
+      out[n] = fmaf(v.w, h[n][4 * q + 3], out[n]);
+    }
+  }
+}
+
+template <bool BACKWARD, int GC>  // GC = groups gathered per round per warp
 __global__ void __launch_bounds__(TA_THREADS, 2) k_tower_a(b200_deepfm_args_t a) {
   extern __shared__ __align__(16) float smem[];
   const Layout l = layout(a.G);
@@ -137,178 +160,228 @@ __global__ void __launch_bounds__(TA_THREADS, 2) k_tower_a(b200_deepfm_args_t a)
   const int B = a.B, G = a.G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int part = warp % NPART;
-  const int sl = (warp / NPART) * 32 + lane;  // sample slot within the block
+  const int sl0 = (warp / NPART) * SLAB + lane;  // sample slots of this lane: sl0 + 32*n
   float loss_acc = 0.f;
   const long long nblk = ((long long)B + SPB - 1) / SPB;
   for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const long long b = blk * SPB + sl;
-    const bool live = b < B;
-    const long long bb = live ? b : B - 1;  // dead lanes replay the last sample, results discarded
-    float h[H1];
-    float lin = 0.f;
+    long long bb[NS];
+    bool live[NS];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      const long long b = blk * SPB + sl0 + 32 * n;
+      live[n] = b < B;
+      bb[n] = live[n] ? b : B - 1;  // dead lanes replay the last sample, results discarded
+    }
+    float h[NS][H1];
+    float lin[NS];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+      lin[n] = 0.f;
+#pragma unroll
+      for (int j = 0; j < H1; ++j) h[n][j] = part == 0 ? sp.b1[j] : 0.f;
+    }
     if (part == 0) {
 #pragma unroll
-      for (int j = 0; j < H1; ++j) h[j] = sp.b1[j];
-#pragma unroll
       for (int e = 0; e < ND; ++e) {
-        const float x = a.dense[bb * ND + e];
-        lin = fmaf(sp.wd[e], x, lin);
-        axpy16(h, sp.w1t + e * H1, x);
+        float x[NS];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+          x[n] = a.dense[bb[n] * ND + e];
+          lin[n] = fmaf(sp.wd[e], x[n], lin[n]);
+        }
+        axpy16x(h, sp.w1t + e * H1, x);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < H1; ++j) h[j] = 0.f;
     }
-    float s[D];
+    float s[NS][D], q[NS];
 #pragma unroll
-    for (int d = 0; d < D; ++d) s[d] = 0.f;
-    float q = 0.f;
-    // pass 1 over this warp's groups: GC rank loads, then 3*GC independent row loads in flight
+    for (int n = 0; n < NS; ++n) {
+      q[n] = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s[n][d] = 0.f;
+    }
+    // pass 1 over this warp's groups: GC*NS rank loads, then 3*GC*NS independent row loads in flight
     for (int g0 = part; g0 < G; g0 += NPART * GC) {
-      int r[GC];
+      int r[GC][NS];
 #pragma unroll
       for (int u = 0; u < GC; ++u) {
         const int g = g0 + u * NPART;
-        r[u] = g < G ? a.inv[(long long)g * B + bb] : 0;
+#pragma unroll
+        for (int n = 0; n < NS; ++n) r[u][n] = g < G ? a.inv[(long long)g * B + bb[n]] : 0;
       }
-      float4 e0[GC], e1[GC];
-      float wv[GC];
+      float4 e0[GC][NS], e1[GC][NS];
+      float wv[GC][NS];
 #pragma unroll
       for (int u = 0; u < GC; ++u) {
         const int g = g0 + u * NPART < G ? g0 + u * NPART : part;
-        const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + r[u]) * D);
-        e0[u] = row[0];
-        e1[u] = row[1];
-        wv[u] = a.bet_wide[(long long)g * B + r[u]];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+          const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + r[u][n]) * D);
+          e0[u][n] = row[0];
+          e1[u][n] = row[1];
+          wv[u][n] = a.bet_wide[(long long)g * B + r[u][n]];
+        }
       }
 #pragma unroll
       for (int u = 0; u < GC; ++u) {
         const int g = g0 + u * NPART;
         if (g < G) {
-          sinv[g * SPB + sl] = r[u];
-          lin += wv[u];
-          const float ev[D] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
           const float* w = sp.w1t + (ND + g * D) * H1;
+          float ev[D][NS];
+#pragma unroll
+          for (int n = 0; n < NS; ++n) {
+            sinv[g * SPB + sl0 + 32 * n] = r[u][n];
+            lin[n] += wv[u][n];
+            ev[0][n] = e0[u][n].x; ev[1][n] = e0[u][n].y; ev[2][n] = e0[u][n].z; ev[3][n] = e0[u][n].w;
+            ev[4][n] = e1[u][n].x; ev[5][n] = e1[u][n].y; ev[6][n] = e1[u][n].z; ev[7][n] = e1[u][n].w;
+          }
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            s[d] += ev[d];
-            q = fmaf(ev[d], ev[d], q);
-            axpy16(h, w + d * H1, ev[d]);
+#pragma unroll
+            for (int n = 0; n < NS; ++n) {
+              s[n][d] += ev[d][n];
+              q[n] = fmaf(ev[d][n], ev[d][n], q[n]);
+            }
+            axpy16x(h, w + d * H1, ev[d]);
           }
         }
       }
     }
     // combine the NPART partial sums of each sample through shared memory
-    {
-      float* mine = red + (part * RW) * SPB + sl;
 #pragma unroll
-      for (int j = 0; j < H1; ++j) mine[j * SPB] = h[j];
+    for (int n = 0; n < NS; ++n) {
+      float* mine = red + (part * RW) * SPB + sl0 + 32 * n;
 #pragma unroll
-      for (int d = 0; d < D; ++d) mine[(H1 + d) * SPB] = s[d];
-      mine[(H1 + D) * SPB] = q;
-      mine[(H1 + D + 1) * SPB] = lin;
+      for (int j = 0; j < H1; ++j) mine[j * SPB] = h[n][j];
+#pragma unroll
+      for (int d = 0; d < D; ++d) mine[(H1 + d) * SPB] = s[n][d];
+      mine[(H1 + D) * SPB] = q[n];
+      mine[(H1 + D + 1) * SPB] = lin[n];
     }
     __syncthreads();
+    float dz[NS], dh1[NS][H1];
 #pragma unroll
-    for (int j = 0; j < H1; ++j) h[j] = 0.f;
+    for (int n = 0; n < NS; ++n) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) s[d] = 0.f;
-    q = 0.f;
-    lin = 0.f;
+      for (int j = 0; j < H1; ++j) h[n][j] = 0.f;
 #pragma unroll
-    for (int pt = 0; pt < NPART; ++pt) {
-      const float* src = red + (pt * RW) * SPB + sl;
+      for (int d = 0; d < D; ++d) s[n][d] = 0.f;
+      q[n] = 0.f;
+      lin[n] = 0.f;
 #pragma unroll
-      for (int j = 0; j < H1; ++j) h[j] += src[j * SPB];
+      for (int pt = 0; pt < NPART; ++pt) {
+        const float* src = red + (pt * RW) * SPB + sl0 + 32 * n;
 #pragma unroll
-      for (int d = 0; d < D; ++d) s[d] += src[(H1 + d) * SPB];
-      q += src[(H1 + D) * SPB];
-      lin += src[(H1 + D + 1) * SPB];
+        for (int j = 0; j < H1; ++j) h[n][j] += src[j * SPB];
+#pragma unroll
+        for (int d = 0; d < D; ++d) s[n][d] += src[(H1 + d) * SPB];
+        q[n] += src[(H1 + D) * SPB];
+        lin[n] += src[(H1 + D + 1) * SPB];
+      }
+      float a1[H1];
+#pragma unroll
+      for (int j = 0; j < H1; ++j) a1[j] = fmaxf(h[n][j], 0.f);
+      float h2[H2], dnn = 0.f;
+#pragma unroll
+      for (int k = 0; k < H2; ++k) {
+        h2[k] = fmaxf(sp.b2[k] + dot16(a1, sp.w2 + k * H1), 0.f);
+        dnn = fmaf(sp.w3[k], h2[k], dnn);
+      }
+      float ss = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) ss = fmaf(s[n][d], s[n][d], ss);
+      const float z = lin[n] + dnn + 0.5f * (ss - q[n]);
+      const long long b = blk * SPB + sl0 + 32 * n;
+      if (part == 0 && live[n] && a.logits != nullptr) a.logits[b] = z;
+      dz[n] = 0.f;
+      if (BACKWARD) {
+        const float y = a.labels[bb[n]];
+        const float lb = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));  // BCE with logits
+        if (part == 0 && live[n]) loss_acc += lb;
+        const float p = 1.f / (1.f + expf(-z));
+        dz[n] = live[n] ? (p - y) / (float)B : 0.f;
+        float dh2[H2];
+#pragma unroll
+        for (int k = 0; k < H2; ++k) dh2[k] = h2[k] > 0.f ? dz[n] * sp.w3[k] : 0.f;
+#pragma unroll
+        for (int j = 0; j < H1; ++j) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < H2; ++k) acc = fmaf(sp.w2[k * H1 + j], dh2[k], acc);
+          dh1[n][j] = h[n][j] > 0.f ? acc : 0.f;
+        }
+        if (part == 0 && live[n]) {  // backward state for k_tower_b: [dh1 16 | a1 16 | dh2 4 | h2 4 | dz | pad 3]
+          float4* sc = reinterpret_cast<float4*>(a.scratch + b * SCR);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            sc[qd] = make_float4(dh1[n][4 * qd], dh1[n][4 * qd + 1], dh1[n][4 * qd + 2], dh1[n][4 * qd + 3]);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) sc[4 + qd] = make_float4(a1[4 * qd], a1[4 * qd + 1], a1[4 * qd + 2], a1[4 * qd + 3]);
+          sc[8] = make_float4(dh2[0], dh2[1], dh2[2], dh2[3]);
+          sc[9] = make_float4(h2[0], h2[1], h2[2], h2[3]);
+          sc[10] = make_float4(dz[n], 0.f, 0.f, 0.f);
+        }
+      }
     }
-    float a1[H1];
-#pragma unroll
-    for (int j = 0; j < H1; ++j) a1[j] = fmaxf(h[j], 0.f);
-    float h2[H2], dnn = 0.f;
-#pragma unroll
-    for (int k = 0; k < H2; ++k) {
-      h2[k] = fmaxf(sp.b2[k] + dot16(a1, sp.w2 + k * H1), 0.f);
-      dnn = fmaf(sp.w3[k], h2[k], dnn);
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) ss = fmaf(s[d], s[d], ss);
-    const float z = lin + dnn + 0.5f * (ss - q);
-    if (part == 0 && live && a.logits != nullptr) a.logits[b] = z;
     if (BACKWARD) {
-      const float y = a.labels[bb];
-      const float lb = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));  // BCE with logits
-      if (part == 0 && live) loss_acc += lb;
-      const float p = 1.f / (1.f + expf(-z));
-      const float dz = live ? (p - y) / (float)B : 0.f;
-      float dh2[H2];
-#pragma unroll
-      for (int k = 0; k < H2; ++k) dh2[k] = h2[k] > 0.f ? dz * sp.w3[k] : 0.f;
-      float dh1[H1];
-#pragma unroll
-      for (int j = 0; j < H1; ++j) {
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < H2; ++k) acc = fmaf(sp.w2[k * H1 + j], dh2[k], acc);
-        dh1[j] = h[j] > 0.f ? acc : 0.f;
-      }
-      if (part == 0 && live) {  // per-sample backward state for k_tower_b: [dh1 16 | a1 16 | dh2 4 | h2 4 | dz | pad 3]
-        float4* sc = reinterpret_cast<float4*>(a.scratch + b * SCR);
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) sc[qd] = make_float4(dh1[4 * qd], dh1[4 * qd + 1], dh1[4 * qd + 2], dh1[4 * qd + 3]);
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) sc[4 + qd] = make_float4(a1[4 * qd], a1[4 * qd + 1], a1[4 * qd + 2], a1[4 * qd + 3]);
-        sc[8] = make_float4(dh2[0], dh2[1], dh2[2], dh2[3]);
-        sc[9] = make_float4(h2[0], h2[1], h2[2], h2[3]);
-        sc[10] = make_float4(dz, 0.f, 0.f, 0.f);
-      }
       // pass 2: d loss / d embedding rows of this warp's groups, reduced per unique id
       // (deduplicate_indexed_slices' sum)
       for (int g0 = part; g0 < G; g0 += NPART * GC) {
-        int r[GC];
-        float4 e0[GC], e1[GC];
+        int r[GC][NS];
+        float4 e0[GC][NS], e1[GC][NS];
 #pragma unroll
         for (int u = 0; u < GC; ++u) {
           const int g = g0 + u * NPART < G ? g0 + u * NPART : part;
-          r[u] = sinv[g * SPB + sl];
-          const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + r[u]) * D);
-          e0[u] = row[0];
-          e1[u] = row[1];
+#pragma unroll
+          for (int n = 0; n < NS; ++n) {
+            r[u][n] = sinv[g * SPB + sl0 + 32 * n];
+            const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + r[u][n]) * D);
+            e0[u][n] = row[0];
+            e1[u][n] = row[1];
+          }
         }
 #pragma unroll
         for (int u = 0; u < GC; ++u) {
           const int g = g0 + u * NPART;
           if (g >= G) break;  // warp-uniform
-          const float ev[D] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
           const float* w = sp.w1t + (ND + g * D) * H1;
-          float x[D + 1];
+          float x[NS][D + 1];
+          float ev[D][NS];
 #pragma unroll
-          for (int d = 0; d < D; ++d) x[d] = fmaf(dz, s[d] - ev[d], dot16(dh1, w + d * H1));
-          x[D] = dz;  // wide row gradient
-          // warp-level id dedup: lanes hitting the same row combine (lane order), lowest lane writes
-          const int key = live ? r[u] : -1 - lane;
-          const unsigned peers = __match_any_sync(0xffffffffu, key);
-          const bool leader = (__ffs(peers) - 1) == lane;
-          unsigned rest = peers & ~(1u << lane);
-          const int maxn = __reduce_max_sync(0xffffffffu, (unsigned)__popc(peers));
-          for (int it = 1; it < maxn; ++it) {
-            const int src = rest ? __ffs(rest) - 1 : lane;
-#pragma unroll
-            for (int e = 0; e <= D; ++e) {
-              const float yv = __shfl_sync(0xffffffffu, x[e], src);
-              if (leader && rest) x[e] += yv;
-            }
-            rest &= rest - 1;
+          for (int n = 0; n < NS; ++n) {
+            ev[0][n] = e0[u][n].x; ev[1][n] = e0[u][n].y; ev[2][n] = e0[u][n].z; ev[3][n] = e0[u][n].w;
+            ev[4][n] = e1[u][n].x; ev[5][n] = e1[u][n].y; ev[6][n] = e1[u][n].z; ev[7][n] = e1[u][n].w;
           }
-          if (live && leader) {
-            float* od = a.gsum_deep + ((long long)g * B + r[u]) * D;
-            atomicAdd(reinterpret_cast<float4*>(od), make_float4(x[0], x[1], x[2], x[3]));
-            atomicAdd(reinterpret_cast<float4*>(od + 4), make_float4(x[4], x[5], x[6], x[7]));
-            atomicAdd(a.gsum_wide + (long long)g * B + r[u], x[D]);
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            float dt[NS];
+            dot16x(dt, dh1, w + d * H1);
+#pragma unroll
+            for (int n = 0; n < NS; ++n) x[n][d] = fmaf(dz[n], s[n][d] - ev[d][n], dt[n]);
+          }
+#pragma unroll
+          for (int n = 0; n < NS; ++n) {
+            x[n][D] = dz[n];  // wide row gradient
+            // warp-level id dedup: lanes hitting the same row combine (lane order), lowest lane writes
+            const int key = live[n] ? r[u][n] : -1 - lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const bool leader = (__ffs(peers) - 1) == lane;
+            unsigned rest = peers & ~(1u << lane);
+            const int maxn = __reduce_max_sync(0xffffffffu, (unsigned)__popc(peers));
+            for (int it = 1; it < maxn; ++it) {
+              const int src = rest ? __ffs(rest) - 1 : lane;
+#pragma unroll
+              for (int e = 0; e <= D; ++e) {
+                const float yv = __shfl_sync(0xffffffffu, x[n][e], src);
+                if (leader && rest) x[n][e] += yv;
+              }
+              rest &= rest - 1;
+            }
+            if (live[n] && leader) {
+              float* od = a.gsum_deep + ((long long)g * B + r[u][n]) * D;
+              atomicAdd(reinterpret_cast<float4*>(od), make_float4(x[n][0], x[n][1], x[n][2], x[n][3]));
+              atomicAdd(reinterpret_cast<float4*>(od + 4), make_float4(x[n][4], x[n][5], x[n][6], x[n][7]));
+              atomicAdd(a.gsum_wide + (long long)g * B + r[u][n], x[n][D]);
+            }
           }
         }
       }
@@ -331,10 +404,13 @@ __host__ inline size_t tower_a_smem(int G) {
 // then thread e owns input column e with 16 accumulators; the remaining threads own db1 and
 // the small gradients (dW2, db2, dw3, dw_dense).  One atomicAdd per output per block.
 constexpr int S_CHUNK = 64;
-constexpr int TB_THREADS = 416;
+constexpr int TB_COLW = 96;                    // threads owning dW1/db1 columns (3 warps)
+constexpr int TB_CPT = 4;                      // columns per thread: each staged dh1 row feeds 64 FMAs
+constexpr int TB_THREADS = TB_COLW + 32;       // + one warp for the small gradients
 constexpr int N_SMALL = H2 * H1 + H2 + H2 + ND;  // dW2 64 | db2 4 | dw3 4 | dw_dense 13
 
-__host__ __device__ inline int tb_xpad(int G) { return (G * D + ND + 3) / 4 * 4; }  // tile row: [deep G*8 | dense 13 | pad]
+// tile row: [deep G*8 | dense 13 | 1.0 (bias column) | pad]
+__host__ __device__ inline int tb_xpad(int G) { return (G * D + ND + 1 + 3) / 4 * 4; }
 __host__ inline size_t tower_b_smem(int G) {
   return ((size_t)S_CHUNK * SCR + (size_t)S_CHUNK * tb_xpad(G)) * sizeof(float) + (size_t)G * S_CHUNK * sizeof(int);
 }
@@ -343,19 +419,17 @@ __global__ void __launch_bounds__(TB_THREADS) k_tower_b(b200_deepfm_args_t a) {
   extern __shared__ __align__(16) float smem_b[];
   const Layout l = layout(a.G);
   const int B = a.B, G = a.G, t = threadIdx.x;
-  const int IN = l.in, XP = tb_xpad(G), NDEEP = G * D;
-  float* sc = smem_b;                                   // [S][SCR]
-  float* xt = sc + S_CHUNK * SCR;                       // [S][XP]
+  const int IN = l.in, XP = tb_xpad(G), NDEEP = G * D, NCOL = IN + 1;
+  float* sc = smem_b;                                     // [S][SCR]
+  float* xt = sc + S_CHUNK * SCR;                         // [S][XP]
   int* sinv = reinterpret_cast<int*>(xt + S_CHUNK * XP);  // [G][S]
-  // role of this thread
-  const bool is_col = t < IN;      // tile column t -> dW1 column (deep columns first in the tile)
-  const bool is_b1 = t == IN;      // db1
-  const int small = t - (IN + 1);  // small outputs
-  const bool is_small = small >= 0 && small < N_SMALL;
-  float acc[H1];
+  const bool is_col = t < TB_COLW;
+  float acc[TB_CPT][H1];
 #pragma unroll
-  for (int j = 0; j < H1; ++j) acc[j] = 0.f;
-  float sacc = 0.f;
+  for (int i = 0; i < TB_CPT; ++i)
+#pragma unroll
+    for (int j = 0; j < H1; ++j) acc[i][j] = 0.f;
+  float sacc[3] = {0.f, 0.f, 0.f};  // small outputs o = (t - TB_COLW) + 32*i
   const long long nchunk = ((long long)B + S_CHUNK - 1) / S_CHUNK;
   for (long long c = blockIdx.x; c < nchunk; c += gridDim.x) {
     const long long b0 = c * S_CHUNK;
@@ -365,9 +439,9 @@ __global__ void __launch_bounds__(TB_THREADS) k_tower_b(b200_deepfm_args_t a) {
       const float4* src = reinterpret_cast<const float4*>(a.scratch + b0 * SCR);
       float4* dst = reinterpret_cast<float4*>(sc);
       for (int i = t; i < n * (SCR / 4); i += TB_THREADS) dst[i] = src[i];
-      for (int i = t; i < n * ND; i += TB_THREADS) {
-        const int s_ = i / ND, e = i - s_ * ND;
-        xt[s_ * XP + NDEEP + e] = a.dense[b0 * ND + i];
+      for (int i = t; i < n * (ND + 1); i += TB_THREADS) {
+        const int s_ = i / (ND + 1), e = i - s_ * (ND + 1);
+        xt[s_ * XP + NDEEP + e] = e < ND ? a.dense[(b0 + s_) * ND + e] : 1.0f;
       }
       for (int i = t; i < G * n; i += TB_THREADS) {  // coalesced rank loads
         const int g = i / n, s_ = i - g * n;
@@ -375,6 +449,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_tower_b(b200_deepfm_args_t a) {
       }
     }
     __syncthreads();
+#pragma unroll 4
     for (int i = t; i < n * G; i += TB_THREADS) {  // independent 32 B row gathers, group fastest
       const int s_ = i / G, g = i - s_ * G;
       const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + sinv[g * S_CHUNK + s_]) * D);
@@ -385,42 +460,66 @@ __global__ void __launch_bounds__(TB_THREADS) k_tower_b(b200_deepfm_args_t a) {
     }
     __syncthreads();
     if (is_col) {
-#pragma unroll 4
-      for (int s_ = 0; s_ < n; ++s_) axpy16(acc, sc + s_ * SCR, xt[s_ * XP + t]);
-    } else if (is_b1) {
-      for (int s_ = 0; s_ < n; ++s_) axpy16(acc, sc + s_ * SCR, 1.0f);
-    } else if (is_small) {
+#pragma unroll 2
+      for (int s_ = 0; s_ < n; ++s_) {
+        const float4* d4 = reinterpret_cast<const float4*>(sc + s_ * SCR);
+        const float4 q0 = d4[0], q1 = d4[1], q2 = d4[2], q3 = d4[3];
+        const float dh[H1] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+        for (int i = 0; i < TB_CPT; ++i) {
+          const int col = t + TB_COLW * i;
+          const float x = col < NCOL ? xt[s_ * XP + col] : 0.f;
+#pragma unroll
+          for (int j = 0; j < H1; ++j) acc[i][j] = fmaf(dh[j], x, acc[i][j]);
+        }
+      }
+    } else {
       for (int s_ = 0; s_ < n; ++s_) {
         const float* r = sc + s_ * SCR;
-        float v;
-        if (small < H2 * H1) v = r[32 + small / H1] * r[16 + small % H1];            // dh2[k] * a1[j]
-        else if (small < H2 * H1 + H2) v = r[32 + small - H2 * H1];                   // dh2[k]
-        else if (small < H2 * H1 + 2 * H2) v = r[40] * r[36 + small - H2 * H1 - H2];  // dz * h2[k]
-        else v = r[40] * xt[s_ * XP + NDEEP + small - H2 * H1 - 2 * H2];              // dz * dense[e]
-        sacc += v;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int small = (t - TB_COLW) + 32 * i;
+          float v = 0.f;
+          if (small < H2 * H1) v = r[32 + small / H1] * r[16 + small % H1];             // dh2[k] * a1[j]
+          else if (small < H2 * H1 + H2) v = r[32 + small - H2 * H1];                    // dh2[k]
+          else if (small < H2 * H1 + 2 * H2) v = r[40] * r[36 + small - H2 * H1 - H2];   // dz * h2[k]
+          else if (small < N_SMALL) v = r[40] * xt[s_ * XP + NDEEP + small - H2 * H1 - 2 * H2];  // dz * dense[e]
+          sacc[i] += v;
+        }
       }
     }
   }
   if (is_col) {
-    const int col = t < NDEEP ? ND + t : t - NDEEP;  // tile column -> W1 input index (dense first)
 #pragma unroll
-    for (int j = 0; j < H1; ++j) atomicAdd(a.grads + l.o_w1 + j * IN + col, acc[j]);
-  } else if (is_b1) {
+    for (int i = 0; i < TB_CPT; ++i) {
+      const int col = t + TB_COLW * i;
+      if (col < NDEEP + ND) {
+        const int e = col < NDEEP ? ND + col : col - NDEEP;  // tile column -> W1 input index (dense first)
 #pragma unroll
-    for (int j = 0; j < H1; ++j) atomicAdd(a.grads + l.o_b1 + j, acc[j]);
-  } else if (is_small) {
-    int off;
-    if (small < H2 * H1) off = l.o_w2 + small;
-    else if (small < H2 * H1 + H2) off = l.o_b2 + small - H2 * H1;
-    else if (small < H2 * H1 + 2 * H2) off = l.o_w3 + small - H2 * H1 - H2;
-    else off = l.o_wd + small - H2 * H1 - 2 * H2;
-    atomicAdd(a.grads + off, sacc);
+        for (int j = 0; j < H1; ++j) atomicAdd(a.grads + l.o_w1 + j * IN + e, acc[i][j]);
+      } else if (col == NDEEP + ND) {
+#pragma unroll
+        for (int j = 0; j < H1; ++j) atomicAdd(a.grads + l.o_b1 + j, acc[i][j]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int small = (t - TB_COLW) + 32 * i;
+      if (small >= N_SMALL) continue;
+      int off;
+      if (small < H2 * H1) off = l.o_w2 + small;
+      else if (small < H2 * H1 + H2) off = l.o_b2 + small - H2 * H1;
+      else if (small < H2 * H1 + 2 * H2) off = l.o_w3 + small - H2 * H1 - H2;
+      else off = l.o_wd + small - H2 * H1 - 2 * H2;
+      atomicAdd(a.grads + off, sacc[i]);
+    }
   }
 }
 
 int check_args(const b200_deepfm_args_t* a, bool backward) {
   if (!a || a->G < 1 || a->B < 1) { g_msg = "bad shape"; return -1; }
-  if (ND + a->G * D + 1 + N_SMALL > TB_THREADS) { g_msg = "too many id groups for the fused tower (max 39)"; return -1; }
+  if (ND + a->G * D + 1 > TB_COLW * TB_CPT) { g_msg = "too many id groups for the fused tower (max 46)"; return -1; }
   if (!a->inv || !a->bet_wide || !a->bet_deep || !a->dense || !a->params) { g_msg = "null input"; return -1; }
   if (backward && (!a->labels || !a->grads || !a->gsum_wide || !a->gsum_deep || !a->loss || !a->scratch || !a->n_unique)) {
     g_msg = "null output";
@@ -445,18 +544,25 @@ int b200_deepfm_fwd_bwd(const b200_deepfm_args_t* args, void* stream) {
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = tower_a_smem(args->G);
   static bool attr_done[64] = {false};
+  static int gc = 0;
+  if (gc == 0) {
+    const char* e = getenv("B200_TOWER_GC");  // tuning knob: row gathers in flight per lane
+    gc = (e && atoi(e) == 2) ? 2 : 1;
+  }
   if (dev < 64 && !attr_done[dev]) {
-    cudaFuncSetAttribute(k_tower_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(k_tower_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_tower_a<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(k_tower_a<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(k_tower_a<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     attr_done[dev] = true;
   }
   dim3 gp(8, args->G);
   k_tower_prep<<<gp, 256, 0, st>>>(*args, l.total);
   long long blocks = ((long long)args->B + SPB - 1) / SPB;
   long long cap = (long long)n_sm * 8;
-  k_tower_a<true><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
+  if (gc == 2) k_tower_a<true, 2><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
+  else k_tower_a<true, 1><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
   long long chunks = ((long long)args->B + S_CHUNK - 1) / S_CHUNK;
-  cap = (long long)n_sm * 2;
+  cap = (long long)n_sm * 2;  // 2 blocks per SM by shared memory
   static bool attr_b[64] = {false};
   if (dev < 64 && !attr_b[dev]) {
     cudaFuncSetAttribute(k_tower_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
@@ -477,10 +583,10 @@ int b200_deepfm_forward(const b200_deepfm_args_t* args, void* stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = tower_a_smem(args->G);
-  cudaFuncSetAttribute(k_tower_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_tower_a<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
   long long blocks = ((long long)args->B + SPB - 1) / SPB;
   long long cap = (long long)n_sm * 8;
-  k_tower_a<false><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
+  k_tower_a<false, 1><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_msg = cudaGetErrorString(e); return -2; }

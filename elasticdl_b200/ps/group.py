@@ -63,7 +63,7 @@ class PSGroup:
 
     def __init__(self, n_shards, opt_type, opt_args, device=None, lr_staleness_modulation=False,
                  local_shards=None, shard_devices=None, reproduce_q1=False, track_rows=True,
-                 process_group=None, seed=0):
+                 process_group=None, seed=0, use_async=True, grads_to_wait=1, sync_version_tolerance=0):
         self._h = None
         self.lib = _lib.lib()
         if not torch.cuda.is_available():
@@ -76,6 +76,15 @@ class PSGroup:
         self.opt_type, self.opt_args = opt_type, opt_args
         self.process_group = process_group
         self.seed = int(seed)
+        # PS-side mode flags (python/ps/parameter_server.py / go/cmd/elasticdl_ps/main.go:32-35).
+        # The Go PS is async only (server.go:177); sync-SGD follows python/ps/servicer.py:168-238.
+        self.use_async = bool(use_async)
+        self.grads_to_wait = int(grads_to_wait)
+        self.sync_version_tolerance = int(sync_version_tolerance)
+        import threading
+
+        self._sync_lock = threading.Lock()
+        self._sync_buffer = {"n": 0, "dense": {}, "sparse": {}}
         flags = (1 if reproduce_q1 else 0) | (0 if track_rows else 2)
         h = ctypes.c_void_p()
         check(self.lib.b200ps_create(self.n_shards, self.device.index, opt_type.encode(), opt_args.encode(),

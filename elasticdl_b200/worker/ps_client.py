@@ -161,6 +161,8 @@ class PSClient(object):
         Every shard applies exactly one ApplyGradients and bumps its version
         (quirk Q7).  Returns (accepted, max_version)."""
         g = self.group
+        if not getattr(g, "use_async", True):
+            return self._push_gradients_sync(grads, edl_grads, learning_rate, model_versions)
         # 1. group by name; same-name merge (ps_client.py:203-217)
         dense, indexed = {}, {}
         for grad in grads:
@@ -217,3 +219,61 @@ class PSClient(object):
         versions = g.push_end(sync=True)
         g.check()
         return True, max(versions)
+
+    # ------------------------------------------------------------------ sync-SGD
+    def _push_gradients_sync(self, grads, edl_grads, learning_rate, model_versions):
+        """Sync-SGD as the Python PS implements it (python/ps/servicer.py:168-238): pushes older
+        than version - sync_version_tolerance are rejected; accepted pushes are buffered; when
+        grads_to_wait of them have arrived, dense gradients are AVERAGED and sparse gradients
+        SUMMED (concatenated, then deduplicated) and applied once -- the dense reduce is fused
+        with the optimizer update in one kernel (b200ps_push_dense_reduce) -- and the version
+        advances by one.  The buffer lives on the owning PSGroup, shared by all client views."""
+        g = self.group
+        owner = getattr(g, "_owner", None) or g
+        state = g.snapshot()
+        version = max(s[0] for s in state)
+        mv = max(model_versions) if len(model_versions) else 0
+        if mv < version - owner.sync_version_tolerance:  # servicer.py:168-175
+            return False, version
+        with owner._sync_lock:
+            buf = owner._sync_buffer
+            for grad in grads:
+                tid, dim, is_dense, shape = g.lookup(grad.name)
+                if grad.indices is not None:
+                    vals, ids = buf["sparse"].setdefault(grad.name, ([], []))
+                    vals.append(g._f32(grad.values).reshape(-1, dim).clone())
+                    ids.append(g._ids(grad.indices).clone())
+                else:
+                    t = g._f32(grad.values).reshape(-1).clone()
+                    if t.numel() != int(np.prod(shape)):
+                        raise ValueError("grad size mismatch for %s" % grad.name)
+                    buf["dense"].setdefault(grad.name, []).append(t)
+            for grad in edl_grads:
+                tid, dim, is_dense, shape = g.lookup(grad.name)
+                vals, ids = buf["sparse"].setdefault(grad.name, ([], []))
+                v = g._f32(grad.values).reshape(-1, dim)
+                if v.shape[0] != g._ids(grad.indices).numel():
+                    raise ValueError("grad width is not equal to embedding dim")
+                vals.append(v.clone())
+                ids.append(g._ids(grad.indices).clone())
+            buf["n"] += 1
+            if buf["n"] < owner.grads_to_wait:
+                return True, version
+            # apply: servicer.py:199-224
+            w = owner.grads_to_wait
+            g.push_begin(learning_rate, [version] * self.ps_num)
+            for name, parts in buf["dense"].items():
+                g.push_dense_reduce(name, parts, scale=1.0 / w)
+            row_items = []
+            for name, (vals, ids) in buf["sparse"].items():
+                tid, dim, _, _ = g.lookup(name)
+                uniq, n_unique, gsum, k = self._dedup(name, vals, ids, dim)
+                row_items.append((tid, k, uniq, n_unique, gsum))
+            if row_items:
+                g.push_rows(row_items)
+            versions = g.push_end(sync=True)
+            g.check()
+            buf["n"] = 0
+            buf["dense"].clear()
+            buf["sparse"].clear()
+            return True, max(versions)

@@ -524,3 +524,52 @@ def test_four_concurrent_workers_async_sgd_census_shapes():
             want[keys] = s.tables[n].get(keys)
         assert np.allclose(got, want, rtol=1e-5, atol=1e-6), n
     group.close()
+
+
+# ------------------------------------------------------------------ sync-SGD
+def test_sync_sgd_pserver_servicer_test_py_366():
+    """grads_to_wait 2: dense averaged / sparse summed, third push with version 0 -> rejected."""
+    from elasticdl_b200.common.tensor_utils import Tensor
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+
+    group = PSGroup(1, "SGD", "learning_rate=0.1;momentum=0.0;nesterov=false;", device=0,
+                    use_async=False, grads_to_wait=2)
+    client = PSClient(group)
+    rng = np.random.RandomState(3)
+    var = {"v0": rng.rand(3, 2).astype(F), "v1": rng.rand(3).astype(F)}
+    g0 = {"v0": rng.rand(3, 2).astype(F), "v1": rng.rand(3).astype(F)}
+    g1 = {"v0": rng.rand(3, 2).astype(F), "v1": rng.rand(3).astype(F)}
+    client.partition_dense_parameters(var.keys())
+    client.push_dense_parameters([Tensor(n, v, None) for n, v in var.items()], 0, 0)
+    client.push_embedding_table_infos([info("emb", 8, capacity=16)])
+    table = rng.rand(10, 8).astype(F)
+    group.set_rows([("emb", np.arange(10), table)])
+    e0 = (rng.rand(3, 8).astype(F), np.array([3, 1, 3]))
+    e1 = (rng.rand(2, 8).astype(F), np.array([1, 9]))
+    lr = 0.1
+    acc, ver = client.push_gradients([Tensor(n, v, None) for n, v in g0.items()], [Tensor("emb", *e0)], lr, [0])
+    assert (acc, ver) == (True, 0)
+    acc, ver = client.push_gradients([Tensor(n, v, None) for n, v in g1.items()], [Tensor("emb", *e1)], lr, [0])
+    assert (acc, ver) == (True, 1)
+    acc, ver = client.push_gradients([Tensor(n, v, None) for n, v in g1.items()], [], lr, [0])
+    assert (acc, ver) == (False, 1)
+    d = group.pull_dense(list(var))
+    for n in var:
+        assert np.allclose(d[n].cpu().numpy(), var[n] - lr * (g0[n] + g1[n]) / 2, atol=1e-6)
+    want = table.copy()
+    for vals, ids in (e0, e1):
+        for gv, gi in zip(vals, ids):
+            want[gi] -= lr * gv
+    assert np.allclose(client.pull_embedding_vectors("emb", np.arange(10)), want, atol=1e-6)
+    # tolerance lets one-version-stale pushes in
+    group2 = PSGroup(1, "SGD", "learning_rate=0.1;momentum=0.0;nesterov=false;", device=0,
+                     use_async=False, grads_to_wait=1, sync_version_tolerance=1)
+    c2 = PSClient(group2)
+    c2.partition_dense_parameters(["w"])
+    c2.push_dense_parameters([Tensor("w", np.ones(4, dtype=F), None)], 0, 0)
+    assert c2.push_gradients([Tensor("w", np.ones(4, dtype=F), None)], [], lr, [0]) == (True, 1)
+    assert c2.push_gradients([Tensor("w", np.ones(4, dtype=F), None)], [], lr, [0]) == (True, 2)  # stale by 1: ok
+    assert c2.push_gradients([Tensor("w", np.ones(4, dtype=F), None)], [], lr, [0]) == (False, 2)  # stale by 2
+    group.close()
+    group2.close()
