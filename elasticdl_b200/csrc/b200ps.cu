@@ -288,6 +288,8 @@ int alloc_table_on_shard(b200ps_t* ps, Table& t, int s, int table_id) {
 // class 2: dim % 8 == 0 (32 B sector per thread), 1: dim % 4 == 0, 0: scalar.
 int vec_class(const Table& t) {
   // record slabs are 256 B aligned and row_stride is a multiple of 4 floats for vector classes
+  if (!t.is_dense && t.dim == 8 && t.row_stride % 4 == 0) return 3;  // lanes-per-record kernels
+  if (!t.is_dense && t.dim == 1 && t.row_stride == 4) return 4;       // one float4 record per row
   if (t.dim % 8 == 0 && t.row_stride % 4 == 0) return 2;
   if (t.dim % 4 == 0 && t.row_stride % 4 == 0) return 1;
   return 0;
@@ -295,14 +297,16 @@ int vec_class(const Table& t) {
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
+constexpr int kClasses = 5;
 struct Split {
-  SegBatch b[3];
-  long long max_work[3] = {0, 0, 0};
+  SegBatch b[kClasses];
+  long long max_work[kClasses] = {0, 0, 0, 0, 0};
 };
 
-int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense, Split* out) {
+int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense, Split* out, bool push = false,
+               bool allow_d1 = false) {
   if (nseg < 0 || nseg > kMaxSegs) return fail(B200PS_EINVAL, "nseg out of range (max " + std::to_string(kMaxSegs) + ")");
-  for (int c = 0; c < 3; ++c) out->b[c].nseg = 0;
+  for (int c = 0; c < kClasses; ++c) out->b[c].nseg = 0;
   for (int i = 0; i < nseg; ++i) {
     const b200ps_seg_t& sg = segs[i];
     if (sg.table < 0 || sg.table >= (int)ps->tables.size()) return fail(B200PS_ENOTFOUND, "unknown table id " + std::to_string(sg.table));
@@ -311,12 +315,17 @@ int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense
     if (sg.n < 0) return fail(B200PS_EINVAL, "negative segment length");
     if (sg.n == 0 && !want_dense) continue;
     int c = vec_class(t);
-    if (c > 0 && !aligned16(sg.rows_dev)) c = 0;
+    if (c > 0 && c != 4 && !aligned16(sg.rows_dev)) c = 0;
+    if (c == 4 && !allow_d1) c = 0;  // gather / scatter of one float per row: the scalar kernel is already minimal
     long long work;
     if (want_dense) {
       long long numel = t.rows * t.dim;
       c = (numel % 4 == 0 && aligned16(sg.rows_dev)) ? 1 : 0;
       work = c ? numel / 4 : numel;
+    } else if (c == 3) {
+      work = (long long)sg.n * (push ? 8 : 2);
+    } else if (c == 4) {
+      work = sg.n;
     } else {
       int W = c == 0 ? 1 : 4 * c;
       work = (long long)sg.n * (t.dim / W);
@@ -330,7 +339,7 @@ int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense
 
 template <typename F>
 int for_each_class(b200ps_t* ps, Split& sp, F&& launch) {
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < kClasses; ++c) {
     if (sp.b[c].nseg == 0) continue;
     dim3 grid(grid_for(ps, sp.max_work[c]), sp.b[c].nseg);
     launch(c, grid, sp.b[c]);
@@ -367,6 +376,9 @@ int b200ps_create(int n_shards, int client_device, const char* opt_type, const c
   DeviceGuard g(client_device);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, client_device) == cudaSuccess) ps->n_sm = prop.multiProcessorCount;
+  // rows are 32 B sectors scattered over GBs: ask L2 not to over-fetch 64 B per miss (a hint)
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  cudaGetLastError();
   cudaError_t e = cudaMalloc(&ps->d_rt, sizeof(PushRt));
   if (e == cudaSuccess) e = cudaMemset(ps->d_rt, 0, sizeof(PushRt));
   if (e == cudaSuccess) e = cudaMalloc(&ps->d_err, 64);
@@ -663,7 +675,10 @@ static int rows_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
   return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
-    if (write) {
+    if (c == 3) {
+      if (write) k_rows_copy_d8<true><<<grid, 256, 0, st>>>(gv, b, slot);
+      else k_rows_copy_d8<false><<<grid, 256, 0, st>>>(gv, b, slot);
+    } else if (write) {
       if (c == 2) k_rows_copy<2, true><<<grid, 256, 0, st>>>(gv, b, slot);
       else if (c == 1) k_rows_copy<1, true><<<grid, 256, 0, st>>>(gv, b, slot);
       else k_rows_copy<0, true><<<grid, 256, 0, st>>>(gv, b, slot);
@@ -749,14 +764,16 @@ int b200ps_push_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   if (rc) return rc;
   DeviceGuard g(ps->client_device);
   Split sp;
-  rc = split_segs(ps, segs, nseg, false, &sp);
+  rc = split_segs(ps, segs, nseg, false, &sp, true, true);
   if (rc) return rc;
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
   OptParams o = ps->opt;
   return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
     DISPATCH_OPT(o.kind, {
-      if (c == 2) k_push_rows<OPT, 2><<<grid, 256, 0, st>>>(gv, b, o);
+      if (c == 3) k_push_rows_d8<OPT><<<grid, 256, 0, st>>>(gv, b, o);
+      else if (c == 4) k_push_rows_d1<OPT><<<grid, 256, 0, st>>>(gv, b, o);
+      else if (c == 2) k_push_rows<OPT, 2><<<grid, 256, 0, st>>>(gv, b, o);
       else if (c == 1) k_push_rows<OPT, 1><<<grid, 256, 0, st>>>(gv, b, o);
       else k_push_rows<OPT, 0><<<grid, 256, 0, st>>>(gv, b, o);
     });

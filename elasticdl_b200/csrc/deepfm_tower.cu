@@ -403,7 +403,7 @@ __host__ inline size_t tower_a_smem(int G) {
 // k_tower_a and the gathered input rows X (cooperative, fully independent 32 B row gathers) --
 // then thread e owns input column e with 16 accumulators; the remaining threads own db1 and
 // the small gradients (dW2, db2, dw3, dw_dense).  One atomicAdd per output per block.
-constexpr int S_CHUNK = 64;
+constexpr int S_CHUNK = 32;  // 52 KB of shared memory per block -> 4 blocks (16 warps) per SM
 constexpr int TB_COLW = 96;                    // threads owning dW1/db1 columns (3 warps)
 constexpr int TB_CPT = 4;                      // columns per thread: each staged dh1 row feeds 64 FMAs
 constexpr int TB_THREADS = TB_COLW + 32;       // + one warp for the small gradients
@@ -415,7 +415,7 @@ __host__ inline size_t tower_b_smem(int G) {
   return ((size_t)S_CHUNK * SCR + (size_t)S_CHUNK * tb_xpad(G)) * sizeof(float) + (size_t)G * S_CHUNK * sizeof(int);
 }
 
-__global__ void __launch_bounds__(TB_THREADS) k_tower_b(b200_deepfm_args_t a) {
+__global__ void __launch_bounds__(TB_THREADS, 4) k_tower_b(b200_deepfm_args_t a) {
   extern __shared__ __align__(16) float smem_b[];
   const Layout l = layout(a.G);
   const int B = a.B, G = a.G, t = threadIdx.x;
@@ -562,7 +562,7 @@ int b200_deepfm_fwd_bwd(const b200_deepfm_args_t* args, void* stream) {
   if (gc == 2) k_tower_a<true, 2><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
   else k_tower_a<true, 1><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
   long long chunks = ((long long)args->B + S_CHUNK - 1) / S_CHUNK;
-  cap = (long long)n_sm * 2;  // 2 blocks per SM by shared memory
+  cap = (long long)n_sm * 4;  // 4 blocks per SM by shared memory / registers
   static bool attr_b[64] = {false};
   if (dev < 64 && !attr_b[dev]) {
     cudaFuncSetAttribute(k_tower_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
