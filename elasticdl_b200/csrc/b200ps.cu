@@ -323,7 +323,7 @@ int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense
       c = (numel % 4 == 0 && aligned16(sg.rows_dev)) ? 1 : 0;
       work = c ? numel / 4 : numel;
     } else if (c == 3) {
-      work = (long long)sg.n * (push ? 8 : 2);
+      work = (long long)sg.n * (push ? d8_lanes(ps->opt.kind) : 2);
     } else if (c == 4) {
       work = sg.n;
     } else {
@@ -341,7 +341,12 @@ template <typename F>
 int for_each_class(b200ps_t* ps, Split& sp, F&& launch) {
   for (int c = 0; c < kClasses; ++c) {
     if (sp.b[c].nseg == 0) continue;
-    dim3 grid(grid_for(ps, sp.max_work[c]), sp.b[c].nseg);
+    // the cap on resident work applies to the whole launch, not to each segment: a segment's
+    // blocks loop (grid-stride) instead of launching thousands of blocks that exit at once
+    int gx = grid_for(ps, sp.max_work[c]);
+    const int per_seg_cap = (ps->n_sm * 16 + sp.b[c].nseg - 1) / sp.b[c].nseg;
+    if (gx > per_seg_cap) gx = per_seg_cap < 4 ? 4 : per_seg_cap;
+    dim3 grid(gx, sp.b[c].nseg);
     launch(c, grid, sp.b[c]);
     ps->launches++;
     CUDA_OK(cudaGetLastError());

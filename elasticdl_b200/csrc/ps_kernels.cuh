@@ -279,20 +279,26 @@ __global__ void __launch_bounds__(256) k_rows_copy_d8(GroupView gv, SegBatch sb,
   }
 }
 
+__host__ __device__ constexpr int d8_lanes(int opt) {  // lanes per record: power of two >= 2*(1+S)
+  return opt_slots(opt) == 0 ? 2 : opt_slots(opt) == 1 ? 4 : 8;
+}
+
 template <int OPT>
 __global__ void __launch_bounds__(256) k_push_rows_d8(GroupView gv, SegBatch sb, OptParams o) {
   constexpr int S = opt_slots(OPT);
   constexpr int R4 = 2 * (1 + S);  // 16 B chunks per record
+  constexpr int LPR = d8_lanes(OPT);
   const b200ps_seg_t& sg = sb.seg[blockIdx.y];
   const TableView& tv = gv.tables[sg.table];
   const int n = seg_count(sg);
-  const int lane = threadIdx.x & 31, c = lane & 7;
-  const long long rows_pad = ((long long)n + 3) / 4 * 4;
-  const long long stride = (long long)gridDim.x * blockDim.x / 8;
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 8; row < rows_pad; row += stride) {
+  const int lane = threadIdx.x & 31, c = lane & (LPR - 1);
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  const long long rows_pad = ((long long)n + RPW - 1) / RPW * RPW;
+  const long long stride = (long long)gridDim.x * blockDim.x / LPR;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR; row < rows_pad; row += stride) {
     const bool live = row < n;
     long long id = (live && c == 0) ? sg.ids_dev[row] : 0;
-    id = __shfl_sync(0xffffffffu, id, 0, 8);
+    id = __shfl_sync(0xffffffffu, id, 0, LPR);
     RowLoc loc = locate(gv, tv, live ? id : 0);
     const bool ok = live && loc.ok;
     if (live && !loc.ok && c == 0) atomicOr(gv.err, kErrRange);
@@ -303,9 +309,9 @@ __global__ void __launch_bounds__(256) k_push_rows_d8(GroupView gv, SegBatch sb,
     if (ok && c == 0) mark_present(tv, loc);
     // slot chunks of half h = c & 1 live in lanes h, h+2, h+4, h+6 of the octet
     float4 p = v, s0 = v, s1 = v, s2 = v;
-    if (S > 0) s0 = shfl4(v, (c & 1) + 2, 8);
-    if (S > 1) s1 = shfl4(v, (c & 1) + 4, 8);
-    if (S > 2) s2 = shfl4(v, (c & 1) + 6, 8);
+    if (S > 0) s0 = shfl4(v, (c & 1) + 2, LPR);
+    if (S > 1) s1 = shfl4(v, (c & 1) + 4, LPR);
+    if (S > 2) s2 = shfl4(v, (c & 1) + 6, LPR);
     if (c < 2) {
       const float lr = gv.rt->lr[loc.shard], alpha = gv.rt->alpha[loc.shard], l2adj = gv.rt->l2adj[loc.shard];
       float* gf = reinterpret_cast<float*>(&g);
@@ -318,9 +324,9 @@ __global__ void __launch_bounds__(256) k_push_rows_d8(GroupView gv, SegBatch sb,
     }
     // hand the updated slot chunks back to the lanes that own their 16 B of the record
     float4 out = p;
-    if (S > 0) { const float4 t = shfl4(s0, c & 1, 8); if ((c >> 1) == 1) out = t; }
-    if (S > 1) { const float4 t = shfl4(s1, c & 1, 8); if ((c >> 1) == 2) out = t; }
-    if (S > 2) { const float4 t = shfl4(s2, c & 1, 8); if ((c >> 1) == 3) out = t; }
+    if (S > 0) { const float4 t = shfl4(s0, c & 1, LPR); if ((c >> 1) == 1) out = t; }
+    if (S > 1) { const float4 t = shfl4(s1, c & 1, LPR); if ((c >> 1) == 2) out = t; }
+    if (S > 2) { const float4 t = shfl4(s2, c & 1, LPR); if ((c >> 1) == 3) out = t; }
     if (ok && c < R4) st_f4(rec, out);
   }
 }
