@@ -64,6 +64,7 @@ SYMBOLS = {
     "b200ps_shard_export": (_i, [_vp, _i, _vp, _sz, ctypes.POINTER(_sz)]),
     "b200ps_shard_import": (_i, [_vp, _i, _vp, _sz]),
     "b200ps_table_register": (_i, [_vp, ctypes.c_char_p, _i, ctypes.c_char_p, _i64, ctypes.c_uint64]),
+    "b200ps_table_register_hashed": (_i, [_vp, ctypes.c_char_p, _i, ctypes.c_char_p, _i64, ctypes.c_uint64]),
     "b200ps_dense_register": (_i, [_vp, ctypes.c_char_p, _i, _i64, _i]),
     "b200ps_lookup": (_i, [_vp, ctypes.c_char_p]),
     "b200ps_commit": (_i, [_vp]),

@@ -62,6 +62,8 @@ struct Table {
   int64_t row_stride = 0;
   int64_t slot_off[kMaxSlots + 1] = {0, 0, 0, 0};
   size_t present_off = 0;  // byte offset of the bitmap inside the allocation
+  size_t keys_off = 0;     // byte offset of the key array (hashed tables), 0 = direct-indexed
+  bool hashed = false;
   size_t bytes = 0;
   bool uniform = false;
   uint64_t seed = 0;
@@ -239,6 +241,7 @@ void fill_view(b200ps_t* ps, const Table& t, TableView* v) {
   for (int s = 0; s < ps->n_shards; ++s) {
     v->base[s] = (float*)t.alloc[s].ptr;
     v->present[s] = (t.present_off && t.alloc[s].ptr) ? (uint32_t*)((char*)t.alloc[s].ptr + t.present_off) : nullptr;
+    v->keys[s] = (t.hashed && t.alloc[s].ptr) ? (long long*)((char*)t.alloc[s].ptr + t.keys_off) : nullptr;
   }
   v->rows = t.rows;
   v->row_stride = t.row_stride;
@@ -269,6 +272,12 @@ int alloc_table_on_shard(b200ps_t* ps, Table& t, int s, int table_id) {
   a.n_shards = ps->n_shards;
   a.is_dense = t.is_dense;
   a.seed = t.seed;
+  if (t.hashed) {
+    // slot-keyed initial values: which id gets which draw depends on insertion order, exactly like the
+    // reference's RandomUniform(seed = len(map)) (embedding_table.go:51-54) -- excluded from parity
+    a.is_dense = 1;
+    a.seed = t.seed ^ (0x9E3779B97F4A7C15ULL * (uint64_t)(s + 1));
+  }
   bool need_kernel = t.uniform || (ps->opt.kind == kFTRL && ps->opt.init_accum != 0.0f);
   if (need_kernel) {
     if (t.bytes > t.present_off && t.present_off) CUDA_OK(cudaMemsetAsync((char*)p + t.present_off, 0, t.bytes - t.present_off, 0));
@@ -278,6 +287,11 @@ int alloc_table_on_shard(b200ps_t* ps, Table& t, int s, int table_id) {
     CUDA_OK(cudaGetLastError());
   } else {
     CUDA_OK(cudaMemsetAsync(p, 0, t.bytes, 0));
+  }
+  if (t.hashed) {  // after the slab fill: every slot starts unclaimed
+    k_fill_keys<<<grid_for(ps, t.rows), 256>>>((long long*)((char*)p + t.keys_off), t.rows);
+    ps->launches++;
+    CUDA_OK(cudaGetLastError());
   }
   CUDA_OK(cudaDeviceSynchronize());
   (void)table_id;
@@ -619,6 +633,36 @@ int b200ps_table_register(b200ps_t* ps, const char* name, int dim, const char* i
   t.present_off = bitmap ? rec_bytes : 0;
   t.bytes = (rec_bytes + bitmap + (2u << 20) - 1) / (2u << 20) * (2u << 20);  // IPC-exportable whole blocks
   t.uniform = initializer && strcmp(initializer, "uniform") == 0;  // embedding_table.go:51 (quirk Q6)
+  t.seed = seed;
+  return register_common(ps, std::move(t));
+}
+
+int b200ps_table_register_hashed(b200ps_t* ps, const char* name, int dim, const char* initializer,
+                                 int64_t expected_rows, uint64_t seed) {
+  if (!ps || !name || dim < 1 || expected_rows < 1) return fail(B200PS_EINVAL, "bad table definition");
+  std::lock_guard<std::mutex> lk(ps->mu);
+  auto it = ps->by_name.find(name);
+  if (it != ps->by_name.end()) return it->second;
+  Table t;
+  t.name = name;
+  t.dim = dim;
+  t.owner = -1;
+  t.is_dense = false;
+  t.hashed = true;
+  int64_t per_shard = (expected_rows + ps->n_shards - 1) / ps->n_shards;
+  int64_t slots = 1024;
+  while (slots < 2 * per_shard) slots <<= 1;  // load factor <= 0.5
+  t.rows = slots;
+  int slots_n = opt_slots(ps->opt.kind);
+  int64_t rec = (int64_t)dim * (slots_n + 1);
+  rec = (rec + 3) / 4 * 4;
+  t.row_stride = rec;
+  for (int k = 0; k <= kMaxSlots; ++k) t.slot_off[k] = (int64_t)k * dim;
+  size_t rec_bytes = ((size_t)t.rows * rec * sizeof(float) + 255) / 256 * 256;
+  t.present_off = 0;  // the key array is the created-row record
+  t.keys_off = rec_bytes;
+  t.bytes = (rec_bytes + (size_t)t.rows * sizeof(long long) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  t.uniform = initializer && strcmp(initializer, "uniform") == 0;
   t.seed = seed;
   return register_common(ps, std::move(t));
 }
@@ -1005,10 +1049,20 @@ int b200ps_finish_init(b200ps_t* ps, int shard, int32_t version, void* stream) {
 static int present_scan(b200ps_t* ps, int table, int shard, int64_t* ids_dev, int64_t cap, int64_t* n) {
   if (!ps || table < 0 || table >= (int)ps->tables.size() || shard < 0 || shard >= ps->n_shards || !n) return fail(B200PS_EINVAL, "bad argument");
   const Table& t = ps->tables[table];
-  if (t.is_dense || !t.present_off) return fail(B200PS_ESTATE, "created rows are not tracked for " + t.name);
+  if (t.is_dense || (!t.present_off && !t.hashed)) return fail(B200PS_ESTATE, "created rows are not tracked for " + t.name);
   if (!t.alloc[shard].ptr) return fail(B200PS_ESTATE, "shard not attached");
   DeviceGuard g(ps->client_device);
   CUDA_OK(cudaMemsetAsync(ps->d_count, 0, 8, 0));
+  if (t.hashed) {
+    k_key_ids<<<grid_for(ps, t.rows), 256>>>((const long long*)((const char*)t.alloc[shard].ptr + t.keys_off), t.rows, ids_dev,
+                                              cap, ps->d_count);
+    ps->launches++;
+    CUDA_OK(cudaGetLastError());
+    unsigned long long c = 0;
+    CUDA_OK(cudaMemcpy(&c, ps->d_count, 8, cudaMemcpyDeviceToHost));
+    *n = (int64_t)c;
+    return B200PS_OK;
+  }
   k_present_ids<<<grid_for(ps, t.rows), 256>>>((const uint32_t*)((const char*)t.alloc[shard].ptr + t.present_off), t.rows,
                                                 shard, ps->n_shards, ids_dev, cap, ps->d_count);
   ps->launches++;
@@ -1032,6 +1086,7 @@ int b200ps_check(b200ps_t* ps) {
   CUDA_OK(cudaMemcpy(&e, ps->d_err, 4, cudaMemcpyDeviceToHost));
   if (e) {
     CUDA_OK(cudaMemset(ps->d_err, 0, 4));
+    if (e & kErrFull) return fail(B200PS_ERANGE, "hashed embedding table is full (raise expected_rows)");
     if (e & kErrRange) return fail(B200PS_ERANGE, "embedding id outside the registered table capacity (or negative)");
     return fail(B200PS_EINVAL, "device-side error word " + std::to_string(e));
   }

@@ -69,6 +69,29 @@ struct RowLoc {
   bool ok;
 };
 
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33; return x;
+}
+
+// Hashed table (unbounded ids, the reference's map[int64]*Tensor, embedding_table.go:22-58):
+// find the slot of `id` on its shard, claiming an empty slot on first touch (lazy creation on
+// pull OR push, kernel_test.go:56-66).  Linear probing, system-scope CAS (the shard may be a peer).
+__device__ __forceinline__ int64_t probe_slot(long long* keys, int64_t rows, int64_t id, bool* ok) {
+  const uint64_t mask = (uint64_t)rows - 1;  // rows is a power of two
+  uint64_t h = mix64((uint64_t)id) & mask;
+  for (int64_t tries = 0; tries < rows; ++tries) {
+    long long k = *(volatile long long*)(keys + h);
+    if (k == kEmptySlot)
+      k = (long long)atomicCAS_system((unsigned long long*)(keys + h), (unsigned long long)kEmptySlot, (unsigned long long)id);
+    if (k == kEmptySlot || k == id) return (int64_t)h;
+    h = (h + 1) & mask;
+  }
+  *ok = false;
+  return 0;
+}
+
 __device__ __forceinline__ RowLoc locate(const GroupView& gv, const TableView& tv, int64_t id) {
   RowLoc r;
   int64_t slot;
@@ -83,6 +106,15 @@ __device__ __forceinline__ RowLoc locate(const GroupView& gv, const TableView& t
     r.shard = (int)(id - slot * gv.n_shards);
   }
   r.ok = (id >= 0) && (slot < tv.rows);
+  if (tv.keys[r.shard] != nullptr) {  // hashed: `slot` so far is id / N, the key
+    r.ok = id >= 0;
+    bool found = true;
+    slot = r.ok ? probe_slot(tv.keys[r.shard], tv.rows, id, &found) : 0;
+    if (!found) {
+      atomicOr(gv.err, kErrFull);
+      r.ok = false;
+    }
+  }
   r.slot = slot;
   r.rec = tv.base[r.shard] + slot * tv.row_stride;
   return r;
@@ -512,11 +544,6 @@ __global__ void k_finish_init(ShardCtl* ctl, int version) {
 // the counter-based generator shared with the oracle (oracle_uniform_init) or
 // zeros; slots = their constant.
 // ---------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
-  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
-  x ^= x >> 33; return x;
-}
 __host__ __device__ __forceinline__ float uniform_init(uint64_t seed, int64_t id, int64_t col) {
   uint64_t h = mix64(seed ^ mix64((uint64_t)id * 0x9E3779B97F4A7C15ULL + (uint64_t)col));
   float u = (float)(h >> 40) * (1.0f / 16777216.0f);
@@ -550,6 +577,23 @@ __global__ void __launch_bounds__(256) k_init_rows(InitArgs a) {
       v = uniform_init(a.seed, id, c);
     }
     a.base[row * a.row_stride + a.slot_off[k] + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_fill_keys(long long* keys, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) keys[i] = kEmptySlot;
+}
+
+__global__ void __launch_bounds__(256) k_key_ids(const long long* keys, long long rows, int64_t* ids, long long cap,
+                                                 unsigned long long* count) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < rows; slot += stride) {
+    const long long k = keys[slot];
+    if (k != kEmptySlot) {
+      unsigned long long at = atomicAdd(count, 1ULL);
+      if (ids != nullptr && (long long)at < cap) ids[at] = k;
+    }
   }
 }
 

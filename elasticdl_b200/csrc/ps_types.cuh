@@ -42,6 +42,7 @@ struct OptParams {
 struct TableView {
   float* base[kMaxShards];        // record slab / param array on each shard (peer-mapped)
   uint32_t* present[kMaxShards];  // created-row bitmap (nullptr: untracked)
+  long long* keys[kMaxShards];    // hashed tables (unbounded ids): open-addressing key array, else nullptr
   int64_t rows;                   // rows per shard (striped) / total rows (dense)
   int64_t row_stride;             // floats between consecutive rows
   int64_t slot_off[kMaxSlots + 1];  // float offset of [param, slot0, slot1, slot2] from the row start
@@ -85,6 +86,7 @@ struct SegBatch {
   int nseg;
 };
 
-enum ErrBits : unsigned { kErrRange = 1u, kErrWidth = 2u };
+enum ErrBits : unsigned { kErrRange = 1u, kErrWidth = 2u, kErrFull = 4u };
+constexpr long long kEmptySlot = (long long)0x8000000000000000ULL;
 
 }  // namespace b200ps_impl

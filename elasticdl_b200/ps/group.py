@@ -95,6 +95,8 @@ class PSGroup:
         for s in self.local_shards:
             check(self.lib.b200ps_shard_create_local(self._h, s, int(devs.get(s, self.device.index))))
         self.tables = {}  # name -> (id, dim, is_dense, shape)
+        self.table_initializers = {}  # name -> initializer string (EmbeddingTableInfo.initializer)
+        self.dense_owner = {}  # dense parameter name -> shard
         self._pinned_state = torch.empty(3 * _lib.MAX_SHARDS, dtype=torch.int64).pin_memory()
         self._pinned_versions = torch.empty(_lib.MAX_SHARDS, dtype=torch.int32).pin_memory()
         self._ws = None
@@ -154,12 +156,21 @@ class PSGroup:
         check(self.lib.b200ps_commit(self._h))
 
     # ------------------------------------------------------------------ definition
-    def register_table(self, name, dim, initializer="uniform", capacity=None):
-        """≙ push_embedding_table_infos for one table (idempotent)."""
+    def register_table(self, name, dim, initializer="uniform", capacity=None, expected_rows=None):
+        """≙ push_embedding_table_infos for one table (idempotent).  capacity (= the layer's
+        input_dim) gives a direct-indexed table; without it ids are unbounded and the table is
+        hashed, sized for `expected_rows` distinct ids (default DEFAULT_CAPACITY)."""
         if name in self.tables:
             return self.tables[name][0]
-        cap = int(capacity) if capacity else DEFAULT_CAPACITY
         seed = table_seed(self.seed, name)
+        self.table_initializers[name] = str(initializer)
+        if not capacity:
+            cap = int(expected_rows or DEFAULT_CAPACITY)
+            tid = check(self.lib.b200ps_table_register_hashed(self._h, name.encode(), int(dim),
+                                                              str(initializer).encode(), cap, seed))
+            self.tables[name] = (tid, int(dim), False, (None, int(dim)))
+            return tid
+        cap = int(capacity)
         tid = check(self.lib.b200ps_table_register(self._h, name.encode(), int(dim), str(initializer).encode(),
                                                    cap, seed))
         self.tables[name] = (tid, int(dim), False, (cap, int(dim)))
@@ -174,6 +185,7 @@ class PSGroup:
         dim = numel // rows if rows else 1
         tid = check(self.lib.b200ps_dense_register(self._h, name.encode(), int(shard), rows, dim))
         self.tables[name] = (tid, dim, True, shape)
+        self.dense_owner[name] = int(shard)
         return tid
 
     def commit(self):

@@ -101,6 +101,14 @@ int b200ps_shard_import(b200ps_t* ps, int shard_id, const void* blob, size_t siz
  * anything else zero-fills.  Returns the table id (>= 0) or an error. */
 int b200ps_table_register(b200ps_t* ps, const char* name, int dim, const char* initializer,
                           int64_t capacity, uint64_t seed);
+/* Same, for UNBOUNDED ids (an ElasticDL Embedding used without input_dim, e.g.
+ * model_zoo/deepfm_edl_embedding): the shard keeps an open-addressing key array in HBM and a
+ * row is created on first pull or push, like the Go map (embedding_table.go:41-58).
+ * expected_rows sizes the slot pool (load factor <= 0.5); running out of slots raises
+ * B200PS_ERANGE at the next b200ps_check.  "uniform" rows get slot-keyed draws (insertion-order
+ * dependent, as the reference's seed = len(map) is). */
+int b200ps_table_register_hashed(b200ps_t* ps, const char* name, int dim, const char* initializer,
+                                 int64_t expected_rows, uint64_t seed);
 /* ≙ PushModel's dense part: Model.InitFromModelPB + InitOptimizer slots
  * (model.go:70-72, optimizer.go:146-150).  A dense parameter is a [rows, dim]
  * matrix on one shard (1-D: rows = numel, dim = 1) so that IndexedSlices

@@ -573,3 +573,119 @@ def test_sync_sgd_pserver_servicer_test_py_366():
     assert c2.push_gradients([Tensor("w", np.ones(4, dtype=F), None)], [], lr, [0]) == (False, 2)  # stale by 2
     group.close()
     group2.close()
+
+
+# ------------------------------------------------------------------ hashed tables: unbounded ids (embedding_table.go:22-58)
+@pytest.mark.parametrize("n_shards", [1, 3])
+@pytest.mark.parametrize("dim", [1, 8, 10])
+def test_hashed_table_unbounded_ids(n_shards, dim):
+    """An ElasticDL Embedding without input_dim: ids are arbitrary int64, rows are created lazily on
+    first pull OR push (kernel_test.go:56-66), len(table) counts the created rows."""
+    from elasticdl_b200.common.tensor_utils import EmbeddingTableInfo, Tensor
+
+    group, client, oc = make_pair(n_shards, "adam")
+    client.push_embedding_table_infos([EmbeddingTableInfo("h", dim, "zero", 1)])  # no capacity -> hashed
+    oc.push_embedding_table_infos([oinfo("h", dim)])
+    rng = np.random.RandomState(dim * 10 + n_shards)
+    ids = np.unique(rng.randint(0, 2 ** 40, size=3000).astype(np.int64))
+    rng.shuffle(ids)
+    vals = rng.randn(len(ids), dim).astype(F)
+    half = len(ids) // 2
+    group.set_rows([("h", ids[:half], vals[:half])])
+    for s in oc.servers:
+        m = ids[:half] % n_shards == s.id
+        s.tables["h"].set(ids[:half][m], vals[:half][m])
+    q = rng.choice(ids[:half], 2000)
+    assert np.array_equal(client.pull_embedding_vectors("h", q), oc.pull_embedding_vectors("h", q))
+    assert group.table_size("h") == half
+    # pushes create the second half lazily (zero rows) and update the first half
+    versions, oversions = [0] * n_shards, [0] * n_shards
+    for step in range(3):
+        pid = rng.choice(ids, 1500).astype(np.int64)  # with duplicates
+        g = rng.randn(1500, dim).astype(F)
+        a1 = client.push_gradients([], [Tensor("h", g, pid)], 0.0, versions)
+        a2 = oc.push_gradients([], [O.Tensor("h", g.copy(), pid)], 0.0, oversions)
+        assert a1 == a2
+        versions, oversions = [a1[1]] * n_shards, [a2[1]] * n_shards
+    created = np.sort(np.concatenate([s.tables["h"].keys() for s in oc.servers]))
+    assert group.table_size("h") == len(created)
+    got_ids = np.sort(np.concatenate([group.table_ids("h", s).cpu().numpy() for s in range(n_shards)]))
+    assert np.array_equal(got_ids, created)
+    want = oc.pull_embedding_vectors("h", created)
+    got = client.pull_embedding_vectors("h", created)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+    for k, sn in enumerate(oc.servers[0].opt.slot_names):
+        gs = group.slot_rows("h", created, k + 1).cpu().numpy()
+        ws = np.zeros_like(gs)
+        for s in oc.servers:
+            m = created % n_shards == s.id
+            ws[m] = s.opt.table_slots[sn]["h"].get(created[m])
+        assert np.allclose(gs, ws, rtol=1e-5, atol=1e-7), sn
+    group.close()
+
+
+def test_hashed_table_uniform_and_full():
+    from elasticdl_b200.common.tensor_utils import EmbeddingTableInfo
+
+    group, client, _ = make_pair(2, "sgd")
+    group.register_table("u", 8, "uniform", None, expected_rows=600)
+    group.commit()
+    ids = np.arange(0, 400, dtype=np.int64) * 7919 + 2 ** 35
+    a = client.pull_embedding_vectors("u", ids)
+    assert a.min() >= -0.05 and a.max() < 0.05 and a.std() > 0.01
+    assert np.array_equal(client.pull_embedding_vectors("u", ids), a)  # stable once created
+    assert group.table_size("u") == 400
+    # 2 shards x 1024 slots: the 2049th distinct id on some shard cannot be placed
+    with pytest.raises(ValueError, match="full"):
+        client.pull_embedding_vectors("u", np.arange(5000, dtype=np.int64) * 2 + 1)
+    group.close()
+
+
+# ------------------------------------------------------------------ checkpoint save / re-sharded restore (SURVEY 8f-2)
+def test_checkpoint_resharding_2_to_3_checkpoint_test_go_25(tmp_path):
+    """Save with 2 shards, restore with 3: ids {0,2,4} U {1,3,5} land on shards {0,3} {1,4} {2,5}
+    (checkpoint_test.go:25-82); dense parameters re-hash by name; slots are not checkpointed (Q9)."""
+    from elasticdl_b200.common.tensor_utils import Tensor
+    from elasticdl_b200.ps import checkpoint as ck
+
+    group, client, _ = make_pair(2, "adam")
+    client.push_embedding_table_infos([info("e1", 2, capacity=64), info("hashed", 4, capacity=None)])
+    ids = np.array([0, 2, 4, 1, 3, 5], dtype=np.int64)
+    vals = np.arange(12, dtype=F).reshape(6, 2)
+    group.set_rows([("e1", ids, vals)])
+    hid = np.array([7, 2 ** 33 + 1, 12], dtype=np.int64)
+    hval = np.arange(12, dtype=F).reshape(3, 4) + 100
+    group.set_rows([("hashed", hid, hval)])
+    dense = {"dense/kernel:0": np.arange(6, dtype=F).reshape(2, 3), "dense/bias:0": np.array([9, 8, 7], dtype=F)}
+    client.partition_dense_parameters(dense.keys())
+    for ps_id in set(client.parameter_to_ps.values()):
+        client.push_dense_parameters([Tensor(n, v, None) for n, v in dense.items()], ps_id, 0)
+    for _ in range(3):  # move the version to 3 and dirty the optimizer slots
+        client.push_gradients([Tensor(n, np.ones_like(v), None) for n, v in dense.items()],
+                              [Tensor("e1", np.ones((2, 2), dtype=F), np.array([0, 1]))], 0.0, [0, 0])
+    want_rows = client.pull_embedding_vectors("e1", ids)
+    want_dense = {n: group.pull_dense([n])[n].cpu().numpy() for n in dense}
+    vdir = ck.save(group, str(tmp_path), keep_checkpoint_max=2)
+    assert vdir.endswith("version-3") and ck.is_valid_version_dir(vdir)
+    assert sorted(__import__("os").listdir(vdir)) == ["variables-0-of-2.ckpt", "variables-1-of-2.ckpt"]
+    # the files parse back: per-shard contents follow id % 2
+    _, infos, d0, t0 = ck.decode_model(open(vdir + "/variables-0-of-2.ckpt", "rb").read())
+    assert sorted(t0["e1"][0].tolist()) == [0, 2, 4] and {i[0] for i in infos} == {"e1", "hashed"}
+    group.close()
+
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+
+    g3 = PSGroup(3, *OPTS["adam"], device=0)
+    c3 = PSClient(g3)
+    c3.push_embedding_table_infos([info("e1", 2, capacity=64)])  # "hashed" is created from the checkpoint's infos
+    assert ck.load(g3, c3, ck.latest_version_dir(str(tmp_path))) == 3
+    assert [sorted(g3.table_ids("e1", s).cpu().tolist()) for s in range(3)] == [[0, 3], [1, 4], [2, 5]]
+    assert np.array_equal(c3.pull_embedding_vectors("e1", ids), want_rows)
+    assert np.array_equal(c3.pull_embedding_vectors("hashed", hid), hval)
+    versions = [-1] * 3
+    params, uninit = c3.pull_dense_parameters([0, 1, 2], versions)
+    assert uninit == [] and all(np.array_equal(params[n], want_dense[n]) for n in dense)
+    assert all(versions[p] == 3 for p in c3.ps_to_parameter)
+    assert not g3.slot_rows("e1", ids, 1).any()  # slots start from zero again (quirk Q9)
+    g3.close()
