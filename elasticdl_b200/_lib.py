@@ -64,12 +64,15 @@ SYMBOLS = {
     "b200ps_shard_export": (_i, [_vp, _i, _vp, _sz, ctypes.POINTER(_sz)]),
     "b200ps_shard_import": (_i, [_vp, _i, _vp, _sz]),
     "b200ps_table_register": (_i, [_vp, ctypes.c_char_p, _i, ctypes.c_char_p, _i64, ctypes.c_uint64]),
+    "b200ps_table_register_pair": (_i, [_vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, _i64, ctypes.c_uint64]),
     "b200ps_table_register_hashed": (_i, [_vp, ctypes.c_char_p, _i, ctypes.c_char_p, _i64, ctypes.c_uint64]),
     "b200ps_dense_register": (_i, [_vp, ctypes.c_char_p, _i, _i64, _i]),
     "b200ps_lookup": (_i, [_vp, ctypes.c_char_p]),
     "b200ps_commit": (_i, [_vp]),
     "b200ps_pull_rows": (_i, [_vp, _segp, _i, _vp]),
     "b200ps_set_rows": (_i, [_vp, _segp, _i, _vp]),
+    "b200ps_pull_rows_pair": (_i, [_vp, _segp, ctypes.POINTER(_vp), _i, _vp]),
+    "b200ps_push_rows_pair": (_i, [_vp, _segp, ctypes.POINTER(_vp), _i, _vp]),
     "b200ps_pull_dense": (_i, [_vp, _segp, _i, _vp]),
     "b200ps_set_dense": (_i, [_vp, _segp, _i, _vp]),
     "b200ps_slot_rows": (_i, [_vp, _i, _i, _segp, _i, _vp]),
@@ -82,6 +85,7 @@ SYMBOLS = {
     "b200ps_bump_step": (_i, [_vp, _vp]),
     "b200ps_unique_workspace": (_sz, [_i, _i64]),
     "b200ps_unique": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200ps_unique_bounded": (_i, [_vp, _vp, _i, _i64, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ps_segment_sum": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp]),
     "b200ps_gather_rows": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp]),
     "b200ps_shard_state": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_int32)]),

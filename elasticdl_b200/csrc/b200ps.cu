@@ -64,6 +64,9 @@ struct Table {
   size_t present_off = 0;  // byte offset of the bitmap inside the allocation
   size_t keys_off = 0;     // byte offset of the key array (hashed tables), 0 = direct-indexed
   bool hashed = false;
+  int pair_of = -1;        // >= 0: this table shares the record slab of table `pair_of` (b200ps_table_register_pair)
+  int pair_b = -1;         // table A of a pair: id of its partner
+  size_t base_off = 0;     // byte offset of this table's first float inside the shared allocation
   size_t bytes = 0;
   bool uniform = false;
   uint64_t seed = 0;
@@ -239,7 +242,7 @@ int ready(b200ps_t* ps) {
 void fill_view(b200ps_t* ps, const Table& t, TableView* v) {
   memset(v, 0, sizeof(*v));
   for (int s = 0; s < ps->n_shards; ++s) {
-    v->base[s] = (float*)t.alloc[s].ptr;
+    v->base[s] = t.alloc[s].ptr ? (float*)((char*)t.alloc[s].ptr + t.base_off) : nullptr;
     v->present[s] = (t.present_off && t.alloc[s].ptr) ? (uint32_t*)((char*)t.alloc[s].ptr + t.present_off) : nullptr;
     v->keys[s] = (t.hashed && t.alloc[s].ptr) ? (long long*)((char*)t.alloc[s].ptr + t.keys_off) : nullptr;
   }
@@ -301,6 +304,9 @@ int alloc_table_on_shard(b200ps_t* ps, Table& t, int s, int table_id) {
 // Splits a batch by vector class so that each launch is homogeneous:
 // class 2: dim % 8 == 0 (32 B sector per thread), 1: dim % 4 == 0, 0: scalar.
 int vec_class(const Table& t) {
+  // paired tables interleave two tables' sections: only the generic kernels address them singly
+  if (t.pair_b >= 0) return 2;
+  if (t.pair_of >= 0) return 0;
   // record slabs are 256 B aligned and row_stride is a multiple of 4 floats for vector classes
   if (!t.is_dense && t.dim == 8 && t.row_stride % 4 == 0) return 3;  // lanes-per-record kernels
   if (!t.is_dense && t.dim == 1 && t.row_stride == 4) return 4;       // one float4 record per row
@@ -513,11 +519,16 @@ int b200ps_shard_create_local(b200ps_t* ps, int shard_id, int device) {
   // tables registered before this shard existed
   for (size_t i = 0; i < ps->tables.size(); ++i) {
     Table& t = ps->tables[i];
-    if ((t.owner < 0 || t.owner == shard_id) && !t.alloc[shard_id].ptr) {
+    if (t.pair_of < 0 && (t.owner < 0 || t.owner == shard_id) && !t.alloc[shard_id].ptr) {
       int rc = alloc_table_on_shard(ps, t, shard_id, (int)i);
       if (rc) return rc;
     }
   }
+  for (auto& t : ps->tables)
+    if (t.pair_of >= 0 && !t.alloc[shard_id].ptr && ps->tables[t.pair_of].alloc[shard_id].ptr) {
+      t.alloc[shard_id] = ps->tables[t.pair_of].alloc[shard_id];
+      t.alloc[shard_id].borrowed = true;
+    }
   ps->dirty = true;
   return B200PS_OK;
 }
@@ -535,7 +546,7 @@ int b200ps_shard_export(b200ps_t* ps, int shard_id, void* blob, size_t cap, size
   entries.push_back(ce);
   for (size_t i = 0; i < ps->tables.size(); ++i) {
     Table& t = ps->tables[i];
-    if (!t.alloc[shard_id].ptr) continue;
+    if (!t.alloc[shard_id].ptr || t.pair_of >= 0) continue;
     BlobEntry e{};
     e.table = (int)i;
     e.bytes = t.alloc[shard_id].bytes;
@@ -575,6 +586,11 @@ int b200ps_shard_import(b200ps_t* ps, int shard_id, const void* blob, size_t siz
     a->bytes = e[i].bytes;
     a->imported = true;
   }
+  for (auto& t : ps->tables)  // a pair's second table aliases the first one's mapping
+    if (t.pair_of >= 0 && !t.alloc[shard_id].ptr && ps->tables[t.pair_of].alloc[shard_id].ptr) {
+      t.alloc[shard_id] = ps->tables[t.pair_of].alloc[shard_id];
+      t.alloc[shard_id].borrowed = true;
+    }
   sh.attached = true;
   ps->dirty = true;
   return B200PS_OK;
@@ -635,6 +651,56 @@ int b200ps_table_register(b200ps_t* ps, const char* name, int dim, const char* i
   t.uniform = initializer && strcmp(initializer, "uniform") == 0;  // embedding_table.go:51 (quirk Q6)
   t.seed = seed;
   return register_common(ps, std::move(t));
+}
+
+int b200ps_table_register_pair(b200ps_t* ps, const char* name_a, const char* name_b, const char* initializer,
+                               int64_t capacity, uint64_t seed) {
+  if (!ps || !name_a || !name_b || capacity < 1) return fail(B200PS_EINVAL, "bad table definition");
+  std::lock_guard<std::mutex> lk(ps->mu);
+  auto ia = ps->by_name.find(name_a), ib = ps->by_name.find(name_b);
+  if (ia != ps->by_name.end() && ib != ps->by_name.end()) return ia->second;
+  if (ia != ps->by_name.end() || ib != ps->by_name.end()) return fail(B200PS_ESTATE, "one table of the pair is already registered");
+  const int slots = opt_slots(ps->opt.kind);
+  const int64_t sec = 12;  // [A(8) | B(1) | pad(3)] floats
+  Table a;
+  a.name = name_a;
+  a.dim = 8;
+  a.owner = -1;
+  a.rows = (capacity + ps->n_shards - 1) / ps->n_shards;
+  a.row_stride = sec * (slots + 1);
+  for (int k = 0; k <= kMaxSlots; ++k) a.slot_off[k] = (int64_t)k * sec;
+  size_t rec_bytes = ((size_t)a.rows * a.row_stride * sizeof(float) + 255) / 256 * 256;
+  size_t bitmap = (ps->flags & 2u) ? 0 : (((size_t)a.rows + 31) / 32 * 4 + 255) / 256 * 256;
+  a.present_off = bitmap ? rec_bytes : 0;
+  a.bytes = (rec_bytes + 2 * bitmap + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  a.uniform = initializer && strcmp(initializer, "uniform") == 0;
+  a.seed = seed;
+  a.pair_b = (int)ps->tables.size() + 1;
+  if (a.uniform) return fail(B200PS_EINVAL, "paired tables support the zero initializer only (set rows explicitly)");
+  int id_a = register_common(ps, std::move(a));
+  if (id_a < 0) return id_a;
+  Table b;
+  b.name = name_b;
+  b.dim = 1;
+  b.owner = -1;
+  const Table& ra = ps->tables[id_a];
+  b.rows = ra.rows;
+  b.row_stride = ra.row_stride;
+  for (int k = 0; k <= kMaxSlots; ++k) b.slot_off[k] = (int64_t)k * sec;
+  b.base_off = 8 * sizeof(float);
+  b.present_off = bitmap ? rec_bytes + bitmap : 0;
+  b.bytes = ra.bytes;
+  b.n_slots = ra.n_slots;
+  b.pair_of = id_a;
+  for (int s = 0; s < ps->n_shards; ++s) {  // shares A's allocation
+    b.alloc[s] = ra.alloc[s];
+    b.alloc[s].borrowed = true;
+  }
+  int id_b = (int)ps->tables.size();
+  ps->tables.push_back(std::move(b));
+  ps->by_name[name_b] = id_b;
+  ps->dirty = true;
+  return id_a;
 }
 
 int b200ps_table_register_hashed(b200ps_t* ps, const char* name, int dim, const char* initializer,
@@ -829,6 +895,65 @@ int b200ps_push_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   });
 }
 
+static int pair_batch(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const* rows_b, int nseg, PairBatch* pb,
+                      long long* max_n) {
+  if (nseg < 1 || nseg > kMaxSegs / 2) return fail(B200PS_EINVAL, "pair launches take 1.." + std::to_string(kMaxSegs / 2) + " segments");
+  *max_n = 0;
+  for (int i = 0; i < nseg; ++i) {
+    const b200ps_seg_t& sg = segs_a[i];
+    if (sg.table < 0 || sg.table >= (int)ps->tables.size() || ps->tables[sg.table].pair_b < 0)
+      return fail(B200PS_EINVAL, "segment table is not the first table of a registered pair");
+    if (!aligned16(sg.rows_dev) || !rows_b[i]) return fail(B200PS_EINVAL, "pair rows must be 16 B aligned / non-null");
+    pb->a[i] = sg;
+    pb->rows_b[i] = rows_b[i];
+    pb->table_b[i] = ps->tables[sg.table].pair_b;
+    if (sg.n > *max_n) *max_n = sg.n;
+  }
+  pb->nseg = nseg;
+  return B200PS_OK;
+}
+
+static dim3 pair_grid(b200ps_t* ps, long long threads, int nseg) {
+  int gx = grid_for(ps, threads);
+  const int per_seg_cap = (ps->n_sm * 16 + nseg - 1) / nseg;
+  if (gx > per_seg_cap) gx = per_seg_cap < 4 ? 4 : per_seg_cap;
+  return dim3(gx, nseg);
+}
+
+int b200ps_pull_rows_pair(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const* rows_b, int nseg, void* stream) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  DeviceGuard g(ps->client_device);
+  PairBatch pb;
+  long long max_n;
+  rc = pair_batch(ps, segs_a, rows_b, nseg, &pb, &max_n);
+  if (rc) return rc;
+  k_pair_pull<<<pair_grid(ps, max_n * 4, nseg), 256, 0, (cudaStream_t)stream>>>(group_view(ps), pb);
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
+int b200ps_push_rows_pair(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const* grads_b, int nseg, void* stream) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  DeviceGuard g(ps->client_device);
+  PairBatch pb;
+  long long max_n;
+  rc = pair_batch(ps, segs_a, grads_b, nseg, &pb, &max_n);
+  if (rc) return rc;
+  GroupView gv = group_view(ps);
+  OptParams o = ps->opt;
+  const int S = opt_slots(o.kind);
+  const int lpr = 3 * (1 + S) <= 4 ? 4 : 3 * (1 + S) <= 8 ? 8 : 16;
+  dim3 grid = pair_grid(ps, max_n * lpr, nseg);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_OPT(o.kind, k_pair_push<OPT><<<grid, 256, 0, st>>>(gv, pb, o));
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
 int b200ps_push_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream) {
   int rc = ready(ps);
   if (rc) return rc;
@@ -920,8 +1045,19 @@ size_t b200ps_unique_workspace(int T, int64_t k) {
          align256((size_t)T * ntiles * 4) + 256;
 }
 
+int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, const int64_t* bounds,
+                          int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
+
 int b200ps_unique(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, int64_t* uniq_dev, int32_t* inv_dev,
                   int32_t* n_unique_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return b200ps_unique_bounded(ps, ids_dev, T, k, nullptr, uniq_dev, inv_dev, n_unique_dev, workspace_dev,
+                               workspace_bytes, stream);
+}
+
+int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, const int64_t* bounds,
+                          int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
+                          size_t workspace_bytes, void* stream) {
   if (T < 1 || T > 65535 || k < 1 || k > (1LL << 30)) return fail(B200PS_EINVAL, "bad unique shape");
   if (workspace_bytes < b200ps_unique_workspace(T, k)) return fail(B200PS_EINVAL, "unique workspace too small");
   DeviceGuard g(client_dev(ps));
@@ -935,9 +1071,14 @@ int b200ps_unique(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, int64_
   ws.fp = (int*)p; p += align256((size_t)T * k * 4);
   ws.rank_at = (int*)p; p += align256((size_t)T * k * 4);
   ws.tile_cnt = (int*)p;
-  k_uniq_clear<<<grid_for(ps, (long long)T * ws.cap), 256, 0, st>>>(ws, T);
+  UniqueBounds ub{};
+  const int use_bounds = bounds != nullptr && T <= kMaxSegs;
+  if (use_bounds)
+    for (int t = 0; t < T; ++t) ub.bound[t] = bounds[t] > 0 && bounds[t] <= ws.cap ? (int)bounds[t] : 0;
+  dim3 gc((unsigned)((ws.cap + 2047) / 2048), T);
+  k_uniq_clear<<<gc, 256, 0, st>>>(ws, T, ub, use_bounds);
   dim3 gk((unsigned)((k + 255) / 256), T), gt(ws.ntiles, T);
-  k_uniq_insert<<<gk, 256, 0, st>>>(ids_dev, k, ws);
+  k_uniq_insert<<<gk, 256, 0, st>>>(ids_dev, k, ws, ub, use_bounds);
   k_uniq_flag<<<gt, 256, 0, st>>>(k, ws);
   k_uniq_scan_tiles<<<T, 1024, 0, st>>>(ws, n_unique_dev);
   k_uniq_rank<<<gt, 256, 0, st>>>(ids_dev, k, ws, uniq_dev);

@@ -363,6 +363,109 @@ __global__ void __launch_bounds__(256) k_push_rows_d8(GroupView gv, SegBatch sb,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Paired tables (b200ps_table_register_pair): a dim-8 table A and a dim-1 table B that are always
+// addressed with the SAME ids (DeepFM's deep and wide embeddings of one id group,
+// model_zoo/dac_ctr/deepfm_model.py:42-49) share one record per id,
+//   [ A.p(8) B.p(1) pad(3) | A.s0(8) B.s0(1) pad(3) | ... ]   (48 B sections),
+// so one request per id serves both tables: a pull is ONE 48 B read (lanes 0-1: A, lane 2: B)
+// and an update is ONE contiguous read and ONE contiguous write of 48*(1+S) B.  Remote (NVLink)
+// reads are bounded by outstanding requests x latency, so halving the requests halves the time.
+// Each logical table stays addressable on its own through its TableView (generic kernels).
+// ---------------------------------------------------------------------------
+struct PairBatch {
+  b200ps_seg_t a[kMaxSegs / 2];  // table A (dim 8): ids, n_dev, rows
+  float* rows_b[kMaxSegs / 2];   // table B (dim 1) rows of the same ids
+  int32_t table_b[kMaxSegs / 2];
+  int nseg;
+};
+
+__global__ void __launch_bounds__(256) k_pair_pull(GroupView gv, PairBatch pb) {
+  const b200ps_seg_t& sg = pb.a[blockIdx.y];
+  const TableView& ta = gv.tables[sg.table];
+  const TableView& tb = gv.tables[pb.table_b[blockIdx.y]];
+  float* rows_b = pb.rows_b[blockIdx.y];
+  const int n = seg_count(sg);
+  const int lane = threadIdx.x & 31, c = lane & 3;
+  const long long rows_pad = ((long long)n + 7) / 8 * 8;
+  const long long stride = (long long)gridDim.x * blockDim.x / 4;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; row < rows_pad; row += stride) {
+    const bool live = row < n;
+    long long id = (live && c == 0) ? sg.ids_dev[row] : 0;
+    id = __shfl_sync(0xffffffffu, id, 0, 4);
+    if (!live) continue;
+    RowLoc loc = locate(gv, ta, id);
+    if (!loc.ok) {
+      if (c == 0) atomicOr(gv.err, kErrRange);
+      continue;
+    }
+    if (c < 3) {
+      const float4 x = ld_f4(loc.rec + 4 * c);  // lanes 0,1: A row; lane 2: [B.p, pad]
+      if (c == 0) mark_present(ta, loc);
+      if (c == 2) {
+        mark_present(tb, loc);
+        rows_b[row] = x.x;
+      } else {
+        st_f4(sg.rows_dev + row * 8 + 4 * c, x);
+      }
+    }
+  }
+}
+
+template <int OPT>
+__global__ void __launch_bounds__(256) k_pair_push(GroupView gv, PairBatch pb, OptParams o) {
+  constexpr int S = opt_slots(OPT);
+  constexpr int R4 = 3 * (1 + S);                       // 16 B chunks per record
+  constexpr int LPR = R4 <= 4 ? 4 : R4 <= 8 ? 8 : 16;   // lanes per record
+  const b200ps_seg_t& sg = pb.a[blockIdx.y];
+  const TableView& ta = gv.tables[sg.table];
+  const TableView& tb = gv.tables[pb.table_b[blockIdx.y]];
+  const float* grad_b = pb.rows_b[blockIdx.y];
+  const int n = seg_count(sg);
+  const int lane = threadIdx.x & 31, c = lane & (LPR - 1);
+  constexpr int RPW = 32 / LPR;
+  const long long rows_pad = ((long long)n + RPW - 1) / RPW * RPW;
+  const long long stride = (long long)gridDim.x * blockDim.x / LPR;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR; row < rows_pad; row += stride) {
+    const bool live = row < n;
+    long long id = (live && c == 0) ? sg.ids_dev[row] : 0;
+    id = __shfl_sync(0xffffffffu, id, 0, LPR);
+    RowLoc loc = locate(gv, ta, live ? id : 0);
+    const bool ok = live && loc.ok;
+    if (live && !loc.ok && c == 0) atomicOr(gv.err, kErrRange);
+    float* rec = loc.rec + 4 * c;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), g = v;
+    if (ok && c < R4) v = ld_f4(rec);
+    if (ok && c < 2) g = ld_f4(sg.rows_dev + row * 8 + 4 * c);
+    if (ok && c == 2) g.x = grad_b[row];
+    if (ok && c == 0) mark_present(ta, loc);
+    if (ok && c == 2) mark_present(tb, loc);
+    // chunk q of section k lives in lane 3k + q; bring the slot chunks to lanes q = 0,1,2
+    const int q = c < 3 ? c : 0;
+    float4 p = v, s0 = v, s1 = v, s2 = v;
+    if (S > 0) s0 = shfl4(v, q + 3, LPR);
+    if (S > 1) s1 = shfl4(v, q + 6, LPR);
+    if (S > 2) s2 = shfl4(v, q + 9, LPR);
+    if (c < 3) {
+      const float lr = gv.rt->lr[loc.shard], alpha = gv.rt->alpha[loc.shard], l2adj = gv.rt->l2adj[loc.shard];
+      float* gf = reinterpret_cast<float*>(&g);
+      float* pf = reinterpret_cast<float*>(&p);
+      float* af = reinterpret_cast<float*>(&s0);
+      float* bf = reinterpret_cast<float*>(&s1);
+      float* cf = reinterpret_cast<float*>(&s2);
+      const int ne = c == 2 ? 1 : 4;  // lane 2 holds the single B element, its padding stays untouched
+      for (int e = 0; e < ne; ++e) opt_update<OPT>(gf[e], pf[e], af[e], bf[e], cf[e], lr, alpha, l2adj, o);
+    }
+    // return section k's chunks to lanes 3k + q
+    const int sec = c / 3, qq = c - 3 * sec;
+    float4 out = p;
+    if (S > 0) { const float4 t = shfl4(s0, qq, LPR); if (sec == 1) out = t; }
+    if (S > 1) { const float4 t = shfl4(s1, qq, LPR); if (sec == 2) out = t; }
+    if (S > 2) { const float4 t = shfl4(s2, qq, LPR); if (sec == 3) out = t; }
+    if (ok && c < R4) st_f4(rec, out);
+  }
+}
+
 // dim-1 tables: the record [p, s0, s1, s2] (16 B) is one float4 per row.
 template <int OPT>
 __global__ void __launch_bounds__(256) k_push_rows_d1(GroupView gv, SegBatch sb, OptParams o) {
@@ -619,6 +722,10 @@ __global__ void __launch_bounds__(256) k_present_ids(const uint32_t* present, lo
 constexpr long long kEmptyKey = (long long)0x8000000000000000ULL;
 constexpr int kTile = 1024;  // ids per block in B / D (256 threads x 4)
 
+struct UniqueBounds {  // per segment: ids are known to be < bound (0 = unknown).  bound <= cap turns the
+  int bound[kMaxSegs];  // segment's table into a direct-address array: no keys, no CAS, no probing
+};
+
 struct UniqueWs {
   long long* keys;  // [T][cap]
   int* minpos;      // [T][cap]
@@ -629,17 +736,31 @@ struct UniqueWs {
   int ntiles;
 };
 
-__global__ void __launch_bounds__(256) k_uniq_clear(UniqueWs ws, int T) {
-  const long long total = (long long)T * ws.cap;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    ws.keys[i] = kEmptyKey;
-    ws.minpos[i] = 0x7fffffff;
+__global__ void __launch_bounds__(256) k_uniq_clear(UniqueWs ws, int T, UniqueBounds ub, int use_bounds) {
+  const int t = blockIdx.y;
+  const int direct = use_bounds && ub.bound[t] > 0 && ub.bound[t] <= ws.cap;
+  const int n = direct ? ub.bound[t] : ws.cap;
+  long long* keys = ws.keys + (long long)t * ws.cap;
+  int* minpos = ws.minpos + (long long)t * ws.cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (!direct) keys[i] = kEmptyKey;
+    minpos[i] = 0x7fffffff;
   }
 }
 
-__global__ void __launch_bounds__(256) k_uniq_insert(const int64_t* ids, long long k, UniqueWs ws) {
+__global__ void __launch_bounds__(256) k_uniq_insert(const int64_t* ids, long long k, UniqueWs ws, UniqueBounds ub,
+                                                     int use_bounds) {
   const int t = blockIdx.y;
+  if (use_bounds && ub.bound[t] > 0 && ub.bound[t] <= ws.cap) {  // direct-address segment (block-uniform)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    long long id = ids[t * k + i];
+    if (id < 0 || id >= ub.bound[t]) id = 0;  // out-of-range ids are reported by the table kernels
+    int* minpos = ws.minpos + (long long)t * ws.cap;
+    if (*(volatile int*)&minpos[id] > (int)i) atomicMin(&minpos[id], (int)i);
+    ws.fp[t * k + i] = (int)id;
+    return;
+  }
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < k;
   const int lane = threadIdx.x & 31;

@@ -176,6 +176,28 @@ class PSGroup:
         self.tables[name] = (tid, int(dim), False, (cap, int(dim)))
         return tid
 
+    def register_pair(self, name_a, name_b, capacity, initializer="zero"):
+        """A dim-8 table `name_a` and a dim-1 table `name_b` addressed with the same ids, stored as
+        one record per id (b200ps_table_register_pair); both stay addressable by name."""
+        if name_a in self.tables and name_b in self.tables:
+            return self.tables[name_a][0], self.tables[name_b][0]
+        seed = table_seed(self.seed, name_a)
+        ta = check(self.lib.b200ps_table_register_pair(self._h, name_a.encode(), name_b.encode(),
+                                                       str(initializer).encode(), int(capacity), seed))
+        tb = check(self.lib.b200ps_lookup(self._h, name_b.encode()))
+        self.tables[name_a] = (ta, 8, False, (int(capacity), 8))
+        self.tables[name_b] = (tb, 1, False, (int(capacity), 1))
+        self.table_initializers[name_a] = self.table_initializers[name_b] = str(initializer)
+        return ta, tb
+
+    def pair_call(self, fn, seg_items, rows_b):
+        """fn = b200ps_pull_rows_pair / b200ps_push_rows_pair over [(tid_a, n, ids, n_dev, rows_a)] + B rows."""
+        half = _lib.MAX_SEGS // 2
+        for i in range(0, len(seg_items), half):
+            arr, n = self.make_segs(seg_items[i:i + half])
+            ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in rows_b[i:i + half]])
+            check(fn(self._h, arr, ptrs, n, self._stream()))
+
     def register_dense(self, name, shape, shard):
         if name in self.tables:
             return self.tables[name][0]

@@ -137,11 +137,14 @@ class HostFeeder:
 
 class DeepFMPSEngine:
     def __init__(self, group, batch, lr=1e-3, init_std=0.01, seed=7, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM,
-                 init_rows=True, tower="fused"):
+                 init_rows=True, tower="fused", paired=True):
         """tower="fused": the hand-written CUDA tower (csrc/deepfm_tower.cu);
         tower="torch": torch autograd over library kernels (kept for A/B measurements and tests)."""
         assert tower in ("fused", "torch")
         self.tower_kind = tower
+        # paired=True: the deep (dim 8) and wide (dim 1) tables of an id group share one record
+        # per id, so one request per id serves both (ps_kernels.cuh "Paired tables")
+        self.paired = bool(paired) and deep_dim == 8
         self.group = group
         self.B = int(batch)
         self.G = len(group_rows)
@@ -152,8 +155,13 @@ class DeepFMPSEngine:
         G, B, D = self.G, self.B, self.D
         self.wide_names = ["group_%d_wide/embeddings:0" % i for i in range(G)]
         self.deep_names = ["group_%d_deep/embeddings:0" % i for i in range(G)]
-        self.wide_ids = [group.register_table(n, 1, "zero", r) for n, r in zip(self.wide_names, group_rows)]
-        self.deep_ids = [group.register_table(n, D, "zero", r) for n, r in zip(self.deep_names, group_rows)]
+        if self.paired:
+            ids_ab = [group.register_pair(d, w, r) for d, w, r in zip(self.deep_names, self.wide_names, group_rows)]
+            self.deep_ids = [a for a, _ in ids_ab]
+            self.wide_ids = [b for _, b in ids_ab]
+        else:
+            self.wide_ids = [group.register_table(n, 1, "zero", r) for n, r in zip(self.wide_names, group_rows)]
+            self.deep_ids = [group.register_table(n, D, "zero", r) for n, r in zip(self.deep_names, group_rows)]
         torch.manual_seed(seed)
         self.tower = DeepFMTower(G, D).to(dev)
         n_flat = int(group.lib.b200_deepfm_param_count(G))
@@ -213,6 +221,9 @@ class DeepFMPSEngine:
         self.loss_buf = torch.zeros(1, **f32)
         self.logits_buf = torch.empty(B, **f32)
         self.zero_versions = [0] * group.n_shards
+        import ctypes as _ct0
+
+        self.bounds = (_ct0.c_int64 * G)(*[int(r) for r in group_rows])  # id ranges: small groups dedup by direct address
         self.loss_fn = torch.nn.BCEWithLogitsLoss()
         self._build_segs()
         self.steps = 0
@@ -229,6 +240,22 @@ class DeepFMPSEngine:
         self.push_segs = [g.make_segs(self._seg_items(self.wide_ids, self.gsum_w, 1)),
                           g.make_segs(self._seg_items(self.deep_ids, self.gsum_d, self.D))]
         self.pull_dense_segs = g.make_segs([(tid, 0, None, None, p) for tid, (_, p) in zip(self.dense_ids, self.params)])
+        import ctypes as _ct
+        from elasticdl_b200 import _lib as _l
+
+        half, B = _l.MAX_SEGS // 2, self.B
+
+        def pair_plan(rows_a, rows_b):
+            items = self._seg_items(self.deep_ids, rows_a, self.D)
+            plan = []
+            for i in range(0, self.G, half):
+                arr, n = g.make_segs(items[i:i + half])
+                ptrs = (_ct.c_void_p * n)(*[rows_b[t * B:(t + 1) * B].data_ptr() for t in range(i, min(i + half, self.G))])
+                plan.append((arr, ptrs, n))
+            return plan
+
+        self.pull_pair = pair_plan(self.bet_d, self.bet_w)
+        self.push_pair = pair_plan(self.gsum_d, self.gsum_w)
         grad_views = [self.flat_grads[off:off + n] for off, n in self.flat_views]
         self.push_dense_segs = g.make_segs([(tid, 0, None, None, gv) for tid, gv in zip(self.dense_ids, grad_views)])
         from elasticdl_b200._lib import DeepFMArgs
@@ -266,14 +293,20 @@ class DeepFMPSEngine:
         check(lib.b200ps_pull_dense(h, arr, n, st))
         # (2) unique ids per group; wide and deep tables of a group share them
         e = mark("unique")
-        check(lib.b200ps_unique(h, ids.data_ptr(), G, B, self.uniq.data_ptr(), self.inv.data_ptr(),
-                                self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st))
+        check(lib.b200ps_unique_bounded(h, ids.data_ptr(), G, B, self.bounds, self.uniq.data_ptr(), self.inv.data_ptr(),
+                                        self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st))
         done(e)
         # (3) pull the unique rows of all 76 tables
-        for name, (arr, n) in zip(("pull_wide", "pull_deep"), self.pull_segs):
-            e = mark(name)
-            check(lib.b200ps_pull_rows(h, arr, n, st))
+        if self.paired:
+            e = mark("pull_pair")
+            for arr, ptrs, n in self.pull_pair:
+                check(lib.b200ps_pull_rows_pair(h, arr, ptrs, n, st))
             done(e)
+        else:
+            for name, (arr, n) in zip(("pull_wide", "pull_deep"), self.pull_segs):
+                e = mark(name)
+                check(lib.b200ps_pull_rows(h, arr, n, st))
+                done(e)
         if self.tower_kind == "fused":
             # (4-6) gather + tower forward/backward + per-unique-id gradient sums: three launches
             e_t = mark("tower_fwd_bwd")
@@ -293,10 +326,16 @@ class DeepFMPSEngine:
         g.push_begin(self.lr, self.zero_versions)
         arr, n = dense_segs
         check(lib.b200ps_push_dense(h, arr, n, st))
-        for name, (arr, n) in zip(("push_wide", "push_deep"), self.push_segs):
-            e = mark(name)
-            check(lib.b200ps_push_rows(h, arr, n, st))
+        if self.paired:
+            e = mark("push_pair")
+            for arr, ptrs, n in self.push_pair:
+                check(lib.b200ps_push_rows_pair(h, arr, ptrs, n, st))
             done(e)
+        else:
+            for name, (arr, n) in zip(("push_wide", "push_deep"), self.push_segs):
+                e = mark(name)
+                check(lib.b200ps_push_rows(h, arr, n, st))
+                done(e)
         g.push_end(sync=False)
         self.steps += 1
         return loss.detach().reshape(())
@@ -387,6 +426,8 @@ class DeepFMPSEngine:
             U = sum(uniq_per_step) / max(len(uniq_per_step), 1)
             nbytes = {
                 "pull_wide": U * (8 + 8 * 1), "pull_deep": U * (8 + 8 * D),
+                "pull_pair": U * (8 + 8 * D + 8 * 1),
+                "push_pair": U * (8 + 4 * D + 4 * 1 + (1 + opt_slots) * 8 * (D + 1)),
                 "push_wide": U * (8 + 4 * 1 + (1 + opt_slots) * 8 * 1),
                 "push_deep": U * (8 + 4 * D + (1 + opt_slots) * 8 * D),
                 "segment_sum_deep": k * (4 + 4 * D) + U * 4 * D,

@@ -101,6 +101,13 @@ int b200ps_shard_import(b200ps_t* ps, int shard_id, const void* blob, size_t siz
  * anything else zero-fills.  Returns the table id (>= 0) or an error. */
 int b200ps_table_register(b200ps_t* ps, const char* name, int dim, const char* initializer,
                           int64_t capacity, uint64_t seed);
+/* Two tables that are always addressed with the same ids -- a dim-8 table A and a dim-1 table B
+ * (DeepFM's deep and wide embeddings of one id group) -- stored as ONE record per id so that one
+ * memory request per id serves both (see ps_kernels.cuh "Paired tables").  Both names stay
+ * individually addressable by every other call; b200ps_pull_rows_pair / b200ps_push_rows_pair
+ * serve both at once.  Zero initializer only.  Returns A's id; B's id is b200ps_lookup(name_b). */
+int b200ps_table_register_pair(b200ps_t* ps, const char* name_a, const char* name_b, const char* initializer,
+                               int64_t capacity, uint64_t seed);
 /* Same, for UNBOUNDED ids (an ElasticDL Embedding used without input_dim, e.g.
  * model_zoo/deepfm_edl_embedding): the shard keeps an open-addressing key array in HBM and a
  * row is created on first pull or push, like the Go map (embedding_table.go:41-58).
@@ -129,6 +136,12 @@ int b200ps_pull_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
 /* ≙ EmbeddingTable.SetEmbeddingVectors / dense push_model rows
  * (embedding_table.go:71-77). */
 int b200ps_set_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream);
+
+/* Paired pull / push: segs_a[i] addresses table A of a pair (ids, n_dev, A rows [n,8]);
+ * rows_b[i] / grads_b[i] are the dim-1 rows of table B for the same ids.  At most
+ * B200PS_MAX_SEGS / 2 segments per call.  push_rows_pair belongs between push_begin and push_end. */
+int b200ps_pull_rows_pair(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const* rows_b, int nseg, void* stream);
+int b200ps_push_rows_pair(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const* grads_b, int nseg, void* stream);
 
 /* ≙ PullDenseParameters payload (server.go:144-160): copy whole dense
  * parameters owner-shard -> dst (segs[i].rows_dev; ids_dev/n ignored). */
@@ -178,6 +191,11 @@ int b200ps_bump_step(b200ps_t* ps, void* stream);
  * n_unique_dev[t] = number of distinct ids.  Workspace from
  * b200ps_unique_workspace(T, k) bytes. */
 size_t b200ps_unique_workspace(int T, int64_t k);
+/* Same with host-side knowledge of the id range of each segment (bounds[t] = table capacity, 0 =
+ * unknown): small-range segments use a direct-address position array instead of the hash table. */
+int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, const int64_t* bounds,
+                          int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
+                          size_t workspace_bytes, void* stream);
 int b200ps_unique(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, int64_t* uniq_dev,
                   int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev, size_t workspace_bytes,
                   void* stream);

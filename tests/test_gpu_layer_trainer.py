@@ -137,10 +137,10 @@ def _torch_reference_grads(eng, tower, wide0, deep0, ids, dense, labels):
     return float(loss), grads
 
 
-@pytest.mark.parametrize("tower_kind", ["fused", "torch"])
+@pytest.mark.parametrize("tower_kind,paired", [("fused", True), ("fused", False), ("torch", True)])
 @pytest.mark.parametrize("n_shards,B,rows", [(1, 256, [5, 9, 300, 2000, 17]), (4, 1000, [3, 50000, 7, 100]),
                                              (2, 4096, None)])
-def test_deepfm_engine_step_matches_oracle_adam(n_shards, B, rows, tower_kind):
+def test_deepfm_engine_step_matches_oracle_adam(n_shards, B, rows, tower_kind, paired):
     """One engine step: (a) the tower's gradients == plain torch fp32 autograd over dense tables,
     (b) the PS state after the push == the oracle's Adam applied to those gradients."""
     import copy
@@ -154,7 +154,7 @@ def test_deepfm_engine_step_matches_oracle_adam(n_shards, B, rows, tower_kind):
         rows = [min(r, 20000) for r in rows]
     D, G = 8, len(rows)
     group = PSGroup(n_shards, *ADAM, device=0)
-    eng = DeepFMPSEngine(group, B, group_rows=rows, tower=tower_kind)
+    eng = DeepFMPSEngine(group, B, group_rows=rows, tower=tower_kind, paired=paired)
     dev = torch.device("cuda", 0)
     ids, dense, labels = synthetic_batch(B, 5, dev, "zipf", group_rows=rows)
     wide0 = [group.pull_rows([(n, torch.arange(r))])[0] for n, r in zip(eng.wide_names, rows)]

@@ -689,3 +689,33 @@ def test_checkpoint_resharding_2_to_3_checkpoint_test_go_25(tmp_path):
     assert all(versions[p] == 3 for p in c3.ps_to_parameter)
     assert not g3.slot_rows("e1", ids, 1).any()  # slots start from zero again (quirk Q9)
     g3.close()
+
+
+def test_unique_bounded_direct_address_segments():
+    """b200ps_unique_bounded: segments whose id range fits the table dedup by direct address;
+    results must equal the hashed path / tf.unique exactly."""
+    import ctypes
+
+    from elasticdl_b200 import _lib
+
+    group, _, _ = make_pair(1)
+    rng = np.random.RandomState(11)
+    T, k = 5, 6000
+    bounds = [7, 300, 0, 5000, 10 ** 6]  # 0 = unknown, 1e6 > table capacity -> hashed
+    ids = np.stack([rng.randint(0, b if b else 10 ** 5, size=k) for b in bounds]).astype(np.int64)
+    d_ids = torch.from_numpy(ids).cuda().view(-1)
+    lib = _lib.lib()
+    need = lib.b200ps_unique_workspace(T, k)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    uniq = torch.empty(T * k, dtype=torch.int64, device="cuda")
+    inv = torch.empty(T * k, dtype=torch.int32, device="cuda")
+    n = torch.empty(T, dtype=torch.int32, device="cuda")
+    arr = (ctypes.c_int64 * T)(*bounds)
+    for _ in range(2):  # twice: the workspace is reused dirty
+        _lib.check(lib.b200ps_unique_bounded(group._h, d_ids.data_ptr(), T, k, arr, uniq.data_ptr(), inv.data_ptr(),
+                                             n.data_ptr(), ws.data_ptr(), ws.numel(), group._stream()))
+        u, i, c = uniq.cpu().numpy().reshape(T, k), inv.cpu().numpy().reshape(T, k), n.cpu().numpy()
+        for t in range(T):
+            wu, wi = O.unique_first_occurrence(ids[t])
+            assert c[t] == len(wu) and np.array_equal(u[t, : c[t]], wu) and np.array_equal(i[t], wi), t
+    group.close()
