@@ -83,6 +83,10 @@ SYMBOLS = {
     "b200ps_push_dense_reduce": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _f, _vp]),
     "b200ps_push_end": (_i, [_vp, _vp, _vp]),
     "b200ps_bump_step": (_i, [_vp, _vp]),
+    "b200ps_kernel_sgd": (_i, [_vp, _vp, _f, ctypes.c_longlong, _vp]),
+    "b200ps_kernel_momentum": (_i, [_vp, _vp, _vp, _f, _i, _f, ctypes.c_longlong, _vp]),
+    "b200ps_kernel_adam": (_i, [_vp, _vp, _vp, _vp, _f, ctypes.c_longlong, ctypes.c_longlong, _f, _f, _f, _vp, _vp]),
+    "b200ps_kernel_adagrad": (_i, [_vp, _vp, _vp, _f, ctypes.c_longlong, _f, _vp]),
     "b200ps_unique_workspace": (_sz, [_i, _i64]),
     "b200ps_unique": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ps_unique_bounded": (_i, [_vp, _vp, _i, _i64, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -1027,6 +1027,70 @@ int b200ps_push_end(b200ps_t* ps, int32_t* versions_out_host, void* stream) {
   return B200PS_OK;
 }
 
+// ---- kernel_api.h drop-ins on raw device arrays --------------------------------
+}  // extern "C"
+
+template <int OPT>
+static int raw_dense(const float* g, float* p, float* s0, float* s1, float* s2, long long n, float lr, float alpha,
+                     float l2adj, const OptParams& o, void* stream) {
+  if (!g || !p || n < 0) return fail(B200PS_EINVAL, "null array");
+  if (n == 0) return B200PS_OK;
+  bool vec = n % 4 == 0 && aligned16(g) && aligned16(p) && (!s0 || aligned16(s0)) && (!s1 || aligned16(s1)) &&
+             (!s2 || aligned16(s2));
+  long long work = vec ? n / 4 : n;
+  int grid = grid_for(nullptr, work);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) k_raw_dense<OPT, 4><<<grid, 256, 0, st>>>(g, p, s0, s1, s2, n, lr, alpha, l2adj, o);
+  else k_raw_dense<OPT, 1><<<grid, 256, 0, st>>>(g, p, s0, s1, s2, n, lr, alpha, l2adj, o);
+  count_launch(nullptr, 1);
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
+extern "C" {
+
+int b200ps_kernel_sgd(const float* grad, float* param, float lr, long long size, void* stream) {
+  OptParams o{};
+  o.kind = kSGD;
+  return raw_dense<kSGD>(grad, param, nullptr, nullptr, nullptr, size, lr, 0.f, 0.f, o, stream);
+}
+
+int b200ps_kernel_momentum(const float* grad, float* param, float* velocity, float mu, int nesterov, float lr,
+                           long long size, void* stream) {
+  if (!velocity) return fail(B200PS_EINVAL, "null velocity");
+  OptParams o{};
+  o.kind = kMomentum;
+  o.mu = mu;
+  o.nesterov = nesterov;
+  return raw_dense<kMomentum>(grad, param, velocity, nullptr, nullptr, size, lr, 0.f, 0.f, o, stream);
+}
+
+int b200ps_kernel_adam(const float* grad, float* param, float* m, float* v, float lr, long long size, long long step,
+                       float beta1, float beta2, float epsilon, float* max_square, void* stream) {
+  if (!m || !v) return fail(B200PS_EINVAL, "null moment array");
+  OptParams o{};
+  o.kind = max_square ? kAMSGrad : kAdam;
+  o.beta1 = beta1;
+  o.beta2 = beta2;
+  o.epsilon = epsilon;
+  o.c1 = (float)(1.0 - (double)beta1);
+  o.c2 = (float)(1.0 - (double)beta2);
+  // kernel_api.cc:67: lr *= sqrt(1 - pow(beta2, step)) / (1 - pow(beta1, step)), double math on the host
+  float alpha = (float)((double)lr * (std::sqrt(1.0 - std::pow((double)beta2, (double)step)) /
+                                      (1.0 - std::pow((double)beta1, (double)step))));
+  if (max_square) return raw_dense<kAMSGrad>(grad, param, m, v, max_square, size, lr, alpha, 0.f, o, stream);
+  return raw_dense<kAdam>(grad, param, m, v, nullptr, size, lr, alpha, 0.f, o, stream);
+}
+
+int b200ps_kernel_adagrad(const float* grad, float* param, float* m, float lr, long long size, float epsilon,
+                          void* stream) {
+  if (!m) return fail(B200PS_EINVAL, "null accumulator");
+  OptParams o{};
+  o.kind = kAdagrad;
+  o.epsilon = epsilon;
+  return raw_dense<kAdagrad>(grad, param, m, nullptr, nullptr, size, lr, 0.f, 0.f, o, stream);
+}
+
 // ---- unique / segment sum ------------------------------------------------------
 
 static int uniq_cap(int64_t k) {

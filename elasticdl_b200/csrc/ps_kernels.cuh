@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) k_push_rows_d8(GroupView gv, SegBatch sb,
     const bool live = row < n;
     long long id = (live && c == 0) ? sg.ids_dev[row] : 0;
     id = __shfl_sync(0xffffffffu, id, 0, LPR);
-    RowLoc loc = locate(gv, tv, live ? id : 0);
+    RowLoc loc = live ? locate(gv, tv, id) : RowLoc{nullptr, 0, 0, false};  // dead lanes must not claim a hashed slot
     const bool ok = live && loc.ok;
     if (live && !loc.ok && c == 0) atomicOr(gv.err, kErrRange);
     float* rec = loc.rec + 4 * c;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(256) k_pair_push(GroupView gv, PairBatch pb, O
     const bool live = row < n;
     long long id = (live && c == 0) ? sg.ids_dev[row] : 0;
     id = __shfl_sync(0xffffffffu, id, 0, LPR);
-    RowLoc loc = locate(gv, ta, live ? id : 0);
+    RowLoc loc = live ? locate(gv, ta, id) : RowLoc{nullptr, 0, 0, false};
     const bool ok = live && loc.ok;
     if (live && !loc.ok && c == 0) atomicOr(gv.err, kErrRange);
     float* rec = loc.rec + 4 * c;
@@ -568,6 +568,44 @@ __global__ void __launch_bounds__(256) k_push_dense(GroupView gv, SegBatch sb, O
 template <int OPT, int VEC, bool TWICE>
 __global__ void __launch_bounds__(256) k_push_dense_reduce(GroupView gv, int table, ReplicaGrads rg, OptParams o) {
   dense_update_range<OPT, VEC, TWICE>(gv, gv.tables[table], rg, o);
+}
+
+// The reference's own C ABI (go/pkg/kernel/capi/kernel_api.h:10-37) on raw device arrays:
+// grad / param / slot pointers + size, in place.
+template <int OPT, int VEC>
+__global__ void __launch_bounds__(256) k_raw_dense(const float* __restrict__ G, float* P, float* S0, float* S1, float* S2,
+                                                   long long n, float lr, float alpha, float l2adj, OptParams o) {
+  constexpr int S = opt_slots(OPT);
+  const long long nvec = n / VEC;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float g[VEC], p[VEC], s0[VEC], s1[VEC], s2[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(g) = ld_f4(G + 4 * i);
+      *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(P + 4 * i);
+      if (S > 0) *reinterpret_cast<float4*>(s0) = *reinterpret_cast<const float4*>(S0 + 4 * i);
+      if (S > 1) *reinterpret_cast<float4*>(s1) = *reinterpret_cast<const float4*>(S1 + 4 * i);
+      if (S > 2) *reinterpret_cast<float4*>(s2) = *reinterpret_cast<const float4*>(S2 + 4 * i);
+    } else {
+      g[0] = G[i]; p[0] = P[i];
+      if (S > 0) s0[0] = S0[i];
+      if (S > 1) s1[0] = S1[i];
+      if (S > 2) s2[0] = S2[i];
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) opt_update<OPT>(g[e], p[e], s0[e], s1[e], s2[e], lr, alpha, l2adj, o);
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(P + 4 * i) = *reinterpret_cast<float4*>(p);
+      if (S > 0) *reinterpret_cast<float4*>(S0 + 4 * i) = *reinterpret_cast<float4*>(s0);
+      if (S > 1) *reinterpret_cast<float4*>(S1 + 4 * i) = *reinterpret_cast<float4*>(s1);
+      if (S > 2) *reinterpret_cast<float4*>(S2 + 4 * i) = *reinterpret_cast<float4*>(s2);
+    } else {
+      P[i] = p[0];
+      if (S > 0) S0[i] = s0[0];
+      if (S > 1) S1[i] = s1[0];
+      if (S > 2) S2[i] = s2[0];
+    }
+  }
 }
 
 // pull_dense / set_dense: whole-parameter copy owner shard <-> caller buffer.

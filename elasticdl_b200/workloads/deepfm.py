@@ -137,13 +137,16 @@ class HostFeeder:
 
 class DeepFMPSEngine:
     def __init__(self, group, batch, lr=1e-3, init_std=0.01, seed=7, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM,
-                 init_rows=True, tower="fused", paired=True):
+                 init_rows=True, tower="fused", paired=None):
         """tower="fused": the hand-written CUDA tower (csrc/deepfm_tower.cu);
         tower="torch": torch autograd over library kernels (kept for A/B measurements and tests)."""
         assert tower in ("fused", "torch")
         self.tower_kind = tower
         # paired=True: the deep (dim 8) and wide (dim 1) tables of an id group share one record
         # per id, so one request per id serves both (ps_kernels.cuh "Paired tables")
+        # (default: when rows live on peer GPUs -- remote reads are bounded by requests in flight)
+        if paired is None:
+            paired = group.n_shards > 1
         self.paired = bool(paired) and deep_dim == 8
         self.group = group
         self.B = int(batch)

@@ -181,6 +181,18 @@ int b200ps_push_end(b200ps_t* ps, int32_t* versions_out_host, void* stream);
 /* step++ only (a failed ApplyGradients still bumps it, quirk Q2). */
 int b200ps_bump_step(b200ps_t* ps, void* stream);
 
+/* ---- the reference's native C ABI, on device arrays -------------------
+ * One-to-one with go/pkg/kernel/capi/kernel_api.h:10-37 (same argument order and meaning, a
+ * stream appended): in-place dense optimizer kernels on raw float arrays, same arithmetic
+ * (kernel_api.cc:6-96).  max_square == NULL selects plain Adam, else AMSGrad. */
+int b200ps_kernel_sgd(const float* grad, float* param, float lr, long long size, void* stream);
+int b200ps_kernel_momentum(const float* grad, float* param, float* velocity, float mu, int nesterov, float lr,
+                           long long size, void* stream);
+int b200ps_kernel_adam(const float* grad, float* param, float* m, float* v, float lr, long long size, long long step,
+                       float beta1, float beta2, float epsilon, float* max_square, void* stream);
+int b200ps_kernel_adagrad(const float* grad, float* param, float* m, float lr, long long size, float epsilon,
+                          void* stream);
+
 /* ---- id dedup (client side of the exchange) -------------------------- */
 
 /* These three take `ps` only for the device and the launch counter; ps may be

@@ -719,3 +719,53 @@ def test_unique_bounded_direct_address_segments():
             wu, wi = O.unique_first_occurrence(ids[t])
             assert c[t] == len(wu) and np.array_equal(u[t, : c[t]], wu) and np.array_equal(i[t], wi), t
     group.close()
+
+
+# ------------------------------------------------------------------ kernel_api.h drop-ins on raw device arrays
+@pytest.mark.parametrize("n", [10, 1001, 4096 * 33])
+def test_raw_kernel_api_matches_oracle_bit_exact(n):
+    """b200ps_kernel_{sgd,momentum,adam,adagrad} == kernel_api.cc via the oracle, bit for bit
+    (kernel_test.go:25-47 asserts exact equality for SGD)."""
+    import ctypes
+
+    from elasticdl_b200 import _lib
+
+    lib = _lib.lib()
+    rng = np.random.RandomState(n)
+    g, p, m, v, ms = [rng.rand(n).astype(F) for _ in range(5)]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def dev(*arrs):
+        return [torch.from_numpy(a.copy()).cuda() for a in arrs]
+
+    # SGD
+    dg, dp = dev(g, p)
+    _lib.check(lib.b200ps_kernel_sgd(dg.data_ptr(), dp.data_ptr(), 0.1, n, st))
+    want = p.copy()
+    O.lib.oracle_sgd(O._f32(g), O._f32(want), 0.1, n)
+    assert np.array_equal(dp.cpu().numpy(), want)
+    # Momentum / Nesterov
+    for nesterov in (0, 1):
+        dg, dp, dv = dev(g, p, v)
+        _lib.check(lib.b200ps_kernel_momentum(dg.data_ptr(), dp.data_ptr(), dv.data_ptr(), 0.9, nesterov, 0.05, n, st))
+        wp, wv = p.copy(), v.copy()
+        O.lib.oracle_momentum(O._f32(g), O._f32(wp), O._f32(wv), 0.9, nesterov, 0.05, n)
+        assert np.array_equal(dp.cpu().numpy(), wp) and np.array_equal(dv.cpu().numpy(), wv)
+    # Adam / AMSGrad (kernel_test.go:69-180: step 5, lr .1, betas .9/.999, eps 1e-8)
+    for ams in (False, True):
+        dg, dp, dm, dv, dms = dev(g, p, m, v, ms)
+        _lib.check(lib.b200ps_kernel_adam(dg.data_ptr(), dp.data_ptr(), dm.data_ptr(), dv.data_ptr(), 0.1, n, 5, 0.9,
+                                          0.999, 1e-8, dms.data_ptr() if ams else None, st))
+        wp, wm, wv, wms = p.copy(), m.copy(), v.copy(), ms.copy()
+        O.lib.oracle_adam(O._f32(g), O._f32(wp), O._f32(wm), O._f32(wv), 0.1, n, 5, 0.9, 0.999, 1e-8,
+                          O._f32(wms) if ams else O._null_f32())
+        assert np.array_equal(dp.cpu().numpy(), wp) and np.array_equal(dm.cpu().numpy(), wm)
+        assert np.array_equal(dv.cpu().numpy(), wv)
+        if ams:
+            assert np.array_equal(dms.cpu().numpy(), wms)
+    # Adagrad
+    dg, dp, dm = dev(g, p, m)
+    _lib.check(lib.b200ps_kernel_adagrad(dg.data_ptr(), dp.data_ptr(), dm.data_ptr(), 0.05, n, 1e-7, st))
+    wp, wm = p.copy(), m.copy()
+    O.lib.oracle_adagrad(O._f32(g), O._f32(wp), O._f32(wm), 0.05, n, 1e-7)
+    assert np.array_equal(dp.cpu().numpy(), wp) and np.array_equal(dm.cpu().numpy(), wm)
