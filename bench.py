@@ -149,8 +149,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tower", default="fused", choices=["fused", "torch"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
-    ap.add_argument("--paired", default="auto", choices=["auto", "on", "off"],
-                    help="store each group's deep+wide rows as one record per id (auto: when shards are remote)")
+    ap.add_argument("--paired", default="off", choices=["on", "off"],
+                    help="store each group's deep+wide rows as one record per id")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "owner", "direct"],
+                    help="multi-GPU row exchange: owner-computes bulk exchange (default for N>1) or direct peer access")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -195,9 +197,10 @@ def main():
 
     group = PSGroup(world, "Adam", ADAM_ARGS, device=local_rank,
                     local_shards=[rank] if world > 1 else None)
-    paired = world > 1 if args.paired == "auto" else args.paired == "on"
-    engine = DeepFMPSEngine(group, args.batch, tower=args.tower, paired=paired)
+    engine = DeepFMPSEngine(group, args.batch, tower=args.tower, paired=args.paired == "on",
+                            exchange=None if args.exchange == "auto" else args.exchange)
     config["record_layout"] = "paired deep+wide record per id" if engine.paired else "one record slab per table"
+    config["exchange"] = engine.exchange
     use_graph = args.tower == "fused" and not args.no_graph
     if world > 1:
         dist.barrier()

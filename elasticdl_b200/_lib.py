@@ -73,6 +73,9 @@ SYMBOLS = {
     "b200ps_set_rows": (_i, [_vp, _segp, _i, _vp]),
     "b200ps_pull_rows_pair": (_i, [_vp, _segp, ctypes.POINTER(_vp), _i, _vp]),
     "b200ps_push_rows_pair": (_i, [_vp, _segp, ctypes.POINTER(_vp), _i, _vp]),
+    "b200ps_xchg_create": (_i, [_vp, _i, _i, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "b200ps_xchg_pull": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200ps_xchg_push": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "b200ps_pull_dense": (_i, [_vp, _segp, _i, _vp]),
     "b200ps_set_dense": (_i, [_vp, _segp, _i, _vp]),
     "b200ps_slot_rows": (_i, [_vp, _i, _i, _segp, _i, _vp]),
@@ -89,6 +92,7 @@ SYMBOLS = {
     "b200ps_kernel_adagrad": (_i, [_vp, _vp, _vp, _f, ctypes.c_longlong, _f, _vp]),
     "b200ps_unique_workspace": (_sz, [_i, _i64]),
     "b200ps_unique": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200ps_unique_bounded_workspace": (_sz, [_i, _i64, ctypes.POINTER(_i64)]),
     "b200ps_unique_bounded": (_i, [_vp, _vp, _i, _i64, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ps_segment_sum": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp]),
     "b200ps_gather_rows": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp]),

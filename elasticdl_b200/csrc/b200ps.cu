@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "ps_kernels.cuh"
+#include "ps_exchange.cuh"
 
 using namespace b200ps_impl;
 
@@ -64,6 +65,7 @@ struct Table {
   size_t present_off = 0;  // byte offset of the bitmap inside the allocation
   size_t keys_off = 0;     // byte offset of the key array (hashed tables), 0 = direct-indexed
   bool hashed = false;
+  bool raw = false;        // plain zero-filled bytes (the exchange buffer), no rows
   int pair_of = -1;        // >= 0: this table shares the record slab of table `pair_of` (b200ps_table_register_pair)
   int pair_b = -1;         // table A of a pair: id of its partner
   size_t base_off = 0;     // byte offset of this table's first float inside the shared allocation
@@ -116,6 +118,11 @@ struct b200ps {
   long long* d_state = nullptr;
   long long launches = 0;
   int n_sm = 148;
+  // owner-computes exchange (b200ps_xchg_*)
+  int x_table = -1, x_G = 0, x_B = 0, x_me = -1;
+  long long x_cap = 0, x_off_req = 0, x_off_resp = 0, x_off_upd = 0;
+  int* d_x_deep = nullptr;
+  int* d_x_wide = nullptr;
   std::mutex mu;
 };
 
@@ -281,7 +288,7 @@ int alloc_table_on_shard(b200ps_t* ps, Table& t, int s, int table_id) {
     a.is_dense = 1;
     a.seed = t.seed ^ (0x9E3779B97F4A7C15ULL * (uint64_t)(s + 1));
   }
-  bool need_kernel = t.uniform || (ps->opt.kind == kFTRL && ps->opt.init_accum != 0.0f);
+  bool need_kernel = !t.raw && (t.uniform || (ps->opt.kind == kFTRL && ps->opt.init_accum != 0.0f));
   if (need_kernel) {
     if (t.bytes > t.present_off && t.present_off) CUDA_OK(cudaMemsetAsync((char*)p + t.present_off, 0, t.bytes - t.present_off, 0));
     long long work = t.rows * (long long)t.dim * (t.n_slots + 1);
@@ -441,6 +448,8 @@ int b200ps_destroy(b200ps_t* ps) {
   cudaFree(ps->d_versions);
   cudaFree(ps->d_count);
   cudaFree(ps->d_state);
+  cudaFree(ps->d_x_deep);
+  cudaFree(ps->d_x_wide);
   delete ps;
   return B200PS_OK;
 }
@@ -954,6 +963,113 @@ int b200ps_push_rows_pair(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const
   return B200PS_OK;
 }
 
+// ---- owner-computes exchange (ps_exchange.cuh) ----------------------------------
+int b200ps_xchg_create(b200ps_t* ps, int G, int B, const int32_t* deep_tables, const int32_t* wide_tables) {
+  if (!ps || G < 1 || B < 1 || !deep_tables || !wide_tables) return fail(B200PS_EINVAL, "bad exchange definition");
+  if (ps->x_table >= 0) return fail(B200PS_ESTATE, "exchange already created");
+  int me = -1, n_local = 0;
+  for (int s = 0; s < ps->n_shards; ++s)
+    if (ps->shard[s].local) { me = s; ++n_local; }
+  if (n_local != 1) return fail(B200PS_ESTATE, "the exchange needs exactly one local shard per process (rank-per-GPU)");
+  for (int g = 0; g < G; ++g) {
+    if (deep_tables[g] < 0 || deep_tables[g] >= (int)ps->tables.size() || wide_tables[g] < 0 ||
+        wide_tables[g] >= (int)ps->tables.size())
+      return fail(B200PS_ENOTFOUND, "unknown table id in exchange definition");
+    if (ps->tables[deep_tables[g]].dim != 8 || ps->tables[wide_tables[g]].dim != 1)
+      return fail(B200PS_EWIDTH, "the exchange moves dim-8 / dim-1 table pairs");
+  }
+  ps->x_G = G;
+  ps->x_B = B;
+  ps->x_me = me;
+  ps->x_cap = (long long)G * B;
+  const long long n = ps->n_shards;
+  ps->x_off_req = 4096;
+  ps->x_off_resp = ps->x_off_req + n * ps->x_cap * kXEntryReq;
+  ps->x_off_upd = ps->x_off_resp + n * ps->x_cap * kXEntryResp;
+  const long long bytes = ps->x_off_upd + n * ps->x_cap * kXEntryUpd;
+  static_assert(sizeof(XHeader) <= 4096, "exchange header must fit its page");
+  {
+    std::lock_guard<std::mutex> lk(ps->mu);
+    Table t;
+    t.name = "__xchg__";
+    t.dim = 1;
+    t.owner = -1;
+    t.raw = true;
+    t.rows = bytes / 4;
+    t.row_stride = 1;
+    t.bytes = ((size_t)bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+    int id = register_common(ps, std::move(t));
+    if (id < 0) return id;
+    ps->x_table = id;
+  }
+  DeviceGuard g(ps->client_device);
+  CUDA_OK(cudaMalloc(&ps->d_x_deep, sizeof(int) * G));
+  CUDA_OK(cudaMalloc(&ps->d_x_wide, sizeof(int) * G));
+  CUDA_OK(cudaMemcpy(ps->d_x_deep, deep_tables, sizeof(int) * G, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(ps->d_x_wide, wide_tables, sizeof(int) * G, cudaMemcpyHostToDevice));
+  return B200PS_OK;
+}
+
+static int xview(b200ps_t* ps, XView* x) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  if (ps->x_table < 0) return fail(B200PS_ESTATE, "b200ps_xchg_create not called");
+  const Table& t = ps->tables[ps->x_table];
+  for (int s = 0; s < ps->n_shards; ++s) {
+    if (!t.alloc[s].ptr) return fail(B200PS_ESTATE, "exchange buffer of shard " + std::to_string(s) + " is not mapped (sync peers)");
+    x->buf[s] = (char*)t.alloc[s].ptr;
+  }
+  x->off_req = ps->x_off_req;
+  x->off_resp = ps->x_off_resp;
+  x->off_upd = ps->x_off_upd;
+  x->cap = ps->x_cap;
+  x->deep_tab = ps->d_x_deep;
+  x->wide_tab = ps->d_x_wide;
+  x->n = ps->n_shards;
+  x->me = ps->x_me;
+  x->G = ps->x_G;
+  x->B = ps->x_B;
+  return B200PS_OK;
+}
+
+int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, float* bet_deep_dev,
+                     float* bet_wide_dev, void* stream) {
+  XView x;
+  int rc = xview(ps, &x);
+  if (rc) return rc;
+  DeviceGuard g(ps->client_device);
+  cudaStream_t st = (cudaStream_t)stream;
+  GroupView gv = group_view(ps);
+  const int per_src = ps->n_sm * 16 / ps->n_shards < 4 ? 4 : ps->n_sm * 16 / ps->n_shards;
+  k_x_begin<<<1, 32, 0, st>>>(x);
+  k_x_send<false><<<grid_for(ps, x.cap), 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, nullptr, nullptr);
+  k_x_serve<<<dim3(per_src, ps->n_shards), 256, 0, st>>>(x, gv);
+  k_x_unscatter<<<dim3(per_src, ps->n_shards), 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
+  ps->launches += 4;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
+int b200ps_xchg_push(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, const float* gsum_deep_dev,
+                     const float* gsum_wide_dev, void* stream) {
+  XView x;
+  int rc = xview(ps, &x);
+  if (rc) return rc;
+  DeviceGuard g(ps->client_device);
+  cudaStream_t st = (cudaStream_t)stream;
+  GroupView gv = group_view(ps);
+  OptParams o = ps->opt;
+  const int per_src = ps->n_sm * 16 / ps->n_shards < 4 ? 4 : ps->n_sm * 16 / ps->n_shards;
+  k_x_begin<<<1, 32, 0, st>>>(x);
+  k_x_send<true><<<grid_for(ps, x.cap), 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, gsum_deep_dev, gsum_wide_dev);
+  dim3 grid(per_src, ps->n_shards);
+  DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
+  k_x_wait_applied<<<1, 32, 0, st>>>(x, gv);
+  ps->launches += 4;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
 int b200ps_push_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream) {
   int rc = ready(ps);
   if (rc) return rc;
@@ -1101,6 +1217,18 @@ static int uniq_cap(int64_t k) {
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+static size_t bounded_extra(int T, const int64_t* bounds) {
+  size_t extra = 0;
+  if (bounds && T <= kMaxSegs)
+    for (int t = 0; t < T; ++t)
+      if (bounds[t] > 0 && bounds[t] <= (1LL << 30)) extra += align256((size_t)bounds[t] * 4);
+  return extra;
+}
+
+size_t b200ps_unique_bounded_workspace(int T, int64_t k, const int64_t* bounds) {
+  return b200ps_unique_workspace(T, k) + bounded_extra(T, bounds);
+}
+
 size_t b200ps_unique_workspace(int T, int64_t k) {
   if (T < 1 || k < 1) return 256;
   size_t cap = (size_t)uniq_cap(k);
@@ -1124,6 +1252,7 @@ int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k
                           size_t workspace_bytes, void* stream) {
   if (T < 1 || T > 65535 || k < 1 || k > (1LL << 30)) return fail(B200PS_EINVAL, "bad unique shape");
   if (workspace_bytes < b200ps_unique_workspace(T, k)) return fail(B200PS_EINVAL, "unique workspace too small");
+  if (bounds && workspace_bytes < b200ps_unique_bounded_workspace(T, k, bounds)) bounds = nullptr;  // no room: hash everything
   DeviceGuard g(client_dev(ps));
   cudaStream_t st = (cudaStream_t)stream;
   UniqueWs ws;
@@ -1137,13 +1266,22 @@ int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k
   ws.tile_cnt = (int*)p;
   UniqueBounds ub{};
   const int use_bounds = bounds != nullptr && T <= kMaxSegs;
-  if (use_bounds)
-    for (int t = 0; t < T; ++t) ub.bound[t] = bounds[t] > 0 && bounds[t] <= ws.cap ? (int)bounds[t] : 0;
-  dim3 gc((unsigned)((ws.cap + 2047) / 2048), T);
+  long long max_clear = ws.cap;
+  if (use_bounds) {
+    ub.dpos = (int*)((char*)workspace_dev + b200ps_unique_workspace(T, k));
+    long long off = 0;
+    for (int t = 0; t < T; ++t) {
+      ub.bound[t] = bounds[t] > 0 && bounds[t] <= (1LL << 30) ? (int)bounds[t] : 0;
+      ub.off[t] = off;
+      off += (long long)(align256((size_t)ub.bound[t] * 4) / 4);
+      if (ub.bound[t] > max_clear) max_clear = ub.bound[t];
+    }
+  }
+  dim3 gc((unsigned)((max_clear + 2047) / 2048), T);
   k_uniq_clear<<<gc, 256, 0, st>>>(ws, T, ub, use_bounds);
   dim3 gk((unsigned)((k + 255) / 256), T), gt(ws.ntiles, T);
   k_uniq_insert<<<gk, 256, 0, st>>>(ids_dev, k, ws, ub, use_bounds);
-  k_uniq_flag<<<gt, 256, 0, st>>>(k, ws);
+  k_uniq_flag<<<gt, 256, 0, st>>>(k, ws, ub, use_bounds);
   k_uniq_scan_tiles<<<T, 1024, 0, st>>>(ws, n_unique_dev);
   k_uniq_rank<<<gt, 256, 0, st>>>(ids_dev, k, ws, uniq_dev);
   k_uniq_inverse<<<gk, 256, 0, st>>>(k, ws, inv_dev);
@@ -1291,6 +1429,7 @@ int b200ps_check(b200ps_t* ps) {
   CUDA_OK(cudaMemcpy(&e, ps->d_err, 4, cudaMemcpyDeviceToHost));
   if (e) {
     CUDA_OK(cudaMemset(ps->d_err, 0, 4));
+    if (e & kErrTimeout) return fail(B200PS_ESTATE, "exchange wait timed out: a peer rank did not run the same step");
     if (e & kErrFull) return fail(B200PS_ERANGE, "hashed embedding table is full (raise expected_rows)");
     if (e & kErrRange) return fail(B200PS_ERANGE, "embedding id outside the registered table capacity (or negative)");
     return fail(B200PS_EINVAL, "device-side error word " + std::to_string(e));

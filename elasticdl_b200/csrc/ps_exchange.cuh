@@ -1,0 +1,326 @@
+// Owner-computes exchange for rank-per-GPU groups ("all-to-all-v" of the reference's per-shard RPC
+// fan-out, python/worker/ps_client.py:105-130,243-277, over NVLink).
+//
+// Measured on this box (tools/mgpu_probe.py): scattered 32 B accesses to a peer GPU -- reads AND
+// writes -- run at ~130-160 GB/s (a few G sectors/s), while coalesced peer traffic runs at the
+// link rate.  So nothing scattered crosses NVLink here: a requester buckets its unique ids by owner
+// and writes them CONTIGUOUSLY into the owner's inbox; the owner gathers rows from its own HBM and
+// writes them back CONTIGUOUSLY in request order; the requester un-scatters locally.  Updates travel
+// the same way and the owner applies the optimizer to its own shard.  Cross-GPU ordering uses
+// epoch flags in HBM (system-scope fences, last-block-done), all kernels are launched by every rank
+// in the same order (bulk-synchronous step), waits carry a timeout so a dead peer cannot hang a GPU.
+#pragma once
+#include "ps_kernels.cuh"
+
+namespace b200ps_impl {
+
+constexpr int kXEntryReq = 16;   // bytes: {int64 id; int32 dst; int32 grp}
+constexpr int kXEntryResp = 48;  // bytes: {float deep[8]; float wide; int32 dst; pad 2}
+constexpr int kXEntryUpd = 64;   // bytes: {int64 id; int32 grp; int32 pad; float g_deep[8]; float g_wide; pad 3}
+
+struct XHeader {  // at the start of every rank's exchange buffer
+  // owner side, written by the source ranks
+  int req_cnt[kMaxShards];
+  int upd_cnt[kMaxShards];
+  float upd_lr[kMaxShards], upd_alpha[kMaxShards], upd_l2adj[kMaxShards];
+  int flag_req[kMaxShards];  // == epoch when src's requests have landed
+  int flag_upd[kMaxShards];
+  // requester side, written by the owner ranks
+  int flag_resp[kMaxShards];     // [owner] == epoch when that owner's rows have landed
+  int flag_applied[kMaxShards];  // [owner] == epoch when that owner has applied my updates
+  // local scratch (never written remotely)
+  int epoch;
+  int cursor[kMaxShards];  // bucket cursors of the running send kernel
+  int sent[kMaxShards];    // entries sent to each owner by the last request pass
+  unsigned done_blocks;
+  unsigned done_src[kMaxShards];
+  int pad[9];
+};
+
+struct XView {
+  char* buf[kMaxShards];  // every rank's exchange buffer (peer-mapped); buf[me] is local
+  long long off_req, off_resp, off_upd;  // byte offsets of the three regions
+  long long cap;                         // entries per (owner, source) lane = G * B
+  const int* deep_tab;                   // [G] table ids (device)
+  const int* wide_tab;                   // [G]
+  int n, me, G, B;
+};
+
+__device__ __forceinline__ XHeader* xhdr(const XView& x, int r) { return reinterpret_cast<XHeader*>(x.buf[r]); }
+__device__ __forceinline__ char* xreq(const XView& x, int owner, int src) {
+  return x.buf[owner] + x.off_req + ((long long)src * x.cap) * kXEntryReq;
+}
+__device__ __forceinline__ char* xresp(const XView& x, int requester, int owner) {
+  return x.buf[requester] + x.off_resp + ((long long)owner * x.cap) * kXEntryResp;
+}
+__device__ __forceinline__ char* xupd(const XView& x, int owner, int src) {
+  return x.buf[owner] + x.off_upd + ((long long)src * x.cap) * kXEntryUpd;
+}
+
+constexpr unsigned kErrTimeout = 8u;
+
+// Spin until *flag >= epoch (written by a peer with a system-scope fence before it).
+__device__ __forceinline__ void wait_flag(const int* flag, int epoch, unsigned* err) {
+  const volatile int* f = flag;
+  for (long long spins = 0; spins < (1LL << 24); ++spins) {  // ~2 s with the sleep below
+    if (*f >= epoch) {
+      __threadfence_system();
+      return;
+    }
+    __nanosleep(100);
+  }
+  atomicOr(err, kErrTimeout);
+}
+
+__global__ void k_x_begin(XView x) {  // one thread: new epoch, clear the send cursors
+  XHeader* h = xhdr(x, x.me);
+  if (threadIdx.x == 0) {
+    h->epoch += 1;
+    h->done_blocks = 0;
+  }
+  if (threadIdx.x < kMaxShards) {
+    h->cursor[threadIdx.x] = 0;
+    h->done_src[threadIdx.x] = 0;
+  }
+}
+
+// Requester: bucket (id, dst) by owner into the owners' inboxes.  UPD: also ship the gradient rows.
+template <bool UPD>
+__global__ void __launch_bounds__(256) k_x_send(XView x, GroupView gv, const int64_t* __restrict__ uniq,
+                                                const int* __restrict__ n_unique, const float* __restrict__ gsum_d,
+                                                const float* __restrict__ gsum_w) {
+  XHeader* h = xhdr(x, x.me);
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)x.G * x.B;
+  const long long total_pad = (total + 31) / 32 * 32;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_pad; i += stride) {
+    const int g = (int)(i / x.B);
+    const int r = (int)(i - (long long)g * x.B);
+    const bool live = i < total && r < n_unique[g];
+    const long long id = live ? uniq[i] : 0;
+    int owner = -1 - lane;  // dead lanes never match
+    if (live) owner = gv.shard_shift >= 0 ? (int)(id & (x.n - 1)) : (int)(id % x.n);
+    // warp-aggregated cursor bump: lanes with the same owner get consecutive entries (contiguous writes)
+    const unsigned peers = __match_any_sync(0xffffffffu, owner);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (live && lane == leader) base = atomicAdd(&h->cursor[owner], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!live) continue;
+    const int pos = base + __popc(peers & ((1u << lane) - 1));
+    if (!UPD) {
+      int4 e;
+      e.x = (int)(id & 0xffffffffLL);
+      e.y = (int)(id >> 32);
+      e.z = (int)i;  // dst = g * B + r
+      e.w = g;
+      *reinterpret_cast<int4*>(xreq(x, owner, x.me) + (long long)pos * kXEntryReq) = e;
+    } else {
+      float4* dst = reinterpret_cast<float4*>(xupd(x, owner, x.me) + (long long)pos * kXEntryUpd);
+      int4 e;
+      e.x = (int)(id & 0xffffffffLL);
+      e.y = (int)(id >> 32);
+      e.z = g;
+      e.w = 0;
+      const float4* gd = reinterpret_cast<const float4*>(gsum_d + i * 8);
+      dst[0] = *reinterpret_cast<float4*>(&e);
+      dst[1] = gd[0];
+      dst[2] = gd[1];
+      dst[3] = make_float4(gsum_w[i], 0.f, 0.f, 0.f);
+    }
+  }
+  // publish: every block fences its writes; the last block to finish posts the counts and the flags
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&h->done_blocks, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  const int epoch = h->epoch;
+  if (threadIdx.x < x.n) {
+    const int o = threadIdx.x;
+    const int cnt = *(volatile int*)&h->cursor[o];
+    XHeader* oh = xhdr(x, o);
+    if (!UPD) {
+      h->sent[o] = cnt;
+      oh->req_cnt[x.me] = cnt;
+    } else {
+      oh->upd_cnt[x.me] = cnt;
+      oh->upd_lr[x.me] = gv.rt->lr[o];
+      oh->upd_alpha[x.me] = gv.rt->alpha[o];
+      oh->upd_l2adj[x.me] = gv.rt->l2adj[o];
+    }
+    __threadfence_system();
+    if (!UPD) *(volatile int*)&oh->flag_req[x.me] = epoch;
+    else *(volatile int*)&oh->flag_upd[x.me] = epoch;
+  }
+  if (threadIdx.x == 0) h->done_blocks = 0;
+  if (threadIdx.x < kMaxShards) h->cursor[threadIdx.x] = 0;
+}
+
+__device__ __forceinline__ long long entry_id(int4 e) {
+  return (long long)(((unsigned long long)(unsigned)e.y << 32) | (unsigned)e.x);
+}
+
+// Owner: serve the requests of source rank blockIdx.y from the local shard, rows back in request order.
+__global__ void __launch_bounds__(256) k_x_serve(XView x, GroupView gv) {
+  const int src = blockIdx.y;
+  XHeader* h = xhdr(x, x.me);
+  __shared__ int s_epoch, s_cnt;
+  if (threadIdx.x == 0) {
+    s_epoch = h->epoch;
+    wait_flag(&h->flag_req[src], s_epoch, gv.err);
+    s_cnt = *(volatile int*)&h->req_cnt[src];
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  const char* req = xreq(x, x.me, src);
+  char* resp = xresp(x, src, x.me);  // remote (or local when src == me), contiguous
+  const int lane4 = threadIdx.x & 3;  // 4 lanes per entry: deep lo, deep hi, {wide, dst}, idle
+  const long long stride = (long long)gridDim.x * blockDim.x / 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i < cnt; i += stride) {
+    const int4 e = *reinterpret_cast<const int4*>(req + i * kXEntryReq);
+    const long long id = entry_id(e);
+    const TableView& td = gv.tables[x.deep_tab[e.w]];
+    RowLoc loc = locate(gv, td, id);
+    if (!loc.ok) {
+      if (lane4 == 0) atomicOr(gv.err, kErrRange);
+      continue;
+    }
+    float4* out = reinterpret_cast<float4*>(resp + i * kXEntryResp);
+    if (lane4 < 2) {
+      out[lane4] = ld_f4(loc.rec + 4 * lane4);
+      if (lane4 == 0) mark_present(td, loc);
+    } else if (lane4 == 2) {
+      const TableView& tw = gv.tables[x.wide_tab[e.w]];
+      RowLoc lw = locate(gv, tw, id);
+      const float w = lw.ok ? *lw.rec : 0.f;
+      if (lw.ok) mark_present(tw, lw);
+      out[2] = make_float4(w, __int_as_float(e.z), 0.f, 0.f);
+    }
+  }
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&h->done_src[src], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence_system();
+    *(volatile int*)&xhdr(x, src)->flag_resp[x.me] = s_epoch;
+    h->done_src[src] = 0;
+  }
+}
+
+// Requester: rows of owner blockIdx.y have landed in my response region -> bet_d / bet_w.
+__global__ void __launch_bounds__(256) k_x_unscatter(XView x, GroupView gv, float* bet_d, float* bet_w) {
+  const int owner = blockIdx.y;
+  XHeader* h = xhdr(x, x.me);
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) {
+    wait_flag(&h->flag_resp[owner], h->epoch, gv.err);
+    s_cnt = h->sent[owner];
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  const char* resp = xresp(x, x.me, owner);
+  const int lane4 = threadIdx.x & 3;
+  const long long stride = (long long)gridDim.x * blockDim.x / 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i < cnt; i += stride) {
+    const float4* in = reinterpret_cast<const float4*>(resp + i * kXEntryResp);
+    const float4 tail = in[2];
+    const int dst = __float_as_int(tail.y);
+    if (lane4 < 2) *reinterpret_cast<float4*>(bet_d + (long long)dst * 8 + 4 * lane4) = in[lane4];
+    else if (lane4 == 2) bet_w[dst] = tail.x;
+  }
+}
+
+// Owner: apply the updates of source rank blockIdx.y to the local shard (its own ApplyGradients:
+// lr / Adam alpha were fixed by the source's push_begin on this shard).
+template <int OPT>
+__global__ void __launch_bounds__(256) k_x_apply(XView x, GroupView gv, OptParams o) {
+  constexpr int S = opt_slots(OPT);
+  const int src = blockIdx.y;
+  XHeader* h = xhdr(x, x.me);
+  __shared__ int s_epoch, s_cnt;
+  __shared__ float s_lr, s_alpha, s_l2;
+  if (threadIdx.x == 0) {
+    s_epoch = h->epoch;
+    wait_flag(&h->flag_upd[src], s_epoch, gv.err);
+    s_cnt = *(volatile int*)&h->upd_cnt[src];
+    s_lr = *(volatile float*)&h->upd_lr[src];
+    s_alpha = *(volatile float*)&h->upd_alpha[src];
+    s_l2 = *(volatile float*)&h->upd_l2adj[src];
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  const float lr = s_lr, alpha = s_alpha, l2adj = s_l2;
+  const char* upd = xupd(x, x.me, src);
+  const int lane4 = threadIdx.x & 3;  // deep lo, deep hi, wide, idle
+  const long long stride = (long long)gridDim.x * blockDim.x / 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i < cnt; i += stride) {
+    const float4* in = reinterpret_cast<const float4*>(upd + i * kXEntryUpd);
+    const float4 hd = in[0];
+    const int4 e = *reinterpret_cast<const int4*>(&hd);
+    const long long id = entry_id(e);
+    const TableView& td = gv.tables[x.deep_tab[e.z]];
+    RowLoc loc = locate(gv, td, id);
+    if (!loc.ok) {
+      if (lane4 == 0) atomicOr(gv.err, kErrRange);
+      continue;
+    }
+    if (lane4 < 2) {
+      float* rec = loc.rec + 4 * lane4;
+      float4 g = in[1 + lane4], p = ld_f4(rec), s0 = p, s1 = p, s2 = p;
+      if (S > 0) s0 = ld_f4(rec + td.slot_off[1]);
+      if (S > 1) s1 = ld_f4(rec + td.slot_off[2]);
+      if (S > 2) s2 = ld_f4(rec + td.slot_off[3]);
+      if (lane4 == 0) mark_present(td, loc);
+      float* gf = reinterpret_cast<float*>(&g);
+      float* pf = reinterpret_cast<float*>(&p);
+      float* af = reinterpret_cast<float*>(&s0);
+      float* bf = reinterpret_cast<float*>(&s1);
+      float* cf = reinterpret_cast<float*>(&s2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) opt_update<OPT>(gf[k], pf[k], af[k], bf[k], cf[k], lr, alpha, l2adj, o);
+      st_f4(rec, p);
+      if (S > 0) st_f4(rec + td.slot_off[1], s0);
+      if (S > 1) st_f4(rec + td.slot_off[2], s1);
+      if (S > 2) st_f4(rec + td.slot_off[3], s2);
+    } else if (lane4 == 2) {
+      const TableView& tw = gv.tables[x.wide_tab[e.z]];
+      RowLoc lw = locate(gv, tw, id);
+      if (!lw.ok) continue;
+      float* rec = lw.rec;
+      float g = in[3].x, p = *rec, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      if (S > 0) s0 = rec[tw.slot_off[1]];
+      if (S > 1) s1 = rec[tw.slot_off[2]];
+      if (S > 2) s2 = rec[tw.slot_off[3]];
+      mark_present(tw, lw);
+      opt_update<OPT>(g, p, s0, s1, s2, lr, alpha, l2adj, o);
+      *rec = p;
+      if (S > 0) rec[tw.slot_off[1]] = s0;
+      if (S > 1) rec[tw.slot_off[2]] = s1;
+      if (S > 2) rec[tw.slot_off[3]] = s2;
+    }
+  }
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&h->done_src[src], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence_system();
+    *(volatile int*)&xhdr(x, src)->flag_applied[x.me] = s_epoch;
+    h->done_src[src] = 0;
+  }
+}
+
+// Requester: all owners have applied my updates (my next pull observes my own push).
+__global__ void k_x_wait_applied(XView x, GroupView gv) {
+  XHeader* h = xhdr(x, x.me);
+  if (threadIdx.x < x.n) wait_flag(&h->flag_applied[threadIdx.x], h->epoch, gv.err);
+}
+
+}  // namespace b200ps_impl

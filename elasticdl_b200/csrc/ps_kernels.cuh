@@ -760,8 +760,10 @@ __global__ void __launch_bounds__(256) k_present_ids(const uint32_t* present, lo
 constexpr long long kEmptyKey = (long long)0x8000000000000000ULL;
 constexpr int kTile = 1024;  // ids per block in B / D (256 threads x 4)
 
-struct UniqueBounds {  // per segment: ids are known to be < bound (0 = unknown).  bound <= cap turns the
-  int bound[kMaxSegs];  // segment's table into a direct-address array: no keys, no CAS, no probing
+struct UniqueBounds {      // per segment: ids are known to be < bound (0 = unknown): the segment dedups
+  int bound[kMaxSegs];     // through a direct-address position array dpos[off .. off+bound) instead of
+  long long off[kMaxSegs]; // the hash table: no keys, no CAS, no probing
+  int* dpos;
 };
 
 struct UniqueWs {
@@ -776,10 +778,10 @@ struct UniqueWs {
 
 __global__ void __launch_bounds__(256) k_uniq_clear(UniqueWs ws, int T, UniqueBounds ub, int use_bounds) {
   const int t = blockIdx.y;
-  const int direct = use_bounds && ub.bound[t] > 0 && ub.bound[t] <= ws.cap;
+  const int direct = use_bounds && ub.bound[t] > 0;
   const int n = direct ? ub.bound[t] : ws.cap;
   long long* keys = ws.keys + (long long)t * ws.cap;
-  int* minpos = ws.minpos + (long long)t * ws.cap;
+  int* minpos = direct ? ub.dpos + ub.off[t] : ws.minpos + (long long)t * ws.cap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (!direct) keys[i] = kEmptyKey;
     minpos[i] = 0x7fffffff;
@@ -789,12 +791,12 @@ __global__ void __launch_bounds__(256) k_uniq_clear(UniqueWs ws, int T, UniqueBo
 __global__ void __launch_bounds__(256) k_uniq_insert(const int64_t* ids, long long k, UniqueWs ws, UniqueBounds ub,
                                                      int use_bounds) {
   const int t = blockIdx.y;
-  if (use_bounds && ub.bound[t] > 0 && ub.bound[t] <= ws.cap) {  // direct-address segment (block-uniform)
+  if (use_bounds && ub.bound[t] > 0) {  // direct-address segment (block-uniform)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k) return;
     long long id = ids[t * k + i];
     if (id < 0 || id >= ub.bound[t]) id = 0;  // out-of-range ids are reported by the table kernels
-    int* minpos = ws.minpos + (long long)t * ws.cap;
+    int* minpos = ub.dpos + ub.off[t];
     if (*(volatile int*)&minpos[id] > (int)i) atomicMin(&minpos[id], (int)i);
     ws.fp[t * k + i] = (int)id;
     return;
@@ -838,11 +840,11 @@ __device__ __forceinline__ int block_sum_256(int v, int* smem) {
   return tot;  // valid on thread 0
 }
 
-__global__ void __launch_bounds__(256) k_uniq_flag(long long k, UniqueWs ws) {
+__global__ void __launch_bounds__(256) k_uniq_flag(long long k, UniqueWs ws, UniqueBounds ub, int use_bounds) {
   __shared__ int red[8];
   const int t = blockIdx.y;
   const long long base = (long long)blockIdx.x * kTile;
-  const int* minpos = ws.minpos + (long long)t * ws.cap;
+  const int* minpos = (use_bounds && ub.bound[t] > 0) ? ub.dpos + ub.off[t] : ws.minpos + (long long)t * ws.cap;
   int* fp = ws.fp + t * k;
   int cnt = 0;
 #pragma unroll

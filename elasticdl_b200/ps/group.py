@@ -198,6 +198,14 @@ class PSGroup:
             ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in rows_b[i:i + half]])
             check(fn(self._h, arr, ptrs, n, self._stream()))
 
+    def xchg_create(self, G, B, deep_table_ids, wide_table_ids):
+        """Collective: allocate this rank's owner-computes exchange buffer (csrc/ps_exchange.cuh) for G
+        (dim-8, dim-1) table pairs and batches of B ids per group, then map the peers' buffers."""
+        d = (ctypes.c_int32 * G)(*[int(t) for t in deep_table_ids])
+        w = (ctypes.c_int32 * G)(*[int(t) for t in wide_table_ids])
+        check(self.lib.b200ps_xchg_create(self._h, int(G), int(B), d, w))
+        self.commit()
+
     def register_dense(self, name, shape, shard):
         if name in self.tables:
             return self.tables[name][0]

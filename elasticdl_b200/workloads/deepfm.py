@@ -137,7 +137,7 @@ class HostFeeder:
 
 class DeepFMPSEngine:
     def __init__(self, group, batch, lr=1e-3, init_std=0.01, seed=7, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM,
-                 init_rows=True, tower="fused", paired=None):
+                 init_rows=True, tower="fused", paired=None, exchange=None):
         """tower="fused": the hand-written CUDA tower (csrc/deepfm_tower.cu);
         tower="torch": torch autograd over library kernels (kept for A/B measurements and tests)."""
         assert tower in ("fused", "torch")
@@ -146,8 +146,17 @@ class DeepFMPSEngine:
         # per id, so one request per id serves both (ps_kernels.cuh "Paired tables")
         # (default: when rows live on peer GPUs -- remote reads are bounded by requests in flight)
         if paired is None:
-            paired = group.n_shards > 1
+            paired = False
         self.paired = bool(paired) and deep_dim == 8
+        # exchange="owner": rank-per-GPU groups bucket ids by owner and move everything over NVLink in
+        # contiguous runs, the owner serves / updates its own shard (csrc/ps_exchange.cuh);
+        # exchange="direct": kernels dereference the peer shard row by row.
+        if exchange is None:
+            exchange = "owner" if (group.n_shards > 1 and len(group.local_shards) == 1 and deep_dim == 8) else "direct"
+        assert exchange in ("owner", "direct")
+        self.exchange = exchange
+        if exchange == "owner":
+            self.paired = False
         self.group = group
         self.B = int(batch)
         self.G = len(group_rows)
@@ -213,7 +222,10 @@ class DeepFMPSEngine:
         self.uniq = torch.empty(G * B, dtype=torch.int64, device=dev)
         self.inv = torch.empty(G * B, dtype=torch.int32, device=dev)
         self.n_unique = torch.empty(G, dtype=torch.int32, device=dev)
-        self.ws = torch.empty(group.lib.b200ps_unique_workspace(G, B), dtype=torch.uint8, device=dev)
+        import ctypes as _ctb
+
+        self.bounds = (_ctb.c_int64 * G)(*[int(r) for r in group_rows])  # id ranges: dedup by direct address
+        self.ws = torch.empty(group.lib.b200ps_unique_bounded_workspace(G, B, self.bounds), dtype=torch.uint8, device=dev)
         self.bet_w = torch.zeros((G * B, 1), **f32)
         self.bet_d = torch.zeros((G * B, D), **f32)
         self.act_w = torch.empty((G * B, 1), **f32)
@@ -224,11 +236,11 @@ class DeepFMPSEngine:
         self.loss_buf = torch.zeros(1, **f32)
         self.logits_buf = torch.empty(B, **f32)
         self.zero_versions = [0] * group.n_shards
-        import ctypes as _ct0
 
-        self.bounds = (_ct0.c_int64 * G)(*[int(r) for r in group_rows])  # id ranges: small groups dedup by direct address
         self.loss_fn = torch.nn.BCEWithLogitsLoss()
         self._build_segs()
+        if self.exchange == "owner":
+            group.xchg_create(G, B, self.deep_ids, self.wide_ids)
         self.steps = 0
 
     def _seg_items(self, ids_tab, rows, dim):
@@ -300,7 +312,12 @@ class DeepFMPSEngine:
                                         self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st))
         done(e)
         # (3) pull the unique rows of all 76 tables
-        if self.paired:
+        if self.exchange == "owner":
+            e = mark("pull_exchange")
+            check(lib.b200ps_xchg_pull(h, self.uniq.data_ptr(), self.n_unique.data_ptr(), self.bet_d.data_ptr(),
+                                       self.bet_w.data_ptr(), st))
+            done(e)
+        elif self.paired:
             e = mark("pull_pair")
             for arr, ptrs, n in self.pull_pair:
                 check(lib.b200ps_pull_rows_pair(h, arr, ptrs, n, st))
@@ -329,7 +346,12 @@ class DeepFMPSEngine:
         g.push_begin(self.lr, self.zero_versions)
         arr, n = dense_segs
         check(lib.b200ps_push_dense(h, arr, n, st))
-        if self.paired:
+        if self.exchange == "owner":
+            e = mark("push_exchange")
+            check(lib.b200ps_xchg_push(h, self.uniq.data_ptr(), self.n_unique.data_ptr(), self.gsum_d.data_ptr(),
+                                       self.gsum_w.data_ptr(), st))
+            done(e)
+        elif self.paired:
             e = mark("push_pair")
             for arr, ptrs, n in self.push_pair:
                 check(lib.b200ps_push_rows_pair(h, arr, ptrs, n, st))
@@ -429,7 +451,8 @@ class DeepFMPSEngine:
             U = sum(uniq_per_step) / max(len(uniq_per_step), 1)
             nbytes = {
                 "pull_wide": U * (8 + 8 * 1), "pull_deep": U * (8 + 8 * D),
-                "pull_pair": U * (8 + 8 * D + 8 * 1),
+                "pull_pair": U * (8 + 8 * D + 8 * 1), "pull_exchange": U * (8 + 8 * D + 8 * 1),
+                "push_exchange": U * (8 + 4 * D + 4 * 1 + (1 + opt_slots) * 8 * (D + 1)),
                 "push_pair": U * (8 + 4 * D + 4 * 1 + (1 + opt_slots) * 8 * (D + 1)),
                 "push_wide": U * (8 + 4 * 1 + (1 + opt_slots) * 8 * 1),
                 "push_deep": U * (8 + 4 * D + (1 + opt_slots) * 8 * D),

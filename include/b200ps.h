@@ -143,6 +143,19 @@ int b200ps_set_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stre
 int b200ps_pull_rows_pair(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const* rows_b, int nseg, void* stream);
 int b200ps_push_rows_pair(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const* grads_b, int nseg, void* stream);
 
+/* Owner-computes exchange for rank-per-GPU groups (csrc/ps_exchange.cuh): instead of touching peer
+ * rows one by one, each rank buckets its unique ids by owner, ships them contiguously over NVLink,
+ * the owner serves / updates its own shard, and rows return contiguously.  Every rank must issue
+ * the same xchg calls in the same order (bulk-synchronous step).  Tables come in (dim-8, dim-1)
+ * pairs addressed by the same ids; uniq / n_unique / bet / gsum are the [G][B] buffers of
+ * b200ps_unique.  create: collective, then re-export / import the shards (the exchange buffer is
+ * a peer-mapped allocation).  push belongs between b200ps_push_begin and b200ps_push_end. */
+int b200ps_xchg_create(b200ps_t* ps, int G, int B, const int32_t* deep_tables, const int32_t* wide_tables);
+int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, float* bet_deep_dev,
+                     float* bet_wide_dev, void* stream);
+int b200ps_xchg_push(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, const float* gsum_deep_dev,
+                     const float* gsum_wide_dev, void* stream);
+
 /* ≙ PullDenseParameters payload (server.go:144-160): copy whole dense
  * parameters owner-shard -> dst (segs[i].rows_dev; ids_dev/n ignored). */
 int b200ps_pull_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream);
@@ -205,6 +218,7 @@ int b200ps_kernel_adagrad(const float* grad, float* param, float* m, float lr, l
 size_t b200ps_unique_workspace(int T, int64_t k);
 /* Same with host-side knowledge of the id range of each segment (bounds[t] = table capacity, 0 =
  * unknown): small-range segments use a direct-address position array instead of the hash table. */
+size_t b200ps_unique_bounded_workspace(int T, int64_t k, const int64_t* bounds);
 int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, const int64_t* bounds,
                           int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream);

@@ -705,12 +705,12 @@ def test_unique_bounded_direct_address_segments():
     ids = np.stack([rng.randint(0, b if b else 10 ** 5, size=k) for b in bounds]).astype(np.int64)
     d_ids = torch.from_numpy(ids).cuda().view(-1)
     lib = _lib.lib()
-    need = lib.b200ps_unique_workspace(T, k)
+    arr = (ctypes.c_int64 * T)(*bounds)
+    need = lib.b200ps_unique_bounded_workspace(T, k, arr)
     ws = torch.empty(need, dtype=torch.uint8, device="cuda")
     uniq = torch.empty(T * k, dtype=torch.int64, device="cuda")
     inv = torch.empty(T * k, dtype=torch.int32, device="cuda")
     n = torch.empty(T, dtype=torch.int32, device="cuda")
-    arr = (ctypes.c_int64 * T)(*bounds)
     for _ in range(2):  # twice: the workspace is reused dirty
         _lib.check(lib.b200ps_unique_bounded(group._h, d_ids.data_ptr(), T, k, arr, uniq.data_ptr(), inv.data_ptr(),
                                              n.data_ptr(), ws.data_ptr(), ws.numel(), group._stream()))
