@@ -1042,7 +1042,7 @@ int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_uni
   GroupView gv = group_view(ps);
   const int per_src = ps->n_sm * 16 / ps->n_shards < 4 ? 4 : ps->n_sm * 16 / ps->n_shards;
   k_x_begin<<<1, 32, 0, st>>>(x);
-  k_x_send<false><<<grid_for(ps, x.cap), 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, nullptr, nullptr);
+  k_x_send<false><<<ps->n_sm * 2, 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, nullptr, nullptr);
   k_x_serve<<<dim3(per_src, ps->n_shards), 256, 0, st>>>(x, gv);
   k_x_unscatter<<<dim3(per_src, ps->n_shards), 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
   ps->launches += 4;
@@ -1061,7 +1061,7 @@ int b200ps_xchg_push(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_uni
   OptParams o = ps->opt;
   const int per_src = ps->n_sm * 16 / ps->n_shards < 4 ? 4 : ps->n_sm * 16 / ps->n_shards;
   k_x_begin<<<1, 32, 0, st>>>(x);
-  k_x_send<true><<<grid_for(ps, x.cap), 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, gsum_deep_dev, gsum_wide_dev);
+  k_x_send<true><<<ps->n_sm * 2, 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, gsum_deep_dev, gsum_wide_dev);
   dim3 grid(per_src, ps->n_shards);
   DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
   k_x_wait_applied<<<1, 32, 0, st>>>(x, gv);

@@ -85,50 +85,95 @@ __global__ void k_x_begin(XView x) {  // one thread: new epoch, clear the send c
 }
 
 // Requester: bucket (id, dst) by owner into the owners' inboxes.  UPD: also ship the gradient rows.
+// Work is indexed over the LIVE (group, rank) pairs only (prefix of n_unique in shared memory); a
+// block reserves its output range per owner with ONE global atomic per owner (count pass, then
+// write pass), so the eight cursors are not hammered by every warp.
+constexpr int kXChunk = 4096;  // live entries per block iteration (256 threads x 16)
+
 template <bool UPD>
 __global__ void __launch_bounds__(256) k_x_send(XView x, GroupView gv, const int64_t* __restrict__ uniq,
                                                 const int* __restrict__ n_unique, const float* __restrict__ gsum_d,
                                                 const float* __restrict__ gsum_w) {
   XHeader* h = xhdr(x, x.me);
+  __shared__ int s_prefix[kMaxSegs + 1];
+  __shared__ int s_cnt[kMaxShards], s_base[kMaxShards];
   const int lane = threadIdx.x & 31;
-  const long long total = (long long)x.G * x.B;
-  const long long total_pad = (total + 31) / 32 * 32;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_pad; i += stride) {
-    const int g = (int)(i / x.B);
-    const int r = (int)(i - (long long)g * x.B);
-    const bool live = i < total && r < n_unique[g];
-    const long long id = live ? uniq[i] : 0;
-    int owner = -1 - lane;  // dead lanes never match
-    if (live) owner = gv.shard_shift >= 0 ? (int)(id & (x.n - 1)) : (int)(id % x.n);
-    // warp-aggregated cursor bump: lanes with the same owner get consecutive entries (contiguous writes)
-    const unsigned peers = __match_any_sync(0xffffffffu, owner);
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (live && lane == leader) base = atomicAdd(&h->cursor[owner], __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (!live) continue;
-    const int pos = base + __popc(peers & ((1u << lane) - 1));
-    if (!UPD) {
-      int4 e;
-      e.x = (int)(id & 0xffffffffLL);
-      e.y = (int)(id >> 32);
-      e.z = (int)i;  // dst = g * B + r
-      e.w = g;
-      *reinterpret_cast<int4*>(xreq(x, owner, x.me) + (long long)pos * kXEntryReq) = e;
-    } else {
-      float4* dst = reinterpret_cast<float4*>(xupd(x, owner, x.me) + (long long)pos * kXEntryUpd);
-      int4 e;
-      e.x = (int)(id & 0xffffffffLL);
-      e.y = (int)(id >> 32);
-      e.z = g;
-      e.w = 0;
-      const float4* gd = reinterpret_cast<const float4*>(gsum_d + i * 8);
-      dst[0] = *reinterpret_cast<float4*>(&e);
-      dst[1] = gd[0];
-      dst[2] = gd[1];
-      dst[3] = make_float4(gsum_w[i], 0.f, 0.f, 0.f);
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int g = 0; g < x.G; ++g) {
+      s_prefix[g] = acc;
+      int u = n_unique[g];
+      acc += u < x.B ? u : x.B;
     }
+    s_prefix[x.G] = acc;
+  }
+  if (threadIdx.x < kMaxShards) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int total = s_prefix[x.G];
+  for (int chunk = blockIdx.x * kXChunk; chunk < total; chunk += gridDim.x * kXChunk) {
+    long long id_[kXChunk / 256];
+    int slot_[kXChunk / 256];  // g * B + r, -1 = dead
+    // pass 1: locate the live entries of this chunk and count them per owner
+#pragma unroll
+    for (int j = 0; j < kXChunk / 256; ++j) {
+      const int w = chunk + j * 256 + threadIdx.x;
+      slot_[j] = -1;
+      id_[j] = 0;
+      int owner = -1 - lane;
+      if (w < total) {
+        int lo = 0, hi = x.G;  // largest g with prefix[g] <= w
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (s_prefix[mid] <= w) lo = mid; else hi = mid;
+        }
+        slot_[j] = lo * x.B + (w - s_prefix[lo]);
+        id_[j] = uniq[slot_[j]];
+        owner = gv.shard_shift >= 0 ? (int)(id_[j] & (x.n - 1)) : (int)(id_[j] % x.n);
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, owner);
+      if (owner >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&s_cnt[owner], __popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < x.n) {
+      s_base[threadIdx.x] = atomicAdd(&h->cursor[threadIdx.x], s_cnt[threadIdx.x]);
+      s_cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    // pass 2: write the entries; lanes of a warp with the same owner get consecutive positions
+#pragma unroll
+    for (int j = 0; j < kXChunk / 256; ++j) {
+      const bool live = slot_[j] >= 0;
+      const long long id = id_[j];
+      int owner = -1 - lane;
+      if (live) owner = gv.shard_shift >= 0 ? (int)(id & (x.n - 1)) : (int)(id % x.n);
+      const unsigned peers = __match_any_sync(0xffffffffu, owner);
+      const int leader = __ffs(peers) - 1;
+      int loc = 0;
+      if (live && lane == leader) loc = atomicAdd(&s_cnt[owner], __popc(peers));
+      loc = __shfl_sync(0xffffffffu, loc, leader);
+      if (!live) continue;
+      const int pos = s_base[owner] + loc + __popc(peers & ((1u << lane) - 1));
+      int4 e;
+      e.x = (int)(id & 0xffffffffLL);
+      e.y = (int)(id >> 32);
+      if (!UPD) {
+        e.z = slot_[j];  // dst = g * B + r
+        e.w = slot_[j] / x.B;
+        *reinterpret_cast<int4*>(xreq(x, owner, x.me) + (long long)pos * kXEntryReq) = e;
+      } else {
+        e.z = slot_[j] / x.B;
+        e.w = 0;
+        float4* dst = reinterpret_cast<float4*>(xupd(x, owner, x.me) + (long long)pos * kXEntryUpd);
+        const float4* gd = reinterpret_cast<const float4*>(gsum_d + (long long)slot_[j] * 8);
+        dst[0] = *reinterpret_cast<float4*>(&e);
+        dst[1] = gd[0];
+        dst[2] = gd[1];
+        dst[3] = make_float4(gsum_w[slot_[j]], 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < kMaxShards) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
   }
   // publish: every block fences its writes; the last block to finish posts the counts and the flags
   __shared__ bool last;
