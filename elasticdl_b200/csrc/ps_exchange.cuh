@@ -88,7 +88,7 @@ __global__ void k_x_begin(XView x) {  // one thread: new epoch, clear the send c
 // Work is indexed over the LIVE (group, rank) pairs only (prefix of n_unique in shared memory); a
 // block reserves its output range per owner with ONE global atomic per owner (count pass, then
 // write pass), so the eight cursors are not hammered by every warp.
-constexpr int kXChunk = 4096;  // live entries per block iteration (256 threads x 16)
+constexpr int kXChunk = 512;  // live entries per block iteration (256 threads x 2): ~240 busy blocks at 122 K entries
 
 template <bool UPD>
 __global__ void __launch_bounds__(256) k_x_send(XView x, GroupView gv, const int64_t* __restrict__ uniq,

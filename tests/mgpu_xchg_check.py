@@ -72,8 +72,8 @@ def main():
         dist.barrier()
         # ---- push: disjoint rows per pusher: id = q*N*N + pusher*N + owner ----------------------
         k = 1500
-        pid = np.stack([(np.random.RandomState(5 * rnd + g).permutation(max(r // (world * world), 1))[:k] * world * world)
-                        for g, r in enumerate(rows)])
+        pid = [(np.random.RandomState(5 * rnd + g).permutation(max(r // (world * world), 1))[:k] * world * world)
+               for g, r in enumerate(rows)]
         counts = [min(k, max(r // (world * world), 1)) for r in rows]
         p_ids = torch.zeros((G, B), dtype=torch.int64, device=dev)
         p_n = torch.tensor(counts, dtype=torch.int32, device=dev)
