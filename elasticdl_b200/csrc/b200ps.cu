@@ -1050,6 +1050,47 @@ int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_uni
   return B200PS_OK;
 }
 
+// Debug / profiling: one pull + one push with a CUDA event after every kernel; synchronous.
+// ms_out[0..7] = begin, send, serve, unscatter | begin, send, apply, wait.
+int b200ps_xchg_profile(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, float* bet_deep_dev,
+                        float* bet_wide_dev, const float* gsum_deep_dev, const float* gsum_wide_dev, float* ms_out,
+                        void* stream) {
+  XView x;
+  int rc = xview(ps, &x);
+  if (rc) return rc;
+  DeviceGuard g(ps->client_device);
+  cudaStream_t st = (cudaStream_t)stream;
+  GroupView gv = group_view(ps);
+  OptParams o = ps->opt;
+  const int per_src = ps->n_sm * 16 / ps->n_shards < 4 ? 4 : ps->n_sm * 16 / ps->n_shards;
+  dim3 grid(per_src, ps->n_shards);
+  cudaEvent_t ev[9];
+  for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+  cudaEventRecord(ev[0], st);
+  k_x_begin<<<1, 32, 0, st>>>(x);
+  cudaEventRecord(ev[1], st);
+  k_x_send<false><<<ps->n_sm * 2, 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, nullptr, nullptr);
+  cudaEventRecord(ev[2], st);
+  k_x_serve<<<grid, 256, 0, st>>>(x, gv);
+  cudaEventRecord(ev[3], st);
+  k_x_unscatter<<<grid, 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
+  cudaEventRecord(ev[4], st);
+  k_x_begin<<<1, 32, 0, st>>>(x);
+  cudaEventRecord(ev[5], st);
+  k_x_send<true><<<ps->n_sm * 2, 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, gsum_deep_dev, gsum_wide_dev);
+  cudaEventRecord(ev[6], st);
+  DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
+  cudaEventRecord(ev[7], st);
+  k_x_wait_applied<<<1, 32, 0, st>>>(x, gv);
+  cudaEventRecord(ev[8], st);
+  ps->launches += 8;
+  CUDA_OK(cudaStreamSynchronize(st));
+  for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
 int b200ps_xchg_push(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, const float* gsum_deep_dev,
                      const float* gsum_wide_dev, void* stream) {
   XView x;

@@ -155,6 +155,11 @@ int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_uni
                      float* bet_wide_dev, void* stream);
 int b200ps_xchg_push(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, const float* gsum_deep_dev,
                      const float* gsum_wide_dev, void* stream);
+/* Profiling aid: one pull + one push (after a b200ps_push_begin), a CUDA event after every kernel,
+ * synchronous; ms_out[8] = begin, send, serve, unscatter, begin, send, apply, wait_applied. */
+int b200ps_xchg_profile(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, float* bet_deep_dev,
+                        float* bet_wide_dev, const float* gsum_deep_dev, const float* gsum_wide_dev, float* ms_out,
+                        void* stream);
 
 /* ≙ PullDenseParameters payload (server.go:144-160): copy whole dense
  * parameters owner-shard -> dst (segs[i].rows_dev; ids_dev/n ignored). */

@@ -24,15 +24,14 @@ from elasticdl_b200.elasticai_api.pytorch.optimizer import DistributedOptimizer 
 
 
 def resnet50_like_shapes():
-    """214 tensors totalling ~25.6 M parameters (docs/benchmark/ftlib_benchmark.md:40-41,122-123)."""
-    shapes, total = [], 0
-    widths = [64, 256, 512, 1024, 2048]
-    i = 0
-    while len(shapes) < 213:
-        c = widths[i % len(widths)]
-        shapes.append((c, c // 4, 3, 3) if i % 3 == 0 else (c,))
-        i += 1
+    """214 tensors totalling 25.6 M parameters (docs/benchmark/ftlib_benchmark.md:40-41,122-123)."""
+    shapes = []
+    for i in range(53):  # conv-like blocks: kernel + 3 per-channel vectors
+        c = [64, 128, 256, 512][i % 4]
+        shapes += [(c, c // 2, 3, 3), (c,), (c,), (c,)]
+    shapes.append((1000,))
     total = sum(int(torch.Size(s).numel()) for s in shapes)
+    assert len(shapes) == 213 and total < 25_600_000
     shapes.append((25_600_000 - total,))
     return shapes
 
