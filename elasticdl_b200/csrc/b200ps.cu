@@ -1040,7 +1040,8 @@ int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_uni
   DeviceGuard g(ps->client_device);
   cudaStream_t st = (cudaStream_t)stream;
   GroupView gv = group_view(ps);
-  const int per_src = ps->n_sm * 16 / ps->n_shards < 4 ? 4 : ps->n_sm * 16 / ps->n_shards;
+  // few, looping blocks: every block of a kernel that wrote peer memory pays one system fence
+  const int per_src = ps->n_sm * 4 / ps->n_shards < 2 ? 2 : ps->n_sm * 4 / ps->n_shards;
   k_x_begin<<<1, 32, 0, st>>>(x);
   k_x_send<false><<<ps->n_sm * 2, 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, nullptr, nullptr);
   k_x_serve<<<dim3(per_src, ps->n_shards), 256, 0, st>>>(x, gv);
@@ -1062,7 +1063,8 @@ int b200ps_xchg_profile(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_
   cudaStream_t st = (cudaStream_t)stream;
   GroupView gv = group_view(ps);
   OptParams o = ps->opt;
-  const int per_src = ps->n_sm * 16 / ps->n_shards < 4 ? 4 : ps->n_sm * 16 / ps->n_shards;
+  // few, looping blocks: every block of a kernel that wrote peer memory pays one system fence
+  const int per_src = ps->n_sm * 4 / ps->n_shards < 2 ? 2 : ps->n_sm * 4 / ps->n_shards;
   dim3 grid(per_src, ps->n_shards);
   cudaEvent_t ev[9];
   for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
@@ -1100,7 +1102,8 @@ int b200ps_xchg_push(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_uni
   cudaStream_t st = (cudaStream_t)stream;
   GroupView gv = group_view(ps);
   OptParams o = ps->opt;
-  const int per_src = ps->n_sm * 16 / ps->n_shards < 4 ? 4 : ps->n_sm * 16 / ps->n_shards;
+  // few, looping blocks: every block of a kernel that wrote peer memory pays one system fence
+  const int per_src = ps->n_sm * 4 / ps->n_shards < 2 ? 2 : ps->n_sm * 4 / ps->n_shards;
   k_x_begin<<<1, 32, 0, st>>>(x);
   k_x_send<true><<<ps->n_sm * 2, 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, gsum_deep_dev, gsum_wide_dev);
   dim3 grid(per_src, ps->n_shards);

@@ -59,15 +59,43 @@ __device__ __forceinline__ char* xupd(const XView& x, int owner, int src) {
 
 constexpr unsigned kErrTimeout = 8u;
 
-// Spin until *flag >= epoch (written by a peer with a system-scope fence before it).
+// Spin until *flag >= epoch.  The flag is posted with a system-scope release after the data; it is
+// read with a system-scope ACQUIRE load, and everything a peer wrote is then read with ld.global.cg
+// (L2 only -- peer writes land in this GPU's L2/HBM, a stale L1 line must not be hit).  A full
+// __threadfence_system() here costs an L1 invalidate per block and dominated these kernels.
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int4 ldcg_i4(const void* p) {
+  int4 v;
+  asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldcg_f4(const void* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldcg_i(const int* p) {
+  int v;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldcg_f(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void wait_flag(const int* flag, int epoch, unsigned* err) {
-  const volatile int* f = flag;
   for (long long spins = 0; spins < (1LL << 24); ++spins) {  // ~2 s with the sleep below
-    if (*f >= epoch) {
-      __threadfence_system();
-      return;
-    }
-    __nanosleep(100);
+    if (ld_acquire_sys(flag) >= epoch) return;
+    __nanosleep(64);
   }
   atomicOr(err, kErrTimeout);
 }
@@ -204,9 +232,8 @@ __global__ void __launch_bounds__(256) k_x_send(XView x, GroupView gv, const int
       oh->upd_alpha[x.me] = gv.rt->alpha[o];
       oh->upd_l2adj[x.me] = gv.rt->l2adj[o];
     }
-    __threadfence_system();
-    if (!UPD) *(volatile int*)&oh->flag_req[x.me] = epoch;
-    else *(volatile int*)&oh->flag_upd[x.me] = epoch;
+    if (!UPD) st_release_sys(&oh->flag_req[x.me], epoch);
+    else st_release_sys(&oh->flag_upd[x.me], epoch);
   }
   if (threadIdx.x == 0) h->done_blocks = 0;
   if (threadIdx.x < kMaxShards) h->cursor[threadIdx.x] = 0;
@@ -224,7 +251,7 @@ __global__ void __launch_bounds__(256) k_x_serve(XView x, GroupView gv) {
   if (threadIdx.x == 0) {
     s_epoch = h->epoch;
     wait_flag(&h->flag_req[src], s_epoch, gv.err);
-    s_cnt = *(volatile int*)&h->req_cnt[src];
+    s_cnt = ldcg_i(&h->req_cnt[src]);
   }
   __syncthreads();
   const int cnt = s_cnt;
@@ -233,7 +260,7 @@ __global__ void __launch_bounds__(256) k_x_serve(XView x, GroupView gv) {
   const int lane4 = threadIdx.x & 3;  // 4 lanes per entry: deep lo, deep hi, {wide, dst}, idle
   const long long stride = (long long)gridDim.x * blockDim.x / 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i < cnt; i += stride) {
-    const int4 e = *reinterpret_cast<const int4*>(req + i * kXEntryReq);
+    const int4 e = ldcg_i4(req + i * kXEntryReq);
     const long long id = entry_id(e);
     const TableView& td = gv.tables[x.deep_tab[e.w]];
     RowLoc loc = locate(gv, td, id);
@@ -259,8 +286,7 @@ __global__ void __launch_bounds__(256) k_x_serve(XView x, GroupView gv) {
   if (threadIdx.x == 0) last = atomicAdd(&h->done_src[src], 1u) == gridDim.x - 1;
   __syncthreads();
   if (last && threadIdx.x == 0) {
-    __threadfence_system();
-    *(volatile int*)&xhdr(x, src)->flag_resp[x.me] = s_epoch;
+    st_release_sys(&xhdr(x, src)->flag_resp[x.me], s_epoch);
     h->done_src[src] = 0;
   }
 }
@@ -280,10 +306,10 @@ __global__ void __launch_bounds__(256) k_x_unscatter(XView x, GroupView gv, floa
   const int lane4 = threadIdx.x & 3;
   const long long stride = (long long)gridDim.x * blockDim.x / 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i < cnt; i += stride) {
-    const float4* in = reinterpret_cast<const float4*>(resp + i * kXEntryResp);
-    const float4 tail = in[2];
+    const char* in = resp + i * kXEntryResp;
+    const float4 tail = ldcg_f4(in + 32);
     const int dst = __float_as_int(tail.y);
-    if (lane4 < 2) *reinterpret_cast<float4*>(bet_d + (long long)dst * 8 + 4 * lane4) = in[lane4];
+    if (lane4 < 2) *reinterpret_cast<float4*>(bet_d + (long long)dst * 8 + 4 * lane4) = ldcg_f4(in + 16 * lane4);
     else if (lane4 == 2) bet_w[dst] = tail.x;
   }
 }
@@ -300,10 +326,10 @@ __global__ void __launch_bounds__(256) k_x_apply(XView x, GroupView gv, OptParam
   if (threadIdx.x == 0) {
     s_epoch = h->epoch;
     wait_flag(&h->flag_upd[src], s_epoch, gv.err);
-    s_cnt = *(volatile int*)&h->upd_cnt[src];
-    s_lr = *(volatile float*)&h->upd_lr[src];
-    s_alpha = *(volatile float*)&h->upd_alpha[src];
-    s_l2 = *(volatile float*)&h->upd_l2adj[src];
+    s_cnt = ldcg_i(&h->upd_cnt[src]);
+    s_lr = ldcg_f(&h->upd_lr[src]);
+    s_alpha = ldcg_f(&h->upd_alpha[src]);
+    s_l2 = ldcg_f(&h->upd_l2adj[src]);
   }
   __syncthreads();
   const int cnt = s_cnt;
@@ -312,9 +338,8 @@ __global__ void __launch_bounds__(256) k_x_apply(XView x, GroupView gv, OptParam
   const int lane4 = threadIdx.x & 3;  // deep lo, deep hi, wide, idle
   const long long stride = (long long)gridDim.x * blockDim.x / 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i < cnt; i += stride) {
-    const float4* in = reinterpret_cast<const float4*>(upd + i * kXEntryUpd);
-    const float4 hd = in[0];
-    const int4 e = *reinterpret_cast<const int4*>(&hd);
+    const char* in = upd + i * kXEntryUpd;
+    const int4 e = ldcg_i4(in);
     const long long id = entry_id(e);
     const TableView& td = gv.tables[x.deep_tab[e.z]];
     RowLoc loc = locate(gv, td, id);
@@ -324,7 +349,7 @@ __global__ void __launch_bounds__(256) k_x_apply(XView x, GroupView gv, OptParam
     }
     if (lane4 < 2) {
       float* rec = loc.rec + 4 * lane4;
-      float4 g = in[1 + lane4], p = ld_f4(rec), s0 = p, s1 = p, s2 = p;
+      float4 g = ldcg_f4(in + 16 + 16 * lane4), p = ld_f4(rec), s0 = p, s1 = p, s2 = p;
       if (S > 0) s0 = ld_f4(rec + td.slot_off[1]);
       if (S > 1) s1 = ld_f4(rec + td.slot_off[2]);
       if (S > 2) s2 = ld_f4(rec + td.slot_off[3]);
@@ -345,7 +370,7 @@ __global__ void __launch_bounds__(256) k_x_apply(XView x, GroupView gv, OptParam
       RowLoc lw = locate(gv, tw, id);
       if (!lw.ok) continue;
       float* rec = lw.rec;
-      float g = in[3].x, p = *rec, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      float g = ldcg_f(reinterpret_cast<const float*>(in + 48)), p = *rec, s0 = 0.f, s1 = 0.f, s2 = 0.f;
       if (S > 0) s0 = rec[tw.slot_off[1]];
       if (S > 1) s1 = rec[tw.slot_off[2]];
       if (S > 2) s2 = rec[tw.slot_off[3]];
@@ -358,13 +383,12 @@ __global__ void __launch_bounds__(256) k_x_apply(XView x, GroupView gv, OptParam
     }
   }
   __shared__ bool last;
-  __threadfence_system();
+  __threadfence();  // rows are local; the flag's system-scope release orders them for the source's next pull
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(&h->done_src[src], 1u) == gridDim.x - 1;
   __syncthreads();
   if (last && threadIdx.x == 0) {
-    __threadfence_system();
-    *(volatile int*)&xhdr(x, src)->flag_applied[x.me] = s_epoch;
+    st_release_sys(&xhdr(x, src)->flag_applied[x.me], s_epoch);
     h->done_src[src] = 0;
   }
 }
