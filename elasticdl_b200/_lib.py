@@ -76,7 +76,7 @@ SYMBOLS = {
     "b200ps_xchg_create": (_i, [_vp, _i, _i, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "b200ps_xchg_pull": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "b200ps_xchg_profile": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), _vp]),
-    "b200ps_xchg_push": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200ps_xchg_push": (_i, [_vp, _vp, _vp, _vp]),
     "b200ps_pull_dense": (_i, [_vp, _segp, _i, _vp]),
     "b200ps_set_dense": (_i, [_vp, _segp, _i, _vp]),
     "b200ps_slot_rows": (_i, [_vp, _i, _i, _segp, _i, _vp]),

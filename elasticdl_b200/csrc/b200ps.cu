@@ -120,7 +120,8 @@ struct b200ps {
   int n_sm = 148;
   // owner-computes exchange (b200ps_xchg_*)
   int x_table = -1, x_G = 0, x_B = 0, x_me = -1;
-  long long x_cap = 0, x_off_req = 0, x_off_resp = 0, x_off_upd = 0;
+  long long x_cap = 0, x_off_ids = 0, x_off_resp = 0, x_off_upd = 0, x_off_served = 0;
+  bool x_pulled = false;
   int* d_x_deep = nullptr;
   int* d_x_wide = nullptr;
   std::mutex mu;
@@ -983,10 +984,11 @@ int b200ps_xchg_create(b200ps_t* ps, int G, int B, const int32_t* deep_tables, c
   ps->x_me = me;
   ps->x_cap = (long long)G * B;
   const long long n = ps->n_shards;
-  ps->x_off_req = 4096;
-  ps->x_off_resp = ps->x_off_req + n * ps->x_cap * kXEntryReq;
-  ps->x_off_upd = ps->x_off_resp + n * ps->x_cap * kXEntryResp;
-  const long long bytes = ps->x_off_upd + n * ps->x_cap * kXEntryUpd;
+  ps->x_off_ids = 4096;
+  ps->x_off_resp = ps->x_off_ids + ps->x_cap * 8;
+  ps->x_off_upd = ps->x_off_resp + n * ps->x_cap * kXEntry;
+  ps->x_off_served = ps->x_off_upd + n * ps->x_cap * kXEntry;
+  const long long bytes = ps->x_off_served + n * ps->x_cap * kXServed;
   static_assert(sizeof(XHeader) <= 4096, "exchange header must fit its page");
   {
     std::lock_guard<std::mutex> lk(ps->mu);
@@ -1019,9 +1021,10 @@ static int xview(b200ps_t* ps, XView* x) {
     if (!t.alloc[s].ptr) return fail(B200PS_ESTATE, "exchange buffer of shard " + std::to_string(s) + " is not mapped (sync peers)");
     x->buf[s] = (char*)t.alloc[s].ptr;
   }
-  x->off_req = ps->x_off_req;
+  x->off_ids = ps->x_off_ids;
   x->off_resp = ps->x_off_resp;
   x->off_upd = ps->x_off_upd;
+  x->off_served = ps->x_off_served;
   x->cap = ps->x_cap;
   x->deep_tab = ps->d_x_deep;
   x->wide_tab = ps->d_x_wide;
@@ -1032,6 +1035,12 @@ static int xview(b200ps_t* ps, XView* x) {
   return B200PS_OK;
 }
 
+// grid.x per peer: few, looping blocks -- every block of a kernel that wrote peer memory pays one system fence
+static int xchg_per_peer(b200ps_t* ps) {
+  const int v = ps->n_sm * 4 / ps->n_shards;
+  return v < 2 ? 2 : v;
+}
+
 int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, float* bet_deep_dev,
                      float* bet_wide_dev, void* stream) {
   XView x;
@@ -1040,19 +1049,37 @@ int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_uni
   DeviceGuard g(ps->client_device);
   cudaStream_t st = (cudaStream_t)stream;
   GroupView gv = group_view(ps);
-  // few, looping blocks: every block of a kernel that wrote peer memory pays one system fence
-  const int per_src = ps->n_sm * 4 / ps->n_shards < 2 ? 2 : ps->n_sm * 4 / ps->n_shards;
-  k_x_begin<<<1, 32, 0, st>>>(x);
-  k_x_send<false><<<ps->n_sm * 2, 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, nullptr, nullptr);
-  k_x_serve<<<dim3(per_src, ps->n_shards), 256, 0, st>>>(x, gv);
-  k_x_unscatter<<<dim3(per_src, ps->n_shards), 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
-  ps->launches += 4;
+  dim3 grid(xchg_per_peer(ps), ps->n_shards);
+  k_x_post<<<ps->n_sm, 256, 0, st>>>(x, uniq_dev, n_unique_dev);
+  k_x_serve<<<grid, 256, 0, st>>>(x, gv);
+  k_x_unscatter<<<grid, 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
+  ps->launches += 3;
+  ps->x_pulled = true;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
+int b200ps_xchg_push(b200ps_t* ps, const float* gsum_deep_dev, const float* gsum_wide_dev, void* stream) {
+  XView x;
+  int rc = xview(ps, &x);
+  if (rc) return rc;
+  if (!ps->x_pulled) return fail(B200PS_ESTATE, "b200ps_xchg_push follows the b200ps_xchg_pull of the same id lists");
+  ps->x_pulled = false;
+  DeviceGuard g(ps->client_device);
+  cudaStream_t st = (cudaStream_t)stream;
+  GroupView gv = group_view(ps);
+  OptParams o = ps->opt;
+  dim3 grid(xchg_per_peer(ps), ps->n_shards);
+  k_x_send_upd<<<grid, 256, 0, st>>>(x, gv, gsum_deep_dev, gsum_wide_dev);
+  DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
+  k_x_wait_applied<<<1, 32, 0, st>>>(x, gv);
+  ps->launches += 3;
   CUDA_OK(cudaGetLastError());
   return B200PS_OK;
 }
 
 // Debug / profiling: one pull + one push with a CUDA event after every kernel; synchronous.
-// ms_out[0..7] = begin, send, serve, unscatter | begin, send, apply, wait.
+// ms_out[0..5] = post, serve, unscatter | send_upd, apply, wait_applied.
 int b200ps_xchg_profile(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, float* bet_deep_dev,
                         float* bet_wide_dev, const float* gsum_deep_dev, const float* gsum_wide_dev, float* ms_out,
                         void* stream) {
@@ -1063,53 +1090,26 @@ int b200ps_xchg_profile(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_
   cudaStream_t st = (cudaStream_t)stream;
   GroupView gv = group_view(ps);
   OptParams o = ps->opt;
-  // few, looping blocks: every block of a kernel that wrote peer memory pays one system fence
-  const int per_src = ps->n_sm * 4 / ps->n_shards < 2 ? 2 : ps->n_sm * 4 / ps->n_shards;
-  dim3 grid(per_src, ps->n_shards);
-  cudaEvent_t ev[9];
+  dim3 grid(xchg_per_peer(ps), ps->n_shards);
+  cudaEvent_t ev[7];
   for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
   cudaEventRecord(ev[0], st);
-  k_x_begin<<<1, 32, 0, st>>>(x);
+  k_x_post<<<ps->n_sm, 256, 0, st>>>(x, uniq_dev, n_unique_dev);
   cudaEventRecord(ev[1], st);
-  k_x_send<false><<<ps->n_sm * 2, 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, nullptr, nullptr);
-  cudaEventRecord(ev[2], st);
   k_x_serve<<<grid, 256, 0, st>>>(x, gv);
-  cudaEventRecord(ev[3], st);
+  cudaEventRecord(ev[2], st);
   k_x_unscatter<<<grid, 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
+  cudaEventRecord(ev[3], st);
+  k_x_send_upd<<<grid, 256, 0, st>>>(x, gv, gsum_deep_dev, gsum_wide_dev);
   cudaEventRecord(ev[4], st);
-  k_x_begin<<<1, 32, 0, st>>>(x);
+  DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
   cudaEventRecord(ev[5], st);
-  k_x_send<true><<<ps->n_sm * 2, 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, gsum_deep_dev, gsum_wide_dev);
+  k_x_wait_applied<<<1, 32, 0, st>>>(x, gv);
   cudaEventRecord(ev[6], st);
-  DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
-  cudaEventRecord(ev[7], st);
-  k_x_wait_applied<<<1, 32, 0, st>>>(x, gv);
-  cudaEventRecord(ev[8], st);
-  ps->launches += 8;
+  ps->launches += 6;
   CUDA_OK(cudaStreamSynchronize(st));
-  for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
   for (auto& e : ev) cudaEventDestroy(e);
-  CUDA_OK(cudaGetLastError());
-  return B200PS_OK;
-}
-
-int b200ps_xchg_push(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, const float* gsum_deep_dev,
-                     const float* gsum_wide_dev, void* stream) {
-  XView x;
-  int rc = xview(ps, &x);
-  if (rc) return rc;
-  DeviceGuard g(ps->client_device);
-  cudaStream_t st = (cudaStream_t)stream;
-  GroupView gv = group_view(ps);
-  OptParams o = ps->opt;
-  // few, looping blocks: every block of a kernel that wrote peer memory pays one system fence
-  const int per_src = ps->n_sm * 4 / ps->n_shards < 2 ? 2 : ps->n_sm * 4 / ps->n_shards;
-  k_x_begin<<<1, 32, 0, st>>>(x);
-  k_x_send<true><<<ps->n_sm * 2, 256, 0, st>>>(x, gv, uniq_dev, n_unique_dev, gsum_deep_dev, gsum_wide_dev);
-  dim3 grid(per_src, ps->n_shards);
-  DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
-  k_x_wait_applied<<<1, 32, 0, st>>>(x, gv);
-  ps->launches += 4;
   CUDA_OK(cudaGetLastError());
   return B200PS_OK;
 }

@@ -348,8 +348,7 @@ class DeepFMPSEngine:
         check(lib.b200ps_push_dense(h, arr, n, st))
         if self.exchange == "owner":
             e = mark("push_exchange")
-            check(lib.b200ps_xchg_push(h, self.uniq.data_ptr(), self.n_unique.data_ptr(), self.gsum_d.data_ptr(),
-                                       self.gsum_w.data_ptr(), st))
+            check(lib.b200ps_xchg_push(h, self.gsum_d.data_ptr(), self.gsum_w.data_ptr(), st))
             done(e)
         elif self.paired:
             e = mark("push_pair")

@@ -144,19 +144,21 @@ int b200ps_pull_rows_pair(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const
 int b200ps_push_rows_pair(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const* grads_b, int nseg, void* stream);
 
 /* Owner-computes exchange for rank-per-GPU groups (csrc/ps_exchange.cuh): instead of touching peer
- * rows one by one, each rank buckets its unique ids by owner, ships them contiguously over NVLink,
- * the owner serves / updates its own shard, and rows return contiguously.  Every rank must issue
- * the same xchg calls in the same order (bulk-synchronous step).  Tables come in (dim-8, dim-1)
- * pairs addressed by the same ids; uniq / n_unique / bet / gsum are the [G][B] buffers of
- * b200ps_unique.  create: collective, then re-export / import the shards (the exchange buffer is
- * a peer-mapped allocation).  push belongs between b200ps_push_begin and b200ps_push_end. */
+ * rows one by one, each rank publishes its unique-id lists; every owner streams them over NVLink,
+ * serves the ids it owns (id % N) from its own shard and returns the rows contiguously; gradient
+ * rows travel back in the same order and the owner applies the optimizer to its own shard.  Every
+ * rank must issue the same xchg calls in the same order (bulk-synchronous step).  Tables come in
+ * (dim-8, dim-1) pairs addressed by the same ids; uniq / n_unique / bet / gsum are the [G][B]
+ * buffers of b200ps_unique.  create: collective, then re-export / import the shards (the exchange
+ * buffer is a peer-mapped allocation).  push belongs between b200ps_push_begin and b200ps_push_end
+ * and updates the rows of the b200ps_xchg_pull that precedes it (gsum indexed like that pull's
+ * bet rows); a push without its pull returns B200PS_ESTATE. */
 int b200ps_xchg_create(b200ps_t* ps, int G, int B, const int32_t* deep_tables, const int32_t* wide_tables);
 int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, float* bet_deep_dev,
                      float* bet_wide_dev, void* stream);
-int b200ps_xchg_push(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, const float* gsum_deep_dev,
-                     const float* gsum_wide_dev, void* stream);
+int b200ps_xchg_push(b200ps_t* ps, const float* gsum_deep_dev, const float* gsum_wide_dev, void* stream);
 /* Profiling aid: one pull + one push (after a b200ps_push_begin), a CUDA event after every kernel,
- * synchronous; ms_out[8] = begin, send, serve, unscatter, begin, send, apply, wait_applied. */
+ * synchronous; ms_out[6] = post, serve, unscatter, send_upd, apply, wait_applied. */
 int b200ps_xchg_profile(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, float* bet_deep_dev,
                         float* bet_wide_dev, const float* gsum_deep_dev, const float* gsum_wide_dev, float* ms_out,
                         void* stream);

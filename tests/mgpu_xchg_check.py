@@ -94,12 +94,14 @@ def main():
             p_ids[g, :len(idg)] = torch.from_numpy(idg).to(dev)
             gs_d[g * B:g * B + len(idg)] = torch.from_numpy(gd).to(dev)
             gs_w[g * B:g * B + len(idg)] = torch.from_numpy(gw).to(dev)
+        # a push rides on the routing of the pull before it: pull the rows about to be updated
+        check(lib.b200ps_xchg_pull(h, p_ids.data_ptr(), p_n.data_ptr(), bet_d.data_ptr(), bet_w.data_ptr(), group._stream()))
         for r in range(world):  # deterministic per-shard step order: rank r's ApplyGradients is the r-th
             if r == rank:
                 group.push_begin(0.001, [0] * world)
             torch.cuda.synchronize()
             dist.barrier()
-        check(lib.b200ps_xchg_push(h, p_ids.data_ptr(), p_n.data_ptr(), gs_d.data_ptr(), gs_w.data_ptr(), group._stream()))
+        check(lib.b200ps_xchg_push(h, gs_d.data_ptr(), gs_w.data_ptr(), group._stream()))
         group.push_end(sync=True)
         group.check()
         dist.barrier()

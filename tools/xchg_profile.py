@@ -30,8 +30,8 @@ def main():
         eng.step(ids, dense, labels)
     torch.cuda.synchronize()
     dist.barrier()
-    ms = (ctypes.c_float * 8)()
-    acc = [0.0] * 8
+    ms = (ctypes.c_float * 6)()
+    acc = [0.0] * 6
     n = 10
     for _ in range(n):
         group.push_begin(0.001, [0] * world)
@@ -41,10 +41,10 @@ def main():
                                             eng.bet_w.data_ptr(), eng.gsum_d.data_ptr(), eng.gsum_w.data_ptr(), ms,
                                             group._stream()))
         group.push_end(sync=True)
-        for i in range(8):
+        for i in range(6):
             acc[i] += ms[i] * 1e3 / n
     group.check()
-    names = ["begin", "send_req", "serve", "unscatter", "begin2", "send_upd", "apply", "wait_applied"]
+    names = ["post", "serve", "unscatter", "send_upd", "apply", "wait_applied"]
     out = {k: round(v, 1) for k, v in zip(names, acc)}
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
