@@ -28,12 +28,11 @@ namespace b200ps_impl {
 
 constexpr int kXEntry = 48;    // bytes: response {float deep[8]; float wide; int32 dst; pad 2}; update {float g[8]; float gw; pad 3}
 constexpr int kXServed = 16;   // bytes: {int64 id; int32 grp; int32 pad}   (owner-local)
-constexpr int kXChunk = 1024;  // ids scanned per block iteration in k_x_serve (256 threads x 4)
+constexpr int kXChunk = 512;   // ids scanned per block iteration in k_x_serve (256 threads x 2)
 
 struct XHeader {  // first page of every rank's exchange buffer
-  // read by the owners: live id count per group of this rank's request
-  int nuniq[kMaxSegs];
   // written by source ranks into the OWNER's header
+  int nuniq[kMaxShards][kMaxSegs];  // [src][g] live id count per group of src's request
   int flag_ids[kMaxShards];  // == epoch when src's id lists are published
   int flag_upd[kMaxShards];  // == epoch when src's gradient rows have landed
   float upd_lr[kMaxShards], upd_alpha[kMaxShards], upd_l2adj[kMaxShards];
@@ -113,17 +112,43 @@ __device__ __forceinline__ void wait_flag(const int* flag, int epoch, unsigned* 
   atomicOr(err, kErrTimeout);
 }
 
+// Largest g with prefix[g] <= w (prefix[0] == 0, prefix[G] == total > w).
+__device__ __forceinline__ int group_of(const int* prefix, int G, int w) {
+  int lo = 0, hi = G;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (prefix[mid] <= w) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 // Requester: publish this step's unique-id lists (the live prefix of every group) and open a new epoch.
-__global__ void __launch_bounds__(256) k_x_post(XView x, const int64_t* __restrict__ uniq, const int* __restrict__ n_unique) {
+__global__ void __launch_bounds__(256) k_x_post(XView x, const long long* uniq, const int* __restrict__ n_unique) {
   XHeader* h = xhdr(x, x.me);
   long long* ids = xids(x, x.me);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (int g = 0; g < x.G; ++g) {
-    int u = n_unique[g];
-    u = u < x.B ? u : x.B;
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < u; r += stride)
-      ids[(long long)g * x.B + r] = uniq[(long long)g * x.B + r];
-    if (blockIdx.x == 0 && threadIdx.x == 0) h->nuniq[g] = u;
+  __shared__ int s_prefix[kMaxSegs + 1];
+  __shared__ int s_u[kMaxSegs];
+  if (threadIdx.x < x.G) {
+    const int u = n_unique[threadIdx.x];
+    s_u[threadIdx.x] = u < x.B ? u : x.B;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int g = 0; g < x.G; ++g) {
+      s_prefix[g] = acc;
+      acc += s_u[g];
+    }
+    s_prefix[x.G] = acc;
+  }
+  __syncthreads();
+  const int total = s_prefix[x.G];
+  if (uniq != ids) {  // not published in place (b200ps_xchg_ids): copy the live prefixes
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+      const int g = group_of(s_prefix, x.G, w);
+      const long long slot = (long long)g * x.B + (w - s_prefix[g]);
+      ids[slot] = uniq[slot];
+    }
   }
   __shared__ bool last;
   __threadfence_system();
@@ -131,7 +156,7 @@ __global__ void __launch_bounds__(256) k_x_post(XView x, const int64_t* __restri
   if (threadIdx.x == 0) last = atomicAdd(&h->done_blocks, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!last) return;
-  __threadfence_system();
+  __threadfence();
   const int epoch = *(volatile int*)&h->epoch + 1;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -142,13 +167,15 @@ __global__ void __launch_bounds__(256) k_x_post(XView x, const int64_t* __restri
     h->cursor[threadIdx.x] = 0;
     h->done_src[threadIdx.x] = 0;
   }
-  __threadfence_system();
-  __syncthreads();
+  for (int i = threadIdx.x; i < x.n * x.G; i += blockDim.x)  // counts travel to the owners with the flag
+    xhdr(x, i / x.G)->nuniq[x.me][i % x.G] = s_u[i % x.G];
+  __syncthreads();  // the releases below are cumulative over everything this block has synchronised with
   if (threadIdx.x < x.n) st_release_sys(&xhdr(x, threadIdx.x)->flag_ids[x.me], epoch);
 }
 
 // Owner: stream source blockIdx.y's id lists, keep the ids this shard owns, gather and return the rows.
 __global__ void __launch_bounds__(256) k_x_serve(XView x, GroupView gv) {
+  constexpr int PER = kXChunk / 256;
   const int src = blockIdx.y;
   XHeader* h = xhdr(x, x.me);
   __shared__ int s_prefix[kMaxSegs + 1];
@@ -162,8 +189,7 @@ __global__ void __launch_bounds__(256) k_x_serve(XView x, GroupView gv) {
     s_n = 0;
   }
   __syncthreads();
-  const XHeader* sh = xhdr(x, src);
-  if (threadIdx.x < x.G) s_u[threadIdx.x] = ldcg_i(&sh->nuniq[threadIdx.x]);
+  if (threadIdx.x < x.G) s_u[threadIdx.x] = ldcg_i(&h->nuniq[src][threadIdx.x]);
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -180,25 +206,31 @@ __global__ void __launch_bounds__(256) k_x_serve(XView x, GroupView gv) {
   char* served = xserved(x, x.me, src);
   const int lane = threadIdx.x & 31, lane4 = threadIdx.x & 3;
   const bool pow2 = (x.n & (x.n - 1)) == 0;
-  for (int chunk = blockIdx.x * kXChunk; chunk < total; chunk += gridDim.x * kXChunk) {
-    // pass 1: scan kXChunk ids, compact the ones this shard owns into shared memory
+  long long nid[PER];
+  int nslot[PER];
+  auto fetch = [&](int chunk) {  // issue the (remote) id loads of a chunk; consumed one iteration later
 #pragma unroll
-    for (int j = 0; j < kXChunk / 256; ++j) {
+    for (int j = 0; j < PER; ++j) {
       const int w = chunk + j * 256 + threadIdx.x;
-      bool mine = false;
-      long long id = 0;
-      int slot = 0;
+      nslot[j] = -1;
+      nid[j] = 0;
       if (w < total) {
-        int lo = 0, hi = x.G;  // largest g with prefix[g] <= w
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (s_prefix[mid] <= w) lo = mid; else hi = mid;
-        }
-        slot = lo * x.B + (w - s_prefix[lo]);
-        id = ldcg_ll(ids + slot);
-        const int owner = pow2 ? (int)(id & (x.n - 1)) : (int)(((id % x.n) + x.n) % x.n);
-        mine = owner == x.me;
+        const int g = group_of(s_prefix, x.G, w);
+        nslot[j] = g * x.B + (w - s_prefix[g]);
+        nid[j] = ldcg_ll(ids + nslot[j]);
       }
+    }
+  };
+  int chunk = blockIdx.x * kXChunk;
+  if (chunk < total) fetch(chunk);
+  for (; chunk < total; chunk += gridDim.x * kXChunk) {
+    // pass 1: compact the ids this shard owns into shared memory
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const long long id = nid[j];
+      const int slot = nslot[j];
+      const int owner = pow2 ? (int)(id & (x.n - 1)) : (int)(((id % x.n) + x.n) % x.n);
+      const bool mine = slot >= 0 && owner == x.me;
       const unsigned m = __ballot_sync(0xffffffffu, mine);
       int base = 0;
       if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
@@ -209,6 +241,8 @@ __global__ void __launch_bounds__(256) k_x_serve(XView x, GroupView gv) {
         s_slot[p] = slot;
       }
     }
+    const int next = chunk + gridDim.x * kXChunk;
+    if (next < total) fetch(next);
     __syncthreads();
     const int n = s_n;
     if (threadIdx.x == 0) s_base = n ? atomicAdd(&h->cursor[src], n) : 0;
@@ -256,7 +290,7 @@ __global__ void __launch_bounds__(256) k_x_serve(XView x, GroupView gv) {
   if (threadIdx.x == 0) last = atomicAdd(&h->done_src[src], 1u) == gridDim.x - 1;
   __syncthreads();
   if (last && threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence();
     const int cnt = *(volatile int*)&h->cursor[src];
     h->served_cnt[src] = cnt;
     XHeader* rh = xhdr(x, src);
@@ -299,13 +333,24 @@ __global__ void __launch_bounds__(256) k_x_send_upd(XView x, GroupView gv, const
   char* upd = xupd(x, owner, x.me);  // remote, contiguous
   const int lane4 = threadIdx.x & 3;
   const long long stride = (long long)gridDim.x * blockDim.x / 4;
-  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i < cnt; i += stride) {
-    const int dst = __float_as_int(ldcg_f(reinterpret_cast<const float*>(resp + i * kXEntry + 36)));
-    char* out = upd + i * kXEntry;
-    if (lane4 < 2)
-      *reinterpret_cast<float4*>(out + 16 * lane4) = *reinterpret_cast<const float4*>(gsum_d + (long long)dst * 8 + 4 * lane4);
-    else if (lane4 == 2)
-      *reinterpret_cast<float4*>(out + 32) = make_float4(gsum_w[dst], 0.f, 0.f, 0.f);
+  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i0 < cnt; i0 += 2 * stride) {
+    // two entries in flight per lane group: dst -> gradient row -> contiguous remote store
+    const long long i1 = i0 + stride;
+    const bool two = i1 < cnt;
+    const int d0 = __float_as_int(ldcg_f(reinterpret_cast<const float*>(resp + i0 * kXEntry + 36)));
+    const int d1 = two ? __float_as_int(ldcg_f(reinterpret_cast<const float*>(resp + i1 * kXEntry + 36))) : d0;
+    float4 v0, v1;
+    if (lane4 < 2) {
+      v0 = *reinterpret_cast<const float4*>(gsum_d + (long long)d0 * 8 + 4 * lane4);
+      v1 = *reinterpret_cast<const float4*>(gsum_d + (long long)d1 * 8 + 4 * lane4);
+    } else {
+      v0 = make_float4(gsum_w[d0], 0.f, 0.f, 0.f);
+      v1 = make_float4(gsum_w[d1], 0.f, 0.f, 0.f);
+    }
+    if (lane4 < 3) {
+      *reinterpret_cast<float4*>(upd + i0 * kXEntry + 16 * lane4) = v0;
+      if (two) *reinterpret_cast<float4*>(upd + i1 * kXEntry + 16 * lane4) = v1;
+    }
   }
   __shared__ bool last;
   __threadfence_system();
@@ -313,14 +358,13 @@ __global__ void __launch_bounds__(256) k_x_send_upd(XView x, GroupView gv, const
   if (threadIdx.x == 0) last = atomicAdd(&h->done_blocks, 1u) == gridDim.x * gridDim.y - 1;
   __syncthreads();
   if (!last) return;
-  __threadfence_system();
+  __threadfence();
   if (threadIdx.x < x.n) {
     const int o = threadIdx.x;
     XHeader* oh = xhdr(x, o);
     oh->upd_lr[x.me] = gv.rt->lr[o];
     oh->upd_alpha[x.me] = gv.rt->alpha[o];
     oh->upd_l2adj[x.me] = gv.rt->l2adj[o];
-    __threadfence_system();
     st_release_sys(&oh->flag_upd[x.me], *(volatile int*)&h->epoch);
   }
   if (threadIdx.x == 0) h->done_blocks = 0;
