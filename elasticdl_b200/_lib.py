@@ -74,7 +74,6 @@ SYMBOLS = {
     "b200ps_pull_rows_pair": (_i, [_vp, _segp, ctypes.POINTER(_vp), _i, _vp]),
     "b200ps_push_rows_pair": (_i, [_vp, _segp, ctypes.POINTER(_vp), _i, _vp]),
     "b200ps_xchg_create": (_i, [_vp, _i, _i, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
-    "b200ps_xchg_ids": (_i, [_vp, ctypes.POINTER(ctypes.c_void_p)]),
     "b200ps_xchg_pull": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "b200ps_xchg_profile": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), _vp]),
     "b200ps_xchg_push": (_i, [_vp, _vp, _vp, _vp]),

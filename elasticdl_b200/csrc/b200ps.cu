@@ -984,12 +984,12 @@ int b200ps_xchg_create(b200ps_t* ps, int G, int B, const int32_t* deep_tables, c
   ps->x_me = me;
   ps->x_cap = (long long)G * B;
   const long long n = ps->n_shards;
-  ps->x_off_ids = 8192;
-  ps->x_off_resp = ps->x_off_ids + ps->x_cap * 8;
-  ps->x_off_upd = ps->x_off_resp + n * ps->x_cap * kXEntry;
-  ps->x_off_served = ps->x_off_upd + n * ps->x_cap * kXEntry;
+  ps->x_off_ids = 4096;
+  ps->x_off_resp = ps->x_off_ids + ps->x_cap * kXIdEntry;
+  ps->x_off_upd = ps->x_off_resp + n * ps->x_cap * kXResp;
+  ps->x_off_served = ps->x_off_upd + n * ps->x_cap * kXUpd;
   const long long bytes = ps->x_off_served + n * ps->x_cap * kXServed;
-  static_assert(sizeof(XHeader) <= 8192, "exchange header must fit its two pages");
+  static_assert(sizeof(XHeader) <= 4096, "exchange header must fit its page");
   {
     std::lock_guard<std::mutex> lk(ps->mu);
     Table t;
@@ -1035,16 +1035,7 @@ static int xview(b200ps_t* ps, XView* x) {
   return B200PS_OK;
 }
 
-int b200ps_xchg_ids(b200ps_t* ps, int64_t** ids_dev) {
-  XView x;
-  int rc = xview(ps, &x);
-  if (rc) return rc;
-  if (!ids_dev) return fail(B200PS_EINVAL, "ids_dev is null");
-  *ids_dev = reinterpret_cast<int64_t*>(x.buf[x.me] + x.off_ids);
-  return B200PS_OK;
-}
-
-// grid.x per peer: few, looping blocks -- every block of a kernel that wrote peer memory pays one system fence
+// grid.x per peer
 static int xchg_per_peer(b200ps_t* ps) {
   static const int mult = [] {
     const char* e = getenv("B200_XCHG_BLOCKS");  // blocks per SM over all peers (tuning knob)
@@ -1064,11 +1055,7 @@ int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_uni
   cudaStream_t st = (cudaStream_t)stream;
   GroupView gv = group_view(ps);
   dim3 grid(xchg_per_peer(ps), ps->n_shards);
-  {
-    const long long* u = reinterpret_cast<const long long*>(uniq_dev);
-    const bool in_place = (const char*)u == x.buf[x.me] + x.off_ids;
-    k_x_post<<<in_place ? 1 : ps->n_sm, 256, 0, st>>>(x, u, n_unique_dev);
-  }
+  k_x_post<<<ps->n_sm, 256, 0, st>>>(x, uniq_dev, n_unique_dev);
   k_x_serve<<<grid, 256, 0, st>>>(x, gv);
   k_x_unscatter<<<grid, 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
   ps->launches += 3;
@@ -1112,11 +1099,7 @@ int b200ps_xchg_profile(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_
   cudaEvent_t ev[7];
   for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
   cudaEventRecord(ev[0], st);
-  {
-    const long long* u = reinterpret_cast<const long long*>(uniq_dev);
-    const bool in_place = (const char*)u == x.buf[x.me] + x.off_ids;
-    k_x_post<<<in_place ? 1 : ps->n_sm, 256, 0, st>>>(x, u, n_unique_dev);
-  }
+  k_x_post<<<ps->n_sm, 256, 0, st>>>(x, uniq_dev, n_unique_dev);
   cudaEventRecord(ev[1], st);
   k_x_serve<<<grid, 256, 0, st>>>(x, gv);
   cudaEventRecord(ev[2], st);

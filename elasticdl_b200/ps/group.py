@@ -205,20 +205,6 @@ class PSGroup:
         w = (ctypes.c_int32 * G)(*[int(t) for t in wide_table_ids])
         check(self.lib.b200ps_xchg_create(self._h, int(G), int(B), d, w))
         self.commit()
-        self._xchg_shape = (int(G), int(B))
-
-    def xchg_ids(self):
-        """The [G*B] int64 region peers read this rank's id lists from, as a torch tensor (no copy):
-        unique() into it and xchg_pull publishes in place."""
-        ptr = ctypes.c_void_p()
-        check(self.lib.b200ps_xchg_ids(self._h, ctypes.byref(ptr)))
-        G, B = self._xchg_shape
-
-        class _Region:  # zero-copy view of library-owned device memory
-            __cuda_array_interface__ = {"shape": (G * B,), "typestr": "<i8", "data": (ptr.value, False), "version": 3}
-
-        with torch.cuda.device(self.device):
-            return torch.as_tensor(_Region(), device=self.device)
 
     def register_dense(self, name, shape, shard):
         if name in self.tables:

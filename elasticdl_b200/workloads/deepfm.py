@@ -219,11 +219,7 @@ class DeepFMPSEngine:
                 group.finish_init(s, 0)
         # persistent buffers
         f32 = dict(dtype=torch.float32, device=dev)
-        if self.exchange == "owner":  # id lists are published in place: unique writes into the exchange buffer
-            group.xchg_create(G, B, self.deep_ids, self.wide_ids)
-            self.uniq = group.xchg_ids()
-        else:
-            self.uniq = torch.empty(G * B, dtype=torch.int64, device=dev)
+        self.uniq = torch.empty(G * B, dtype=torch.int64, device=dev)
         self.inv = torch.empty(G * B, dtype=torch.int32, device=dev)
         self.n_unique = torch.empty(G, dtype=torch.int32, device=dev)
         import ctypes as _ctb
@@ -243,6 +239,8 @@ class DeepFMPSEngine:
 
         self.loss_fn = torch.nn.BCEWithLogitsLoss()
         self._build_segs()
+        if self.exchange == "owner":
+            group.xchg_create(G, B, self.deep_ids, self.wide_ids)
         self.steps = 0
 
     def _seg_items(self, ids_tab, rows, dim):

@@ -154,9 +154,6 @@ int b200ps_push_rows_pair(b200ps_t* ps, const b200ps_seg_t* segs_a, float* const
  * and updates the rows of the b200ps_xchg_pull that precedes it (gsum indexed like that pull's
  * bet rows); a push without its pull returns B200PS_ESTATE. */
 int b200ps_xchg_create(b200ps_t* ps, int G, int B, const int32_t* deep_tables, const int32_t* wide_tables);
-/* The [G][B] int64 region of this rank's exchange buffer that peers read the id lists from: let
- * b200ps_unique write there and pass the same pointer to b200ps_xchg_pull to skip its copy. */
-int b200ps_xchg_ids(b200ps_t* ps, int64_t** ids_dev);
 int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_unique_dev, float* bet_deep_dev,
                      float* bet_wide_dev, void* stream);
 int b200ps_xchg_push(b200ps_t* ps, const float* gsum_deep_dev, const float* gsum_wide_dev, void* stream);

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 timeout 300 $TR tests/mgpu_xchg_check.py > gpurun_out/xv_check.log 2>&1; echo "check rc=$?"
 tail -2 gpurun_out/xv_check.log
-for m in 4 8; do
+for m in 4; do
   B200_XCHG_BLOCKS=$m timeout 200 $TR tools/xchg_profile.py 2>&1 | grep '^{' | tee gpurun_out/xv_prof_$m.json
 done
 for x in owner direct; do
