@@ -8,7 +8,7 @@ tail -2 gpurun_out/xv_check.log
 for m in 4; do
   B200_XCHG_BLOCKS=$m timeout 200 $TR tools/xchg_profile.py 2>&1 | grep '^{' | tee gpurun_out/xv_prof_$m.json
 done
-for x in owner direct; do
+for x in ${MODES:-owner direct}; do
   timeout 300 $TR bench.py --gpus $N --steps 50 --warmup 5 --exchange $x --no-cpu-baseline 2>&1 | grep '^{' > gpurun_out/xv_${x}_$N.json
   python - <<PY
 import json
