@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tower", default="fused", choices=["fused", "torch"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
+    ap.add_argument("--lookahead", default="on", choices=["on", "off"],
+                    help="deduplicate the ids of batch i+1 on a second stream while batch i trains (graph mode)")
     ap.add_argument("--paired", default="off", choices=["on", "off"],
                     help="store each group's deep+wide rows as one record per id")
     ap.add_argument("--exchange", default="auto", choices=["auto", "owner", "direct"],
@@ -202,6 +204,9 @@ def main():
     config["record_layout"] = "paired deep+wide record per id" if engine.paired else "one record slab per table"
     config["exchange"] = engine.exchange
     use_graph = args.tower == "fused" and not args.no_graph
+    lookahead = use_graph and args.lookahead == "on"
+    config["pipeline"] = ("CUDA graph per step; id dedup of batch i+1 overlapped with step i on a second stream"
+                          if lookahead else ("CUDA graph per step" if use_graph else "eager launches"))
     if world > 1:
         dist.barrier()
     B = args.batch
@@ -257,13 +262,25 @@ def main():
     ms = ms_eager
     if use_graph:
         # ---- headline: the same step replayed from a CUDA graph (inputs resident in HBM) ----
-        engine.capture()
+        if lookahead:
+            # batch i trains while the ids of batch i+1 are deduplicated on a second stream
+            engine.prepare(devb[0][0])
+            engine.capture_ahead()
+
+            def graph_step(i):
+                _, dense_i, labels_i = devb[i % args.pool]
+                return engine.step_ahead_graph(dense_i, labels_i, devb[(i + 1) % args.pool][0])
+        else:
+            engine.capture()
+
+            def graph_step(i):
+                return engine.step_graph(*devb[i % args.pool])
         for i in range(args.warmup):
-            engine.step_graph(*devb[i % args.pool])
+            graph_step(i)
         sync_all()
         e0.record()
-        for i in range(args.steps):
-            engine.step_graph(*devb[i % args.pool])
+        for i in range(args.warmup, args.warmup + args.steps):
+            graph_step(i)
         e1.record()
         sync_all()
         ms = max_over_ranks(e0.elapsed_time(e1))
@@ -277,16 +294,21 @@ def main():
     # ---- end to end: host buffers in, loss out, every step ----------------------------
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    feeder = engine.host_feeder(2) if use_graph else None
+    ahead = 2 if lookahead else 1  # batches in flight ahead of the running step
+    feeder = engine.host_feeder(ahead + 1, lookahead=lookahead) if use_graph else None
+    if feeder is not None and lookahead:
+        engine.prepare(devb[0][0])  # graphs exist already; the feeder re-prepares on its first batch
+        sync_all()
     e2.record()
     if feeder is not None:
-        feeder.submit(*host[0])
+        for j in range(min(ahead, args.steps)):
+            feeder.submit(*host[j % args.pool])
     for i in range(args.steps):
         if feeder is not None:
-            # every step's inputs come from pinned host memory; the copy of batch i+1 (side stream)
-            # overlaps the kernels of batch i, like the reference's dataset.prefetch(1)
-            if i + 1 < args.steps:
-                feeder.submit(*host[(i + 1) % args.pool])
+            # every step's inputs come from pinned host memory; the copies of the next batches (side
+            # stream) overlap the kernels of batch i, like the reference's dataset.prefetch(1)
+            if i + ahead < args.steps:
+                feeder.submit(*host[(i + ahead) % args.pool])
             loss = feeder.run_next()
         else:
             hi, hd, hl = host[i % args.pool]

@@ -97,9 +97,17 @@ def flatten_tower(tower, flat):
 
 
 class HostFeeder:
-    def __init__(self, engine, depth=2):
-        if getattr(engine, "graph", None) is None:
+    """Pinned-host batches -> staging slots on a copy stream -> the captured step.
+    lookahead=True drives engine.step_ahead_graph: slot k's dense/labels train while slot k+1's
+    ids are deduplicated, so two batches must have landed before a step starts (depth >= 3)."""
+
+    def __init__(self, engine, depth=2, lookahead=False):
+        self.lookahead = bool(lookahead)
+        if self.lookahead:
+            depth = max(depth, 3)
+        elif getattr(engine, "graph", None) is None:
             engine.capture()
+        self.started = False
         self.e = engine
         dev, G, B = engine.device, engine.G, engine.B
         self.depth = depth
@@ -129,7 +137,19 @@ class HostFeeder:
         k = self.tail % self.depth
         main = torch.cuda.current_stream(self.e.device)
         main.wait_event(self.ready[k])
-        loss = self.e.step_graph(*self.slots[k])
+        if not self.lookahead:
+            loss = self.e.step_graph(*self.slots[k])
+        else:
+            if not self.started:
+                self.e.prepare(self.slots[k][0])
+                if self.e.graphs_ahead is None:
+                    self.e.capture_ahead()
+                self.started = True
+            k1 = k
+            if self.tail + 1 < self.head:  # the next batch was submitted: its ids are deduplicated now
+                k1 = (self.tail + 1) % self.depth
+                main.wait_event(self.ready[k1])
+            loss = self.e.step_ahead_graph(self.slots[k][1], self.slots[k][2], self.slots[k1][0])
         self.free[k].record(main)
         self.tail += 1
         return loss
@@ -219,9 +239,6 @@ class DeepFMPSEngine:
                 group.finish_init(s, 0)
         # persistent buffers
         f32 = dict(dtype=torch.float32, device=dev)
-        self.uniq = torch.empty(G * B, dtype=torch.int64, device=dev)
-        self.inv = torch.empty(G * B, dtype=torch.int32, device=dev)
-        self.n_unique = torch.empty(G, dtype=torch.int32, device=dev)
         import ctypes as _ctb
 
         self.bounds = (_ctb.c_int64 * G)(*[int(r) for r in group_rows])  # id ranges: dedup by direct address
@@ -238,10 +255,30 @@ class DeepFMPSEngine:
         self.zero_versions = [0] * group.n_shards
 
         self.loss_fn = torch.nn.BCEWithLogitsLoss()
-        self._build_segs()
+        # everything addressed through one (uniq, inv, n_unique) triple is a "plan"; the lookahead
+        # pipeline (prepare / step_ahead) alternates between two of them
+        self.plans = [self._make_plan()]
+        self.cur = 0
+        self.side = None
+        self.graph = None
+        self.graphs_ahead = None
         if self.exchange == "owner":
             group.xchg_create(G, B, self.deep_ids, self.wide_ids)
         self.steps = 0
+
+    _PLAN_ATTRS = ("uniq", "inv", "n_unique", "pull_segs", "push_segs", "pull_pair", "push_pair", "tower_args")
+
+    def _make_plan(self):
+        dev, G, B = self.device, self.G, self.B
+        self.uniq = torch.empty(G * B, dtype=torch.int64, device=dev)
+        self.inv = torch.empty(G * B, dtype=torch.int32, device=dev)
+        self.n_unique = torch.empty(G, dtype=torch.int32, device=dev)
+        self._build_segs()
+        return {k: getattr(self, k) for k in self._PLAN_ATTRS}
+
+    def _use(self, p):
+        self.__dict__.update(self.plans[p])
+        self.cur = p
 
     def _seg_items(self, ids_tab, rows, dim):
         B = self.B
@@ -307,10 +344,10 @@ class DeepFMPSEngine:
         arr, n = self.pull_dense_segs
         check(lib.b200ps_pull_dense(h, arr, n, st))
         # (2) unique ids per group; wide and deep tables of a group share them
-        e = mark("unique")
-        check(lib.b200ps_unique_bounded(h, ids.data_ptr(), G, B, self.bounds, self.uniq.data_ptr(), self.inv.data_ptr(),
-                                        self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st))
-        done(e)
+        if ids is not None:
+            e = mark("unique")
+            self._unique_into(ids)
+            done(e)
         # (3) pull the unique rows of all 76 tables
         if self.exchange == "owner":
             e = mark("pull_exchange")
@@ -364,6 +401,76 @@ class DeepFMPSEngine:
         self.steps += 1
         return loss.detach().reshape(())
 
+    def _unique_into(self, ids):
+        """tf.unique per id group into the current plan, on the current stream."""
+        g = self.group
+        check(g.lib.b200ps_unique_bounded(g._h, ids.data_ptr(), self.G, self.B, self.bounds, self.uniq.data_ptr(),
+                                          self.inv.data_ptr(), self.n_unique.data_ptr(), self.ws.data_ptr(),
+                                          self.ws.numel(), g._stream()))
+
+    # ------------------------------------------------------------------ lookahead pipeline
+    def prepare(self, ids):
+        """Start the lookahead pipeline: deduplicate the FIRST batch's ids.  Afterwards every
+        step_ahead(dense_i, labels_i, ids_{i+1}) trains on batch i while the ids of batch i+1 are
+        deduplicated on a second stream (the dedup only depends on the input batch, like the
+        reference's dataset.prefetch(1) work, elasticdl/python/worker/worker.py:334)."""
+        if len(self.plans) == 1:
+            cur = self.cur
+            self.plans.append(self._make_plan())
+            self._use(cur)
+            self.side = torch.cuda.Stream(device=self.device)
+        self._unique_into(ids)
+
+    def step_ahead(self, dense, labels, next_ids, ev=None):
+        """One training step on the prepared batch + the dedup of `next_ids` (int64 [G, B], device)
+        overlapped on the side stream.  Same kernels, same results as step()."""
+        if len(self.plans) != 2:
+            raise RuntimeError("call prepare(first_ids) before step_ahead")
+        main = torch.cuda.current_stream(self.device)
+        p = self.cur
+        self.side.wait_stream(main)  # fork: the other plan's buffers were last read by the previous step
+        self._use(1 - p)
+        with torch.cuda.stream(self.side):
+            self._unique_into(next_ids)
+        self._use(p)
+        loss = self.step(None, dense, labels, ev=ev)
+        main.wait_stream(self.side)  # join
+        self._use(1 - p)
+        return loss
+
+    def capture_ahead(self):
+        """Two CUDA graphs (one per plan parity) of step_ahead over the static input buffers."""
+        if self.tower_kind != "fused":
+            raise RuntimeError("graph capture needs the fused tower (torch autograd allocates)")
+        dev, G, B = self.device, self.G, self.B
+        if len(self.plans) != 2:
+            raise RuntimeError("call prepare(first_ids) before capture_ahead")
+        self.s_ids = torch.zeros((G, B), dtype=torch.int64, device=dev)
+        self.s_dense = torch.zeros((B, N_DENSE), dtype=torch.float32, device=dev)
+        self.s_labels = torch.zeros(B, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize(dev)
+        start, steps = self.cur, self.steps
+        self.graphs_ahead = [None, None]
+        for p in (start, 1 - start):
+            assert self.cur == p
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                self.step_ahead(self.s_dense, self.s_labels, self.s_ids)
+            self.graphs_ahead[p] = gr
+        self._use(start)
+        self.steps = steps  # capture does not execute
+        return self.graphs_ahead
+
+    def step_ahead_graph(self, dense, labels, next_ids):
+        """step_ahead through the captured graphs; inputs may be pinned-host or device tensors."""
+        self.s_ids.copy_(next_ids, non_blocking=True)
+        self.s_dense.copy_(dense, non_blocking=True)
+        self.s_labels.copy_(labels, non_blocking=True)
+        self.graphs_ahead[self.cur].replay()
+        self._use(1 - self.cur)
+        self.steps += 1
+        return self.loss_buf.reshape(())
+
     # ------------------------------------------------------------------ CUDA graph
     def capture(self):
         """Capture one whole step (19 launches + the versions read-back) into a CUDA graph.
@@ -391,11 +498,11 @@ class DeepFMPSEngine:
         self.steps += 1
         return self.loss_buf.reshape(())
 
-    def host_feeder(self, depth=2):
+    def host_feeder(self, depth=2, lookahead=False):
         """Input pipeline for host-resident batches: H2D copies run on a side stream into
         `depth` staging slots and overlap the previous step's kernels (the reference prefetches
         one batch too: dataset.prefetch(1), elasticdl/python/worker/worker.py:334)."""
-        return HostFeeder(self, depth)
+        return HostFeeder(self, depth, lookahead)
 
     def _torch_tower(self, dense, labels, mark, done, st):
         """Steps (4)-(6) with torch autograd over library kernels (A/B reference for the fused tower)."""

@@ -215,6 +215,52 @@ def test_deepfm_engine_step_matches_oracle_adam(n_shards, B, rows, tower_kind, p
     group.close()
 
 
+def _engine_state(group, eng, rows):
+    t = [group.pull_rows([(n, torch.arange(r))])[0].cpu().numpy() for n, r in zip(eng.wide_names + eng.deep_names, rows + rows)]
+    d = group.pull_dense([n for n, _ in eng.params])
+    return t + [d[n].cpu().numpy() for n, _ in eng.params]
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_engine_lookahead_pipeline_is_bit_identical(use_graph):
+    """prepare/step_ahead (dedup of batch i+1 on a second stream while batch i trains) runs the same
+    kernels on the same data as step(): losses, rows, optimizer-updated dense parameters bit for bit."""
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.workloads.deepfm import DeepFMPSEngine, HostFeeder, synthetic_batch
+
+    rows, B, steps = [11, 700, 5000, 9, 64], 256, 6
+    batches = [synthetic_batch(B, 40 + i, torch.device("cuda", 0), "zipf", group_rows=rows) for i in range(steps)]
+    results = []
+    for mode in ("plain", "ahead"):
+        group = PSGroup(2, *ADAM, device=0)
+        eng = DeepFMPSEngine(group, B, group_rows=rows)
+        losses = []
+        if mode == "plain":
+            for ids, dense, labels in batches:
+                losses.append(float(eng.step(ids, dense, labels)))
+        elif not use_graph:
+            eng.prepare(batches[0][0])
+            for i, (_, dense, labels) in enumerate(batches):
+                losses.append(float(eng.step_ahead(dense, labels, batches[min(i + 1, steps - 1)][0])))
+        else:  # through the host feeder: pinned host batches, captured graphs
+            feeder = HostFeeder(eng, 3, lookahead=True)
+            host = [tuple(t.cpu().pin_memory() for t in b) for b in batches]
+            feeder.submit(*host[0])
+            feeder.submit(*host[1])
+            for i in range(steps):
+                if i + 2 < steps:
+                    feeder.submit(*host[i + 2])
+                losses.append(float(feeder.run_next()))
+        group.check()
+        results.append((losses, _engine_state(group, eng, rows), [s_[0] for s_ in group.snapshot()]))
+        group.close()
+    (l0, s0, v0), (l1, s1, v1) = results
+    assert l0 == l1, (l0, l1)
+    assert v0 == v1 == [steps, steps]
+    for a, b in zip(s0, s1):
+        assert np.array_equal(a, b)
+
+
 def test_multi_gpu_peer_shards_via_torchrun():
     """Rank-per-GPU group with CUDA-IPC peer shards (needs >= 2 GPUs; skipped on 1)."""
     import os
@@ -228,3 +274,21 @@ def test_multi_gpu_peer_shards_via_torchrun():
                           "--master-addr", "127.0.0.1", "--master-port", "29533",
                           os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "mgpu_check ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("script,token", [("mgpu_xchg_check.py", "mgpu_xchg_check ok"),
+                                          ("mgpu_allreduce_check.py", "mgpu_allreduce ok")])
+def test_multi_gpu_exchange_and_allreduce_via_torchrun(script, token):
+    """Owner-computes NVLink exchange (pull bit-exact vs direct peer access, push bit-exact vs the
+    oracle) and the allreduce controller over NCCL (needs >= 2 GPUs; skipped on 1)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run: gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29534",
+                          os.path.join(root, "tests", script)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and token in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
