@@ -149,6 +149,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tower", default="fused", choices=["fused", "torch"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE eager step between cudaProfilerStart/Stop after the warm-up and exit "
+                         "(for `ncu --profile-from-start off`; prints no bench line)")
     ap.add_argument("--lookahead", default="on", choices=["on", "off"],
                     help="deduplicate the ids of batch i+1 on a second stream while batch i trains (graph mode)")
     ap.add_argument("--paired", default="off", choices=["on", "off"],
@@ -245,6 +248,13 @@ def main():
     for i in range(args.warmup):
         engine.step(*devb[i % args.pool])
     sync_all()
+    if args.profile_step:
+        torch.cuda.cudart().cudaProfilerStart()
+        engine.step(*devb[args.warmup % args.pool])
+        torch.cuda.synchronize(dev)
+        torch.cuda.cudart().cudaProfilerStop()
+        group.check()
+        return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

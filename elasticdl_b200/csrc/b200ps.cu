@@ -1313,6 +1313,8 @@ int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k
   ws.fp = (int*)p; p += align256((size_t)T * k * 4);
   ws.rank_at = (int*)p; p += align256((size_t)T * k * 4);
   ws.tile_cnt = (int*)p;
+  ws.hdr = (unsigned long long*)((char*)workspace_dev + b200ps_unique_workspace(T, k) - 256);
+  ws.magic = 0xB2005EED00000000ULL ^ mix64(((uint64_t)T << 40) ^ (uint64_t)k);
   UniqueBounds ub{};
   const int use_bounds = bounds != nullptr && T <= kMaxSegs;
   long long max_clear = ws.cap;
@@ -1326,10 +1328,16 @@ int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k
       if (ub.bound[t] > max_clear) max_clear = ub.bound[t];
     }
   }
+  ws.tagged = use_bounds && k <= (1LL << kUniqPosBits);
   dim3 gc((unsigned)((max_clear + 2047) / 2048), T);
   k_uniq_clear<<<gc, 256, 0, st>>>(ws, T, ub, use_bounds);
   dim3 gk((unsigned)((k + 255) / 256), T), gt(ws.ntiles, T);
-  k_uniq_insert<<<gk, 256, 0, st>>>(ids_dev, k, ws, ub, use_bounds);
+  const long long head = k < 2 * kUniqHead ? k : kUniqHead;
+  k_uniq_insert<<<dim3((unsigned)((head + 255) / 256), T), 256, 0, st>>>(ids_dev, k, 0, head, ws, ub, use_bounds);
+  if (head < k) {
+    k_uniq_insert<<<dim3((unsigned)((k - head + 255) / 256), T), 256, 0, st>>>(ids_dev, k, head, k, ws, ub, use_bounds);
+    count_launch(ps, 1);
+  }
   k_uniq_flag<<<gt, 256, 0, st>>>(k, ws, ub, use_bounds);
   k_uniq_scan_tiles<<<T, 1024, 0, st>>>(ws, n_unique_dev);
   k_uniq_rank<<<gt, 256, 0, st>>>(ids_dev, k, ws, uniq_dev);

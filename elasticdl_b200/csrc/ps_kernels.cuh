@@ -774,11 +774,30 @@ struct UniqueWs {
   int* tile_cnt;    // [T][ntiles]
   int cap;          // power of two >= 2k
   int ntiles;
+  // Direct-address segments are not cleared between calls: positions are stored under an epoch
+  // prefix that DEcreases from call to call, so atomicMin prefers this call's entries and stale
+  // ones read as empty.  hdr = {magic, epoch} lives in the workspace (a fresh / foreign workspace
+  // fails the magic test and is cleared); every kUniqEpochs calls the prefix wraps and the
+  // arrays are cleared for real.
+  unsigned long long* hdr;
+  unsigned long long magic;
+  int tagged;  // k <= 2^20: positions fit under the prefix
 };
+
+constexpr int kUniqPosBits = 20;
+constexpr int kUniqEpochs = 2047;  // prefixes 0..2046 keep the value below 0x7fffffff (= empty)
+
+__device__ __forceinline__ int uniq_epoch(const UniqueWs& ws) {  // stable until k_uniq_scan_tiles bumps it
+  return ws.hdr[0] == ws.magic ? (int)(ws.hdr[1] % kUniqEpochs) : 0;
+}
+__device__ __forceinline__ int uniq_prefix(const UniqueWs& ws) {
+  return ws.tagged ? (kUniqEpochs - 1 - uniq_epoch(ws)) << kUniqPosBits : 0;
+}
 
 __global__ void __launch_bounds__(256) k_uniq_clear(UniqueWs ws, int T, UniqueBounds ub, int use_bounds) {
   const int t = blockIdx.y;
   const int direct = use_bounds && ub.bound[t] > 0;
+  if (direct && ws.tagged && uniq_epoch(ws) != 0) return;  // stale prefixes already read as empty
   const int n = direct ? ub.bound[t] : ws.cap;
   long long* keys = ws.keys + (long long)t * ws.cap;
   int* minpos = direct ? ub.dpos + ub.off[t] : ws.minpos + (long long)t * ws.cap;
@@ -788,21 +807,27 @@ __global__ void __launch_bounds__(256) k_uniq_clear(UniqueWs ws, int T, UniqueBo
   }
 }
 
-__global__ void __launch_bounds__(256) k_uniq_insert(const int64_t* ids, long long k, UniqueWs ws, UniqueBounds ub,
-                                                     int use_bounds) {
+// Positions [begin, end) of every segment.  The host launches the first kUniqHead positions on
+// their own: Zipf-hot ids almost surely occur there, so when the bulk launch starts their slots
+// already hold a small position and the check-before-atomic below skips them -- launched as one
+// wave, ~1000 resident blocks all saw "empty" and queued thousands of atomics on the same address.
+constexpr int kUniqHead = 2048;
+__global__ void __launch_bounds__(256) k_uniq_insert(const int64_t* ids, long long k, long long begin, long long end,
+                                                     UniqueWs ws, UniqueBounds ub, int use_bounds) {
   const int t = blockIdx.y;
   if (use_bounds && ub.bound[t] > 0) {  // direct-address segment (block-uniform)
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= k) return;
+    const long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
     long long id = ids[t * k + i];
     if (id < 0 || id >= ub.bound[t]) id = 0;  // out-of-range ids are reported by the table kernels
     int* minpos = ub.dpos + ub.off[t];
-    if (*(volatile int*)&minpos[id] > (int)i) atomicMin(&minpos[id], (int)i);
+    const int v = uniq_prefix(ws) | (int)i;
+    if (*(volatile int*)&minpos[id] > v) atomicMin(&minpos[id], v);
     ws.fp[t * k + i] = (int)id;
     return;
   }
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < k;
+  const long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < end;
   const int lane = threadIdx.x & 31;
   // warp-level id dedup: lanes holding the same id elect the lowest lane (= smallest position),
   // which alone probes the table; Zipf-hot ids then cost one atomic per warp, not one per lane.
@@ -844,14 +869,16 @@ __global__ void __launch_bounds__(256) k_uniq_flag(long long k, UniqueWs ws, Uni
   __shared__ int red[8];
   const int t = blockIdx.y;
   const long long base = (long long)blockIdx.x * kTile;
-  const int* minpos = (use_bounds && ub.bound[t] > 0) ? ub.dpos + ub.off[t] : ws.minpos + (long long)t * ws.cap;
+  const bool direct = use_bounds && ub.bound[t] > 0;
+  const int* minpos = direct ? ub.dpos + ub.off[t] : ws.minpos + (long long)t * ws.cap;
+  const int pos_mask = direct && ws.tagged ? (1 << kUniqPosBits) - 1 : 0x7fffffff;
   int* fp = ws.fp + t * k;
   int cnt = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     long long i = base + j * 256 + threadIdx.x;
     if (i < k) {
-      int f = minpos[fp[i]];
+      int f = minpos[fp[i]] & pos_mask;
       fp[i] = f;
       cnt += (f == (int)i);
     }
@@ -895,6 +922,11 @@ __global__ void __launch_bounds__(1024) k_uniq_scan_tiles(UniqueWs ws, int* n_un
     __syncthreads();
   }
   if (threadIdx.x == 0) n_unique[t] = carry;
+  if (t == 0 && threadIdx.x == 0) {  // insert / flag are done with this call's epoch: open the next one
+    const bool fresh = ws.hdr[0] != ws.magic;
+    ws.hdr[1] = fresh ? 1ULL : ws.hdr[1] + 1ULL;
+    ws.hdr[0] = ws.magic;
+  }
 }
 
 __global__ void __launch_bounds__(256) k_uniq_rank(const int64_t* ids, long long k, UniqueWs ws, int64_t* uniq) {

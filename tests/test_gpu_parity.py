@@ -721,6 +721,39 @@ def test_unique_bounded_direct_address_segments():
     group.close()
 
 
+def test_unique_bounded_epoch_tags_survive_reuse_and_wraparound():
+    """Direct-address segments are not cleared between calls (epoch-prefixed positions, a real
+    clear every 2047 calls): 2100 calls on one dirty workspace with fresh ids each time, and a
+    workspace full of garbage, all equal tf.unique."""
+    import ctypes
+
+    from elasticdl_b200 import _lib
+
+    group, _, _ = make_pair(1)
+    lib = _lib.lib()
+    T, k = 3, 700
+    bounds = [5, 900, 40000]
+    arr = (ctypes.c_int64 * T)(*bounds)
+    need = lib.b200ps_unique_bounded_workspace(T, k, arr)
+    ws = torch.randint(0, 255, (need,), dtype=torch.uint8, device="cuda")  # garbage, not zeros
+    uniq = torch.empty(T * k, dtype=torch.int64, device="cuda")
+    inv = torch.empty(T * k, dtype=torch.int32, device="cuda")
+    n = torch.empty(T, dtype=torch.int32, device="cuda")
+    rng = np.random.RandomState(3)
+    pool = [np.stack([rng.randint(0, b, size=k) for b in bounds]).astype(np.int64) for _ in range(7)]
+    d_pool = [torch.from_numpy(p).cuda().view(-1) for p in pool]
+    for call in range(2100):
+        j = call % len(pool)
+        _lib.check(lib.b200ps_unique_bounded(group._h, d_pool[j].data_ptr(), T, k, arr, uniq.data_ptr(), inv.data_ptr(),
+                                             n.data_ptr(), ws.data_ptr(), ws.numel(), group._stream()))
+        if call < 5 or call % 211 == 0 or 2040 <= call <= 2055 or call == 2099:
+            u, i, c = uniq.cpu().numpy().reshape(T, k), inv.cpu().numpy().reshape(T, k), n.cpu().numpy()
+            for t in range(T):
+                wu, wi = O.unique_first_occurrence(pool[j][t])
+                assert c[t] == len(wu) and np.array_equal(u[t, : c[t]], wu) and np.array_equal(i[t], wi), (call, t)
+    group.close()
+
+
 # ------------------------------------------------------------------ kernel_api.h drop-ins on raw device arrays
 @pytest.mark.parametrize("n", [10, 1001, 4096 * 33])
 def test_raw_kernel_api_matches_oracle_bit_exact(n):
