@@ -1329,7 +1329,10 @@ int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k
     }
   }
   ws.tagged = use_bounds && k <= (1LL << kUniqPosBits);
-  dim3 gc((unsigned)((max_clear + 2047) / 2048), T);
+  // direct-address segments are only cleared once per kUniqEpochs calls: a thin grid-stride launch
+  long long clear_blocks = (max_clear + 2047) / 2048;
+  if (ws.tagged && clear_blocks > 8) clear_blocks = 8;
+  dim3 gc((unsigned)clear_blocks, T);
   k_uniq_clear<<<gc, 256, 0, st>>>(ws, T, ub, use_bounds);
   dim3 gk((unsigned)((k + 255) / 256), T), gt(ws.ntiles, T);
   const long long head = k < 2 * kUniqHead ? k : kUniqHead;

@@ -47,7 +47,17 @@ __global__ void __launch_bounds__(256) k_tower_prep(b200_deepfm_args_t a, int n_
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid == 0) *a.loss = 0.f;
-  for (long long i = tid; i < n_params; i += stride) a.grads[i] = 0.f;
+  if (blockIdx.y == 0) {
+    for (long long i = tid; i < n_params; i += stride) a.grads[i] = 0.f;
+    // W1 transposed to [IN][16] once per step (behind the per-sample scratch): every k_tower_a block
+    // then fills its shared memory with straight 16-byte copies instead of 5072 scattered stores
+    const Layout l = layout(a.G);
+    float* w1t = a.scratch + (long long)a.B * SCR;
+    for (long long i = tid; i < (long long)H1 * l.in; i += stride) {
+      const int j = (int)(i / l.in), e = (int)(i - (long long)j * l.in);
+      w1t[e * H1 + j] = a.params[l.o_w1 + i];
+    }
+  }
   // live rows only: rows >= n_unique[g] are never read by the push
   for (int g = blockIdx.y; g < a.G; g += gridDim.y) {
     const int u = a.n_unique[g];
@@ -80,10 +90,18 @@ __device__ inline SmemParams carve(float* smem, int in) {
 }
 __host__ __device__ inline size_t smem_floats(int in) { return (size_t)in * H1 + H1 + H2 * H1 + H2 + H2 + WD_PAD; }
 
-__device__ inline void load_params(const float* __restrict__ p, const Layout& l, SmemParams s) {
-  for (int i = threadIdx.x; i < H1 * l.in; i += blockDim.x) {
-    int j = i / l.in, e = i - j * l.in;  // coalesced read of w1[j][e]
-    s.w1t[e * H1 + j] = p[l.o_w1 + i];
+// w1t_global: W1 already transposed by k_tower_prep (training), or nullptr (forward only)
+__device__ inline void load_params(const float* __restrict__ p, const float* __restrict__ w1t_global, const Layout& l,
+                                   SmemParams s) {
+  if (w1t_global != nullptr) {
+    const float4* src = reinterpret_cast<const float4*>(w1t_global);
+    float4* dst = reinterpret_cast<float4*>(s.w1t);
+    for (int i = threadIdx.x; i < H1 * l.in / 4; i += blockDim.x) dst[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < H1 * l.in; i += blockDim.x) {
+      int j = i / l.in, e = i - j * l.in;  // coalesced read of w1[j][e]
+      s.w1t[e * H1 + j] = p[l.o_w1 + i];
+    }
   }
   for (int i = threadIdx.x; i < H1; i += blockDim.x) s.b1[i] = p[l.o_b1 + i];
   for (int i = threadIdx.x; i < H2 * H1; i += blockDim.x) s.w2[i] = p[l.o_w2 + i];
@@ -156,7 +174,7 @@ __global__ void __launch_bounds__(TA_THREADS, 2) k_tower_a(b200_deepfm_args_t a)
   SmemParams sp = carve(smem, l.in);
   float* red = smem + smem_floats(l.in);                       // [NPART][RW][SPB]
   int* sinv = reinterpret_cast<int*>(red + NPART * RW * SPB);  // [G][SPB]
-  load_params(a.params, l, sp);
+  load_params(a.params, BACKWARD ? a.scratch + (long long)a.B * SCR : nullptr, l, sp);
   const int B = a.B, G = a.G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int part = warp % NPART;
@@ -361,20 +379,26 @@ __global__ void __launch_bounds__(TA_THREADS, 2) k_tower_a(b200_deepfm_args_t a)
 #pragma unroll
           for (int n = 0; n < NS; ++n) {
             x[n][D] = dz[n];  // wide row gradient
-            // warp-level id dedup: lanes hitting the same row combine (lane order), lowest lane writes
+            // warp-level id dedup: lanes hitting the same row combine pairwise up a tree threaded
+            // through the peer mask (pointer doubling), ceil(log2(max multiplicity)) rounds for the
+            // whole warp -- the small tables of this model put ~10 equal ids in every warp
             const int key = live[n] ? r[u][n] : -1 - lane;
             const unsigned peers = __match_any_sync(0xffffffffu, key);
-            const bool leader = (__ffs(peers) - 1) == lane;
-            unsigned rest = peers & ~(1u << lane);
+            const int rank = __popc(peers & ((1u << lane) - 1));
+            const bool leader = rank == 0;
             const int maxn = __reduce_max_sync(0xffffffffu, (unsigned)__popc(peers));
-            for (int it = 1; it < maxn; ++it) {
-              const int src = rest ? __ffs(rest) - 1 : lane;
+            const unsigned above = peers & ~((2u << lane) - 1);
+            int nxt = above ? __ffs(above) - 1 : -1;  // peer `step` ranks above me
+            for (int step = 1; step < maxn; step <<= 1) {
+              const int src = nxt >= 0 ? nxt : lane;
+              const bool take = nxt >= 0 && (rank & (2 * step - 1)) == 0;
 #pragma unroll
               for (int e = 0; e <= D; ++e) {
                 const float yv = __shfl_sync(0xffffffffu, x[n][e], src);
-                if (leader && rest) x[n][e] += yv;
+                if (take) x[n][e] += yv;
               }
-              rest &= rest - 1;
+              const int nn = __shfl_sync(0xffffffffu, nxt, src);
+              nxt = nxt >= 0 ? nn : -1;
             }
             if (live[n] && leader) {
               float* od = a.gsum_deep + ((long long)g * B + r[u][n]) * D;

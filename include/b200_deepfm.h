@@ -46,7 +46,7 @@ typedef struct {
   float* gsum_deep;        /* [G][B][8] */
   float* loss;             /* [1] mean binary cross entropy with logits */
   float* logits;           /* [B] or NULL */
-  float* scratch;          /* [B][B200_DEEPFM_SCRATCH] */
+  float* scratch;          /* B*B200_DEEPFM_SCRATCH + 16*(13+8G) floats: per-sample backward state, then W1^T */
 } b200_deepfm_args_t;
 
 size_t b200_deepfm_param_count(int G);
