@@ -422,46 +422,31 @@ __host__ inline size_t tower_a_smem(int G) {
   return (smem_floats(ND + G * D) + (size_t)NPART * RW * SPB) * sizeof(float) + (size_t)G * SPB * sizeof(int);
 }
 
-constexpr int S_CHUNK = 32;                    // samples per staged chunk
+// parameter gradients.  dW1 = dH1^T [16 x B] . X [B x IN] is a contraction over the batch: a block
+// stages a chunk of S samples in shared memory -- the per-sample backward state written by
+// k_tower_a and the gathered input rows X (cooperative, fully independent 32 B row gathers) --
+// then thread e owns input column e with 16 accumulators; the remaining threads own db1 and
+// the small gradients (dW2, db2, dw3, dw_dense).  One atomicAdd per output per block.
+constexpr int S_CHUNK = 32;  // 52 KB of shared memory per block -> 4 blocks (16 warps) per SM
 constexpr int TB_COLW = 96;                    // threads owning dW1/db1 columns (3 warps)
 constexpr int TB_CPT = 4;                      // columns per thread: each staged dh1 row feeds 64 FMAs
 constexpr int TB_THREADS = TB_COLW + 32;       // + one warp for the small gradients
-constexpr int TB_MAXG = (TB_COLW * TB_CPT - ND - 1) / D;                     // 46 id groups
-constexpr int TB_IPT = (S_CHUNK * TB_MAXG + TB_THREADS - 1) / TB_THREADS;    // row gathers per thread per chunk
 constexpr int N_SMALL = H2 * H1 + H2 + H2 + ND;  // dW2 64 | db2 4 | dw3 4 | dw_dense 13
 
 // tile row: [deep G*8 | dense 13 | 1.0 (bias column) | pad]
 __host__ __device__ inline int tb_xpad(int G) { return (G * D + ND + 1 + 3) / 4 * 4; }
-__host__ __device__ inline size_t tb_buf_floats(int G) { return (size_t)S_CHUNK * SCR + (size_t)S_CHUNK * tb_xpad(G); }
-__host__ inline size_t tower_b_smem(int G) { return 2 * tb_buf_floats(G) * sizeof(float); }  // double buffered: ~93 KB
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+__host__ inline size_t tower_b_smem(int G) {
+  return ((size_t)S_CHUNK * SCR + (size_t)S_CHUNK * tb_xpad(G)) * sizeof(float) + (size_t)G * S_CHUNK * sizeof(int);
 }
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// parameter gradients.  dW1 = dH1^T [16 x B] . X [B x IN] is a contraction over the batch: a block
-// stages chunks of S samples in shared memory -- the per-sample backward state written by
-// k_tower_a and the gathered input rows X -- then thread e owns input column e with 16
-// accumulators; the last warp owns the small gradients (dW2, db2, dw3, dw_dense).  Staging is
-// asynchronous and double buffered: the ranks of chunk c+2 are in flight in registers and the
-// cp.async row gathers of chunk c+1 land in the other buffer while chunk c is contracted (the
-// first version staged synchronously: half of its time was spent waiting on these gathers).
-// One atomicAdd per output per block.
-__global__ void __launch_bounds__(TB_THREADS, 2) k_tower_b(b200_deepfm_args_t a) {
+__global__ void __launch_bounds__(TB_THREADS, 4) k_tower_b(b200_deepfm_args_t a) {
   extern __shared__ __align__(16) float smem_b[];
   const Layout l = layout(a.G);
   const int B = a.B, G = a.G, t = threadIdx.x;
   const int IN = l.in, XP = tb_xpad(G), NDEEP = G * D, NCOL = IN + 1;
-  float* sc_[2] = {smem_b, smem_b + tb_buf_floats(G)};                      // [S][SCR]
-  float* xt_[2] = {sc_[0] + S_CHUNK * SCR, sc_[1] + S_CHUNK * SCR};         // [S][XP]
+  float* sc = smem_b;                                     // [S][SCR]
+  float* xt = sc + S_CHUNK * SCR;                         // [S][XP]
+  int* sinv = reinterpret_cast<int*>(xt + S_CHUNK * XP);  // [G][S]
   const bool is_col = t < TB_COLW;
   float acc[TB_CPT][H1];
 #pragma unroll
@@ -470,56 +455,34 @@ __global__ void __launch_bounds__(TB_THREADS, 2) k_tower_b(b200_deepfm_args_t a)
     for (int j = 0; j < H1; ++j) acc[i][j] = 0.f;
   float sacc[3] = {0.f, 0.f, 0.f};  // small outputs o = (t - TB_COLW) + 32*i
   const long long nchunk = ((long long)B + S_CHUNK - 1) / S_CHUNK;
-  for (int i = t; i < 2 * S_CHUNK; i += TB_THREADS) xt_[i / S_CHUNK][(i % S_CHUNK) * XP + NDEEP + ND] = 1.0f;  // bias column
-
-  int rk[TB_IPT];  // ranks of the chunk staged next (item i = t + k*TB_THREADS: group i/32, sample i%32)
-  auto load_ranks = [&](long long c) {
+  for (long long c = blockIdx.x; c < nchunk; c += gridDim.x) {
     const long long b0 = c * S_CHUNK;
     const int n = (int)min((long long)S_CHUNK, B - b0);
-#pragma unroll
-    for (int k = 0; k < TB_IPT; ++k) {
-      const int i = t + k * TB_THREADS, g = i / S_CHUNK, s_ = i % S_CHUNK;
-      rk[k] = (g < G && s_ < n) ? a.inv[(long long)g * B + b0 + s_] : -1;
-    }
-  };
-  auto stage = [&](long long c, float* sc, float* xt) {  // asynchronous: returns before the data lands
-    const long long b0 = c * S_CHUNK;
-    const int n = (int)min((long long)S_CHUNK, B - b0);
-    for (int i = t; i < n * (SCR / 4); i += TB_THREADS) cp_async16(sc + 4 * i, a.scratch + b0 * SCR + 4 * i);
-    for (int i = t; i < n * ND; i += TB_THREADS) {
-      const int s_ = i / ND, e = i - s_ * ND;
-      cp_async4(xt + s_ * XP + NDEEP + e, a.dense + b0 * ND + i);
-    }
-#pragma unroll
-    for (int k = 0; k < TB_IPT; ++k) {
-      if (rk[k] >= 0) {
-        const int i = t + k * TB_THREADS, g = i / S_CHUNK, s_ = i % S_CHUNK;
-        const float* row = a.bet_deep + ((long long)g * B + rk[k]) * D;
-        float* dst = xt + s_ * XP + g * D;
-        cp_async16(dst, row);
-        cp_async16(dst + 4, row + 4);
+    __syncthreads();
+    {
+      const float4* src = reinterpret_cast<const float4*>(a.scratch + b0 * SCR);
+      float4* dst = reinterpret_cast<float4*>(sc);
+      for (int i = t; i < n * (SCR / 4); i += TB_THREADS) dst[i] = src[i];
+      for (int i = t; i < n * (ND + 1); i += TB_THREADS) {
+        const int s_ = i / (ND + 1), e = i - s_ * (ND + 1);
+        xt[s_ * XP + NDEEP + e] = e < ND ? a.dense[(b0 + s_) * ND + e] : 1.0f;
+      }
+      for (int i = t; i < G * n; i += TB_THREADS) {  // coalesced rank loads
+        const int g = i / n, s_ = i - g * n;
+        sinv[g * S_CHUNK + s_] = a.inv[(long long)g * B + b0 + s_];
       }
     }
-  };
-  const long long step = gridDim.x;
-  long long c = blockIdx.x;
-  if (c < nchunk) {
-    load_ranks(c);
-    stage(c, sc_[0], xt_[0]);
-    if (c + step < nchunk) load_ranks(c + step);
-  }
-  cp_async_commit();
-  for (int it = 0; c < nchunk; c += step, ++it) {
-    const float* sc = sc_[it & 1];
-    const float* xt = xt_[it & 1];
-    if (c + step < nchunk) {
-      stage(c + step, sc_[(it + 1) & 1], xt_[(it + 1) & 1]);
-      if (c + 2 * step < nchunk) load_ranks(c + 2 * step);
-    }
-    cp_async_commit();
-    cp_async_wait<1>();  // everything but the group just committed: chunk c has landed
     __syncthreads();
-    const int n = (int)min((long long)S_CHUNK, B - c * S_CHUNK);
+#pragma unroll 4
+    for (int i = t; i < n * G; i += TB_THREADS) {  // independent 32 B row gathers, group fastest
+      const int s_ = i / G, g = i - s_ * G;
+      const float4* row = reinterpret_cast<const float4*>(a.bet_deep + ((long long)g * B + sinv[g * S_CHUNK + s_]) * D);
+      const float4 e0 = row[0], e1 = row[1];
+      float4* dst = reinterpret_cast<float4*>(xt + s_ * XP + g * D);
+      dst[0] = e0;
+      dst[1] = e1;
+    }
+    __syncthreads();
     if (is_col) {
 #pragma unroll 2
       for (int s_ = 0; s_ < n; ++s_) {
@@ -549,9 +512,7 @@ __global__ void __launch_bounds__(TB_THREADS, 2) k_tower_b(b200_deepfm_args_t a)
         }
       }
     }
-    __syncthreads();  // this buffer is staged again by the next iteration
   }
-  cp_async_wait<0>();
   if (is_col) {
 #pragma unroll
     for (int i = 0; i < TB_CPT; ++i) {
@@ -625,7 +586,7 @@ int b200_deepfm_fwd_bwd(const b200_deepfm_args_t* args, void* stream) {
   if (gc == 2) k_tower_a<true, 2><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
   else k_tower_a<true, 1><<<(unsigned)(blocks < cap ? blocks : cap), TA_THREADS, smem, st>>>(*args);
   long long chunks = ((long long)args->B + S_CHUNK - 1) / S_CHUNK;
-  cap = (long long)n_sm * 2;  // 2 blocks per SM (double-buffered shared memory)
+  cap = (long long)n_sm * 4;  // 4 blocks per SM by shared memory / registers
   static bool attr_b[64] = {false};
   if (dev < 64 && !attr_b[dev]) {
     cudaFuncSetAttribute(k_tower_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
