@@ -366,24 +366,8 @@ int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense
   return B200PS_OK;
 }
 
-// Blocks of 256 threads of `kernel` that fit one SM (register / shared-memory limited): the flat row
-// kernels launch exactly one resident wave -- a partial second wave would cost a whole extra block
-// lifetime (measured: 1184 blocks on 888 slots took longer than the unbalanced per-segment grid).
-static int resident_blocks_per_sm(const void* kernel) {
-  static std::mutex mu;
-  static std::unordered_map<const void*, int> cache;
-  std::lock_guard<std::mutex> lk(mu);
-  auto it = cache.find(kernel);
-  if (it != cache.end()) return it->second;
-  int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, 0) != cudaSuccess || nb < 1) nb = 4;
-  cudaGetLastError();
-  cache[kernel] = nb;
-  return nb;
-}
-
-template <typename K, typename F>
-int for_each_class(b200ps_t* ps, Split& sp, K&& kernel_of, F&& launch, bool dense = false) {
+template <typename F>
+int for_each_class(b200ps_t* ps, Split& sp, F&& launch, bool dense = false) {
   for (int c = 0; c < kClasses; ++c) {
     if (sp.b[c].nseg == 0) continue;
     dim3 grid;
@@ -397,7 +381,7 @@ int for_each_class(b200ps_t* ps, Split& sp, K&& kernel_of, F&& launch, bool dens
       // row kernels stride a flat 1-D grid over the concatenated segments (ps_kernels.cuh FlatWork):
       // one wave of resident blocks, the live lengths are only known on the device
       long long blocks = (sp.sum_work[c] + 255) / 256;
-      const long long cap = (long long)ps->n_sm * resident_blocks_per_sm(kernel_of(c));
+      const long long cap = (long long)ps->n_sm * 8;
       grid = dim3((unsigned)(blocks < 1 ? 1 : blocks > cap ? cap : blocks));
     }
     launch(c, grid, sp.b[c]);
@@ -824,13 +808,7 @@ static int rows_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   if (rc) return rc;
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
-  auto kernel_of = [&](int c) -> const void* {
-    if (c == 3) return write ? (const void*)k_rows_copy_d8<true> : (const void*)k_rows_copy_d8<false>;
-    if (c == 2) return write ? (const void*)k_rows_copy<2, true> : (const void*)k_rows_copy<2, false>;
-    if (c == 1) return write ? (const void*)k_rows_copy<1, true> : (const void*)k_rows_copy<1, false>;
-    return write ? (const void*)k_rows_copy<0, true> : (const void*)k_rows_copy<0, false>;
-  };
-  return for_each_class(ps, sp, kernel_of, [&](int c, dim3 grid, const SegBatch& b) {
+  return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
     if (c == 3) {
       if (write) k_rows_copy_d8<true><<<grid, 256, 0, st>>>(gv, b, slot);
       else k_rows_copy_d8<false><<<grid, 256, 0, st>>>(gv, b, slot);
@@ -863,7 +841,7 @@ static int dense_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* st
   if (rc) return rc;
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
-  return for_each_class(ps, sp, [](int) -> const void* { return nullptr; }, [&](int c, dim3 grid, const SegBatch& b) {
+  return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
     if (write) {
       if (c) k_dense_copy<4, true><<<grid, 256, 0, st>>>(gv, b, slot);
       else k_dense_copy<1, true><<<grid, 256, 0, st>>>(gv, b, slot);
@@ -925,18 +903,7 @@ int b200ps_push_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
   OptParams o = ps->opt;
-  auto kernel_of = [&](int c) -> const void* {
-    const void* k = nullptr;
-    DISPATCH_OPT(o.kind, {
-      if (c == 3) k = (const void*)k_push_rows_d8<OPT>;
-      else if (c == 4) k = (const void*)k_push_rows_d1<OPT>;
-      else if (c == 2) k = (const void*)k_push_rows<OPT, 2>;
-      else if (c == 1) k = (const void*)k_push_rows<OPT, 1>;
-      else k = (const void*)k_push_rows<OPT, 0>;
-    });
-    return k;
-  };
-  return for_each_class(ps, sp, kernel_of, [&](int c, dim3 grid, const SegBatch& b) {
+  return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
     DISPATCH_OPT(o.kind, {
       if (c == 3) k_push_rows_d8<OPT><<<grid, 256, 0, st>>>(gv, b, o);
       else if (c == 4) k_push_rows_d1<OPT><<<grid, 256, 0, st>>>(gv, b, o);
@@ -1172,7 +1139,7 @@ int b200ps_push_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* st
   cudaStream_t st = (cudaStream_t)stream;
   OptParams o = ps->opt;
   const bool twice = (ps->flags & 1u) && o.kind == kAMSGrad;
-  return for_each_class(ps, sp, [](int) -> const void* { return nullptr; }, [&](int c, dim3 grid, const SegBatch& b) {
+  return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
     if (twice) {
       if (c) k_push_dense<kAMSGrad, 4, true><<<grid, 256, 0, st>>>(gv, b, o);
       else k_push_dense<kAMSGrad, 1, true><<<grid, 256, 0, st>>>(gv, b, o);

@@ -175,26 +175,6 @@ __device__ __forceinline__ int flat_seg(const FlatWork& fw, int nseg, long long 
   return lo;
 }
 
-// Grid-stride loop over the flat items.  The id of the NEXT item is loaded before the current one
-// is processed: id -> row address -> row data is the critical path of every row kernel and a
-// thread runs a few items back to back, so the id load of item k+1 hides behind item k.
-struct FlatItem {
-  int si;         // segment
-  long long w;    // item offset inside the segment
-  long long id;   // ids_dev[row] (0 when this lane does not load it)
-};
-template <typename Fetch, typename Body>
-__device__ __forceinline__ void flat_loop(long long first, long long stride, long long total, Fetch&& fetch, Body&& body) {
-  if (first >= total) return;
-  FlatItem cur = fetch(first);
-  for (long long it = first; it < total; it += stride) {
-    FlatItem nxt = cur;
-    if (it + stride < total) nxt = fetch(it + stride);
-    body(cur);
-    cur = nxt;
-  }
-}
-
 // 128-bit accesses that do not pollute L1 (every row is touched once per launch).
 __device__ __forceinline__ float4 ld_f4(const float* p) {
   float4 v;
@@ -218,29 +198,22 @@ __global__ void __launch_bounds__(256) k_rows_copy(GroupView gv, SegBatch sb, in
   constexpr int W = VPT == 0 ? 1 : 4 * VPT;  // floats per thread
   __shared__ FlatWork fw;
   const long long total = flat_setup<1>(sb, fw, true, gv, W);
-  auto fetch = [&](long long it) {
-    FlatItem f;
-    f.si = flat_seg(fw, sb.nseg, it);
-    f.w = it - fw.prefix[f.si];
-    const b200ps_seg_t& sg = sb.seg[f.si];
-    const int chunks = gv.tables[sg.table].dim / W;
-    const long long row = chunks == 1 ? f.w : f.w / chunks;
-    f.id = row < fw.n[f.si] ? sg.ids_dev[row] : 0;
-    return f;
-  };
-  flat_loop((long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, total, fetch, [&](const FlatItem& f) {
-    const b200ps_seg_t& sg = sb.seg[f.si];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += stride) {
+    const int si = flat_seg(fw, sb.nseg, it);
+    const b200ps_seg_t& sg = sb.seg[si];
     const TableView& tv = gv.tables[sg.table];
     const int dim = tv.dim;
     const int chunks = dim / W;
-    const long long row = chunks == 1 ? f.w : f.w / chunks;
-    if (row >= fw.n[f.si]) return;
-    const int c = chunks == 1 ? 0 : (int)(f.w - row * chunks);
-    RowLoc loc = locate(gv, tv, f.id);
+    const long long w = it - fw.prefix[si];
+    const long long row = chunks == 1 ? w : w / chunks;
+    const int c = chunks == 1 ? 0 : (int)(w - row * chunks);
+    const int64_t id = sg.ids_dev[row];
+    RowLoc loc = locate(gv, tv, id);
     float* user = sg.rows_dev + row * dim + c * W;
     if (!loc.ok) {
       atomicOr(gv.err, kErrRange);
-      return;
+      continue;
     }
     float* rec = loc.rec + tv.slot_off[slot] + c * W;
     if (VPT == 0) {
@@ -254,7 +227,7 @@ __global__ void __launch_bounds__(256) k_rows_copy(GroupView gv, SegBatch sb, in
 #pragma unroll
       for (int v = 0; v < VPT; ++v) st_f4((WRITE ? rec : user) + 4 * v, x[v]);
     }
-  });
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -357,32 +330,27 @@ __global__ void __launch_bounds__(256) k_rows_copy_d8(GroupView gv, SegBatch sb,
   __shared__ FlatWork fw;
   const long long total = flat_setup<16>(sb, fw, false, gv, 8);  // 16 rows per warp stay in one segment
   const int lane = threadIdx.x & 31, c = lane & 1;
-  auto fetch = [&](long long it) {
-    FlatItem f;
-    f.si = flat_seg(fw, sb.nseg, it);
-    f.w = it - fw.prefix[f.si];
-    f.id = (c == 0 && f.w < fw.n[f.si]) ? sb.seg[f.si].ids_dev[f.w] : 0;
-    return f;
-  };
-  flat_loop(((long long)blockIdx.x * blockDim.x + threadIdx.x) / 2, (long long)gridDim.x * blockDim.x / 2, total, fetch,
-            [&](const FlatItem& f) {
-    const b200ps_seg_t& sg = sb.seg[f.si];
+  const long long stride = (long long)gridDim.x * blockDim.x / 2;
+  for (long long it = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 2; it < total; it += stride) {
+    const int si = flat_seg(fw, sb.nseg, it);
+    const b200ps_seg_t& sg = sb.seg[si];
     const TableView& tv = gv.tables[sg.table];
-    const long long row = f.w;
-    const bool live = row < fw.n[f.si];
-    const long long id = __shfl_sync(0xffffffffu, f.id, 0, 2);
-    if (!live) return;
+    const long long row = it - fw.prefix[si];
+    const bool live = row < fw.n[si];
+    long long id = (live && c == 0) ? sg.ids_dev[row] : 0;
+    id = __shfl_sync(0xffffffffu, id, 0, 2);
+    if (!live) continue;
     RowLoc loc = locate(gv, tv, id);
     if (!loc.ok) {
       if (c == 0) atomicOr(gv.err, kErrRange);
-      return;
+      continue;
     }
     float* rec = loc.rec + tv.slot_off[slot] + 4 * c;
     float* user = sg.rows_dev + row * 8 + 4 * c;
     const float4 x = ld_f4(WRITE ? user : rec);
     if (c == 0) mark_present(tv, loc);
     st_f4(WRITE ? rec : user, x);
-  });
+  }
 }
 
 __host__ __device__ constexpr int d8_lanes(int opt) {  // lanes per record: power of two >= 2*(1+S)
@@ -398,20 +366,15 @@ __global__ void __launch_bounds__(256) k_push_rows_d8(GroupView gv, SegBatch sb,
   __shared__ FlatWork fw;
   const long long total = flat_setup<RPW>(sb, fw, false, gv, 8);
   const int lane = threadIdx.x & 31, c = lane & (LPR - 1);
-  auto fetch = [&](long long it) {
-    FlatItem f;
-    f.si = flat_seg(fw, sb.nseg, it);
-    f.w = it - fw.prefix[f.si];
-    f.id = (c == 0 && f.w < fw.n[f.si]) ? sb.seg[f.si].ids_dev[f.w] : 0;
-    return f;
-  };
-  flat_loop(((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR, (long long)gridDim.x * blockDim.x / LPR, total, fetch,
-            [&](const FlatItem& f) {
-    const b200ps_seg_t& sg = sb.seg[f.si];
+  const long long stride = (long long)gridDim.x * blockDim.x / LPR;
+  for (long long it = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR; it < total; it += stride) {
+    const int si = flat_seg(fw, sb.nseg, it);
+    const b200ps_seg_t& sg = sb.seg[si];
     const TableView& tv = gv.tables[sg.table];
-    const long long row = f.w;
-    const bool live = row < fw.n[f.si];
-    const long long id = __shfl_sync(0xffffffffu, f.id, 0, LPR);
+    const long long row = it - fw.prefix[si];
+    const bool live = row < fw.n[si];
+    long long id = (live && c == 0) ? sg.ids_dev[row] : 0;
+    id = __shfl_sync(0xffffffffu, id, 0, LPR);
     RowLoc loc = live ? locate(gv, tv, id) : RowLoc{nullptr, 0, 0, false};  // dead lanes must not claim a hashed slot
     const bool ok = live && loc.ok;
     if (live && !loc.ok && c == 0) atomicOr(gv.err, kErrRange);
@@ -441,7 +404,7 @@ __global__ void __launch_bounds__(256) k_push_rows_d8(GroupView gv, SegBatch sb,
     if (S > 1) { const float4 t = shfl4(s1, c & 1, LPR); if ((c >> 1) == 2) out = t; }
     if (S > 2) { const float4 t = shfl4(s2, c & 1, LPR); if ((c >> 1) == 3) out = t; }
     if (ok && c < R4) st_f4(rec, out);
-  });
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -553,21 +516,16 @@ __global__ void __launch_bounds__(256) k_push_rows_d1(GroupView gv, SegBatch sb,
   constexpr int S = opt_slots(OPT);
   __shared__ FlatWork fw;
   const long long total = flat_setup<1>(sb, fw, false, gv, 1);
-  auto fetch = [&](long long it) {
-    FlatItem f;
-    f.si = flat_seg(fw, sb.nseg, it);
-    f.w = it - fw.prefix[f.si];
-    f.id = sb.seg[f.si].ids_dev[f.w];
-    return f;
-  };
-  flat_loop((long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, total, fetch, [&](const FlatItem& f) {
-    const b200ps_seg_t& sg = sb.seg[f.si];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += stride) {
+    const int si = flat_seg(fw, sb.nseg, it);
+    const b200ps_seg_t& sg = sb.seg[si];
     const TableView& tv = gv.tables[sg.table];
-    const long long row = f.w;
-    RowLoc loc = locate(gv, tv, f.id);
+    const long long row = it - fw.prefix[si];
+    RowLoc loc = locate(gv, tv, sg.ids_dev[row]);
     if (!loc.ok) {
       atomicOr(gv.err, kErrRange);
-      return;
+      continue;
     }
     float4 r = ld_f4(loc.rec);
     const float g = sg.rows_dev[row];
@@ -575,7 +533,7 @@ __global__ void __launch_bounds__(256) k_push_rows_d1(GroupView gv, SegBatch sb,
     opt_update<OPT>(g, r.x, r.y, r.z, r.w, gv.rt->lr[loc.shard], gv.rt->alpha[loc.shard], gv.rt->l2adj[loc.shard], o);
     if (S == 0) *loc.rec = r.x;  // keep the padding untouched: one 4 B store
     else st_f4(loc.rec, r);
-  });
+  }
 }
 
 // ---------------------------------------------------------------------------
