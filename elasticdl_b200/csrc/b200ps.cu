@@ -328,7 +328,7 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 constexpr int kClasses = 5;
 struct Split {
   SegBatch b[kClasses];
-  long long sum_work[kClasses] = {0, 0, 0, 0, 0};  // threads' worth of work over all segments (upper bound: sg.n)
+  long long max_work[kClasses] = {0, 0, 0, 0, 0};
 };
 
 int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense, Split* out, bool push = false,
@@ -360,30 +360,21 @@ int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense
     }
     SegBatch& b = out->b[c];
     b.seg[b.nseg++] = sg;
-    out->sum_work[c] += want_dense ? 0 : work + 32;  // + per-segment padding of the flat schedule
-    if (want_dense && work > out->sum_work[c]) out->sum_work[c] = work;  // dense launches keep a (blocks, segment) grid
+    if (work > out->max_work[c]) out->max_work[c] = work;
   }
   return B200PS_OK;
 }
 
 template <typename F>
-int for_each_class(b200ps_t* ps, Split& sp, F&& launch, bool dense = false) {
+int for_each_class(b200ps_t* ps, Split& sp, F&& launch) {
   for (int c = 0; c < kClasses; ++c) {
     if (sp.b[c].nseg == 0) continue;
-    dim3 grid;
-    if (dense) {
-      // whole-parameter kernels: (blocks, segment) grid, the cap on resident work applies to the launch
-      int gx = grid_for(ps, sp.sum_work[c]);
-      const int per_seg_cap = (ps->n_sm * 16 + sp.b[c].nseg - 1) / sp.b[c].nseg;
-      if (gx > per_seg_cap) gx = per_seg_cap < 4 ? 4 : per_seg_cap;
-      grid = dim3(gx, sp.b[c].nseg);
-    } else {
-      // row kernels stride a flat 1-D grid over the concatenated segments (ps_kernels.cuh FlatWork):
-      // one wave of resident blocks, the live lengths are only known on the device
-      long long blocks = (sp.sum_work[c] + 255) / 256;
-      const long long cap = (long long)ps->n_sm * 8;
-      grid = dim3((unsigned)(blocks < 1 ? 1 : blocks > cap ? cap : blocks));
-    }
+    // the cap on resident work applies to the whole launch, not to each segment: a segment's
+    // blocks loop (grid-stride) instead of launching thousands of blocks that exit at once
+    int gx = grid_for(ps, sp.max_work[c]);
+    const int per_seg_cap = (ps->n_sm * 16 + sp.b[c].nseg - 1) / sp.b[c].nseg;
+    if (gx > per_seg_cap) gx = per_seg_cap < 4 ? 4 : per_seg_cap;
+    dim3 grid(gx, sp.b[c].nseg);
     launch(c, grid, sp.b[c]);
     ps->launches++;
     CUDA_OK(cudaGetLastError());
@@ -849,7 +840,7 @@ static int dense_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* st
       if (c) k_dense_copy<4, false><<<grid, 256, 0, st>>>(gv, b, slot);
       else k_dense_copy<1, false><<<grid, 256, 0, st>>>(gv, b, slot);
     }
-  }, true);
+  });
 }
 
 int b200ps_pull_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream) {
@@ -1149,7 +1140,7 @@ int b200ps_push_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* st
       if (c) k_push_dense<OPT, 4, false><<<grid, 256, 0, st>>>(gv, b, o);
       else k_push_dense<OPT, 1, false><<<grid, 256, 0, st>>>(gv, b, o);
     });
-  }, true);
+  });
 }
 
 int b200ps_push_dense_reduce(b200ps_t* ps, int dense_id, const float* const* grads_dev, int n_replicas, float scale,

@@ -139,42 +139,6 @@ __device__ __forceinline__ int seg_count(const b200ps_seg_t& sg) {
   return n;
 }
 
-// Flat work scheduling.  One launch serves many segments whose live lengths are only known on the
-// device (n_dev) and differ by four orders of magnitude (DeepFM: 1 .. 13 K unique ids per table), so
-// a (blocks, segment) grid leaves most blocks idle and makes the long segments loop.  Instead every
-// block builds the prefix of the per-segment item counts in shared memory and the grid strides
-// over the concatenation; PAD keeps the lane groups of one warp inside one segment.
-struct FlatWork {
-  long long prefix[kMaxSegs + 1];
-  int n[kMaxSegs];
-};
-template <int PAD>
-__device__ __forceinline__ long long flat_setup(const SegBatch& sb, FlatWork& fw, bool per_chunk, const GroupView& gv,
-                                                int floats_per_item) {
-  for (int i = threadIdx.x; i < sb.nseg; i += blockDim.x) fw.n[i] = seg_count(sb.seg[i]);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    long long acc = 0;
-    for (int i = 0; i < sb.nseg; ++i) {
-      fw.prefix[i] = acc;
-      long long items = fw.n[i];
-      if (per_chunk) items *= gv.tables[sb.seg[i].table].dim / floats_per_item;
-      acc += (items + PAD - 1) / PAD * PAD;
-    }
-    fw.prefix[sb.nseg] = acc;
-  }
-  __syncthreads();
-  return fw.prefix[sb.nseg];
-}
-__device__ __forceinline__ int flat_seg(const FlatWork& fw, int nseg, long long item) {  // largest s: prefix[s] <= item
-  int lo = 0, hi = nseg;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (fw.prefix[mid] <= item) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
 // 128-bit accesses that do not pollute L1 (every row is touched once per launch).
 __device__ __forceinline__ float4 ld_f4(const float* p) {
   float4 v;
@@ -195,17 +159,15 @@ __device__ __forceinline__ void st_f4(float* p, float4 v) {
 // ---------------------------------------------------------------------------
 template <int VPT, bool WRITE>
 __global__ void __launch_bounds__(256) k_rows_copy(GroupView gv, SegBatch sb, int slot) {
+  const b200ps_seg_t& sg = sb.seg[blockIdx.y];
+  const TableView& tv = gv.tables[sg.table];
+  const int n = seg_count(sg);
+  const int dim = tv.dim;
   constexpr int W = VPT == 0 ? 1 : 4 * VPT;  // floats per thread
-  __shared__ FlatWork fw;
-  const long long total = flat_setup<1>(sb, fw, true, gv, W);
+  const int chunks = dim / W;
+  const long long work = (long long)n * chunks;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += stride) {
-    const int si = flat_seg(fw, sb.nseg, it);
-    const b200ps_seg_t& sg = sb.seg[si];
-    const TableView& tv = gv.tables[sg.table];
-    const int dim = tv.dim;
-    const int chunks = dim / W;
-    const long long w = it - fw.prefix[si];
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < work; w += stride) {
     const long long row = chunks == 1 ? w : w / chunks;
     const int c = chunks == 1 ? 0 : (int)(w - row * chunks);
     const int64_t id = sg.ids_dev[row];
@@ -238,18 +200,16 @@ __global__ void __launch_bounds__(256) k_rows_copy(GroupView gv, SegBatch sb, in
 template <int OPT, int VPT>
 __global__ void __launch_bounds__(256) k_push_rows(GroupView gv, SegBatch sb, OptParams o) {
   constexpr int S = opt_slots(OPT);
+  const b200ps_seg_t& sg = sb.seg[blockIdx.y];
+  const TableView& tv = gv.tables[sg.table];
+  const int n = seg_count(sg);
+  const int dim = tv.dim;
   constexpr int W = VPT == 0 ? 1 : 4 * VPT;
-  __shared__ FlatWork fw;
-  const long long total = flat_setup<1>(sb, fw, true, gv, W);
+  const int chunks = dim / W;
+  const long long work = (long long)n * chunks;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += stride) {
-    const int si = flat_seg(fw, sb.nseg, it);
-    const b200ps_seg_t& sg = sb.seg[si];
-    const TableView& tv = gv.tables[sg.table];
-    const int dim = tv.dim;
-    const int chunks = dim / W;
-    const int64_t o0 = tv.slot_off[1], o1 = tv.slot_off[2], o2 = tv.slot_off[3];
-    const long long w = it - fw.prefix[si];
+  const int64_t o0 = tv.slot_off[1], o1 = tv.slot_off[2], o2 = tv.slot_off[3];
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < work; w += stride) {
     const long long row = chunks == 1 ? w : w / chunks;
     const int c = chunks == 1 ? 0 : (int)(w - row * chunks);
     const int64_t id = sg.ids_dev[row];
@@ -327,16 +287,14 @@ __device__ __forceinline__ float4 shfl4(float4 v, int src, int width) {
 
 template <bool WRITE>
 __global__ void __launch_bounds__(256) k_rows_copy_d8(GroupView gv, SegBatch sb, int slot) {
-  __shared__ FlatWork fw;
-  const long long total = flat_setup<16>(sb, fw, false, gv, 8);  // 16 rows per warp stay in one segment
+  const b200ps_seg_t& sg = sb.seg[blockIdx.y];
+  const TableView& tv = gv.tables[sg.table];
+  const int n = seg_count(sg);
   const int lane = threadIdx.x & 31, c = lane & 1;
+  const long long rows_pad = ((long long)n + 15) / 16 * 16;  // keep warps converged for the shuffles
   const long long stride = (long long)gridDim.x * blockDim.x / 2;
-  for (long long it = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 2; it < total; it += stride) {
-    const int si = flat_seg(fw, sb.nseg, it);
-    const b200ps_seg_t& sg = sb.seg[si];
-    const TableView& tv = gv.tables[sg.table];
-    const long long row = it - fw.prefix[si];
-    const bool live = row < fw.n[si];
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 2; row < rows_pad; row += stride) {
+    const bool live = row < n;
     long long id = (live && c == 0) ? sg.ids_dev[row] : 0;
     id = __shfl_sync(0xffffffffu, id, 0, 2);
     if (!live) continue;
@@ -362,17 +320,15 @@ __global__ void __launch_bounds__(256) k_push_rows_d8(GroupView gv, SegBatch sb,
   constexpr int S = opt_slots(OPT);
   constexpr int R4 = 2 * (1 + S);  // 16 B chunks per record
   constexpr int LPR = d8_lanes(OPT);
-  constexpr int RPW = 32 / LPR;  // rows per warp
-  __shared__ FlatWork fw;
-  const long long total = flat_setup<RPW>(sb, fw, false, gv, 8);
+  const b200ps_seg_t& sg = sb.seg[blockIdx.y];
+  const TableView& tv = gv.tables[sg.table];
+  const int n = seg_count(sg);
   const int lane = threadIdx.x & 31, c = lane & (LPR - 1);
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  const long long rows_pad = ((long long)n + RPW - 1) / RPW * RPW;
   const long long stride = (long long)gridDim.x * blockDim.x / LPR;
-  for (long long it = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR; it < total; it += stride) {
-    const int si = flat_seg(fw, sb.nseg, it);
-    const b200ps_seg_t& sg = sb.seg[si];
-    const TableView& tv = gv.tables[sg.table];
-    const long long row = it - fw.prefix[si];
-    const bool live = row < fw.n[si];
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR; row < rows_pad; row += stride) {
+    const bool live = row < n;
     long long id = (live && c == 0) ? sg.ids_dev[row] : 0;
     id = __shfl_sync(0xffffffffu, id, 0, LPR);
     RowLoc loc = live ? locate(gv, tv, id) : RowLoc{nullptr, 0, 0, false};  // dead lanes must not claim a hashed slot
@@ -514,14 +470,11 @@ __global__ void __launch_bounds__(256) k_pair_push(GroupView gv, PairBatch pb, O
 template <int OPT>
 __global__ void __launch_bounds__(256) k_push_rows_d1(GroupView gv, SegBatch sb, OptParams o) {
   constexpr int S = opt_slots(OPT);
-  __shared__ FlatWork fw;
-  const long long total = flat_setup<1>(sb, fw, false, gv, 1);
+  const b200ps_seg_t& sg = sb.seg[blockIdx.y];
+  const TableView& tv = gv.tables[sg.table];
+  const int n = seg_count(sg);
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += stride) {
-    const int si = flat_seg(fw, sb.nseg, it);
-    const b200ps_seg_t& sg = sb.seg[si];
-    const TableView& tv = gv.tables[sg.table];
-    const long long row = it - fw.prefix[si];
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
     RowLoc loc = locate(gv, tv, sg.ids_dev[row]);
     if (!loc.ok) {
       atomicOr(gv.err, kErrRange);
