@@ -31,6 +31,20 @@ ADAM_ARGS = "learning_rate=0.001;beta_1=0.9;beta_2=0.999;epsilon=1e-07;amsgrad=f
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback
 
 
+def ncu_traffic(kernel, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the committed
+    `ncu --set full` capture of this workload at N=1 (profiles/ncu_traffic.json); None when the capture
+    does not cover the configuration (a number taken under ncu is never measured live by the bench)."""
+    if world != 1:
+        return None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            k = json.load(f)["kernels"][kernel]
+        return k["dram_read_bytes"] + k["dram_write_bytes"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -354,7 +368,7 @@ def main():
         line["kernels"] = kern
         k = kern[top]
         line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
-                            "frac": k["gbs"] / peak, "traffic": None, "peak_kind": peak_kind,
+                            "frac": k["gbs"] / peak, "traffic": ncu_traffic(top, world) if (args.batch == 32768 and args.dist == "zipf") else None, "peak_kind": peak_kind,
                             "algorithmic_bytes_per_launch": k["bytes"], "us_per_launch": k["ms"] * 1e3}
         if "pull_deep" in kern:
             line["pull_gbs"] = kern["pull_deep"]["gbs"]
