@@ -776,9 +776,10 @@ struct UniqueWs {
   int ntiles;
   // Direct-address segments are not cleared between calls: positions are stored under an epoch
   // prefix that DEcreases from call to call, so atomicMin prefers this call's entries and stale
-  // ones read as empty.  hdr = {magic, epoch} lives in the workspace (a fresh / foreign workspace
-  // fails the magic test and is cleared); every kUniqEpochs calls the prefix wraps and the
-  // arrays are cleared for real.
+  // ones read as empty.  hdr = {magic, epoch, cleared cycle} lives in the workspace (a fresh / foreign
+  // workspace fails the magic test and is cleared); every kUniqEpochs calls the prefix wraps and
+  // the arrays are cleared for real by the first tagged call of the new cycle (calls without
+  // bounds share the workspace and the epoch counter but never touch these arrays).
   unsigned long long* hdr;
   unsigned long long magic;
   int tagged;  // k <= 2^20: positions fit under the prefix
@@ -790,6 +791,9 @@ constexpr int kUniqEpochs = 2047;  // prefixes 0..2046 keep the value below 0x7f
 __device__ __forceinline__ int uniq_epoch(const UniqueWs& ws) {  // stable until k_uniq_scan_tiles bumps it
   return ws.hdr[0] == ws.magic ? (int)(ws.hdr[1] % kUniqEpochs) : 0;
 }
+__device__ __forceinline__ bool uniq_need_clear(const UniqueWs& ws) {
+  return ws.hdr[0] != ws.magic || ws.hdr[2] != ws.hdr[1] / kUniqEpochs;
+}
 __device__ __forceinline__ int uniq_prefix(const UniqueWs& ws) {
   return ws.tagged ? (kUniqEpochs - 1 - uniq_epoch(ws)) << kUniqPosBits : 0;
 }
@@ -797,7 +801,7 @@ __device__ __forceinline__ int uniq_prefix(const UniqueWs& ws) {
 __global__ void __launch_bounds__(256) k_uniq_clear(UniqueWs ws, int T, UniqueBounds ub, int use_bounds) {
   const int t = blockIdx.y;
   const int direct = use_bounds && ub.bound[t] > 0;
-  if (direct && ws.tagged && uniq_epoch(ws) != 0) return;  // stale prefixes already read as empty
+  if (direct && ws.tagged && !uniq_need_clear(ws)) return;  // stale prefixes already read as empty
   const int n = direct ? ub.bound[t] : ws.cap;
   long long* keys = ws.keys + (long long)t * ws.cap;
   int* minpos = direct ? ub.dpos + ub.off[t] : ws.minpos + (long long)t * ws.cap;
@@ -924,7 +928,10 @@ __global__ void __launch_bounds__(1024) k_uniq_scan_tiles(UniqueWs ws, int* n_un
   if (threadIdx.x == 0) n_unique[t] = carry;
   if (t == 0 && threadIdx.x == 0) {  // insert / flag are done with this call's epoch: open the next one
     const bool fresh = ws.hdr[0] != ws.magic;
-    ws.hdr[1] = fresh ? 1ULL : ws.hdr[1] + 1ULL;
+    const unsigned long long epoch = fresh ? 0ULL : ws.hdr[1];
+    if (ws.tagged) ws.hdr[2] = epoch / kUniqEpochs;  // the position arrays are valid for this cycle
+    else if (fresh) ws.hdr[2] = ~0ULL;
+    ws.hdr[1] = epoch + 1ULL;
     ws.hdr[0] = ws.magic;
   }
 }
