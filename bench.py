@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4096)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tower", default="fused", choices=["fused", "torch"])
+    ap.add_argument("--tower", default="fused", choices=["fused", "mma", "torch"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop after the warm-up and exit "
@@ -220,7 +220,7 @@ def main():
                             exchange=None if args.exchange == "auto" else args.exchange)
     config["record_layout"] = "paired deep+wide record per id" if engine.paired else "one record slab per table"
     config["exchange"] = engine.exchange
-    use_graph = args.tower == "fused" and not args.no_graph
+    use_graph = args.tower != "torch" and not args.no_graph
     lookahead = use_graph and args.lookahead == "on"
     config["pipeline"] = ("CUDA graph per step; id dedup of batch i+1 overlapped with step i on a second stream"
                           if lookahead else ("CUDA graph per step" if use_graph else "eager launches"))
@@ -256,7 +256,7 @@ def main():
         return ms
 
     def my_launches():
-        return group.launch_count + _lib.lib().b200ps_launch_count(None) + _lib.lib().b200_deepfm_launch_count()
+        return group.launch_count + _lib.lib().b200ps_launch_count(None) + _lib.lib().b200_deepfm_launch_count() + _lib.lib().b200_deepfm_mma_launch_count()
 
     # ---- eager pass: every kernel launched from the host, CUDA-event pairs around the PS kernels ----
     for i in range(args.warmup):

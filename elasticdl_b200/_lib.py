@@ -110,6 +110,8 @@ SYMBOLS = {
     "b200_deepfm_param_count": (_sz, [_i]),
     "b200_deepfm_fwd_bwd": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
     "b200_deepfm_forward": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
+    "b200_deepfm_fwd_bwd_mma": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
+    "b200_deepfm_mma_launch_count": (_i64, []),
     "b200_deepfm_launch_count": (_i64, []),
 }
 

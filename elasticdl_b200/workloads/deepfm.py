@@ -159,8 +159,9 @@ class DeepFMPSEngine:
     def __init__(self, group, batch, lr=1e-3, init_std=0.01, seed=7, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM,
                  init_rows=True, tower="fused", paired=None, exchange=None):
         """tower="fused": the hand-written CUDA tower (csrc/deepfm_tower.cu);
+        tower="mma": its tensor-core variant (csrc/deepfm_tower_mma.cu, rows gathered once, 3xTF32 mma.sync);
         tower="torch": torch autograd over library kernels (kept for A/B measurements and tests)."""
-        assert tower in ("fused", "torch")
+        assert tower in ("fused", "mma", "torch")
         self.tower_kind = tower
         # paired=True: the deep (dim 8) and wide (dim 1) tables of an id group share one record
         # per id, so one request per id serves both (ps_kernels.cuh "Paired tables")
@@ -364,14 +365,15 @@ class DeepFMPSEngine:
                 e = mark(name)
                 check(lib.b200ps_pull_rows(h, arr, n, st))
                 done(e)
-        if self.tower_kind == "fused":
+        if self.tower_kind in ("fused", "mma"):
             # (4-6) gather + tower forward/backward + per-unique-id gradient sums: three launches
             e_t = mark("tower_fwd_bwd")
             a = self.tower_args
             a.dense, a.labels = dense.data_ptr(), labels.data_ptr()
             import ctypes as _ct
 
-            rc = lib.b200_deepfm_fwd_bwd(_ct.byref(a), st)
+            fn = lib.b200_deepfm_fwd_bwd_mma if self.tower_kind == "mma" else lib.b200_deepfm_fwd_bwd
+            rc = fn(_ct.byref(a), st)
             if rc:
                 raise RuntimeError("b200_deepfm_fwd_bwd failed (%d)" % rc)
             done(e_t)
@@ -440,7 +442,7 @@ class DeepFMPSEngine:
 
     def capture_ahead(self):
         """Two CUDA graphs (one per plan parity) of step_ahead over the static input buffers."""
-        if self.tower_kind != "fused":
+        if self.tower_kind == "torch":
             raise RuntimeError("graph capture needs the fused tower (torch autograd allocates)")
         dev, G, B = self.device, self.G, self.B
         if len(self.plans) != 2:
@@ -476,7 +478,7 @@ class DeepFMPSEngine:
         """Capture one whole step (19 launches + the versions read-back) into a CUDA graph.
         Every buffer the step touches is persistent, so the graph replays on new inputs
         copied into the static input buffers.  lr is baked in: re-capture to change it."""
-        if self.tower_kind != "fused":
+        if self.tower_kind == "torch":
             raise RuntimeError("graph capture needs the fused tower (torch autograd allocates)")
         dev, G, B = self.device, self.G, self.B
         self.s_ids = torch.zeros((G, B), dtype=torch.int64, device=dev)

@@ -52,6 +52,11 @@ typedef struct {
 size_t b200_deepfm_param_count(int G);
 /* forward + backward of one batch; asynchronous on `stream` (cudaStream_t). */
 int b200_deepfm_fwd_bwd(const b200_deepfm_args_t* args, void* stream);
+/* Same contract as b200_deepfm_fwd_bwd, computed by the tensor-core tower (csrc/deepfm_tower_mma.cu): the
+ * rows of a chunk of samples are gathered once into a shared-memory tile and the three first-layer
+ * contractions run as 3xTF32 mma.sync.  `scratch` is not used. */
+int b200_deepfm_fwd_bwd_mma(const b200_deepfm_args_t* args, void* stream);
+int64_t b200_deepfm_mma_launch_count(void);
 /* forward only (logits), for evaluation. */
 int b200_deepfm_forward(const b200_deepfm_args_t* args, void* stream);
 /* kernels launched by the two calls above so far */
