@@ -28,6 +28,7 @@ constexpr int ND = B200_DEEPFM_NDENSE, D = B200_DEEPFM_DIM, H1 = B200_DEEPFM_H1,
 constexpr int MT = 32;                 // samples per chunk: two m16 tiles
 constexpr int THREADS = 128;           // 4 warps
 constexpr int MAX_NT_W = 12;           // dW1 n-tiles per warp (KP/8 <= 48 -> G <= 46)
+constexpr int IPT = 12;                // groups gathered per thread per chunk (4 warps x 12 >= 46)
 constexpr int HS = 17, DHS = 20, SS = 12, SMS = 8;  // strides of the small per-sample buffers
 constexpr int N_SMALL = H2 * H1 + H2 + H2 + ND;      // dW2 64 | db2 4 | dw3 4 | dw_dense 13
 
@@ -153,22 +154,39 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_tower_mma(b200_deepfm_arg
     const long long b0 = ch * MT;
     const int n = (int)min((long long)MT, B - b0);
     __syncthreads();  // the previous chunk is fully consumed (and the one-time setup is visible)
-    // ---- A: gather the rows of this chunk, once
-    for (int i = tid; i < G * MT; i += THREADS) {
-      const int g = i / MT, s = i - g * MT;
-      float* dst = Xs + s * XS + g * D;
-      if (s < n) {
-        const int r = a.inv[(long long)g * B + b0 + s];
-        sinv[i] = r;
-        const float* row = a.bet_deep + ((long long)g * B + r) * D;
-        cp_async16(dst, row);
-        cp_async16(dst + 4, row + 4);
-        atomicAdd(&lin[s], a.bet_wide[(long long)g * B + r]);
-      } else {
-        sinv[i] = -1;
-        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- A: gather the rows of this chunk, once.  Item i = tid + k * THREADS is (group i / 32,
+    // sample lane): all ranks are loaded first, then all row copies are issued (asynchronous), then the
+    // dim-1 rows -- three batches of independent loads instead of a dependent chain per item
+    {
+      int rk[IPT];
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const int g = warp + 4 * k;
+        rk[k] = (g < G && lane < n) ? a.inv[(long long)g * B + b0 + lane] : -1;
       }
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const int g = warp + 4 * k;
+        if (g < G) {
+          float* dst = Xs + lane * XS + g * D;
+          sinv[g * MT + lane] = rk[k];
+          if (rk[k] >= 0) {
+            const float* row = a.bet_deep + ((long long)g * B + rk[k]) * D;
+            cp_async16(dst, row);
+            cp_async16(dst + 4, row + 4);
+          } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      float wv[IPT];
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) wv[k] = rk[k] >= 0 ? a.bet_wide[(long long)(warp + 4 * k) * B + rk[k]] : 0.f;
+      float wsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) wsum += wv[k];
+      atomicAdd(&lin[lane], wsum);  // four warps share a sample
     }
     for (int i = tid; i < MT * ND; i += THREADS) {
       const int s = i / ND, e = i - s * ND;
