@@ -94,36 +94,47 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def _cpu_reference_once(T, batch, steps, warmup, dist_kind, seed=1234):
-    import ctypes
+class _CpuWorkload:
+    """Inputs of the CPU arm, generated once for the largest thread count and sliced per run."""
 
-    import numpy as np
+    def __init__(self, t_max, batch, dist_kind, seed=1234):
+        import numpy as np
 
-    from elasticdl_b200.workloads.deepfm import DEEP_DIM, GROUP_ROWS, synthetic_batch
-    from oracle import ps_oracle as O
+        from elasticdl_b200.workloads.deepfm import DEEP_DIM, GROUP_ROWS, synthetic_batch
 
-    G = len(GROUP_ROWS)
-    n_shards = 1
-    vp = ctypes.c_void_p
-    ids = np.stack([synthetic_batch(batch, seed + t, "cpu", dist_kind)[0].numpy() for t in range(T)])  # [T, G, B]
-    ids = np.ascontiguousarray(ids, dtype=np.int64)
-    rng = np.random.RandomState(0)
-    total = 0.0
-    for dim in (1, DEEP_DIM):
-        grads = (rng.randn(T, G, batch, dim) * 1e-3).astype(np.float32)
-        tabs = [[O.OracleTable(dim, "zero") for _ in range(G * n_shards)] for _ in range(3)]
-        arrs = [(vp * (G * n_shards))(*[t._h for t in fam]) for fam in tabs]
-        rows = (ctypes.c_double * 2)()
+        self.G, self.batch, self.t_max = len(GROUP_ROWS), batch, t_max
+        ids = np.stack([synthetic_batch(batch, seed + t, "cpu", dist_kind)[0].numpy() for t in range(t_max)])  # [T, G, B]
+        self.ids = np.ascontiguousarray(ids, dtype=np.int64)
+        rng = np.random.RandomState(0)
+        # one thread's gradient block, repeated for the others (the values do not affect the timing)
+        self.grads = {dim: np.ascontiguousarray(np.broadcast_to(
+            (rng.randn(1, self.G, batch, dim) * 1e-3).astype(np.float32), (t_max, self.G, batch, dim)))
+            for dim in (1, DEEP_DIM)}
 
-        def run(n):
-            return O.lib.oracle_bench_ps(T, G, n_shards, arrs[0], arrs[1], arrs[2], O._i64(ids.reshape(-1)),
-                                         O._f32(grads.reshape(-1)), batch, dim, 1e-3, 0.9, 0.999, 1e-7, n, rows)
+    def run(self, T, steps, warmup):
+        import ctypes
 
-        if warmup:
-            run(warmup)
-        total += run(steps)
-        del tabs
-    return T * batch * steps / total
+        from oracle import ps_oracle as O
+
+        G, batch, n_shards = self.G, self.batch, 1
+        vp = ctypes.c_void_p
+        ids = self.ids[:T]
+        total = 0.0
+        for dim, grads_all in self.grads.items():
+            grads = grads_all[:T]
+            tabs = [[O.OracleTable(dim, "zero") for _ in range(G * n_shards)] for _ in range(3)]
+            arrs = [(vp * (G * n_shards))(*[t._h for t in fam]) for fam in tabs]
+            rows = (ctypes.c_double * 2)()
+
+            def run(n):
+                return O.lib.oracle_bench_ps(T, G, n_shards, arrs[0], arrs[1], arrs[2], O._i64(ids.reshape(-1)),
+                                             O._f32(grads.reshape(-1)), batch, dim, 1e-3, 0.9, 0.999, 1e-7, n, rows)
+
+            if warmup:
+                run(warmup)
+            total += run(steps)
+            del tabs
+        return T * batch * steps / total
 
 
 def cpu_reference(batch, steps, warmup, dist_kind, threads=None):
@@ -136,17 +147,131 @@ def cpu_reference(batch, steps, warmup, dist_kind, threads=None):
     and the best is reported.  Returns (samples_per_sec, threads, description)."""
     ncpu = os.cpu_count() or 1
     cands = [threads] if threads else sorted({min(c, ncpu) for c in (8, 16, 32, 64, ncpu)})
+    cands = [c for c in cands if c <= 128] or [min(ncpu, 128)]
+    wl = _CpuWorkload(max(cands), batch, dist_kind)
     best = (0.0, cands[0])
     if len(cands) > 1:
         for T in cands:
-            sps = _cpu_reference_once(T, batch, 1, 1, dist_kind)
+            sps = wl.run(T, 1, 0 if batch >= 16384 else 1)
             if sps > best[0]:
                 best = (sps, T)
     T = best[1]
-    sps = _cpu_reference_once(T, batch, steps, warmup, dist_kind)
+    sps = wl.run(T, steps, warmup)
     return sps, T, ("C restatement of the Go PS path (unique+pull+dedup+SparseAdam, 76 tables, no gRPC/protobuf, "
                     "no tower): best of thread counts %s = %d threads x batch %d x %d steps, %s ids, %d host cores"
                     % (cands, T, batch, steps, dist_kind, ncpu))
+
+
+def parity_check_multi(engine, group, rank, world, dev, lr=1e-3):
+    """Post-timing self-check of the path N > 1 times (outside every timed region), on a fresh batch:
+    (a) b200ps_xchg_pull == b200ps_pull_rows through the direct peer path, bit for bit, every group;
+    (b) one b200ps_xchg_push on rows that are disjoint across ranks (groups with >= 4*world^2 rows;
+        rank r draws ids with (id // world) % world == r, which still hit every owner), then the
+        rows and both Adam slots read back through the direct path must equal the oracle's Adam
+        (kernel_api.cc:40-77 restated, oracle.np_adam) applied to the state read before the push
+        -- bit for bit (ids are unique, so no float reassociation is involved).  The ranks issue
+        push_begin one after the other so that each knows its optimizer step on every shard.
+    The oracle is the checker here, never the thing measured.  Returns the dict printed in the
+    JSON line; raises SystemExit(3) on any mismatch (all ranks agree through an all-reduce)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from elasticdl_b200._lib import check
+    from elasticdl_b200.workloads.deepfm import GROUP_ROWS
+    from oracle import ps_oracle as O
+
+    G, B, D = engine.G, engine.B, engine.D
+    lib, h = group.lib, group._h
+    gen = torch.Generator(device=dev).manual_seed(777 + rank)
+    big = [g for g in range(G) if GROUP_ROWS[g] >= 4 * world * world]
+    ids = torch.empty((G, B), dtype=torch.int64, device=dev)
+    for g in range(G):
+        R = GROUP_ROWS[g]
+        u = torch.rand(B, generator=gen, device=dev, dtype=torch.float64)
+        if g in big:
+            blocks = R // (world * world)  # id = (q * world + rank) * world + owner
+            q = torch.floor(u * blocks).to(torch.int64)
+            owner = torch.randint(0, world, (B,), generator=gen, device=dev)
+            ids[g] = (q * world + rank) * world + owner
+        else:
+            ids[g] = torch.floor(u * R).to(torch.int64)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    base_steps = [st for _, st, _ in group.snapshot()]
+    engine._use(engine.cur)
+    engine._unique_into(ids)
+    st = group._stream()
+    check(lib.b200ps_xchg_pull(h, engine.uniq.data_ptr(), engine.n_unique.data_ptr(), engine.bet_d.data_ptr(),
+                               engine.bet_w.data_ptr(), st))
+    torch.cuda.synchronize(dev)
+    nu = engine.n_unique.cpu().numpy()
+    uniq = engine.uniq.view(G, B)
+    bet_d, bet_w = engine.bet_d.view(G, B, D), engine.bet_w.view(G, B)
+    bad_pull, rows_pull = 0, 0
+    pre = {}
+    for g in range(G):
+        u = int(nu[g])
+        idg = uniq[g, :u].contiguous()
+        d_direct, w_direct = group.pull_rows([(engine.deep_names[g], idg), (engine.wide_names[g], idg)])
+        bad_pull += int((d_direct != bet_d[g, :u]).any().item()) + int((w_direct.view(-1) != bet_w[g, :u]).any().item())
+        rows_pull += u
+        if g in big:
+            pre[g] = (idg, d_direct.cpu().numpy(), w_direct.cpu().numpy(),
+                      [group.slot_rows(engine.deep_names[g], idg, k).cpu().numpy() for k in (1, 2)],
+                      [group.slot_rows(engine.wide_names[g], idg, k).cpu().numpy() for k in (1, 2)])
+    # gradients for the live rows
+    engine.gsum_d.normal_(0.0, 1e-2, generator=gen)
+    engine.gsum_w.normal_(0.0, 1e-2, generator=gen)
+    gs_d, gs_w = engine.gsum_d.view(G, B, D).cpu().numpy(), engine.gsum_w.view(G, B).cpu().numpy()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    for r in range(world):  # ordered ApplyGradients: rank r is the (r+1)-th pusher on every shard
+        if r == rank:
+            group.push_begin(lr, [0] * world)
+            torch.cuda.synchronize(dev)
+        dist.barrier()
+    check(lib.b200ps_xchg_push(h, engine.gsum_d.data_ptr(), engine.gsum_w.data_ptr(), st))
+    group.push_end(sync=False)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    bad_push, rows_push = 0, 0
+    for g in big:
+        idg, p_d, p_w, s_d, s_w = pre[g]
+        u = idg.numel()
+        if u == 0:
+            continue
+        # every id of group g lives on shard id % world: the step this rank used there
+        owners = (idg % world).cpu().numpy()
+        got_d = group.pull_rows([(engine.deep_names[g], idg)])[0].cpu().numpy()
+        got_w = group.pull_rows([(engine.wide_names[g], idg)])[0].cpu().numpy()
+        got_sd = [group.slot_rows(engine.deep_names[g], idg, k).cpu().numpy() for k in (1, 2)]
+        got_sw = [group.slot_rows(engine.wide_names[g], idg, k).cpu().numpy() for k in (1, 2)]
+        for s_ in range(world):
+            m = owners == s_
+            if not m.any():
+                continue
+            step = int(base_steps[s_]) + rank + 1
+            for p0, m0, v0, gr, got, gm, gv_ in ((p_d, s_d[0], s_d[1], gs_d[g, :u], got_d, got_sd[0], got_sd[1]),
+                                                  (p_w, s_w[0], s_w[1], gs_w[g, :u, None], got_w, got_sw[0], got_sw[1])):
+                pp, mm, vv = p0[m].copy(), m0[m].copy(), v0[m].copy()
+                O.np_adam(np.ascontiguousarray(gr[m], dtype=np.float32), pp, mm, vv, lr, step, 0.9, 0.999, 1e-7)
+                bad_push += int(not (np.array_equal(pp, got[m]) and np.array_equal(mm, gm[m]) and np.array_equal(vv, gv_[m])))
+        rows_push += u
+    group.check()
+    t = torch.tensor([bad_pull, bad_push, rows_pull, rows_push], device=dev, dtype=torch.int64)
+    dist.all_reduce(t)
+    bad_pull, bad_push, rows_pull, rows_push = (int(x) for x in t.tolist())
+    res = {"pull": "bit-exact" if bad_pull == 0 else "MISMATCH (%d groups)" % bad_pull,
+           "push": "bit-exact" if bad_push == 0 else "MISMATCH (%d shard-groups)" % bad_push,
+           "rows": rows_pull, "rows_push_checked": rows_push, "world": world,
+           "what": "xchg_pull vs direct peer pull (all 76 tables); xchg_push (Adam, rank-disjoint rows) vs oracle.np_adam on "
+                   "the pre-push state: params and both slots"}
+    if bad_pull or bad_push:
+        if rank == 0:
+            print(json.dumps({"parity_check": res}), file=sys.stderr)
+        raise SystemExit(3)
+    return res
 
 
 def main():
@@ -157,9 +282,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32768, help="samples per GPU per step")
     ap.add_argument("--dist", default="zipf", choices=["zipf", "uniform"])
-    ap.add_argument("--pool", type=int, default=4, help="distinct pre-generated batches cycled through")
-    ap.add_argument("--cpu-batch", type=int, default=4096)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--pool", type=int, default=8, help="distinct pre-generated batches cycled through")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="per-thread batch of the CPU arm (0 = --batch: same config)")
+    ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tower", default="fused", choices=["fused", "mma", "torch"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
@@ -172,7 +297,9 @@ def main():
                     help="store each group's deep+wide rows as one record per id")
     ap.add_argument("--exchange", default="auto", choices=["auto", "owner", "direct"],
                     help="multi-GPU row exchange: owner-computes bulk exchange (default for N>1) or direct peer access")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the post-timing N>1 parity self-check")
     args = ap.parse_args()
+    cpu_batch = args.cpu_batch or args.batch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,16 +308,17 @@ def main():
                           "5549416 rows/family, Adam 1e-3, DNN[16,4]+FM tower",
               "batch_per_gpu": args.batch, "global_batch": args.batch * max(world, 1), "id_distribution": args.dist,
               "ps_shards": max(world, 1), "sharding": "id % N over GPUs (NVLink P2P)" if world > 1 else "1 shard",
-              "step": "pull_dense+unique+pull(76 tables)+tower fwd/bwd+dedup-sum+push(dense+76 tables, Adam)+version++",
-              "l2_policy": "tables (0.6 GB/family) and per-step id sets exceed L2; pool of %d batches cycled" % args.pool}
+              "step": "pull_dense+unique+pull(76 tables)+tower fwd/bwd+dedup-sum+push(dense+76 tables, Adam)+version++"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        sps, T, desc = cpu_reference(args.cpu_batch, max(args.steps, 1), min(args.warmup, 2), args.dist)
+        sps, T, desc = cpu_reference(cpu_batch, max(args.steps, 1), min(args.warmup, 2), args.dist)
+        config["cpu_batch_per_thread"] = cpu_batch
+        config["same_batch"] = cpu_batch == args.batch
         line = {"impl": "reference", "metric": "deepfm_train_samples_per_sec", "value": sps, "unit": "samples/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * args.cpu_batch * T / sps, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1e3 * cpu_batch * T / sps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": T, "kind": "port", "sample": desc},
                 "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,7 +340,7 @@ def main():
 
     from elasticdl_b200 import _lib
     from elasticdl_b200.ps import PSGroup
-    from elasticdl_b200.workloads.deepfm import DeepFMPSEngine, N_DENSE, synthetic_batch
+    from elasticdl_b200.workloads.deepfm import DeepFMPSEngine, N_DENSE, pack_batch, synthetic_batch
 
     group = PSGroup(world, "Adam", ADAM_ARGS, device=local_rank,
                     local_shards=[rank] if world > 1 else None)
@@ -224,23 +352,32 @@ def main():
     lookahead = use_graph and args.lookahead == "on"
     config["pipeline"] = ("CUDA graph per step; id dedup of batch i+1 overlapped with step i on a second stream"
                           if lookahead else ("CUDA graph per step" if use_graph else "eager launches"))
+    config["id_transport"] = ("ids cross PCIe / sit in HBM as int32 (all tables < 2^31 rows), widened to int64 "
+                              "inside the dedup kernel; one packed buffer per batch [ids|dense|labels]")
     if world > 1:
         dist.barrier()
     B = args.batch
     G = engine.G
 
-    # pre-generated batches: pinned host copies (e2e) and device copies (kernel-resident timing)
-    host, devb = [], []
+    # pre-generated batches: packed pinned host copies (e2e) and packed device copies (kernel-resident timing)
+    host, devb, devp = [], [], []
     for p in range(args.pool):
         ids, dense, labels = synthetic_batch(B, 1234 + p + 1000 * rank, dev, args.dist)
         devb.append((ids, dense, labels))
-        host.append(tuple(t.cpu().pin_memory() for t in (ids, dense, labels)))
+        devp.append(pack_batch(ids, dense, labels))
+        host.append(pack_batch(ids.cpu(), dense.cpu(), labels.cpu(), pin=True))
     uniq_per_batch = []
     for ids, _, _ in devb:
         _, _, n = group.unique(ids.view(-1), G)
         uniq_per_batch.append(int(n.sum().item()))
-    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    h2d = host[0].numel()
     loss_pin = torch.empty(args.steps + args.warmup + 8, dtype=torch.float32).pin_memory()
+    u_mean = statistics.mean(uniq_per_batch)
+    rows_mb = u_mean * (96 + 16) / 1e6  # Adam records touched per step: 96 B (dim 8) + 16 B (dim 1) per unique id
+    config["l2_policy"] = ("pool of %d distinct batches cycled: a batch's rows (%.0f MB of records per step, plus "
+                           "~%.0f MB of id / dedup / row buffers) recur after %d other steps, i.e. after > %.0f MB of "
+                           "other traffic vs the 126 MB L2; Zipf-hot rows recur every step by construction of the workload"
+                           % (args.pool, rows_mb, 12 * G * B * 4 / 1e6, args.pool - 1, (args.pool - 1) * rows_mb))
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -288,17 +425,16 @@ def main():
         # ---- headline: the same step replayed from a CUDA graph (inputs resident in HBM) ----
         if lookahead:
             # batch i trains while the ids of batch i+1 are deduplicated on a second stream
-            engine.prepare(devb[0][0])
             engine.capture_ahead()
+            engine.prepare_packed(devp[0])
 
             def graph_step(i):
-                _, dense_i, labels_i = devb[i % args.pool]
-                return engine.step_ahead_graph(dense_i, labels_i, devb[(i + 1) % args.pool][0])
+                return engine.step_ahead_graph(devp[(i + 1) % args.pool])
         else:
             engine.capture()
 
             def graph_step(i):
-                return engine.step_graph(*devb[i % args.pool])
+                return engine.step_graph(devp[i % args.pool])
         for i in range(args.warmup):
             graph_step(i)
         sync_all()
@@ -310,7 +446,6 @@ def main():
         ms = max_over_ranks(e0.elapsed_time(e1))
         group.check()
     clocks = sampler.stop() if rank == 0 else None
-    step_fn = engine.step_graph if use_graph else engine.step
 
     # ---- per-kernel durations from the CUDA events recorded inside the timed region ----
     kern = engine.kernel_report(ev, [uniq_per_batch[i % args.pool] for i in range(args.steps)])
@@ -320,29 +455,43 @@ def main():
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ahead = 2 if lookahead else 1  # batches in flight ahead of the running step
     feeder = engine.host_feeder(ahead + 1, lookahead=lookahead) if use_graph else None
-    if feeder is not None and lookahead:
-        engine.prepare(devb[0][0])  # graphs exist already; the feeder re-prepares on its first batch
-        sync_all()
+    # the link itself: one packed batch per copy, back to back on the copy stream
+    probe = torch.empty_like(devp[0])
+    cs = feeder.copy_stream if feeder is not None else torch.cuda.Stream(device=dev)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(cs):
+        probe.copy_(host[0], non_blocking=True)
+        p0.record(cs)
+        for j in range(8):
+            probe.copy_(host[j % args.pool], non_blocking=True)
+        p1.record(cs)
+    sync_all()
+    h2d_ms = p0.elapsed_time(p1) / 8
     e2.record()
     if feeder is not None:
         for j in range(min(ahead, args.steps)):
-            feeder.submit(*host[j % args.pool])
+            feeder.submit(host[j % args.pool])
     for i in range(args.steps):
         if feeder is not None:
-            # every step's inputs come from pinned host memory; the copies of the next batches (side
-            # stream) overlap the kernels of batch i, like the reference's dataset.prefetch(1)
+            # every step's inputs come from pinned host memory (ONE packed copy per batch); the copies of
+            # the next batches (side stream) overlap the kernels of batch i, like the reference's
+            # dataset.prefetch(1)
             if i + ahead < args.steps:
-                feeder.submit(*host[(i + ahead) % args.pool])
+                feeder.submit(host[(i + ahead) % args.pool])
             loss = feeder.run_next()
         else:
-            hi, hd, hl = host[i % args.pool]
-            loss = engine.step(hi.to(dev, non_blocking=True), hd.to(dev, non_blocking=True),
-                               hl.to(dev, non_blocking=True))
+            hb = host[i % args.pool].to(dev, non_blocking=True)
+            from elasticdl_b200.workloads.deepfm import packed_views
+            loss = engine.step(*packed_views(hb, G, B))
         loss_pin[i].copy_(loss, non_blocking=True)
     e3.record()
     sync_all()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     group.check()
+
+    parity = None
+    if world > 1 and not args.no_parity_check and engine.exchange == "owner":
+        parity = parity_check_multi(engine, group, rank, world, dev)
 
     if rank != 0:
         if world > 1:
@@ -358,25 +507,40 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "h2d_copy_ms_probe": h2d_ms,
+                    "h2d_gbs_probe": h2d / h2d_ms / 1e6,
+                    "id_narrowing": "ids int64 -> int32 on the host side of the boundary (packed batch), widened on the device"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / max(args.steps, 1),
             "launch_mode": "cuda_graph" if use_graph else "eager", "eager_ms_per_step": ms_eager / args.steps,
             "tower": args.tower,
             "final_loss": float(loss_pin[args.steps - 1])}
+    if parity is not None:
+        line["parity_check"] = parity
     if kern:
-        top = max((k for k in kern if "gbs" in kern[k] and k.startswith(("pull", "push"))), key=lambda k: kern[k]["ms"])
+        # the DOMINANT kernel of the step by CUDA-event time, whatever its name
+        top = max((k for k in kern if "gbs" in kern[k]), key=lambda k: kern[k]["ms"])
         line["kernels"] = kern
         k = kern[top]
+        step_bytes = sum(v["bytes"] for v in kern.values() if "bytes" in v)
+        step_ms = ms / args.steps
         line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
-                            "frac": k["gbs"] / peak, "traffic": ncu_traffic(top, world) if (args.batch == 32768 and args.dist == "zipf") else None, "peak_kind": peak_kind,
-                            "algorithmic_bytes_per_launch": k["bytes"], "us_per_launch": k["ms"] * 1e3}
-        if "pull_deep" in kern:
-            line["pull_gbs"] = kern["pull_deep"]["gbs"]
-            line["pull_frac_of_peak"] = kern["pull_deep"]["gbs"] / peak
-    line["unique_ids_per_step"] = statistics.mean(uniq_per_batch)
+                            "frac": k["gbs"] / peak,
+                            "traffic": ncu_traffic(top, world) if (args.batch == 32768 and args.dist == "zipf") else None,
+                            "peak_kind": peak_kind, "algorithmic_bytes_per_launch": k["bytes"], "us_per_launch": k["ms"] * 1e3,
+                            "step_algorithmic_bytes": step_bytes, "step_gbs": step_bytes / step_ms / 1e6,
+                            "step_frac": step_bytes / step_ms / 1e6 / peak,
+                            "per_kernel_frac": {n: v["gbs"] / peak for n, v in kern.items() if "gbs" in v},
+                            "note": "achieved = algorithmic bytes (SURVEY 8d) / CUDA-event time of the eager launch; "
+                                    "step_frac = sum of the step's algorithmic bytes / graph ms_per_step / peak"}
+        pk = "pull" if "pull" in kern else ("pull_deep" if "pull_deep" in kern else None)
+        if pk:
+            line["pull_gbs"] = kern[pk]["gbs"]
+            line["pull_frac_of_peak"] = kern[pk]["gbs"] / peak
+    line["unique_ids_per_step"] = u_mean
     if not args.no_cpu_baseline and world == 1:
-        sps, T, desc = cpu_reference(args.cpu_batch, args.cpu_steps, 1, args.dist)
-        line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": T, "kind": "port", "sample": desc}
+        sps, T, desc = cpu_reference(cpu_batch, args.cpu_steps, 1, args.dist)
+        line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": T, "kind": "port", "sample": desc,
+                                "batch_per_thread": cpu_batch, "same_batch": cpu_batch == args.batch}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

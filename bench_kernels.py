@@ -42,9 +42,14 @@ def main():
     dev = torch.device("cuda", 0)
     rows = 5_549_416
     out = []
+    only = os.environ.get("BK_ONLY", "")  # e.g. "adam:8" -> one optimizer / dim (tuning sweeps)
     for opt_name, opt, S in (("adam", ADAM, 2), ("sgd", SGD, 0)):
+        if only and not only.startswith(opt_name):
+            continue
         group = PSGroup(1, *opt, device=0, track_rows=True)
         for dim in (8, 1, 64):
+            if only and ":" in only and int(only.split(":")[1]) != dim:
+                continue
             name = "t%d" % dim
             tid = group.register_table(name, dim, "zero", rows)
             group.commit()
@@ -83,6 +88,9 @@ def main():
                     print(json.dumps(line), flush=True)
                     out.append(line)
         group.check()
+        if only:
+            group.close()
+            continue
         # dense fused update, ResNet-50-sized parameter (25.6 M fp32)
         n = 25_600_000
         group.register_dense("resnet50_flat", (n,), 0)
@@ -101,6 +109,8 @@ def main():
         group.close()
         del g
         torch.cuda.empty_cache()
+    if only:
+        return
     # unique / segment_sum at scale
     from elasticdl_b200 import ops
 
@@ -110,7 +120,7 @@ def main():
         uniq, inv, nu = ops.unique(ids, 1)
         U = int(nu.item())
         nb = k * 12 + U * 8
-        print(json.dumps({"kernel": "unique(5 launches+clear)", "k": k, "unique": U, "us": ms * 1e3,
+        print(json.dumps({"kernel": "unique(1 persistent kernel)", "k": k, "unique": U, "us": ms * 1e3,
                           "algorithmic_bytes": nb, "gbs": nb / ms / 1e6, "frac_of_peak": nb / ms / 1e6 / peak}), flush=True)
         vals = torch.randn((k, 8), device=dev)
         ms = timeit(lambda: ops.segment_sum(vals, inv, 1, k, 8))

@@ -10,7 +10,7 @@ import os
 from elasticdl_b200 import build as _build
 
 MAX_SHARDS = 16
-MAX_SEGS = 64
+MAX_SEGS = 96
 
 OK, EINVAL, ECUDA, ENOTFOUND, EWIDTH, ERANGE, ESTATE = 0, -1, -2, -3, -4, -5, -6
 
@@ -95,6 +95,7 @@ SYMBOLS = {
     "b200ps_unique": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ps_unique_bounded_workspace": (_sz, [_i, _i64, ctypes.POINTER(_i64)]),
     "b200ps_unique_bounded": (_i, [_vp, _vp, _i, _i64, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200ps_unique_bounded_i32": (_i, [_vp, _vp, _i, _i64, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ps_segment_sum": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp]),
     "b200ps_gather_rows": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp]),
     "b200ps_shard_state": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_int32)]),

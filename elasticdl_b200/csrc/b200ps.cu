@@ -15,6 +15,8 @@
 #include <vector>
 
 #include "ps_kernels.cuh"
+#include "ps_flat.cuh"
+#include "ps_unique.cuh"
 #include "ps_exchange.cuh"
 
 using namespace b200ps_impl;
@@ -309,32 +311,32 @@ int alloc_table_on_shard(b200ps_t* ps, Table& t, int s, int table_id) {
   return B200PS_OK;
 }
 
-// Splits a batch by vector class so that each launch is homogeneous:
+// Direct-indexed tables and dense-parameter row views go through the flat kernels (ps_flat.cuh): one
+// launch for all their segments whatever the dims.  Hashed tables (a probe per row) keep the
+// per-segment kernels, split by vector class so that each launch is homogeneous:
 // class 2: dim % 8 == 0 (32 B sector per thread), 1: dim % 4 == 0, 0: scalar.
-int vec_class(const Table& t) {
-  // paired tables interleave two tables' sections: only the generic kernels address them singly
-  if (t.pair_b >= 0) return 2;
-  if (t.pair_of >= 0) return 0;
-  // record slabs are 256 B aligned and row_stride is a multiple of 4 floats for vector classes
-  if (!t.is_dense && t.dim == 8 && t.row_stride % 4 == 0) return 3;  // lanes-per-record kernels
-  if (!t.is_dense && t.dim == 1 && t.row_stride == 4) return 4;       // one float4 record per row
-  if (t.dim % 8 == 0 && t.row_stride % 4 == 0) return 2;
-  if (t.dim % 4 == 0 && t.row_stride % 4 == 0) return 1;
+bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+int legacy_class(const Table& t, const void* rows) {
+  if (!aligned16(rows) || t.row_stride % 4 != 0) return 0;
+  if (t.dim % 8 == 0) return 2;
+  if (t.dim % 4 == 0) return 1;
   return 0;
 }
 
-bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
-
-constexpr int kClasses = 5;
+constexpr int kClasses = 3;
 struct Split {
-  SegBatch b[kClasses];
-  long long max_work[kClasses] = {0, 0, 0, 0, 0};
+  SegBatch b[kClasses];  // hashed tables / whole dense parameters
+  long long max_work[kClasses] = {0, 0, 0};
+  SegBatch flat;
+  FlatMeta fm;
+  long long flat_items = 0;  // upper bound of lane-items (device-side counts can only lower it)
 };
 
-int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense, Split* out, bool push = false,
-               bool allow_d1 = false) {
+int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense, Split* out, bool push = false) {
   if (nseg < 0 || nseg > kMaxSegs) return fail(B200PS_EINVAL, "nseg out of range (max " + std::to_string(kMaxSegs) + ")");
   for (int c = 0; c < kClasses; ++c) out->b[c].nseg = 0;
+  out->flat.nseg = 0;
   for (int i = 0; i < nseg; ++i) {
     const b200ps_seg_t& sg = segs[i];
     if (sg.table < 0 || sg.table >= (int)ps->tables.size()) return fail(B200PS_ENOTFOUND, "unknown table id " + std::to_string(sg.table));
@@ -342,19 +344,22 @@ int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense
     if (want_dense && !t.is_dense) return fail(B200PS_EINVAL, t.name + " is not a dense parameter");
     if (sg.n < 0) return fail(B200PS_EINVAL, "negative segment length");
     if (sg.n == 0 && !want_dense) continue;
-    int c = vec_class(t);
-    if (c > 0 && c != 4 && !aligned16(sg.rows_dev)) c = 0;
-    if (c == 4 && !allow_d1) c = 0;  // gather / scatter of one float per row: the scalar kernel is already minimal
+    if (!want_dense && !t.hashed) {
+      const int k = out->flat.nseg++;
+      out->flat.seg[k] = sg;
+      const bool vec = !push && t.dim % 4 == 0 && t.row_stride % 4 == 0 && t.base_off % 16 == 0 && aligned16(sg.rows_dev);
+      out->fm.vec[k] = vec ? 1 : 0;
+      out->flat_items += (long long)sg.n * (push ? t.dim : (vec ? t.dim / 4 : t.dim));
+      continue;
+    }
+    int c;
     long long work;
     if (want_dense) {
       long long numel = t.rows * t.dim;
       c = (numel % 4 == 0 && aligned16(sg.rows_dev)) ? 1 : 0;
       work = c ? numel / 4 : numel;
-    } else if (c == 3) {
-      work = (long long)sg.n * (push ? d8_lanes(ps->opt.kind) : 2);
-    } else if (c == 4) {
-      work = sg.n;
     } else {
+      c = legacy_class(t, sg.rows_dev);
       int W = c == 0 ? 1 : 4 * c;
       work = (long long)sg.n * (t.dim / W);
     }
@@ -381,6 +386,26 @@ int for_each_class(b200ps_t* ps, Split& sp, F&& launch) {
   }
   return B200PS_OK;
 }
+
+// Persistent grid of the flat kernels: U rows in flight per thread once the work fills the machine.
+void flat_shape(b200ps_t* ps, long long items, int* U, int* grid) {
+  static const int force_u = [] { const char* e = getenv("B200_FLAT_U"); return e ? atoi(e) : 0; }();      // tuning knobs
+  static const int per_sm = [] { const char* e = getenv("B200_FLAT_BLOCKS"); return e ? atoi(e) : 0; }();
+  const long long cap = (long long)ps->n_sm * (per_sm > 0 ? per_sm : 8);
+  *U = items >= cap * 256 * 4 ? 4 : items >= cap * 256 * 2 ? 2 : 1;
+  if (force_u == 1 || force_u == 2 || force_u == 4) *U = force_u;
+  long long blocks = (items + 256LL * *U - 1) / (256LL * *U);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  *grid = (int)blocks;
+}
+
+#define DISPATCH_U(UVAL, ...)                          \
+  switch (UVAL) {                                       \
+    case 4: { constexpr int U = 4; __VA_ARGS__; } break; \
+    case 2: { constexpr int U = 2; __VA_ARGS__; } break; \
+    default: { constexpr int U = 1; __VA_ARGS__; } break; \
+  }
 
 }  // namespace
 
@@ -799,11 +824,18 @@ static int rows_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   if (rc) return rc;
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
+  if (sp.flat.nseg) {
+    int u_rt, grid;
+    flat_shape(ps, sp.flat_items, &u_rt, &grid);
+    DISPATCH_U(u_rt, {
+      if (write) k_copy_flat<true, U><<<grid, 256, 0, st>>>(gv, sp.flat, sp.fm, slot);
+      else k_copy_flat<false, U><<<grid, 256, 0, st>>>(gv, sp.flat, sp.fm, slot);
+    });
+    ps->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
   return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
-    if (c == 3) {
-      if (write) k_rows_copy_d8<true><<<grid, 256, 0, st>>>(gv, b, slot);
-      else k_rows_copy_d8<false><<<grid, 256, 0, st>>>(gv, b, slot);
-    } else if (write) {
+    if (write) {
       if (c == 2) k_rows_copy<2, true><<<grid, 256, 0, st>>>(gv, b, slot);
       else if (c == 1) k_rows_copy<1, true><<<grid, 256, 0, st>>>(gv, b, slot);
       else k_rows_copy<0, true><<<grid, 256, 0, st>>>(gv, b, slot);
@@ -889,16 +921,21 @@ int b200ps_push_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   if (rc) return rc;
   DeviceGuard g(ps->client_device);
   Split sp;
-  rc = split_segs(ps, segs, nseg, false, &sp, true, true);
+  rc = split_segs(ps, segs, nseg, false, &sp, true);
   if (rc) return rc;
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
   OptParams o = ps->opt;
+  if (sp.flat.nseg) {
+    int u_rt, grid;
+    flat_shape(ps, sp.flat_items, &u_rt, &grid);
+    DISPATCH_OPT(o.kind, DISPATCH_U(u_rt, { k_push_flat<OPT, U><<<grid, 256, 0, st>>>(gv, sp.flat, o); }));
+    ps->launches++;
+    CUDA_OK(cudaGetLastError());
+  }
   return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
     DISPATCH_OPT(o.kind, {
-      if (c == 3) k_push_rows_d8<OPT><<<grid, 256, 0, st>>>(gv, b, o);
-      else if (c == 4) k_push_rows_d1<OPT><<<grid, 256, 0, st>>>(gv, b, o);
-      else if (c == 2) k_push_rows<OPT, 2><<<grid, 256, 0, st>>>(gv, b, o);
+      if (c == 2) k_push_rows<OPT, 2><<<grid, 256, 0, st>>>(gv, b, o);
       else if (c == 1) k_push_rows<OPT, 1><<<grid, 256, 0, st>>>(gv, b, o);
       else k_push_rows<OPT, 0><<<grid, 256, 0, st>>>(gv, b, o);
     });
@@ -1281,73 +1318,100 @@ size_t b200ps_unique_bounded_workspace(int T, int64_t k, const int64_t* bounds) 
 size_t b200ps_unique_workspace(int T, int64_t k) {
   if (T < 1 || k < 1) return 256;
   size_t cap = (size_t)uniq_cap(k);
-  size_t ntiles = (size_t)((k + kTile - 1) / kTile);
+  size_t ntiles = (size_t)((k + kUTile - 1) / kUTile);
   return align256((size_t)T * cap * 8) + align256((size_t)T * cap * 4) + 2 * align256((size_t)T * k * 4) +
-         align256((size_t)T * ntiles * 4) + 256;
+         align256((size_t)T * ntiles * 8) + 256;
 }
 
-int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, const int64_t* bounds,
-                          int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
-                          size_t workspace_bytes, void* stream);
+static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int64_t k, const int64_t* bounds,
+                       int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
+                       size_t workspace_bytes, void* stream) {
+  if (T < 1 || T > 65535 || k < 1 || k > (1LL << 29)) return fail(B200PS_EINVAL, "bad unique shape");
+  if (!ids_dev || !uniq_dev || !inv_dev || !n_unique_dev || !workspace_dev) return fail(B200PS_EINVAL, "null argument");
+  if (workspace_bytes < b200ps_unique_workspace(T, k)) return fail(B200PS_EINVAL, "unique workspace too small");
+  if (bounds && workspace_bytes < b200ps_unique_bounded_workspace(T, k, bounds)) bounds = nullptr;  // no room: hash everything
+  const int dev = client_dev(ps);
+  DeviceGuard g(dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  UArgs a{};
+  a.ids = ids_dev;
+  a.ids32 = ids32;
+  a.k = k;
+  a.T = T;
+  a.cap = uniq_cap(k);
+  a.ntiles = (int)((k + kUTile - 1) / kUTile);
+  char* p = (char*)workspace_dev;
+  a.keys = (long long*)p; p += align256((size_t)T * a.cap * 8);
+  a.minpos = (int*)p; p += align256((size_t)T * a.cap * 4);
+  a.fp = (int*)p; p += align256((size_t)T * k * 4);
+  a.rank_at = (int*)p; p += align256((size_t)T * k * 4);
+  a.status = (unsigned long long*)p;
+  a.hdr = (unsigned long long*)((char*)workspace_dev + b200ps_unique_workspace(T, k) - 256);
+  a.magic = 0xB2005EED00000000ULL ^ mix64(((uint64_t)T << 40) ^ (uint64_t)k);
+  a.use_bounds = bounds != nullptr && T <= kMaxSegs;
+  a.n_direct = 0;
+  if (a.use_bounds) {
+    a.ub.dpos = (int*)((char*)workspace_dev + b200ps_unique_workspace(T, k));
+    long long off = 0;
+    for (int t = 0; t < T; ++t) {
+      a.ub.bound[t] = bounds[t] > 0 && bounds[t] <= (1LL << 30) ? (int)bounds[t] : 0;
+      a.ub.off[t] = off;
+      off += (long long)(align256((size_t)a.ub.bound[t] * 4) / 4);
+      if (a.ub.bound[t] > 0) a.n_direct++;
+    }
+  }
+  a.n_hashed = T - a.n_direct;
+  a.tagged = a.use_bounds && k <= (1LL << kUniqPosBits);
+  int shift = 5;
+  while (shift < kUChunkShiftMax && (1LL << shift) < k) ++shift;
+  a.chunk_shift = shift;
+  a.uniq = uniq_dev;
+  a.inv = inv_dev;
+  a.n_unique = n_unique_dev;
+  a.err = ps ? ps->d_err : nullptr;
+  // co-resident grid (the kernel synchronises its phases with a grid barrier)
+  static int occ[64] = {0};
+  static int sms[64] = {0};
+  if (dev < 64 && occ[dev] == 0) {
+    int o = 0, n = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_unique, kUThreads, 0));
+    CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    occ[dev] = o < 1 ? 1 : (o > 4 ? 4 : o);
+    sms[dev] = n < 1 ? 1 : n;
+  }
+  const long long max_blocks = dev < 64 ? (long long)occ[dev] * sms[dev] : 132;
+  const long long nchunk = (k + (1LL << shift) - 1) >> shift;
+  const long long items = nchunk * ((long long)T << shift);
+  long long blocks = (items + kUThreads - 1) / kUThreads;
+  const long long tiles = (long long)T * a.ntiles;
+  if (blocks < tiles) blocks = tiles;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  CUDA_OK(cudaMemsetAsync(a.hdr + 4, 0, 8, st));  // the grid-barrier counter
+  k_unique<<<(unsigned)blocks, kUThreads, 0, st>>>(a);
+  count_launch(ps, 1);
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
 
 int b200ps_unique(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, int64_t* uniq_dev, int32_t* inv_dev,
                   int32_t* n_unique_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
-  return b200ps_unique_bounded(ps, ids_dev, T, k, nullptr, uniq_dev, inv_dev, n_unique_dev, workspace_dev,
-                               workspace_bytes, stream);
+  return unique_impl(ps, ids_dev, 0, T, k, nullptr, uniq_dev, inv_dev, n_unique_dev, workspace_dev, workspace_bytes,
+                     stream);
 }
 
 int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, const int64_t* bounds,
                           int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream) {
-  if (T < 1 || T > 65535 || k < 1 || k > (1LL << 30)) return fail(B200PS_EINVAL, "bad unique shape");
-  if (workspace_bytes < b200ps_unique_workspace(T, k)) return fail(B200PS_EINVAL, "unique workspace too small");
-  if (bounds && workspace_bytes < b200ps_unique_bounded_workspace(T, k, bounds)) bounds = nullptr;  // no room: hash everything
-  DeviceGuard g(client_dev(ps));
-  cudaStream_t st = (cudaStream_t)stream;
-  UniqueWs ws;
-  ws.cap = uniq_cap(k);
-  ws.ntiles = (int)((k + kTile - 1) / kTile);
-  char* p = (char*)workspace_dev;
-  ws.keys = (long long*)p; p += align256((size_t)T * ws.cap * 8);
-  ws.minpos = (int*)p; p += align256((size_t)T * ws.cap * 4);
-  ws.fp = (int*)p; p += align256((size_t)T * k * 4);
-  ws.rank_at = (int*)p; p += align256((size_t)T * k * 4);
-  ws.tile_cnt = (int*)p;
-  ws.hdr = (unsigned long long*)((char*)workspace_dev + b200ps_unique_workspace(T, k) - 256);
-  ws.magic = 0xB2005EED00000000ULL ^ mix64(((uint64_t)T << 40) ^ (uint64_t)k);
-  UniqueBounds ub{};
-  const int use_bounds = bounds != nullptr && T <= kMaxSegs;
-  long long max_clear = ws.cap;
-  if (use_bounds) {
-    ub.dpos = (int*)((char*)workspace_dev + b200ps_unique_workspace(T, k));
-    long long off = 0;
-    for (int t = 0; t < T; ++t) {
-      ub.bound[t] = bounds[t] > 0 && bounds[t] <= (1LL << 30) ? (int)bounds[t] : 0;
-      ub.off[t] = off;
-      off += (long long)(align256((size_t)ub.bound[t] * 4) / 4);
-      if (ub.bound[t] > max_clear) max_clear = ub.bound[t];
-    }
-  }
-  ws.tagged = use_bounds && k <= (1LL << kUniqPosBits);
-  // direct-address segments are only cleared once per kUniqEpochs calls: a thin grid-stride launch
-  long long clear_blocks = (max_clear + 2047) / 2048;
-  if (ws.tagged && clear_blocks > 8) clear_blocks = 8;
-  dim3 gc((unsigned)clear_blocks, T);
-  k_uniq_clear<<<gc, 256, 0, st>>>(ws, T, ub, use_bounds);
-  dim3 gk((unsigned)((k + 255) / 256), T), gt(ws.ntiles, T);
-  const long long head = k < 2 * kUniqHead ? k : kUniqHead;
-  k_uniq_insert<<<dim3((unsigned)((head + 255) / 256), T), 256, 0, st>>>(ids_dev, k, 0, head, ws, ub, use_bounds);
-  if (head < k) {
-    k_uniq_insert<<<dim3((unsigned)((k - head + 255) / 256), T), 256, 0, st>>>(ids_dev, k, head, k, ws, ub, use_bounds);
-    count_launch(ps, 1);
-  }
-  k_uniq_flag<<<gt, 256, 0, st>>>(k, ws, ub, use_bounds);
-  k_uniq_scan_tiles<<<T, 1024, 0, st>>>(ws, n_unique_dev);
-  k_uniq_rank<<<gt, 256, 0, st>>>(ids_dev, k, ws, uniq_dev);
-  k_uniq_inverse<<<gk, 256, 0, st>>>(k, ws, inv_dev);
-  count_launch(ps, 6);
-  CUDA_OK(cudaGetLastError());
-  return B200PS_OK;
+  return unique_impl(ps, ids_dev, 0, T, k, bounds, uniq_dev, inv_dev, n_unique_dev, workspace_dev, workspace_bytes,
+                     stream);
+}
+
+int b200ps_unique_bounded_i32(b200ps_t* ps, const int32_t* ids32_dev, int T, int64_t k, const int64_t* bounds,
+                              int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
+                              size_t workspace_bytes, void* stream) {
+  return unique_impl(ps, ids32_dev, 1, T, k, bounds, uniq_dev, inv_dev, n_unique_dev, workspace_dev, workspace_bytes,
+                     stream);
 }
 
 static int dim_class(int dim, const void* a, const void* b) {

@@ -752,234 +752,6 @@ __global__ void __launch_bounds__(256) k_present_ids(const uint32_t* present, lo
 }
 
 // ---------------------------------------------------------------------------
-// unique (tf.unique, first-occurrence order) over T equal-length id segments.
-// A: insert ids into a per-segment open-addressing table, remembering the
-//    smallest position of each id;  B: first-occurrence flags + per-tile counts;
-// C: scan of tile counts;  D: ranks, unique ids;  E: inverse index.
-// ---------------------------------------------------------------------------
-constexpr long long kEmptyKey = (long long)0x8000000000000000ULL;
-constexpr int kTile = 1024;  // ids per block in B / D (256 threads x 4)
-
-struct UniqueBounds {      // per segment: ids are known to be < bound (0 = unknown): the segment dedups
-  int bound[kMaxSegs];     // through a direct-address position array dpos[off .. off+bound) instead of
-  long long off[kMaxSegs]; // the hash table: no keys, no CAS, no probing
-  int* dpos;
-};
-
-struct UniqueWs {
-  long long* keys;  // [T][cap]
-  int* minpos;      // [T][cap]
-  int* fp;          // [T][k]   slot, then first position of the id at i
-  int* rank_at;     // [T][k]
-  int* tile_cnt;    // [T][ntiles]
-  int cap;          // power of two >= 2k
-  int ntiles;
-  // Direct-address segments are not cleared between calls: positions are stored under an epoch
-  // prefix that DEcreases from call to call, so atomicMin prefers this call's entries and stale
-  // ones read as empty.  hdr = {magic, epoch, cleared cycle} lives in the workspace (a fresh / foreign
-  // workspace fails the magic test and is cleared); every kUniqEpochs calls the prefix wraps and
-  // the arrays are cleared for real by the first tagged call of the new cycle (calls without
-  // bounds share the workspace and the epoch counter but never touch these arrays).
-  unsigned long long* hdr;
-  unsigned long long magic;
-  int tagged;  // k <= 2^20: positions fit under the prefix
-};
-
-constexpr int kUniqPosBits = 20;
-constexpr int kUniqEpochs = 2047;  // prefixes 0..2046 keep the value below 0x7fffffff (= empty)
-
-__device__ __forceinline__ int uniq_epoch(const UniqueWs& ws) {  // stable until k_uniq_scan_tiles bumps it
-  return ws.hdr[0] == ws.magic ? (int)(ws.hdr[1] % kUniqEpochs) : 0;
-}
-__device__ __forceinline__ bool uniq_need_clear(const UniqueWs& ws) {
-  return ws.hdr[0] != ws.magic || ws.hdr[2] != ws.hdr[1] / kUniqEpochs;
-}
-__device__ __forceinline__ int uniq_prefix(const UniqueWs& ws) {
-  return ws.tagged ? (kUniqEpochs - 1 - uniq_epoch(ws)) << kUniqPosBits : 0;
-}
-
-__global__ void __launch_bounds__(256) k_uniq_clear(UniqueWs ws, int T, UniqueBounds ub, int use_bounds) {
-  const int t = blockIdx.y;
-  const int direct = use_bounds && ub.bound[t] > 0;
-  if (direct && ws.tagged && !uniq_need_clear(ws)) return;  // stale prefixes already read as empty
-  const int n = direct ? ub.bound[t] : ws.cap;
-  long long* keys = ws.keys + (long long)t * ws.cap;
-  int* minpos = direct ? ub.dpos + ub.off[t] : ws.minpos + (long long)t * ws.cap;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (!direct) keys[i] = kEmptyKey;
-    minpos[i] = 0x7fffffff;
-  }
-}
-
-// Positions [begin, end) of every segment.  The host launches the first kUniqHead positions on
-// their own: Zipf-hot ids almost surely occur there, so when the bulk launch starts their slots
-// already hold a small position and the check-before-atomic below skips them -- launched as one
-// wave, ~1000 resident blocks all saw "empty" and queued thousands of atomics on the same address.
-constexpr int kUniqHead = 2048;
-__global__ void __launch_bounds__(256) k_uniq_insert(const int64_t* ids, long long k, long long begin, long long end,
-                                                     UniqueWs ws, UniqueBounds ub, int use_bounds) {
-  const int t = blockIdx.y;
-  if (use_bounds && ub.bound[t] > 0) {  // direct-address segment (block-uniform)
-    const long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= end) return;
-    long long id = ids[t * k + i];
-    if (id < 0 || id >= ub.bound[t]) id = 0;  // out-of-range ids are reported by the table kernels
-    int* minpos = ub.dpos + ub.off[t];
-    const int v = uniq_prefix(ws) | (int)i;
-    if (*(volatile int*)&minpos[id] > v) atomicMin(&minpos[id], v);
-    ws.fp[t * k + i] = (int)id;
-    return;
-  }
-  const long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < end;
-  const int lane = threadIdx.x & 31;
-  // warp-level id dedup: lanes holding the same id elect the lowest lane (= smallest position),
-  // which alone probes the table; Zipf-hot ids then cost one atomic per warp, not one per lane.
-  const long long id = live ? ids[t * k + i] : (long long)(-1 - lane);
-  const unsigned peers = __match_any_sync(0xffffffffu, id);
-  const int leader = __ffs(peers) - 1;
-  unsigned s = 0;
-  if (live && lane == leader) {
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws.keys + (long long)t * ws.cap);
-    int* minpos = ws.minpos + (long long)t * ws.cap;
-    const unsigned mask = ws.cap - 1;
-    s = (unsigned)mix64((uint64_t)id) & mask;
-    while (true) {
-      unsigned long long prev = keys[s];
-      if (prev == (unsigned long long)kEmptyKey) prev = atomicCAS(&keys[s], (unsigned long long)kEmptyKey, (unsigned long long)id);
-      if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)id) break;
-      s = (s + 1) & mask;
-    }
-    // after the first few occurrences the recorded position is already smaller
-    if (*(volatile int*)&minpos[s] > (int)i) atomicMin(&minpos[s], (int)i);
-  }
-  s = __shfl_sync(0xffffffffu, s, leader);
-  if (live) ws.fp[t * k + i] = (int)s;
-}
-
-__device__ __forceinline__ int block_sum_256(int v, int* smem) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
-  __syncthreads();
-  int tot = 0;
-  if (threadIdx.x < 8) tot = smem[threadIdx.x];
-  if (threadIdx.x < 32) {
-    for (int o = 4; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
-  }
-  return tot;  // valid on thread 0
-}
-
-__global__ void __launch_bounds__(256) k_uniq_flag(long long k, UniqueWs ws, UniqueBounds ub, int use_bounds) {
-  __shared__ int red[8];
-  const int t = blockIdx.y;
-  const long long base = (long long)blockIdx.x * kTile;
-  const bool direct = use_bounds && ub.bound[t] > 0;
-  const int* minpos = direct ? ub.dpos + ub.off[t] : ws.minpos + (long long)t * ws.cap;
-  const int pos_mask = direct && ws.tagged ? (1 << kUniqPosBits) - 1 : 0x7fffffff;
-  int* fp = ws.fp + t * k;
-  int cnt = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    long long i = base + j * 256 + threadIdx.x;
-    if (i < k) {
-      int f = minpos[fp[i]] & pos_mask;
-      fp[i] = f;
-      cnt += (f == (int)i);
-    }
-  }
-  int tot = block_sum_256(cnt, red);
-  if (threadIdx.x == 0) ws.tile_cnt[(long long)t * ws.ntiles + blockIdx.x] = tot;
-}
-
-// one block per segment: exclusive scan of tile counts (in place), total -> n_unique
-__global__ void __launch_bounds__(1024) k_uniq_scan_tiles(UniqueWs ws, int* n_unique) {
-  __shared__ int warp_tot[32];
-  __shared__ int carry;
-  const int t = blockIdx.x;
-  int* cnt = ws.tile_cnt + (long long)t * ws.ntiles;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < ws.ntiles; base += 1024) {
-    int i = base + threadIdx.x;
-    int v = i < ws.ntiles ? cnt[i] : 0;
-    int x = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, x, o);
-      if ((threadIdx.x & 31) >= o) x += y;
-    }
-    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int wv = warp_tot[threadIdx.x];
-      int wx = wv;
-      for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, wx, o);
-        if (threadIdx.x >= o) wx += y;
-      }
-      warp_tot[threadIdx.x] = wx - wv;  // exclusive
-    }
-    __syncthreads();
-    int excl = x - v + warp_tot[threadIdx.x >> 5] + carry;
-    if (i < ws.ntiles) cnt[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) n_unique[t] = carry;
-  if (t == 0 && threadIdx.x == 0) {  // insert / flag are done with this call's epoch: open the next one
-    const bool fresh = ws.hdr[0] != ws.magic;
-    const unsigned long long epoch = fresh ? 0ULL : ws.hdr[1];
-    if (ws.tagged) ws.hdr[2] = epoch / kUniqEpochs;  // the position arrays are valid for this cycle
-    else if (fresh) ws.hdr[2] = ~0ULL;
-    ws.hdr[1] = epoch + 1ULL;
-    ws.hdr[0] = ws.magic;
-  }
-}
-
-__global__ void __launch_bounds__(256) k_uniq_rank(const int64_t* ids, long long k, UniqueWs ws, int64_t* uniq) {
-  __shared__ int warp_tot[8];
-  const int t = blockIdx.y;
-  const long long base = (long long)blockIdx.x * kTile;
-  const int* fp = ws.fp + t * k;
-  int* rank_at = ws.rank_at + t * k;
-  // thread owns 4 CONSECUTIVE positions so that ranks follow position order
-  const long long i0 = base + threadIdx.x * 4;
-  int f[4], c = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    long long i = i0 + j;
-    f[j] = (i < k) && (fp[i] == (int)i);
-    c += f[j];
-  }
-  int x = c;
-  for (int o = 1; o < 32; o <<= 1) {
-    int y = __shfl_up_sync(0xffffffffu, x, o);
-    if ((threadIdx.x & 31) >= o) x += y;
-  }
-  if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
-  __syncthreads();
-  int wbase = 0;
-  for (int w = 0; w < (threadIdx.x >> 5); ++w) wbase += warp_tot[w];
-  int r = ws.tile_cnt[(long long)t * ws.ntiles + blockIdx.x] + wbase + x - c;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (f[j]) {
-      long long i = i0 + j;
-      rank_at[i] = r;
-      uniq[t * k + r] = ids[t * k + i];
-      ++r;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) k_uniq_inverse(long long k, UniqueWs ws, int* inv) {
-  const int t = blockIdx.y;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= k) return;
-  inv[t * k + i] = ws.rank_at[t * k + ws.fp[t * k + i]];
-}
-
-// ---------------------------------------------------------------------------
 // segment_sum: out[t][inv[i], :] += values[t][i, :]   (deduplicate_indexed_slices'
 // sum / gather backward).  Warp-level id dedup: lanes of a warp that hit the
 // same output row combine through shuffles (lane order) and the lowest lane

@@ -1,0 +1,323 @@
+// unique (tf.unique, first-occurrence order + inverse index) over T equal-length id segments as ONE
+// persistent kernel (round 1: seven launches, 48 us at 38 x 32768 ids).
+//
+//   phase 0  (only when something must be cleared) hash keys / position arrays
+//   phase A  insert: position array entry of every id <- min(position), chunk-major so the heads of
+//            all segments go first; lanes of a warp holding the same id elect one writer
+//   ---- grid barrier ----
+//   phase B  per 1024-position tile: first-occurrence flags, block scan, decoupled look-back over
+//            the tile aggregates of the segment (single pass: no scan kernel), global ranks,
+//            unique ids written in rank order, n_unique by the last tile of each segment
+//   ---- grid barrier ----
+//   phase C  inverse index: inv[i] = rank of the first occurrence of ids[i]
+//
+// The grid is sized to be co-resident (occupancy x #SM, capped) so the hand-rolled barrier cannot
+// deadlock: blocks only ever wait for blocks of this same launch, all of which are (or will become)
+// resident because nothing resident waits on anything outside the launch.  Every spin has a bound
+// and raises the error word instead of hanging the GPU.  ids may be int64 or int32 (narrow id
+// transport: the widening happens at the first read); outputs are the same either way.
+// Replaces tf.unique at python/elasticdl/embedding_delegate.py:85 and the key pass of
+// deduplicate_indexed_slices (python/common/tensor_utils.py:53-58).
+#pragma once
+#include "ps_kernels.cuh"
+
+namespace b200ps_impl {
+
+constexpr long long kEmptyKey = (long long)0x8000000000000000ULL;
+constexpr int kUTile = 1024;   // positions per tile (256 threads x 4 consecutive positions)
+constexpr int kUThreads = 256;
+constexpr int kUChunkShiftMax = 11;  // insert order: <= 2048-position chunks, chunk-major over the segments
+constexpr long long kUSpins = 1LL << 22;
+constexpr unsigned kErrUnique = 16u;
+
+struct UniqueBounds {      // per segment: ids are known to be < bound (0 = unknown): the segment dedups
+  int bound[kMaxSegs];     // through a direct-address position array dpos[off .. off+bound) instead of
+  long long off[kMaxSegs]; // the hash table: no keys, no CAS, no probing
+  int* dpos;
+};
+
+// Direct-address segments are not cleared between calls: positions are stored under an epoch prefix
+// that DEcreases from call to call, so atomicMin prefers this call's entries and stale ones read as
+// empty.  hdr = {magic, epoch, cleared cycle, -, barrier counter} lives in the workspace (a fresh /
+// foreign workspace fails the magic test and is cleared); every kUniqEpochs calls the prefix wraps
+// and the arrays are cleared for real by the first tagged call of the new cycle.
+constexpr int kUniqPosBits = 20;
+constexpr int kUniqEpochs = 2047;  // prefixes 0..2046 keep the value below 0x7fffffff (= empty)
+
+struct UArgs {
+  const void* ids;
+  long long k;
+  int T, ids32;
+  long long* keys;              // [T][cap]   (hashed segments)
+  int* minpos;                  // [T][cap]
+  int* fp;                      // [T][k]  slot / id, then first position of the id at i
+  int* rank_at;                 // [T][k]
+  unsigned long long* status;   // [T][ntiles] look-back descriptors {tag:30 | flag:2 | value:32}
+  unsigned long long* hdr;
+  unsigned long long magic;
+  int cap, ntiles, tagged, use_bounds, n_direct, n_hashed;
+  int chunk_shift;              // log2 of the insert chunk (>= 5: whole warps)
+  UniqueBounds ub;
+  int64_t* uniq;
+  int* inv;
+  int* n_unique;
+  unsigned* err;
+};
+
+__device__ __forceinline__ long long u_id(const UArgs& a, long long idx) {
+  return a.ids32 ? (long long)reinterpret_cast<const int*>(a.ids)[idx] : reinterpret_cast<const long long*>(a.ids)[idx];
+}
+__device__ __forceinline__ unsigned long long u_ldv(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void u_stv(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void u_grid_barrier(unsigned* bar, unsigned target, unsigned* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    long long spins = 0;
+    while (*(volatile unsigned*)bar < target) {
+      __nanosleep(40);
+      if (++spins > kUSpins) {
+        if (err) atomicOr(err, kErrUnique);
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+constexpr unsigned kUFlagA = 1u, kUFlagP = 2u;
+__device__ __forceinline__ unsigned long long u_word(unsigned tag, unsigned flag, unsigned value) {
+  return ((unsigned long long)((tag << 2) | flag) << 32) | value;
+}
+
+__global__ void __launch_bounds__(kUThreads) k_unique(UArgs a) {
+  __shared__ int s_warp[kUThreads / 32];
+  __shared__ int s_excl;
+  // header snapshot: stable until block 0 rewrites it after the last barrier
+  const bool fresh = a.hdr[0] != a.magic;
+  const unsigned long long epoch64 = fresh ? 0ULL : a.hdr[1];
+  const bool stale_cycle = fresh || a.hdr[2] != epoch64 / kUniqEpochs;
+  const int epoch = (int)(epoch64 % kUniqEpochs);
+  const int prefix = a.tagged ? (kUniqEpochs - 1 - epoch) << kUniqPosBits : 0;
+  const int pos_mask = a.tagged ? (1 << kUniqPosBits) - 1 : 0x7fffffff;
+  const unsigned tag = (unsigned)((epoch64 + 1ULL) % 0x3ffffffeULL) + 1u;
+  unsigned* bar = reinterpret_cast<unsigned*>(a.hdr + 4);  // zeroed by the host before every launch
+  unsigned target = 0;
+  const long long gsz = (long long)gridDim.x * kUThreads;
+  const long long gtid = (long long)blockIdx.x * kUThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long k = a.k;
+  const int T = a.T;
+
+  // ---- phase 0: clear what this call cannot read as empty ----
+  const bool clear_direct = a.n_direct > 0 && (!a.tagged || stale_cycle);
+  if (a.n_hashed > 0 || clear_direct || fresh) {
+    if (fresh) {  // descriptors of a foreign layout could carry this call's tag
+      const long long n = (long long)T * a.ntiles;
+      for (long long i = gtid; i < n; i += gsz) a.status[i] = 0ULL;
+    }
+    if (a.n_hashed > 0 || clear_direct) {
+    if (!a.use_bounds) {
+      const long long n = (long long)T * a.cap;
+      for (long long i = gtid; i < n; i += gsz) {
+        a.keys[i] = kEmptyKey;
+        a.minpos[i] = 0x7fffffff;
+      }
+    } else {
+      for (int t = 0; t < T; ++t) {
+        if (a.ub.bound[t] > 0) {
+          if (!clear_direct) continue;
+          int* dp = a.ub.dpos + a.ub.off[t];
+          for (long long i = gtid; i < a.ub.bound[t]; i += gsz) dp[i] = 0x7fffffff;
+        } else {
+          long long* keys = a.keys + (long long)t * a.cap;
+          int* mp = a.minpos + (long long)t * a.cap;
+          for (long long i = gtid; i < a.cap; i += gsz) {
+            keys[i] = kEmptyKey;
+            mp[i] = 0x7fffffff;
+          }
+        }
+      }
+    }
+    }
+    target += gridDim.x;
+    u_grid_barrier(bar, target, a.err);
+  }
+
+  // ---- phase A: insert ----
+  {
+    const long long nchunk = (k + (1LL << a.chunk_shift) - 1) >> a.chunk_shift;
+    const long long per_chunk = (long long)T << a.chunk_shift;
+    const long long items = nchunk * per_chunk;  // multiple of 32: warps stay whole
+    for (long long w = gtid; w < items; w += gsz) {
+      const long long c = w / per_chunk;
+      const long long rem = w - c * per_chunk;
+      const int t = (int)(rem >> a.chunk_shift);
+      const long long i = (c << a.chunk_shift) + (rem & ((1LL << a.chunk_shift) - 1));
+      const bool live = i < k;
+      long long id = live ? u_id(a, (long long)t * k + i) : 0;
+      const bool direct = a.use_bounds && a.ub.bound[t] > 0;  // warp-uniform (a chunk is one segment)
+      const unsigned livem = __ballot_sync(0xffffffffu, live);   // dead lanes (tail of the last chunk) never match
+      if (direct) {
+        if (id < 0 || id >= a.ub.bound[t]) id = 0;  // out-of-range ids are reported by the table kernels
+        // warp-level id dedup: equal ids elect their lowest lane = smallest position
+        const unsigned peers = __match_any_sync(0xffffffffu, id) & livem;
+        if (live) {
+          if ((__ffs(peers) - 1) == lane) {
+            int* mp = a.ub.dpos + a.ub.off[t] + id;
+            const int v = prefix | (int)i;
+            if (*(volatile int*)mp > v) atomicMin(mp, v);
+          }
+          a.fp[(long long)t * k + i] = (int)id;
+        }
+      } else {
+        const unsigned peers = __match_any_sync(0xffffffffu, id) & livem;
+        const int leader = live ? __ffs(peers) - 1 : lane;
+        unsigned s = 0;
+        if (live && lane == leader) {
+          unsigned long long* keys = reinterpret_cast<unsigned long long*>(a.keys + (long long)t * a.cap);
+          int* mp = a.minpos + (long long)t * a.cap;
+          const unsigned mask = a.cap - 1;
+          s = (unsigned)mix64((uint64_t)id) & mask;
+          while (true) {
+            unsigned long long prev = keys[s];
+            if (prev == (unsigned long long)kEmptyKey)
+              prev = atomicCAS(&keys[s], (unsigned long long)kEmptyKey, (unsigned long long)id);
+            if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)id) break;
+            s = (s + 1) & mask;
+          }
+          if (*(volatile int*)&mp[s] > (int)i) atomicMin(&mp[s], (int)i);
+        }
+        s = __shfl_sync(0xffffffffu, s, leader);
+        if (live) a.fp[(long long)t * k + i] = (int)s;
+      }
+    }
+  }
+  target += gridDim.x;
+  u_grid_barrier(bar, target, a.err);
+
+  // ---- phase B: flags, single-pass scan over the tiles of each segment, ranks, unique ids ----
+  const long long tiles = (long long)T * a.ntiles;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int t = (int)(tile / a.ntiles);
+    const long long j = tile - (long long)t * a.ntiles;
+    const bool direct = a.use_bounds && a.ub.bound[t] > 0;
+    const int* mp = direct ? a.ub.dpos + a.ub.off[t] : a.minpos + (long long)t * a.cap;
+    const int pm = direct ? pos_mask : 0x7fffffff;
+    int* fp = a.fp + (long long)t * k;
+    const long long i0 = j * kUTile + threadIdx.x * 4;  // 4 CONSECUTIVE positions: ranks follow position order
+    int f[4], c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long i = i0 + q;
+      f[q] = 0;
+      if (i < k) {
+        const int first = mp[fp[i]] & pm;
+        fp[i] = first;
+        f[q] = first == (int)i;
+      }
+      c += f[q];
+    }
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    int wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kUThreads / 32; ++w) {
+      const int v = s_warp[w];
+      if (w < wid) wbase += v;
+      tot += v;
+    }
+    if (wid == 0) {
+      if (lane == 0) u_stv(&a.status[tile], u_word(tag, j == 0 ? kUFlagP : kUFlagA, (unsigned)tot));
+      int excl = 0;
+      long long look = j - 1;  // predecessor tiles of this segment, nearest first, 32 at a time
+      long long spins = 0;
+      while (look >= 0) {
+        const long long idx = look - lane;
+        unsigned long long wv = 0;
+        bool valid = true;  // lanes before the segment start count as an exclusive prefix of 0
+        unsigned flag = kUFlagP, val = 0;
+        if (idx >= 0) {
+          wv = u_ldv(&a.status[(long long)t * a.ntiles + idx]);
+          const unsigned hi = (unsigned)(wv >> 32);
+          valid = (hi >> 2) == tag && (hi & 3u) != 0;
+          flag = hi & 3u;
+          val = (unsigned)wv;
+        }
+        if (!__all_sync(0xffffffffu, valid)) {
+          if (++spins > kUSpins) {
+            if (lane == 0 && a.err) atomicOr(a.err, kErrUnique);
+            break;
+          }
+          __nanosleep(20);
+          continue;
+        }
+        const unsigned pmask = __ballot_sync(0xffffffffu, flag == kUFlagP);
+        const int stop = pmask ? __ffs(pmask) - 1 : 31;  // nearest tile that already knows its inclusive prefix
+        int contrib = lane <= stop ? (int)val : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (pmask) break;
+        look -= 32;
+      }
+      if (lane == 0) {
+        s_excl = excl;
+        if (j > 0) u_stv(&a.status[tile], u_word(tag, kUFlagP, (unsigned)(excl + tot)));
+        if (j == a.ntiles - 1) a.n_unique[t] = excl + tot;
+      }
+    }
+    __syncthreads();
+    int r = s_excl + wbase + x - c;
+    int* rank_at = a.rank_at + (long long)t * k;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (f[q]) {
+        const long long i = i0 + q;
+        rank_at[i] = r;
+        a.uniq[(long long)t * k + r] = u_id(a, (long long)t * k + i);
+        ++r;
+      }
+    }
+    __syncthreads();  // s_warp / s_excl are reused by the next tile
+  }
+  target += gridDim.x;
+  u_grid_barrier(bar, target, a.err);
+
+  // ---- phase C: inverse index ----
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int t = (int)(tile / a.ntiles);
+    const long long j = tile - (long long)t * a.ntiles;
+    const int* fp = a.fp + (long long)t * k;
+    const int* rank_at = a.rank_at + (long long)t * k;
+    int* inv = a.inv + (long long)t * k;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long i = j * kUTile + q * kUThreads + threadIdx.x;
+      if (i < k) inv[i] = rank_at[fp[i]];
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // every block took its header snapshot before barrier 1
+    if (a.tagged) a.hdr[2] = epoch64 / kUniqEpochs;  // the position arrays are valid for this cycle
+    else if (fresh) a.hdr[2] = ~0ULL;
+    a.hdr[1] = epoch64 + 1ULL;
+    a.hdr[0] = a.magic;
+  }
+}
+
+}  // namespace b200ps_impl

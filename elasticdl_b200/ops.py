@@ -33,10 +33,16 @@ def unique(ids, T=1):
     k = ids.numel() // T
     lib = _lib.lib()
     need = lib.b200ps_unique_workspace(T, k)
-    ws = _ws.get(ids.device)
+    # one workspace per (device, stream): two worker threads on different streams must never share
+    # the position / key arrays (a stale one is dropped once its stream has run past the last use)
+    stream = torch.cuda.current_stream(ids.device)
+    key = (ids.device, stream.cuda_stream)
+    ws = _ws.get(key)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(need, dtype=torch.uint8, device=ids.device)
-        _ws[ids.device] = ws
+        ws = torch.zeros(need, dtype=torch.uint8, device=ids.device)
+        if key in _ws:
+            _ws[key].record_stream(stream)
+        _ws[key] = ws
     uniq = torch.empty(T * k, dtype=torch.int64, device=ids.device)
     inv = torch.empty(T * k, dtype=torch.int32, device=ids.device)
     n_unique = torch.empty(T, dtype=torch.int32, device=ids.device)

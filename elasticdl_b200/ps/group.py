@@ -356,7 +356,9 @@ class PSGroup:
         k = ids.numel() // T
         need = self.lib.b200ps_unique_workspace(T, k)
         if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            if self._ws is not None:
+                self._ws.record_stream(torch.cuda.current_stream(self.device))
+            self._ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
         uniq = torch.empty(T * k, dtype=torch.int64, device=self.device)
         inv = torch.empty(T * k, dtype=torch.int32, device=self.device)
         n_unique = torch.empty(T, dtype=torch.int32, device=self.device)

@@ -80,6 +80,34 @@ def synthetic_batch(batch, seed, device, dist="zipf", zipf_s=1.05, group_rows=GR
     return ids, dense, labels
 
 
+def packed_nbytes(G, B):
+    """One training batch as ONE buffer: [ids int32 G x B | dense fp32 B x 13 | labels fp32 B]."""
+    return 4 * G * B + 4 * B * N_DENSE + 4 * B
+
+
+def packed_views(buf, G, B):
+    """(ids int32 [G, B], dense fp32 [B, 13], labels fp32 [B]) views of a packed uint8 buffer."""
+    a, b = 4 * G * B, 4 * G * B + 4 * B * N_DENSE
+    return (buf[:a].view(torch.int32).view(G, B), buf[a:b].view(torch.float32).view(B, N_DENSE),
+            buf[b:b + 4 * B].view(torch.float32))
+
+
+def pack_batch(ids, dense, labels, pin=False):
+    """Pack (ids int64/int32 [G, B], dense [B, 13], labels [B]) into one uint8 buffer on the same
+    device (pin=True: pinned host memory).  ids are narrowed to int32 -- every dac_ctr table has
+    fewer than 2^31 rows; the device widens them again inside the dedup kernel
+    (b200ps_unique_bounded_i32), so the PS sees the same int64 ids."""
+    G, B = ids.shape
+    buf = torch.empty(packed_nbytes(G, B), dtype=torch.uint8, device="cpu" if pin else ids.device)
+    if pin:
+        buf = buf.pin_memory()
+    v_ids, v_dense, v_labels = packed_views(buf, G, B)
+    v_ids.copy_(ids)
+    v_dense.copy_(dense)
+    v_labels.copy_(labels)
+    return buf
+
+
 def flatten_tower(tower, flat):
     """Re-point the tower's parameters at views of one flat buffer laid out as
     include/b200_deepfm.h documents: [w_dense 13 (+3 pad) | w1 | b1 | w2 | b2 | w3]."""
@@ -98,6 +126,8 @@ def flatten_tower(tower, flat):
 
 class HostFeeder:
     """Pinned-host batches -> staging slots on a copy stream -> the captured step.
+    A batch travels as ONE packed buffer (pack_batch: int32 ids | dense | labels) = one H2D copy;
+    submit() also takes the three separate tensors (three copies, ids narrowed on the device).
     lookahead=True drives engine.step_ahead_graph: slot k's dense/labels train while slot k+1's
     ids are deduplicated, so two batches must have landed before a step starts (depth >= 3)."""
 
@@ -105,30 +135,32 @@ class HostFeeder:
         self.lookahead = bool(lookahead)
         if self.lookahead:
             depth = max(depth, 3)
+            if engine.graphs_ahead is None:
+                engine.capture_ahead()
         elif getattr(engine, "graph", None) is None:
             engine.capture()
         self.started = False
         self.e = engine
         dev, G, B = engine.device, engine.G, engine.B
         self.depth = depth
-        self.slots = [(torch.empty((G, B), dtype=torch.int64, device=dev),
-                       torch.empty((B, N_DENSE), dtype=torch.float32, device=dev),
-                       torch.empty(B, dtype=torch.float32, device=dev)) for _ in range(depth)]
+        self.slots = [torch.empty(packed_nbytes(G, B), dtype=torch.uint8, device=dev) for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ready = [torch.cuda.Event() for _ in range(depth)]
         self.free = [torch.cuda.Event() for _ in range(depth)]
         self.head = self.tail = 0
 
-    def submit(self, host_ids, host_dense, host_labels):
-        """Enqueue the H2D copies of one batch (pinned host tensors) on the copy stream."""
+    def submit(self, *host_batch):
+        """Enqueue the H2D copy of one batch (pinned host memory) on the copy stream:
+        submit(packed) or submit(ids, dense, labels)."""
         k = self.head % self.depth
         with torch.cuda.stream(self.copy_stream):
             if self.head >= self.depth:
                 self.copy_stream.wait_event(self.free[k])
-            ids, dense, labels = self.slots[k]
-            ids.copy_(host_ids, non_blocking=True)
-            dense.copy_(host_dense, non_blocking=True)
-            labels.copy_(host_labels, non_blocking=True)
+            if len(host_batch) == 1:
+                self.slots[k].copy_(host_batch[0], non_blocking=True)
+            else:
+                for dst, src in zip(packed_views(self.slots[k], self.e.G, self.e.B), host_batch):
+                    dst.copy_(src, non_blocking=True)
             self.ready[k].record(self.copy_stream)
         self.head += 1
 
@@ -138,18 +170,16 @@ class HostFeeder:
         main = torch.cuda.current_stream(self.e.device)
         main.wait_event(self.ready[k])
         if not self.lookahead:
-            loss = self.e.step_graph(*self.slots[k])
+            loss = self.e.step_graph(self.slots[k])
         else:
             if not self.started:
-                self.e.prepare(self.slots[k][0])
-                if self.e.graphs_ahead is None:
-                    self.e.capture_ahead()
+                self.e.prepare_packed(self.slots[k])
                 self.started = True
             k1 = k
             if self.tail + 1 < self.head:  # the next batch was submitted: its ids are deduplicated now
                 k1 = (self.tail + 1) % self.depth
                 main.wait_event(self.ready[k1])
-            loss = self.e.step_ahead_graph(self.slots[k][1], self.slots[k][2], self.slots[k1][0])
+            loss = self.e.step_ahead_graph(self.slots[k1])
         self.free[k].record(main)
         self.tail += 1
         return loss
@@ -243,7 +273,8 @@ class DeepFMPSEngine:
         import ctypes as _ctb
 
         self.bounds = (_ctb.c_int64 * G)(*[int(r) for r in group_rows])  # id ranges: dedup by direct address
-        self.ws = torch.empty(group.lib.b200ps_unique_bounded_workspace(G, B, self.bounds), dtype=torch.uint8, device=dev)
+        self.ws = torch.zeros(group.lib.b200ps_unique_bounded_workspace(G, B, self.bounds), dtype=torch.uint8, device=dev)
+        self._predict_state = None  # predict() dedups into its own workspace / plan (lazy)
         self.bet_w = torch.zeros((G * B, 1), **f32)
         self.bet_d = torch.zeros((G * B, D), **f32)
         self.act_w = torch.empty((G * B, 1), **f32)
@@ -267,7 +298,8 @@ class DeepFMPSEngine:
             group.xchg_create(G, B, self.deep_ids, self.wide_ids)
         self.steps = 0
 
-    _PLAN_ATTRS = ("uniq", "inv", "n_unique", "pull_segs", "push_segs", "pull_pair", "push_pair", "tower_args")
+    _PLAN_ATTRS = ("uniq", "inv", "n_unique", "pull_segs", "push_segs", "pull_pair", "push_pair", "tower_args",
+                   "pull_names", "push_names")
 
     def _make_plan(self):
         dev, G, B = self.device, self.G, self.B
@@ -288,10 +320,19 @@ class DeepFMPSEngine:
 
     def _build_segs(self):
         g = self.group
-        self.pull_segs = [g.make_segs(self._seg_items(self.wide_ids, self.bet_w, 1)),
-                          g.make_segs(self._seg_items(self.deep_ids, self.bet_d, self.D))]
-        self.push_segs = [g.make_segs(self._seg_items(self.wide_ids, self.gsum_w, 1)),
-                          g.make_segs(self._seg_items(self.deep_ids, self.gsum_d, self.D))]
+        # all 2G tables in ONE flat launch when they fit (csrc/ps_flat.cuh), else one launch per family
+        wide_pull, deep_pull = self._seg_items(self.wide_ids, self.bet_w, 1), self._seg_items(self.deep_ids, self.bet_d, self.D)
+        wide_push, deep_push = self._seg_items(self.wide_ids, self.gsum_w, 1), self._seg_items(self.deep_ids, self.gsum_d, self.D)
+        from elasticdl_b200 import _lib as _l0
+
+        if 2 * self.G <= _l0.MAX_SEGS:
+            self.pull_names, self.push_names = ("pull",), ("push",)
+            self.pull_segs = [g.make_segs(deep_pull + wide_pull)]
+            self.push_segs = [g.make_segs(deep_push + wide_push)]
+        else:
+            self.pull_names, self.push_names = ("pull_wide", "pull_deep"), ("push_wide", "push_deep")
+            self.pull_segs = [g.make_segs(wide_pull), g.make_segs(deep_pull)]
+            self.push_segs = [g.make_segs(wide_push), g.make_segs(deep_push)]
         self.pull_dense_segs = g.make_segs([(tid, 0, None, None, p) for tid, (_, p) in zip(self.dense_ids, self.params)])
         import ctypes as _ct
         from elasticdl_b200 import _lib as _l
@@ -361,7 +402,7 @@ class DeepFMPSEngine:
                 check(lib.b200ps_pull_rows_pair(h, arr, ptrs, n, st))
             done(e)
         else:
-            for name, (arr, n) in zip(("pull_wide", "pull_deep"), self.pull_segs):
+            for name, (arr, n) in zip(self.pull_names, self.pull_segs):
                 e = mark(name)
                 check(lib.b200ps_pull_rows(h, arr, n, st))
                 done(e)
@@ -395,7 +436,7 @@ class DeepFMPSEngine:
                 check(lib.b200ps_push_rows_pair(h, arr, ptrs, n, st))
             done(e)
         else:
-            for name, (arr, n) in zip(("push_wide", "push_deep"), self.push_segs):
+            for name, (arr, n) in zip(self.push_names, self.push_segs):
                 e = mark(name)
                 check(lib.b200ps_push_rows(h, arr, n, st))
                 done(e)
@@ -406,26 +447,29 @@ class DeepFMPSEngine:
     def _unique_into(self, ids):
         """tf.unique per id group into the current plan, on the current stream."""
         g = self.group
-        check(g.lib.b200ps_unique_bounded(g._h, ids.data_ptr(), self.G, self.B, self.bounds, self.uniq.data_ptr(),
-                                          self.inv.data_ptr(), self.n_unique.data_ptr(), self.ws.data_ptr(),
-                                          self.ws.numel(), g._stream()))
+        fn = g.lib.b200ps_unique_bounded_i32 if ids.dtype == torch.int32 else g.lib.b200ps_unique_bounded
+        check(fn(g._h, ids.data_ptr(), self.G, self.B, self.bounds, self.uniq.data_ptr(), self.inv.data_ptr(),
+                 self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(), g._stream()))
 
     # ------------------------------------------------------------------ lookahead pipeline
-    def prepare(self, ids):
-        """Start the lookahead pipeline: deduplicate the FIRST batch's ids.  Afterwards every
-        step_ahead(dense_i, labels_i, ids_{i+1}) trains on batch i while the ids of batch i+1 are
-        deduplicated on a second stream (the dedup only depends on the input batch, like the
-        reference's dataset.prefetch(1) work, elasticdl/python/worker/worker.py:334)."""
+    def _ensure_plans(self):
         if len(self.plans) == 1:
             cur = self.cur
             self.plans.append(self._make_plan())
             self._use(cur)
             self.side = torch.cuda.Stream(device=self.device)
+
+    def prepare(self, ids):
+        """Start the lookahead pipeline: deduplicate the FIRST batch's ids.  Afterwards every
+        step_ahead(dense_i, labels_i, ids_{i+1}) trains on batch i while the ids of batch i+1 are
+        deduplicated on a second stream (the dedup only depends on the input batch, like the
+        reference's dataset.prefetch(1) work, elasticdl/python/worker/worker.py:334)."""
+        self._ensure_plans()
         self._unique_into(ids)
 
     def step_ahead(self, dense, labels, next_ids, ev=None):
-        """One training step on the prepared batch + the dedup of `next_ids` (int64 [G, B], device)
-        overlapped on the side stream.  Same kernels, same results as step()."""
+        """One training step on the prepared batch + the dedup of `next_ids` (int64 or int32 [G, B],
+        device) overlapped on the side stream.  Same kernels, same results as step()."""
         if len(self.plans) != 2:
             raise RuntimeError("call prepare(first_ids) before step_ahead")
         main = torch.cuda.current_stream(self.device)
@@ -441,15 +485,15 @@ class DeepFMPSEngine:
         return loss
 
     def capture_ahead(self):
-        """Two CUDA graphs (one per plan parity) of step_ahead over the static input buffers."""
+        """Two CUDA graphs (one per plan parity) of step_ahead over two static PACKED batch buffers
+        S[0], S[1] (pack_batch layout): graph p trains on the dense / labels of S[p] (its ids were
+        deduplicated into plan p by the previous step) while it deduplicates the ids of S[1 - p]."""
         if self.tower_kind == "torch":
             raise RuntimeError("graph capture needs the fused tower (torch autograd allocates)")
         dev, G, B = self.device, self.G, self.B
-        if len(self.plans) != 2:
-            raise RuntimeError("call prepare(first_ids) before capture_ahead")
-        self.s_ids = torch.zeros((G, B), dtype=torch.int64, device=dev)
-        self.s_dense = torch.zeros((B, N_DENSE), dtype=torch.float32, device=dev)
-        self.s_labels = torch.zeros(B, dtype=torch.float32, device=dev)
+        self._ensure_plans()
+        self.s_packed = [torch.zeros(packed_nbytes(G, B), dtype=torch.uint8, device=dev) for _ in range(2)]
+        views = [packed_views(b, G, B) for b in self.s_packed]
         torch.cuda.synchronize(dev)
         start, steps = self.cur, self.steps
         self.graphs_ahead = [None, None]
@@ -457,17 +501,32 @@ class DeepFMPSEngine:
             assert self.cur == p
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr):
-                self.step_ahead(self.s_dense, self.s_labels, self.s_ids)
+                self.step_ahead(views[p][1], views[p][2], views[1 - p][0])
             self.graphs_ahead[p] = gr
         self._use(start)
         self.steps = steps  # capture does not execute
         return self.graphs_ahead
 
-    def step_ahead_graph(self, dense, labels, next_ids):
-        """step_ahead through the captured graphs; inputs may be pinned-host or device tensors."""
-        self.s_ids.copy_(next_ids, non_blocking=True)
-        self.s_dense.copy_(dense, non_blocking=True)
-        self.s_labels.copy_(labels, non_blocking=True)
+    def _fill(self, dst, batch):
+        """dst: static packed buffer; batch: (packed,) or (ids, dense, labels) -- device or pinned host."""
+        if len(batch) == 1:
+            dst.copy_(batch[0], non_blocking=True)
+        else:
+            for d, src in zip(packed_views(dst, self.G, self.B), batch):
+                d.copy_(src, non_blocking=True)
+
+    def prepare_packed(self, *batch):
+        """Lookahead through the captured graphs: load the FIRST batch and deduplicate its ids."""
+        if self.graphs_ahead is None:
+            self.capture_ahead()
+        self._fill(self.s_packed[self.cur], batch)
+        self._unique_into(packed_views(self.s_packed[self.cur], self.G, self.B)[0])
+
+    def step_ahead_graph(self, *next_batch):
+        """step_ahead through the captured graphs: trains on the batch loaded by the previous call (or
+        prepare_packed) while `next_batch` -- (packed,) or (ids, dense, labels) -- is loaded and its ids
+        are deduplicated.  Inputs may be pinned-host or device tensors."""
+        self._fill(self.s_packed[1 - self.cur], next_batch)
         self.graphs_ahead[self.cur].replay()
         self._use(1 - self.cur)
         self.steps += 1
@@ -475,27 +534,24 @@ class DeepFMPSEngine:
 
     # ------------------------------------------------------------------ CUDA graph
     def capture(self):
-        """Capture one whole step (19 launches + the versions read-back) into a CUDA graph.
-        Every buffer the step touches is persistent, so the graph replays on new inputs
-        copied into the static input buffers.  lr is baked in: re-capture to change it."""
+        """Capture one whole step into a CUDA graph.  Every buffer the step touches is persistent, so
+        the graph replays on new inputs copied into the static packed input buffer.  lr is baked in:
+        re-capture to change it."""
         if self.tower_kind == "torch":
             raise RuntimeError("graph capture needs the fused tower (torch autograd allocates)")
         dev, G, B = self.device, self.G, self.B
-        self.s_ids = torch.zeros((G, B), dtype=torch.int64, device=dev)
-        self.s_dense = torch.zeros((B, N_DENSE), dtype=torch.float32, device=dev)
-        self.s_labels = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.s_one = torch.zeros(packed_nbytes(G, B), dtype=torch.uint8, device=dev)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.step(self.s_ids, self.s_dense, self.s_labels)
+            self.step(*packed_views(self.s_one, G, B))
         self.steps -= 1  # capture does not execute
         return self.graph
 
-    def step_graph(self, ids, dense, labels):
-        """Same step through the captured graph; inputs may be pinned-host or device tensors."""
-        self.s_ids.copy_(ids, non_blocking=True)
-        self.s_dense.copy_(dense, non_blocking=True)
-        self.s_labels.copy_(labels, non_blocking=True)
+    def step_graph(self, *batch):
+        """Same step through the captured graph; batch = (packed,) or (ids, dense, labels), pinned-host
+        or device tensors."""
+        self._fill(self.s_one, batch)
         self.graph.replay()
         self.steps += 1
         return self.loss_buf.reshape(())
@@ -531,21 +587,35 @@ class DeepFMPSEngine:
         return loss, g.make_segs([(tid, 0, None, None, gr) for tid, gr in zip(self.dense_ids, self._dense_grads)])
 
     def predict(self, ids, dense):
-        """Forward only (logits) through the PS: unique -> pull -> fused tower forward."""
+        """Forward only (logits) through the PS: unique -> pull -> fused tower forward.  Uses its own
+        dedup workspace and (uniq, inv, n_unique) plan, so a prepared lookahead batch stays intact."""
         g, lib, h = self.group, self.group.lib, self.group._h
         st = g._stream()
-        arr, n = self.pull_dense_segs
-        check(lib.b200ps_pull_dense(h, arr, n, st))
-        check(lib.b200ps_unique(h, ids.data_ptr(), self.G, self.B, self.uniq.data_ptr(), self.inv.data_ptr(),
-                                self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st))
-        for arr, n in self.pull_segs:
-            check(lib.b200ps_pull_rows(h, arr, n, st))
-        import ctypes as _ct
+        if self._predict_state is None:
+            cur = self.cur
+            ws = torch.zeros(lib.b200ps_unique_workspace(self.G, self.B), dtype=torch.uint8, device=self.device)
+            plan = self._make_plan()
+            self._use(cur)
+            self._predict_state = (ws, plan)
+        ws, plan = self._predict_state
+        saved = {k: getattr(self, k) for k in self._PLAN_ATTRS}
+        self.__dict__.update(plan)
+        try:
+            arr, n = self.pull_dense_segs
+            check(lib.b200ps_pull_dense(h, arr, n, st))
+            ids = ids.to(torch.int64)
+            check(lib.b200ps_unique(h, ids.data_ptr(), self.G, self.B, self.uniq.data_ptr(), self.inv.data_ptr(),
+                                    self.n_unique.data_ptr(), ws.data_ptr(), ws.numel(), st))
+            for arr, n in self.pull_segs:
+                check(lib.b200ps_pull_rows(h, arr, n, st))
+            import ctypes as _ct
 
-        a = self.tower_args
-        a.dense = dense.data_ptr()
-        if lib.b200_deepfm_forward(_ct.byref(a), st):
-            raise RuntimeError("b200_deepfm_forward failed")
+            a = self.tower_args
+            a.dense = dense.data_ptr()
+            if lib.b200_deepfm_forward(_ct.byref(a), st):
+                raise RuntimeError("b200_deepfm_forward failed")
+        finally:
+            self.__dict__.update(saved)
         return self.logits_buf
 
     def kernel_report(self, ev, uniq_per_step, opt_slots=2):
@@ -559,6 +629,11 @@ class DeepFMPSEngine:
             U = sum(uniq_per_step) / max(len(uniq_per_step), 1)
             nbytes = {
                 "pull_wide": U * (8 + 8 * 1), "pull_deep": U * (8 + 8 * D),
+                "pull": U * (8 + 8 * 1) + U * (8 + 8 * D),
+                "push": U * (8 + 4 * 1 + (1 + opt_slots) * 8 * 1) + U * (8 + 4 * D + (1 + opt_slots) * 8 * D),
+                # tower: per (sample, group) one rank read + one deep row + one wide value gathered, the
+                # embedding gradient scattered back (reduced per unique id), + the dense inputs / labels
+                "tower_fwd_bwd": k * (4 + 4 * D + 4) + U * (4 * D + 4) + self.B * 4 * (N_DENSE + 1),
                 "pull_pair": U * (8 + 8 * D + 8 * 1), "pull_exchange": U * (8 + 8 * D + 8 * 1),
                 "push_exchange": U * (8 + 4 * D + 4 * 1 + (1 + opt_slots) * 8 * (D + 1)),
                 "push_pair": U * (8 + 4 * D + 4 * 1 + (1 + opt_slots) * 8 * (D + 1)),

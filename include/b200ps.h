@@ -38,7 +38,7 @@ extern "C" {
 
 #define B200PS_ABI_VERSION 1
 #define B200PS_MAX_SHARDS 16
-#define B200PS_MAX_SEGS 64 /* segments per batched launch */
+#define B200PS_MAX_SEGS 96 /* segments per batched launch (DeepFM: 76 tables in one) */
 
 enum {
   B200PS_OK = 0,
@@ -218,10 +218,11 @@ int b200ps_kernel_adagrad(const float* grad, float* param, float* m, float lr, l
 /* These three take `ps` only for the device and the launch counter; ps may be
  * NULL (current device).
  * tf.unique (embedding_delegate.py:85) for T equal-length id segments in one
- * launch set: uniq_dev[t*k + r] = r-th distinct id of segment t in
- * FIRST-OCCURRENCE order, inv_dev[t*k + i] = rank of ids[t*k + i],
- * n_unique_dev[t] = number of distinct ids.  Workspace from
- * b200ps_unique_workspace(T, k) bytes. */
+ * launch (one persistent kernel, csrc/ps_unique.cuh): uniq_dev[t*k + r] = r-th distinct id of
+ * segment t in FIRST-OCCURRENCE order, inv_dev[t*k + i] = rank of ids[t*k + i],
+ * n_unique_dev[t] = number of distinct ids.  Workspace from b200ps_unique_workspace(T, k) bytes;
+ * its content may be arbitrary on first use (a magic word detects a fresh / foreign workspace),
+ * but one workspace must not be used by two streams at once. */
 size_t b200ps_unique_workspace(int T, int64_t k);
 /* Same with host-side knowledge of the id range of each segment (bounds[t] = table capacity, 0 =
  * unknown): small-range segments use a direct-address position array instead of the hash table. */
@@ -232,6 +233,12 @@ int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k
 int b200ps_unique(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, int64_t* uniq_dev,
                   int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev, size_t workspace_bytes,
                   void* stream);
+/* Narrow id transport: the same dedup over int32 ids (every table capacity < 2^31, e.g. ids that crossed
+ * PCIe as 4-byte words); the widening to int64 happens at the kernel's first read, the outputs
+ * (uniq_dev int64, inv_dev, n_unique_dev) are identical to b200ps_unique_bounded on the widened ids. */
+int b200ps_unique_bounded_i32(b200ps_t* ps, const int32_t* ids32_dev, int T, int64_t k, const int64_t* bounds,
+                              int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
+                              size_t workspace_bytes, void* stream);
 /* deduplicate_indexed_slices' sum (tensor_utils.py:39-60) / gather backward:
  * out[t][inv[t][i], :] += values[t][i, :] with warp-level id dedup; out is
  * zeroed first for rows < k. */

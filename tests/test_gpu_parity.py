@@ -806,3 +806,143 @@ def test_raw_kernel_api_matches_oracle_bit_exact(n):
     wp, wm = p.copy(), m.copy()
     O.lib.oracle_adagrad(O._f32(g), O._f32(wp), O._f32(wm), 0.05, n, 1e-7)
     assert np.array_equal(dp.cpu().numpy(), wp) and np.array_equal(dm.cpu().numpy(), wm)
+
+
+# ------------------------------------------------------------------ round 2: persistent unique, flat row kernels
+@pytest.mark.parametrize("k,hi,T,bounded", [(300_000, 1 << 40, 2, False), (70_001, 50_000, 3, True), (2049, 7, 2, True),
+                                            (33, 1000, 5, False)])
+def test_unique_many_tiles_lookback_int32_and_negative_ids(k, hi, T, bounded):
+    """The single persistent unique kernel: hundreds of tiles per segment (decoupled look-back over more than one
+    32-tile window), a ragged last chunk / tile, negative ids on the hashed path, and the int32 entry point --
+    all equal tf.unique (first-occurrence order, inverse) exactly; int32 and int64 inputs give identical outputs."""
+    import ctypes
+
+    from elasticdl_b200 import _lib
+
+    group, _, _ = make_pair(1)
+    lib = _lib.lib()
+    rng = np.random.RandomState(k % 1000 + T)
+    ids = rng.randint(0, min(hi, 2 ** 62), size=(T, k)).astype(np.int64)
+    if not bounded:
+        ids[:, ::7] *= -1  # negative ids are legal for tf.unique (hashed segments)
+        ids[0, -5:] = [-1, -2, -1, -31, -2]  # collide with nothing: dead lanes of the ragged tail never match
+    d_ids = torch.from_numpy(ids).cuda().view(-1)
+    bounds = (ctypes.c_int64 * T)(*([hi] * T if bounded else [0] * T))
+    need = lib.b200ps_unique_bounded_workspace(T, k, bounds)
+    ws = torch.randint(0, 255, (need,), dtype=torch.uint8, device="cuda")
+    outs = []
+    for narrow in ((False, True) if bounded else (False,)):
+        uniq = torch.empty(T * k, dtype=torch.int64, device="cuda")
+        inv = torch.empty(T * k, dtype=torch.int32, device="cuda")
+        n = torch.empty(T, dtype=torch.int32, device="cuda")
+        src = d_ids.to(torch.int32) if narrow else d_ids
+        fn = lib.b200ps_unique_bounded_i32 if narrow else lib.b200ps_unique_bounded
+        for _ in range(2):
+            _lib.check(fn(group._h, src.data_ptr(), T, k, bounds, uniq.data_ptr(), inv.data_ptr(), n.data_ptr(),
+                          ws.data_ptr(), ws.numel(), group._stream()))
+        group.check()
+        u, i, c = uniq.cpu().numpy().reshape(T, k), inv.cpu().numpy().reshape(T, k), n.cpu().numpy()
+        for t in range(T):
+            wu, wi = O.unique_first_occurrence(ids[t])
+            assert c[t] == len(wu) and np.array_equal(u[t, : c[t]], wu) and np.array_equal(i[t], wi), (t, narrow)
+        outs.append((u, i, c))
+    group.close()
+
+
+@pytest.mark.parametrize("opt", ["sgd", "adam", "amsgrad", "ftrl"])
+@pytest.mark.parametrize("n_shards", [1, 3])
+def test_flat_launch_mixed_tables_device_counts(opt, n_shards):
+    """ONE b200ps_pull_rows / b200ps_push_rows call over nine segments of mixed dims (1, 4, 8, 10, 64), a dense
+    parameter addressed by rows (Indexed* kernels, kernel.go:48-55), empty segments and device-side live counts
+    (n_dev < n): the flat kernels (csrc/ps_flat.cuh) must equal the oracle bit for bit -- params and every slot --
+    and must not touch rows beyond the live counts."""
+    import ctypes
+
+    from elasticdl_b200 import _lib
+    from elasticdl_b200.common.hash_utils import string_to_id
+
+    group, client, oc = make_pair(n_shards, opt)
+    ot, oa = OPTS[opt]
+    rng = np.random.RandomState(5)
+    dims = [8, 1, 64, 10, 4, 1, 8]
+    caps = [5000, 37, 900, 411, 64, 20000, 3]
+    names = ["t%d" % i for i in range(len(dims))]
+    client.push_embedding_table_infos([info(n, d, capacity=c) for n, d, c in zip(names, dims, caps)])
+    oc.push_embedding_table_infos([oinfo(n, d) for n, d in zip(names, dims)])
+    dn = "dense/w:0"
+    dshape = (50, 12)
+    group.register_dense(dn, dshape, string_to_id(dn, n_shards))
+    group.commit()
+    dense0 = rng.randn(*dshape).astype(F)
+    group.set_dense([(dn, dense0)])
+    S = {"sgd": 0, "adam": 2, "amsgrad": 3, "ftrl": 2}[opt]
+    segs, live = [], []
+    for n_, d, c in zip(names + [dn, names[0]], dims + [dshape[1], dims[0]], caps + [dshape[0], caps[0]]):
+        cap_n = min(c, 700)
+        ids = rng.permutation(c)[:cap_n].astype(np.int64)
+        if n_ == names[0] and len(segs) > 0:
+            ids = (ids + 1) % c  # second segment on table 0: other rows mostly; make them disjoint below
+        nl = 0 if n_ == names[4] else int(rng.randint(1, cap_n + 1))
+        segs.append((n_, d, ids, nl))
+    # rows of the two table-0 segments must not overlap (a push applies each row once per launch)
+    a_ids = segs[0][2][: segs[0][3]]
+    b = segs[-1]
+    b_ids = np.array([x for x in b[2] if x not in set(a_ids.tolist())], dtype=np.int64)
+    segs[-1] = (b[0], b[1], b_ids, min(b[3], len(b_ids)))
+    # initial rows everywhere
+    for n_, d, c in zip(names, dims, caps):
+        all_ids = np.arange(c, dtype=np.int64)
+        vals = rng.randn(c, d).astype(F)
+        group.set_rows([(n_, all_ids, vals)])
+        for s_ in oc.servers:
+            m = all_ids % n_shards == s_.id
+            s_.tables[n_].set(all_ids[m], vals[m])
+    lib, h = group.lib, group._h
+    items, keep = [], []
+    for n_, d, ids, nl in segs:
+        tid = group.lookup(n_)[0]
+        t_ids = torch.from_numpy(ids).cuda()
+        n_dev = torch.tensor([nl], dtype=torch.int32, device="cuda")
+        rows = torch.full((len(ids), d), -7.0, dtype=torch.float32, device="cuda")
+        keep.append((t_ids, n_dev, rows))
+        items.append((tid, len(ids), t_ids, n_dev, rows))
+    arr, n = group.make_segs(items)
+    _lib.check(lib.b200ps_pull_rows(h, arr, n, group._stream()))
+    group.check()
+    for (n_, d, ids, nl), (_, _, rows) in zip(segs, keep):
+        got = rows.cpu().numpy()
+        if n_ == dn:
+            want = dense0[ids[:nl]]
+        else:
+            want = oc.pull_embedding_vectors(n_, ids[:nl]) if nl else np.zeros((0, d), F)
+        assert np.array_equal(got[:nl], want), n_
+        assert (got[nl:] == -7.0).all(), n_  # nothing beyond the live count
+    # push: gradients for the live rows, one launch
+    grads = []
+    for (n_, d, ids, nl), (_, _, rows) in zip(segs, keep):
+        g = (rng.randn(len(ids), d) * 0.1).astype(F)
+        rows.copy_(torch.from_numpy(g))
+        grads.append(g)
+    group.push_begin(0.05, [0] * n_shards)
+    _lib.check(lib.b200ps_push_rows(h, arr, n, group._stream()))
+    group.push_end()
+    group.check()
+    # oracle: the same ApplyGradients on every shard (dense-by-rows = Indexed kernels)
+    for s_ in oc.servers:
+        if string_to_id(dn, n_shards) == s_.id:
+            s_.dense[dn] = dense0.copy()
+            s_.opt.init_dense(dn, dshape)
+    t_grads = []
+    for (n_, d, ids, nl), g in zip(segs, grads):
+        if nl:
+            t_grads.append(O.Tensor(n_, g[:nl].copy(), ids[:nl].copy()))
+    dense_g = [t for t in t_grads if t.name == dn]
+    sparse_g = [t for t in t_grads if t.name != dn]
+    oc.partition_dense_parameters([dn])
+    oc.push_gradients(dense_g, sparse_g, 0.05, [0] * n_shards)
+    for n_, d, c in zip(names, dims, caps):
+        all_ids = np.arange(c, dtype=np.int64)
+        assert np.array_equal(client.pull_embedding_vectors(n_, all_ids), oc.pull_embedding_vectors(n_, all_ids)), n_
+    owner = string_to_id(dn, n_shards)
+    assert np.array_equal(group.pull_dense([dn])[dn].cpu().numpy(), oc.servers[owner].dense[dn]), "indexed rows of a dense parameter"
+    group.close()
