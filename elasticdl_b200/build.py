@@ -5,9 +5,10 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(CSRC, "libb200ps.so")
-SOURCES = ["b200ps.cu", "deepfm_tower.cu", "deepfm_tower_mma.cu"]
+SOURCES = ["b200ps.cu", "deepfm_tower.cu", "deepfm_tower_mma.cu", "feature_ids.cu"]
 HEADERS = ["ps_kernels.cuh", "ps_types.cuh", "ps_exchange.cuh", "ps_flat.cuh", "ps_unique.cuh", os.path.join("..", "..", "include", "b200ps.h"),
-           os.path.join("..", "..", "include", "b200_deepfm.h")]
+           os.path.join("..", "..", "include", "b200_deepfm.h"),
+           os.path.join("..", "..", "include", "b200_features.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

@@ -19,9 +19,9 @@ GOLD = os.path.join(ROOT, "tests", "golden", "ref_python_vectors.json")
 def test_abi_exports_every_declared_symbol():
     from elasticdl_b200 import _lib
 
-    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("b200ps.h", "b200_deepfm.h"))
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("b200ps.h", "b200_deepfm.h", "b200_features.h"))
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
-    declared = set(re.findall(r"\b(b200(?:ps|_deepfm)_[a-z_0-9]+)\s*\(", header))
+    declared = set(re.findall(r"\b(b200(?:ps|_deepfm|feat)_[a-z_0-9]+)\s*\(", header))
     assert declared, "no declarations parsed"
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     lib = _lib.lib()
@@ -29,7 +29,7 @@ def test_abi_exports_every_declared_symbol():
         assert getattr(lib, name) is not None
     assert lib.b200ps_abi_version() == 1
     out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "elasticdl_b200", "csrc", "libb200ps.so")], text=True)
-    exported = set(re.findall(r"\b(b200(?:ps|_deepfm)_[a-z_0-9]+)$", out, flags=re.M))
+    exported = set(re.findall(r"\b(b200(?:ps|_deepfm|feat)_[a-z_0-9]+)$", out, flags=re.M))
     assert declared <= exported
 
 
