@@ -286,7 +286,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=0, help="per-thread batch of the CPU arm (0 = --batch: same config)")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tower", default="fused", choices=["fused", "mma", "torch"])
+    ap.add_argument("--tower", default="fused", choices=["tile", "fused", "mma", "torch"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop after the warm-up and exit "
@@ -393,7 +393,7 @@ def main():
         return ms
 
     def my_launches():
-        return group.launch_count + _lib.lib().b200ps_launch_count(None) + _lib.lib().b200_deepfm_launch_count() + _lib.lib().b200_deepfm_mma_launch_count()
+        return group.launch_count + _lib.lib().b200ps_launch_count(None) + _lib.lib().b200_deepfm_launch_count() + _lib.lib().b200_deepfm_mma_launch_count() + _lib.lib().b200_deepfm_tile_launch_count() + _lib.lib().b200feat_launch_count()
 
     # ---- eager pass: every kernel launched from the host, CUDA-event pairs around the PS kernels ----
     for i in range(args.warmup):

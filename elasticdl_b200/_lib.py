@@ -114,6 +114,10 @@ SYMBOLS = {
     "b200_deepfm_fwd_bwd_mma": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
     "b200_deepfm_mma_launch_count": (_i64, []),
     "b200_deepfm_launch_count": (_i64, []),
+    "b200_deepfm_fwd_bwd_tile": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
+    "b200_deepfm_forward_tile": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
+    "b200_deepfm_tile_launch_count": (_i64, []),
+    "b200_deepfm_tile_last_error": (ctypes.c_char_p, []),
     # include/b200_features.h
     "b200feat_last_error": (ctypes.c_char_p, []),
     "b200feat_transform": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _i, _i64, _vp, _i, _vp, _vp]),

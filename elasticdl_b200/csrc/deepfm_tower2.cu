@@ -1,0 +1,481 @@
+// DeepFM tower, tile version (include/b200_deepfm.h: b200_deepfm_fwd_bwd_tile / b200_deepfm_forward_tile).
+//
+// Round 1's tower gathered every embedding row three times (forward, backward, parameter-gradient
+// kernel) with one dependent global gather chain per lane at ~20 % occupancy: 113 us of a 198 us
+// step.  Here a CTA owns a tile of 32 samples and gathers the tile's 38 x 32 rows ONCE, with
+// cp.async (16 B, L2 -> shared memory, no registers held while in flight), into
+//     X[s] = [ deep 38 x 8 | dense 13 | 1 (bias column) | 0 0 | wide 38 | pad ]     (row stride 364 floats:
+//            91 x 16 B, odd, so a warp's 32 rows are bank-conflict free for 128-bit reads)
+// and everything else -- H1 = X W1x, the FM sums, the per-sample middle, dX = dH1 W1x^T + FM term with the
+// per-unique-id reduction, dW1x += dH1^T X and the small gradients -- runs out of shared memory:
+//   G  gather             5 (group, sample) pairs per thread: rank load, 2 cp.async + 1 wide load
+//   F  forward            warp = 40 tile columns (5 id groups), lane = sample: 16 accumulators + FM partials
+//   M  middle             partial records summed through shared memory; every warp redoes the tiny
+//                         per-sample MLP tail (it needs dh1 / dz / FM sums in registers for B1 anyway)
+//   B1 embedding grads    warp = its 5 groups, lane = sample; equal rows of a warp combine up a tree
+//                         (warp-level id dedup), one vector red per distinct row
+//   B2 parameter grads    thread = 2 tile columns x 16 hidden units, accumulated in registers across
+//                         the CTA's tiles, one atomic per output per CTA at the end
+// W1 is presented in TILE COLUMN ORDER (W1x[c][j]: deep columns first, then dense, then b1 as the weight
+// of the constant-1 column) by the prep kernel, so the bias needs no special case and every CTA loads it
+// with straight 16-byte copies.  fp32 SIMT: the step has 1 GFLOP of first-layer work -- the kernel is
+// bound by the row gather and shared-memory bandwidth, not by FMA throughput; tensor cores would need
+// 3xTF32 splitting to keep the fp32-grade parity with the torch reference the tests check.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <string>
+
+#include "../../include/b200_deepfm.h"
+
+namespace {
+
+constexpr int ND = B200_DEEPFM_NDENSE, D = B200_DEEPFM_DIM, H1 = B200_DEEPFM_H1, H2 = B200_DEEPFM_H2;
+constexpr int WD_PAD = 16;
+constexpr int TS = 32;        // samples per tile
+constexpr int THREADS = 256;  // 8 warps
+constexpr int NKP = 8;        // column parts (warps) of phases F / B1
+constexpr int KPC = 40;       // tile columns per part = 5 id groups
+constexpr int NCOL = 320;     // deep 304 | dense 13 | 1 | 0 0   (G <= 38)
+constexpr int XS = 364;       // row stride: 320 + wide 38 + pad, = 91 * 4
+constexpr int XW = 320;       // offset of the wide values inside a row
+constexpr int RW = H1 + D + 2;  // partial record: h[16] | s[8] | q | lin
+constexpr int MS = 44;        // per-sample backward state: dh1 16 | a1 16 | dh2 4 | h2 4 | dz | pad 3
+constexpr int MAXG = 38;
+
+struct Layout {
+  int in, o_wd, o_w1, o_b1, o_w2, o_b2, o_w3, total;
+};
+__host__ __device__ inline Layout layout(int G) {
+  Layout l;
+  l.in = ND + G * D;
+  l.o_wd = 0;
+  l.o_w1 = WD_PAD;
+  l.o_b1 = l.o_w1 + H1 * l.in;
+  l.o_w2 = l.o_b1 + H1;
+  l.o_b2 = l.o_w2 + H2 * H1;
+  l.o_w3 = l.o_b2 + H2;
+  l.total = l.o_w3 + H2;
+  return l;
+}
+
+long long g_launches = 0;
+thread_local std::string g_msg;
+
+// shared memory carve-up (floats)
+constexpr int SM_W1X = NCOL * H1;          // 5120
+constexpr int SM_X = TS * XS;              // 11648
+constexpr int SM_P = NKP * RW * TS;        // 6656   partial records [kp][r][s]; reused as T[r][s] + M[s][MS]
+constexpr int SM_R = MAXG * TS;            // 1216   ranks [g][s]
+constexpr int SM_SMALL = 128;              // b... w2 64 | b2 4 | w3 4 | wd 16
+constexpr size_t SMEM_BYTES = (size_t)(SM_W1X + SM_X + SM_P + SM_R + SM_SMALL) * sizeof(float);
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Tile column c of W1x -> index into the flat parameter / gradient layout, or -1 (padding).
+__host__ __device__ inline int w1x_src(const Layout& l, int G, int c, int j) {
+  const int ndeep = G * D;
+  if (c < ndeep) return l.o_w1 + j * l.in + ND + c;
+  if (c >= MAXG * D && c < MAXG * D + ND) return l.o_w1 + j * l.in + (c - MAXG * D);
+  if (c == MAXG * D + ND) return l.o_b1 + j;
+  return -1;
+}
+
+__global__ void __launch_bounds__(256) k_tile_prep(b200_deepfm_args_t a, int n_params, float* w1x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0 && a.loss) *a.loss = 0.f;
+  if (blockIdx.y == 0) {
+    if (a.grads)
+      for (long long i = tid; i < n_params; i += stride) a.grads[i] = 0.f;
+    const Layout l = layout(a.G);
+    for (long long i = tid; i < (long long)NCOL * H1; i += stride) {
+      const int c = (int)(i / H1), j = (int)(i - (long long)c * H1);
+      const int src = w1x_src(l, a.G, c, j);
+      w1x[i] = src >= 0 ? a.params[src] : 0.f;
+    }
+  }
+  if (a.gsum_deep == nullptr) return;
+  for (int g = blockIdx.y; g < a.G; g += gridDim.y) {  // live rows only: rows >= n_unique[g] are never read by the push
+    const int u = a.n_unique[g];
+    float* gw = a.gsum_wide + (long long)g * a.B;
+    float4* gd = reinterpret_cast<float4*>(a.gsum_deep + (long long)g * a.B * D);
+    for (long long i = tid; i < u; i += stride) gw[i] = 0.f;
+    for (long long i = tid; i < 2LL * u; i += stride) gd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a, const float* __restrict__ w1x_g) {
+  extern __shared__ __align__(16) float smem[];
+  float* W1x = smem;                 // [NCOL][16]
+  float* X = W1x + SM_W1X;           // [TS][XS]
+  float* P = X + SM_X;               // [NKP][RW][TS], later T[RW][TS] and Mst[TS][MS]
+  int* R = reinterpret_cast<int*>(P + SM_P);  // [G][TS]
+  float* small = reinterpret_cast<float*>(R + SM_R);
+  float* s_w2 = small;        // [H2][H1]
+  float* s_b2 = small + 64;   // [H2]
+  float* s_w3 = small + 68;   // [H2]
+  float* s_wd = small + 72;   // [ND]
+  float* T = P;                          // [RW][TS] summed records (first RW*TS floats of P)
+  float* Mst = P + RW * TS + 64;         // [TS][MS] per-sample backward state for B2 (after T, 16 B aligned)
+
+  const Layout l = layout(a.G);
+  const int B = a.B, G = a.G;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  {
+    const float4* src = reinterpret_cast<const float4*>(w1x_g);
+    float4* dst = reinterpret_cast<float4*>(W1x);
+    for (int i = t; i < SM_W1X / 4; i += THREADS) dst[i] = src[i];
+    for (int i = t; i < H2 * H1; i += THREADS) s_w2[i] = a.params[l.o_w2 + i];
+    if (t < H2) { s_b2[t] = a.params[l.o_b2 + t]; s_w3[t] = a.params[l.o_w3 + t]; }
+    if (t < ND) s_wd[t] = a.params[l.o_wd + t];
+  }
+  // B2 accumulators, persistent over the CTA's tiles: thread t < 160 owns tile columns t and t + 160
+  float acc0[H1], acc1[H1];
+  float sacc[3] = {0.f, 0.f, 0.f};  // warp 5: small outputs lane + 32*i (dW2 64 | db2 4 | dw3 4 | dwd 13)
+#pragma unroll
+  for (int j = 0; j < H1; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+  float loss_acc = 0.f;
+  __syncthreads();
+
+  const long long ntile = ((long long)B + TS - 1) / TS;
+  for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const long long b0 = tile * TS;
+    // ---------------- G: gather the tile once ----------------
+    {
+      const int npair = G * TS;
+      constexpr int NP = (MAXG * TS + THREADS - 1) / THREADS;  // 5 (group, sample) pairs per thread
+      int rk[NP];
+#pragma unroll
+      for (int jj = 0; jj < NP; ++jj) {  // all rank loads first, then all row copies: independent chains in flight
+        const int i = t + THREADS * jj;
+        rk[jj] = 0;
+        if (i < npair) {
+          long long b = b0 + (i & 31);
+          if (b >= B) b = B - 1;  // dead samples replay the last one, their results are masked
+          rk[jj] = a.inv[(long long)(i >> 5) * B + b];
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < NP; ++jj) {
+        const int i = t + THREADS * jj;
+        if (i < npair) {
+          const int g = i >> 5, s = i & 31, r = rk[jj];
+          R[g * TS + s] = r;
+          const float* row = a.bet_deep + ((long long)g * B + r) * D;
+          float* dst = X + s * XS + g * D;
+          cp_async16(dst, row);
+          cp_async16(dst + 4, row + 4);
+          X[s * XS + XW + g] = a.bet_wide[(long long)g * B + r];
+        }
+      }
+      for (int i = t; i < TS * (NCOL - G * D); i += THREADS) {  // columns G*8 .. 319: zero, dense, 1, 0, 0
+        const int s = i / (NCOL - G * D), c = G * D + i % (NCOL - G * D);
+        long long b = b0 + s;
+        if (b >= B) b = B - 1;
+        float v = 0.f;
+        if (c >= MAXG * D && c < MAXG * D + ND) v = a.dense[b * ND + (c - MAXG * D)];
+        else if (c == MAXG * D + ND) v = 1.0f;
+        X[s * XS + c] = v;
+      }
+      cp_async_wait_all();
+    }
+    __syncthreads();
+    const bool live = b0 + lane < B;
+    // ---------------- F: partial H1 / FM sums over this warp's 40 columns ----------------
+    {
+      float h[H1];
+#pragma unroll
+      for (int j = 0; j < H1; ++j) h[j] = 0.f;
+      float sd[D], q = 0.f, lin = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) sd[d] = 0.f;
+      const float* xrow = X + lane * XS;
+      const int c0 = warp * KPC;
+#pragma unroll
+      for (int gi = 0; gi < KPC / D; ++gi) {
+        const int c = c0 + gi * D;
+        const float4 xa = *reinterpret_cast<const float4*>(xrow + c);
+        const float4 xb = *reinterpret_cast<const float4*>(xrow + c + 4);
+        const float xv[D] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        const int g = c / D;
+        if (g < G) {  // an embedding group: FM sums + the wide value
+#pragma unroll
+          for (int d = 0; d < D; ++d) { sd[d] += xv[d]; q = fmaf(xv[d], xv[d], q); }
+          lin += xrow[XW + g];
+        } else if (c == MAXG * D) {  // dense columns 304..311 and (next chunk) 312..316: the linear part
+#pragma unroll
+          for (int d = 0; d < D; ++d) lin = fmaf(s_wd[d], xv[d], lin);
+        } else if (c == MAXG * D + D) {
+#pragma unroll
+          for (int d = 0; d < ND - D; ++d) lin = fmaf(s_wd[D + d], xv[d], lin);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float4* w4 = reinterpret_cast<const float4*>(W1x + (c + d) * H1);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const float4 w = w4[qd];
+            h[4 * qd + 0] = fmaf(w.x, xv[d], h[4 * qd + 0]);
+            h[4 * qd + 1] = fmaf(w.y, xv[d], h[4 * qd + 1]);
+            h[4 * qd + 2] = fmaf(w.z, xv[d], h[4 * qd + 2]);
+            h[4 * qd + 3] = fmaf(w.w, xv[d], h[4 * qd + 3]);
+          }
+        }
+      }
+      float* mine = P + (warp * RW) * TS + lane;
+#pragma unroll
+      for (int j = 0; j < H1; ++j) mine[j * TS] = h[j];
+#pragma unroll
+      for (int d = 0; d < D; ++d) mine[(H1 + d) * TS] = sd[d];
+      mine[(H1 + D) * TS] = q;
+      mine[(H1 + D + 1) * TS] = lin;
+    }
+    __syncthreads();
+    // ---------------- M: sum the 8 partial records ----------------
+    float tsum[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp + 8 * i;
+      float v = 0.f;
+      if (r < RW) {
+#pragma unroll
+        for (int kp = 0; kp < NKP; ++kp) v += P[(kp * RW + r) * TS + lane];
+      }
+      tsum[i] = v;
+    }
+    __syncthreads();  // all partials read before T (aliasing P) is written
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp + 8 * i;
+      if (r < RW) T[r * TS + lane] = tsum[i];
+    }
+    __syncthreads();
+    // every warp: the per-sample tail (lane = sample)
+    float hpre[H1], sd[D];
+#pragma unroll
+    for (int j = 0; j < H1; ++j) hpre[j] = T[j * TS + lane];
+#pragma unroll
+    for (int d = 0; d < D; ++d) sd[d] = T[(H1 + d) * TS + lane];
+    const float q = T[(H1 + D) * TS + lane], lin = T[(H1 + D + 1) * TS + lane];
+    float a1[H1];
+#pragma unroll
+    for (int j = 0; j < H1; ++j) a1[j] = fmaxf(hpre[j], 0.f);
+    float h2[H2], dnn = 0.f;
+#pragma unroll
+    for (int k = 0; k < H2; ++k) {
+      float accv = s_b2[k];
+#pragma unroll
+      for (int j = 0; j < H1; ++j) accv = fmaf(s_w2[k * H1 + j], a1[j], accv);
+      h2[k] = fmaxf(accv, 0.f);
+      dnn = fmaf(s_w3[k], h2[k], dnn);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) ss = fmaf(sd[d], sd[d], ss);
+    const float z = lin + dnn + 0.5f * (ss - q);
+    if (warp == 0 && live && a.logits != nullptr) a.logits[b0 + lane] = z;
+    float dz = 0.f, dh1[H1];
+    if (BACKWARD) {
+      const long long bb = live ? b0 + lane : B - 1;
+      const float y = a.labels[bb];
+      const float lb = fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));  // BCE with logits
+      if (warp == 0 && live) loss_acc += lb;
+      const float pr = 1.f / (1.f + expf(-z));
+      dz = live ? (pr - y) / (float)B : 0.f;
+      float dh2[H2];
+#pragma unroll
+      for (int k = 0; k < H2; ++k) dh2[k] = h2[k] > 0.f ? dz * s_w3[k] : 0.f;
+#pragma unroll
+      for (int j = 0; j < H1; ++j) {
+        float accv = 0.f;
+#pragma unroll
+        for (int k = 0; k < H2; ++k) accv = fmaf(s_w2[k * H1 + j], dh2[k], accv);
+        dh1[j] = hpre[j] > 0.f ? accv : 0.f;
+      }
+      if (warp == 0) {  // backward state for B2 (T's region is not overwritten: Mst lies behind it)
+        float4* m4 = reinterpret_cast<float4*>(Mst + lane * MS);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) m4[qd] = make_float4(dh1[4 * qd], dh1[4 * qd + 1], dh1[4 * qd + 2], dh1[4 * qd + 3]);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) m4[4 + qd] = make_float4(a1[4 * qd], a1[4 * qd + 1], a1[4 * qd + 2], a1[4 * qd + 3]);
+        m4[8] = make_float4(dh2[0], dh2[1], dh2[2], dh2[3]);
+        m4[9] = make_float4(h2[0], h2[1], h2[2], h2[3]);
+        m4[10] = make_float4(dz, 0.f, 0.f, 0.f);
+      }
+      // ---------------- B1: d loss / d embedding rows of this warp's groups, reduced per unique id ----------------
+      const float* xrow = X + lane * XS;
+#pragma unroll 1
+      for (int gi = 0; gi < KPC / D; ++gi) {
+        const int g = warp * (KPC / D) + gi;
+        if (g >= G) break;  // warp-uniform
+        const int c = g * D;
+        const float4 xa = *reinterpret_cast<const float4*>(xrow + c);
+        const float4 xb = *reinterpret_cast<const float4*>(xrow + c + 4);
+        const float ev[D] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        float x[D + 1];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float4* w4 = reinterpret_cast<const float4*>(W1x + (c + d) * H1);
+          float dt = 0.f;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const float4 w = w4[qd];
+            dt = fmaf(w.x, dh1[4 * qd + 0], dt);
+            dt = fmaf(w.y, dh1[4 * qd + 1], dt);
+            dt = fmaf(w.z, dh1[4 * qd + 2], dt);
+            dt = fmaf(w.w, dh1[4 * qd + 3], dt);
+          }
+          x[d] = fmaf(dz, sd[d] - ev[d], dt);
+        }
+        x[D] = dz;  // wide row gradient
+        // warp-level id dedup: lanes hitting the same row combine pairwise up a tree threaded through the
+        // peer mask (pointer doubling): ceil(log2(max multiplicity)) rounds for the whole warp
+        const int r = R[g * TS + lane];
+        const int key = live ? r : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(peers & ((1u << lane) - 1));
+        const int maxn = __reduce_max_sync(0xffffffffu, (unsigned)__popc(peers));
+        const unsigned above = peers & ~((2u << lane) - 1);
+        int nxt = above ? __ffs(above) - 1 : -1;
+        for (int step = 1; step < maxn; step <<= 1) {
+          const int src = nxt >= 0 ? nxt : lane;
+          const bool take = nxt >= 0 && (rank & (2 * step - 1)) == 0;
+#pragma unroll
+          for (int e = 0; e <= D; ++e) {
+            const float yv = __shfl_sync(0xffffffffu, x[e], src);
+            if (take) x[e] += yv;
+          }
+          const int nn = __shfl_sync(0xffffffffu, nxt, src);
+          nxt = nxt >= 0 ? nn : -1;
+        }
+        if (live && rank == 0) {
+          float* od = a.gsum_deep + ((long long)g * B + r) * D;
+          atomicAdd(reinterpret_cast<float4*>(od), make_float4(x[0], x[1], x[2], x[3]));
+          atomicAdd(reinterpret_cast<float4*>(od + 4), make_float4(x[4], x[5], x[6], x[7]));
+          atomicAdd(a.gsum_wide + (long long)g * B + r, x[D]);
+        }
+      }
+      __syncthreads();  // Mst complete
+      // ---------------- B2: parameter gradients, accumulated over the CTA's tiles ----------------
+      if (t < NCOL / 2) {
+#pragma unroll 4
+        for (int s = 0; s < TS; ++s) {
+          const float4* d4 = reinterpret_cast<const float4*>(Mst + s * MS);
+          const float4 q0 = d4[0], q1 = d4[1], q2 = d4[2], q3 = d4[3];
+          const float dh[H1] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+          const float x0 = X[s * XS + t], x1 = X[s * XS + t + NCOL / 2];
+#pragma unroll
+          for (int j = 0; j < H1; ++j) {
+            acc0[j] = fmaf(dh[j], x0, acc0[j]);
+            acc1[j] = fmaf(dh[j], x1, acc1[j]);
+          }
+        }
+      } else if (warp == 5) {
+        for (int s = 0; s < TS; ++s) {
+          const float* m = Mst + s * MS;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int o = lane + 32 * i;
+            float v = 0.f;
+            if (o < H2 * H1) v = m[32 + o / H1] * m[16 + o % H1];                         // dh2[k] * a1[j]
+            else if (o < H2 * H1 + H2) v = m[32 + o - H2 * H1];                            // dh2[k]
+            else if (o < H2 * H1 + 2 * H2) v = m[40] * m[36 + o - H2 * H1 - H2];           // dz * h2[k]
+            else if (o < H2 * H1 + 2 * H2 + ND) v = m[40] * X[s * XS + MAXG * D + o - H2 * H1 - 2 * H2];  // dz * dense[e]
+            sacc[i] += v;
+          }
+        }
+      }
+    }
+    __syncthreads();  // X / R / P are rewritten by the next tile's gather
+  }
+  if (BACKWARD) {
+    if (t < NCOL / 2) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c = t + half * (NCOL / 2);
+#pragma unroll
+        for (int j = 0; j < H1; ++j) {
+          const int dst = w1x_src(l, G, c, j);
+          if (dst >= 0) atomicAdd(a.grads + dst, half ? acc1[j] : acc0[j]);
+        }
+      }
+    } else if (warp == 5) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int o = lane + 32 * i;
+        int off = -1;
+        if (o < H2 * H1) off = l.o_w2 + o;
+        else if (o < H2 * H1 + H2) off = l.o_b2 + o - H2 * H1;
+        else if (o < H2 * H1 + 2 * H2) off = l.o_w3 + o - H2 * H1 - H2;
+        else if (o < H2 * H1 + 2 * H2 + ND) off = l.o_wd + o - H2 * H1 - 2 * H2;
+        if (off >= 0) atomicAdd(a.grads + off, sacc[i]);
+      }
+    }
+    if (warp == 0) {
+      for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, o);
+      if (lane == 0) atomicAdd(a.loss, loss_acc / (float)B);
+    }
+  }
+}
+
+int check_args(const b200_deepfm_args_t* a, bool backward) {
+  if (!a || a->G < 1 || a->B < 1) { g_msg = "bad shape"; return -1; }
+  if (a->G > MAXG) { g_msg = "the tile tower holds at most 38 id groups"; return -1; }
+  if (!a->inv || !a->bet_wide || !a->bet_deep || !a->dense || !a->params || !a->scratch) { g_msg = "null input"; return -1; }
+  if (backward && (!a->labels || !a->grads || !a->gsum_wide || !a->gsum_deep || !a->loss || !a->n_unique)) {
+    g_msg = "null output";
+    return -1;
+  }
+  return 0;
+}
+
+template <bool BACKWARD>
+int launch(const b200_deepfm_args_t* args, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  static bool attr_done[64][2] = {};
+  if (dev < 64 && !attr_done[dev][BACKWARD]) {
+    cudaFuncSetAttribute(k_tower_tile<BACKWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    attr_done[dev][BACKWARD] = true;
+  }
+  b200_deepfm_args_t a = *args;
+  if (!BACKWARD) { a.grads = nullptr; a.gsum_deep = nullptr; a.gsum_wide = nullptr; a.loss = nullptr; }
+  float* w1x = a.scratch;  // NCOL*16 floats at the start of the scratch buffer
+  k_tile_prep<<<dim3(4, BACKWARD ? a.G : 1), 256, 0, st>>>(a, layout(a.G).total, w1x);
+  const long long ntile = ((long long)a.B + TS - 1) / TS;
+  static const int per_sm = [] { const char* e = getenv("B200_TILE_CTAS"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+  long long grid = (long long)n_sm * per_sm;
+  if (grid > ntile) grid = ntile;
+  k_tower_tile<BACKWARD><<<(unsigned)grid, THREADS, SMEM_BYTES, st>>>(*args, w1x);
+  g_launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_msg = cudaGetErrorString(e); return -2; }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t b200_deepfm_tile_launch_count(void) { return g_launches; }
+const char* b200_deepfm_tile_last_error(void) { return g_msg.c_str(); }
+
+int b200_deepfm_fwd_bwd_tile(const b200_deepfm_args_t* args, void* stream) {
+  if (check_args(args, true)) return -1;
+  return launch<true>(args, stream);
+}
+
+int b200_deepfm_forward_tile(const b200_deepfm_args_t* args, void* stream) {
+  if (check_args(args, false) || !args->logits) return -1;
+  return launch<false>(args, stream);
+}
+
+}  // extern "C"

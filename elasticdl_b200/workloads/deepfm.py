@@ -188,10 +188,12 @@ class HostFeeder:
 class DeepFMPSEngine:
     def __init__(self, group, batch, lr=1e-3, init_std=0.01, seed=7, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM,
                  init_rows=True, tower="fused", paired=None, exchange=None):
-        """tower="fused": the hand-written CUDA tower (csrc/deepfm_tower.cu);
+        """tower="tile": rows of 32 samples gathered once into shared memory, forward / backward / parameter
+        gradients from the tile (csrc/deepfm_tower2.cu);
+        tower="fused": round 1's hand-written CUDA tower (csrc/deepfm_tower.cu, three row gathers);
         tower="mma": its tensor-core variant (csrc/deepfm_tower_mma.cu, rows gathered once, 3xTF32 mma.sync);
         tower="torch": torch autograd over library kernels (kept for A/B measurements and tests)."""
-        assert tower in ("fused", "mma", "torch")
+        assert tower in ("tile", "fused", "mma", "torch")
         self.tower_kind = tower
         # paired=True: the deep (dim 8) and wide (dim 1) tables of an id group share one record
         # per id, so one request per id serves both (ps_kernels.cuh "Paired tables")
@@ -406,14 +408,14 @@ class DeepFMPSEngine:
                 e = mark(name)
                 check(lib.b200ps_pull_rows(h, arr, n, st))
                 done(e)
-        if self.tower_kind in ("fused", "mma"):
+        if self.tower_kind in ("tile", "fused", "mma"):
             # (4-6) gather + tower forward/backward + per-unique-id gradient sums: three launches
             e_t = mark("tower_fwd_bwd")
             a = self.tower_args
             a.dense, a.labels = dense.data_ptr(), labels.data_ptr()
             import ctypes as _ct
 
-            fn = lib.b200_deepfm_fwd_bwd_mma if self.tower_kind == "mma" else lib.b200_deepfm_fwd_bwd
+            fn = {"mma": lib.b200_deepfm_fwd_bwd_mma, "tile": lib.b200_deepfm_fwd_bwd_tile}.get(self.tower_kind, lib.b200_deepfm_fwd_bwd)
             rc = fn(_ct.byref(a), st)
             if rc:
                 raise RuntimeError("b200_deepfm_fwd_bwd failed (%d)" % rc)
@@ -612,7 +614,8 @@ class DeepFMPSEngine:
 
             a = self.tower_args
             a.dense = dense.data_ptr()
-            if lib.b200_deepfm_forward(_ct.byref(a), st):
+            fwd = lib.b200_deepfm_forward_tile if self.tower_kind == "tile" else lib.b200_deepfm_forward
+            if fwd(_ct.byref(a), st):
                 raise RuntimeError("b200_deepfm_forward failed")
         finally:
             self.__dict__.update(saved)

@@ -57,6 +57,14 @@ int b200_deepfm_fwd_bwd(const b200_deepfm_args_t* args, void* stream);
  * contractions run as 3xTF32 mma.sync.  `scratch` is not used. */
 int b200_deepfm_fwd_bwd_mma(const b200_deepfm_args_t* args, void* stream);
 int64_t b200_deepfm_mma_launch_count(void);
+/* Same contract, computed by the TILE tower (csrc/deepfm_tower2.cu, round 2, the default): a CTA gathers the
+ * rows of 32 samples once into shared memory (cp.async) and runs forward, backward and the
+ * parameter-gradient contraction from that tile -- two launches (prep + tile kernel).  `scratch` needs
+ * 320*16 floats (W1 in tile column order); at most 38 id groups. */
+int b200_deepfm_fwd_bwd_tile(const b200_deepfm_args_t* args, void* stream);
+int b200_deepfm_forward_tile(const b200_deepfm_args_t* args, void* stream);
+int64_t b200_deepfm_tile_launch_count(void);
+const char* b200_deepfm_tile_last_error(void);
 /* forward only (logits), for evaluation. */
 int b200_deepfm_forward(const b200_deepfm_args_t* args, void* stream);
 /* kernels launched by the two calls above so far */

@@ -137,7 +137,7 @@ def _torch_reference_grads(eng, tower, wide0, deep0, ids, dense, labels):
     return float(loss), grads
 
 
-@pytest.mark.parametrize("tower_kind,paired", [("fused", True), ("fused", False), ("torch", True), ("mma", False)])
+@pytest.mark.parametrize("tower_kind,paired", [("tile", False), ("fused", True), ("fused", False), ("torch", True), ("mma", False)])
 @pytest.mark.parametrize("n_shards,B,rows", [(1, 256, [5, 9, 300, 2000, 17]), (4, 1000, [3, 50000, 7, 100]),
                                              (2, 4096, None)])
 def test_deepfm_engine_step_matches_oracle_adam(n_shards, B, rows, tower_kind, paired):
@@ -169,7 +169,7 @@ def test_deepfm_engine_step_matches_oracle_adam(n_shards, B, rows, tower_kind, p
     uniq = eng.uniq.cpu().numpy().reshape(G, B)
     gsum_w = eng.gsum_w.cpu().numpy().reshape(G, B)
     gsum_d = eng.gsum_d.cpu().numpy().reshape(G, B, D)
-    if tower_kind in ("fused", "mma"):
+    if tower_kind in ("tile", "fused", "mma"):
         dense_grads = [eng.flat_grads[off:off + n].cpu().numpy() for off, n in eng.flat_views]
     else:
         dense_grads = [g_.cpu().numpy().reshape(-1) for g_ in eng._dense_grads]
@@ -205,7 +205,7 @@ def test_deepfm_engine_step_matches_oracle_adam(n_shards, B, rows, tower_kind, p
         assert np.array_equal(got, want), name
     assert [s_[0] for s_ in group.snapshot()] == [1] * n_shards
     # forward-only path agrees with the reference logits of the updated model
-    if tower_kind == "fused":
+    if tower_kind in ("fused", "tile"):
         logits = eng.predict(ids, dense).cpu().numpy()
         assert np.isfinite(logits).all()
     # training makes progress on a fixed batch

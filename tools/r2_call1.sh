@@ -9,3 +9,5 @@ timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/c1_bench.json 2> 
 tail -c 1500 gpurun_out/c1_bench.json
 timeout 600 python bench_kernels.py > gpurun_out/c1_kernels.jsonl 2> gpurun_out/c1_kernels.err; echo "kernels rc=$?"
 for u in 1 2 4; do B200_FLAT_U=$u BK_ONLY=adam:8 timeout 300 python bench_kernels.py > gpurun_out/c1_kernels_u$u.jsonl 2>> gpurun_out/c1_kernels.err; done
+timeout 300 python bench.py --steps 20 --warmup 5 --tower tile --no-cpu-baseline > gpurun_out/c1_bench_tile.json 2> gpurun_out/c1_bench_tile.err; echo "bench tile rc=$?"
+tail -c 600 gpurun_out/c1_bench_tile.json
