@@ -20,19 +20,27 @@ SGD = ("SGD", "learning_rate=0.1;momentum=0.0;nesterov=false;")
 
 
 def timeit(fn, iters=20, warmup=3):
+    """Average device time of one call: `iters` calls captured into ONE CUDA graph and replayed between two
+    events (launching them eagerly from Python leaves the GPU idle between kernels shorter than the ~20 us
+    of host work per call, and the event pair then measures the host)."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
-    evs = []
-    for _ in range(iters):
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        g.replay()
         b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    ms = sorted(x.elapsed_time(y) for x, y in evs)
-    return ms[len(ms) // 2]
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b) / iters)
+    return sorted(ms)[1]
 
 
 def main():
