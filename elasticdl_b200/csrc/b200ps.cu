@@ -328,15 +328,17 @@ constexpr int kClasses = 3;
 struct Split {
   SegBatch b[kClasses];  // hashed tables / whole dense parameters
   long long max_work[kClasses] = {0, 0, 0};
-  SegBatch flat;
-  FlatMeta fm;
+  b200ps_seg_t flat[kMaxSegs];  // direct-indexed tables and dense row views: one flat launch
+  unsigned char flat_vec[kMaxSegs];
+  int flat_n = 0;
   long long flat_items = 0;  // upper bound of lane-items (device-side counts can only lower it)
 };
 
 int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense, Split* out, bool push = false) {
   if (nseg < 0 || nseg > kMaxSegs) return fail(B200PS_EINVAL, "nseg out of range (max " + std::to_string(kMaxSegs) + ")");
   for (int c = 0; c < kClasses; ++c) out->b[c].nseg = 0;
-  out->flat.nseg = 0;
+  out->flat_n = 0;
+  const bool flat_ok = ps->n_shards <= 8;  // the flat kernels carry <= 8 per-shard pointers per segment in their parameters
   for (int i = 0; i < nseg; ++i) {
     const b200ps_seg_t& sg = segs[i];
     if (sg.table < 0 || sg.table >= (int)ps->tables.size()) return fail(B200PS_ENOTFOUND, "unknown table id " + std::to_string(sg.table));
@@ -344,12 +346,14 @@ int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense
     if (want_dense && !t.is_dense) return fail(B200PS_EINVAL, t.name + " is not a dense parameter");
     if (sg.n < 0) return fail(B200PS_EINVAL, "negative segment length");
     if (sg.n == 0 && !want_dense) continue;
-    if (!want_dense && !t.hashed) {
-      const int k = out->flat.nseg++;
-      out->flat.seg[k] = sg;
+    if (!want_dense && !t.hashed && flat_ok && t.row_stride < (1LL << 31)) {
+      const int k = out->flat_n++;
+      out->flat[k] = sg;
       const bool vec = !push && t.dim % 4 == 0 && t.row_stride % 4 == 0 && t.base_off % 16 == 0 && aligned16(sg.rows_dev);
-      out->fm.vec[k] = vec ? 1 : 0;
-      out->flat_items += (long long)sg.n * (push ? t.dim : (vec ? t.dim / 4 : t.dim));
+      out->flat_vec[k] = vec ? 1 : 0;
+      // a segment cannot hold more distinct rows than its table has
+      const long long cap = t.is_dense ? t.rows : t.rows * ps->n_shards;
+      out->flat_items += (sg.n < cap ? (long long)sg.n : cap) * (push ? t.dim : (vec ? t.dim / 4 : t.dim));
       continue;
     }
     int c;
@@ -368,6 +372,46 @@ int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense
     if (work > out->max_work[c]) out->max_work[c] = work;
   }
   return B200PS_OK;
+}
+
+// Resolve the flat segments on the host: everything a row access needs travels in the kernel parameters.
+template <int NSMAX>
+void fill_flat(b200ps_t* ps, const Split& sp, bool push, int slot, FlatArgs<NSMAX>* a) {
+  a->nseg = sp.flat_n;
+  a->ns = ps->n_shards;
+  a->shard_shift = -1;
+  if ((ps->n_shards & (ps->n_shards - 1)) == 0) {
+    int sh = 0;
+    while ((1 << sh) < ps->n_shards) ++sh;
+    a->shard_shift = sh;
+  }
+  a->slot = slot;
+  a->rt = ps->d_rt;
+  a->err = ps->d_err;
+  for (int k = 0; k < sp.flat_n; ++k) {
+    const b200ps_seg_t& sg = sp.flat[k];
+    const Table& t = ps->tables[sg.table];
+    FlatSegP& f = a->seg[k];
+    f.ids = sg.ids_dev;
+    f.n_dev = sg.n_dev;
+    f.rows = sg.rows_dev;
+    f.rows_cap = t.rows;
+    for (int j = 0; j <= kMaxSlots; ++j) f.soff[j] = t.slot_off[j];
+    f.n = sg.n;
+    f.stride = (int)t.row_stride;
+    f.dim = t.dim;
+    f.vec = sp.flat_vec[k];
+    f.lpr = push ? t.dim : (f.vec ? t.dim / 4 : t.dim);
+    f.shift = (f.lpr & (f.lpr - 1)) == 0 ? (int)__builtin_ctz((unsigned)f.lpr) : -1;
+    f.owner = t.owner;
+    f.pad = 0;
+    const int ns = NSMAX == 1 ? 1 : ps->n_shards;
+    for (int s = 0; s < ns; ++s) {
+      const Alloc& al = t.alloc[s];
+      a->base[k * ns + s] = al.ptr ? (float*)((char*)al.ptr + t.base_off) : nullptr;
+      a->present[k * ns + s] = (t.present_off && al.ptr) ? (uint32_t*)((char*)al.ptr + t.present_off) : nullptr;
+    }
+  }
 }
 
 template <typename F>
@@ -392,8 +436,8 @@ void flat_shape(b200ps_t* ps, long long items, int* U, int* grid) {
   static const int force_u = [] { const char* e = getenv("B200_FLAT_U"); return e ? atoi(e) : 0; }();      // tuning knobs
   static const int per_sm = [] { const char* e = getenv("B200_FLAT_BLOCKS"); return e ? atoi(e) : 0; }();
   const long long cap = (long long)ps->n_sm * (per_sm > 0 ? per_sm : 8);
-  *U = items >= cap * 256 * 4 ? 4 : items >= cap * 256 * 2 ? 2 : 1;
-  if (force_u == 1 || force_u == 2 || force_u == 4) *U = force_u;
+  *U = items >= cap * 256 * 2 ? 2 : 1;
+  if (force_u == 1 || force_u == 2) *U = force_u;
   long long blocks = (items + 256LL * *U - 1) / (256LL * *U);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -402,7 +446,6 @@ void flat_shape(b200ps_t* ps, long long items, int* U, int* grid) {
 
 #define DISPATCH_U(UVAL, ...)                          \
   switch (UVAL) {                                       \
-    case 4: { constexpr int U = 4; __VA_ARGS__; } break; \
     case 2: { constexpr int U = 2; __VA_ARGS__; } break; \
     default: { constexpr int U = 1; __VA_ARGS__; } break; \
   }
@@ -824,13 +867,24 @@ static int rows_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   if (rc) return rc;
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
-  if (sp.flat.nseg) {
+  if (sp.flat_n) {
     int u_rt, grid;
     flat_shape(ps, sp.flat_items, &u_rt, &grid);
-    DISPATCH_U(u_rt, {
-      if (write) k_copy_flat<true, U><<<grid, 256, 0, st>>>(gv, sp.flat, sp.fm, slot);
-      else k_copy_flat<false, U><<<grid, 256, 0, st>>>(gv, sp.flat, sp.fm, slot);
-    });
+    if (ps->n_shards == 1) {
+      FlatArgs<1> fa;
+      fill_flat(ps, sp, false, slot, &fa);
+      DISPATCH_U(u_rt, {
+        if (write) k_copy_flat<true, U, 1><<<grid, 256, 0, st>>>(fa);
+        else k_copy_flat<false, U, 1><<<grid, 256, 0, st>>>(fa);
+      });
+    } else {
+      FlatArgs<8> fa;
+      fill_flat(ps, sp, false, slot, &fa);
+      DISPATCH_U(u_rt, {
+        if (write) k_copy_flat<true, U, 8><<<grid, 256, 0, st>>>(fa);
+        else k_copy_flat<false, U, 8><<<grid, 256, 0, st>>>(fa);
+      });
+    }
     ps->launches++;
     CUDA_OK(cudaGetLastError());
   }
@@ -926,10 +980,18 @@ int b200ps_push_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
   OptParams o = ps->opt;
-  if (sp.flat.nseg) {
+  if (sp.flat_n) {
     int u_rt, grid;
     flat_shape(ps, sp.flat_items, &u_rt, &grid);
-    DISPATCH_OPT(o.kind, DISPATCH_U(u_rt, { k_push_flat<OPT, U><<<grid, 256, 0, st>>>(gv, sp.flat, o); }));
+    if (ps->n_shards == 1) {
+      FlatArgs<1> fa;
+      fill_flat(ps, sp, true, 0, &fa);
+      DISPATCH_OPT(o.kind, DISPATCH_U(u_rt, { k_push_flat<OPT, U, 1><<<grid, 256, 0, st>>>(fa, o); }));
+    } else {
+      FlatArgs<8> fa;
+      fill_flat(ps, sp, true, 0, &fa);
+      DISPATCH_OPT(o.kind, DISPATCH_U(u_rt, { k_push_flat<OPT, U, 8><<<grid, 256, 0, st>>>(fa, o); }));
+    }
     ps->launches++;
     CUDA_OK(cudaGetLastError());
   }
@@ -1315,10 +1377,13 @@ size_t b200ps_unique_bounded_workspace(int T, int64_t k, const int64_t* bounds) 
   return b200ps_unique_workspace(T, k) + bounded_extra(T, bounds);
 }
 
+// Look-back descriptors are sized for the smallest tile (256 x 4 positions).
+constexpr int kUMinTile = kUThreads * 4;
+
 size_t b200ps_unique_workspace(int T, int64_t k) {
   if (T < 1 || k < 1) return 256;
   size_t cap = (size_t)uniq_cap(k);
-  size_t ntiles = (size_t)((k + kUTile - 1) / kUTile);
+  size_t ntiles = (size_t)((k + kUMinTile - 1) / kUMinTile);
   return align256((size_t)T * cap * 8) + align256((size_t)T * cap * 4) + 2 * align256((size_t)T * k * 4) +
          align256((size_t)T * ntiles * 8) + 256;
 }
@@ -1339,7 +1404,25 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   a.k = k;
   a.T = T;
   a.cap = uniq_cap(k);
-  a.ntiles = (int)((k + kUTile - 1) / kUTile);
+  // co-resident grid (the kernel synchronises its phases with a grid barrier)
+  static int occ[64] = {0};
+  static int sms[64] = {0};
+  if (dev < 64 && occ[dev] == 0) {
+    int o = 0, n = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_unique<16>, kUThreads, 0));
+    CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    occ[dev] = o < 1 ? 1 : (o > 4 ? 4 : o);
+    sms[dev] = n < 1 ? 1 : n;
+  }
+  const long long max_blocks = dev < 64 ? (long long)occ[dev] * sms[dev] : 132;
+  // smallest tile for which every phase is a single pass over the grid
+  int ppt = 16;
+  for (int cand : {4, 8, 12}) {
+    const long long tl = (k + (long long)kUThreads * cand - 1) / ((long long)kUThreads * cand);
+    if ((long long)T * tl <= max_blocks) { ppt = cand; break; }
+  }
+  a.ppt = ppt;
+  a.ntiles = (int)((k + (long long)kUThreads * ppt - 1) / ((long long)kUThreads * ppt));
   char* p = (char*)workspace_dev;
   a.keys = (long long*)p; p += align256((size_t)T * a.cap * 8);
   a.minpos = (int*)p; p += align256((size_t)T * a.cap * 4);
@@ -1362,33 +1445,20 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   }
   a.n_hashed = T - a.n_direct;
   a.tagged = a.use_bounds && k <= (1LL << kUniqPosBits);
-  int shift = 5;
-  while (shift < kUChunkShiftMax && (1LL << shift) < k) ++shift;
-  a.chunk_shift = shift;
   a.uniq = uniq_dev;
   a.inv = inv_dev;
   a.n_unique = n_unique_dev;
   a.err = ps ? ps->d_err : nullptr;
-  // co-resident grid (the kernel synchronises its phases with a grid barrier)
-  static int occ[64] = {0};
-  static int sms[64] = {0};
-  if (dev < 64 && occ[dev] == 0) {
-    int o = 0, n = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_unique, kUThreads, 0));
-    CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    occ[dev] = o < 1 ? 1 : (o > 4 ? 4 : o);
-    sms[dev] = n < 1 ? 1 : n;
-  }
-  const long long max_blocks = dev < 64 ? (long long)occ[dev] * sms[dev] : 132;
-  const long long nchunk = (k + (1LL << shift) - 1) >> shift;
-  const long long items = nchunk * ((long long)T << shift);
-  long long blocks = (items + kUThreads - 1) / kUThreads;
   const long long tiles = (long long)T * a.ntiles;
-  if (blocks < tiles) blocks = tiles;
-  if (blocks > max_blocks) blocks = max_blocks;
+  long long blocks = tiles < max_blocks ? tiles : max_blocks;
   if (blocks < 1) blocks = 1;
   CUDA_OK(cudaMemsetAsync(a.hdr + 4, 0, 8, st));  // the grid-barrier counter
-  k_unique<<<(unsigned)blocks, kUThreads, 0, st>>>(a);
+  switch (ppt) {
+    case 4: k_unique<4><<<(unsigned)blocks, kUThreads, 0, st>>>(a); break;
+    case 8: k_unique<8><<<(unsigned)blocks, kUThreads, 0, st>>>(a); break;
+    case 12: k_unique<12><<<(unsigned)blocks, kUThreads, 0, st>>>(a); break;
+    default: k_unique<16><<<(unsigned)blocks, kUThreads, 0, st>>>(a); break;
+  }
   count_launch(ps, 1);
   CUDA_OK(cudaGetLastError());
   return B200PS_OK;

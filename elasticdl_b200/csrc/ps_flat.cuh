@@ -8,13 +8,15 @@
 //     segments form ONE index space (prefix over the live counts, built per block in shared memory
 //     from the device-side counts) that a persistent grid walks in whole-warp runs, so every SM
 //     carries the same share whatever the split;
-//   * everything a row access depends on besides the id -- the table's per-shard base pointers,
-//     bitmap pointers, strides, slot offsets, this push's lr / Adam alpha per shard -- is staged in
-//     shared memory by the block prologue.  The per-row dependent chain is id -> record -> store
-//     (it was count -> id -> TableView -> runtime scalars -> record -> store);
+//   * everything a row access depends on besides the id -- the table's per-shard base pointers, bitmap
+//     pointers, strides, slot offsets -- is resolved on the HOST and travels in the kernel's parameter
+//     block (up to 21 KB; sm_70+ takes 32 KB): the kernels read it through the constant cache with a
+//     warp-uniform index and never touch the device-side table directory.  The per-row dependent
+//     chain is id -> record -> store (it was count -> id -> TableView -> runtime scalars -> record ->
+//     store).  [The first flat version staged the directory into shared memory per block: with 1184
+//     blocks x 76 segments that prologue was half of the kernel -- ncu, profiles/r2_02.]
 //   * each thread keeps U independent rows in flight: all id loads, then all record / gradient
-//     loads, then the arithmetic and the stores (Little's law: 6.5 TB/s x ~1 us needs ~44 KB in
-//     flight per SM; one 16 B load per thread at 50 % occupancy was 16 KB);
+//     loads, then the arithmetic and the stores;
 //   * the update is "lane = (row, column)": the 8 lanes of a dim-8 row read 32 contiguous bytes of
 //     param, of each slot and of the gradient -- one full sector per array per row, no shuffles --
 //     and every lane executes exactly one element update (the d8 kernel ran four on 2 of 8 lanes).
@@ -26,22 +28,24 @@
 
 namespace b200ps_impl {
 
-struct FlatMeta {                 // host-side knowledge about the segments of one launch
-  unsigned char vec[kMaxSegs];    // copy kernels: 1 = dim % 4 == 0 and rows_dev 16 B aligned -> 16 B chunks
+struct FlatSegP {          // one segment, fully resolved by the host (96 B)
+  const int64_t* ids;
+  const int32_t* n_dev;    // live count on the device (<= n) or nullptr
+  float* rows;             // user rows [n, dim]
+  long long rows_cap;      // rows per shard (striped) / total rows (dense view)
+  long long soff[kMaxSlots + 1];
+  int n, stride, dim, lpr; // lpr = lanes per row
+  int shift, owner, vec, pad;  // shift = log2(lpr) or -1; vec: 16 B chunks (copy kernels)
 };
 
-struct FlatShared {
-  long long prefix[kMaxSegs + 1];  // lane-items before segment s (prefix[nseg] = total)
-  float* base[kMaxSegs][kMaxShards];
-  uint32_t* present[kMaxSegs][kMaxShards];
-  long long rows_cap[kMaxSegs];
-  long long stride[kMaxSegs];
-  long long soff[kMaxSegs][kMaxSlots + 1];
-  int lpr[kMaxSegs];    // lanes per row
-  int shift[kMaxSegs];  // log2(lpr) or -1
-  int dim[kMaxSegs];
-  int owner[kMaxSegs];
-  float lr[kMaxShards], alpha[kMaxShards], l2adj[kMaxShards];
+template <int NSMAX>
+struct FlatArgs {
+  FlatSegP seg[kMaxSegs];
+  float* base[kMaxSegs * NSMAX];        // [seg * ns + shard]
+  uint32_t* present[kMaxSegs * NSMAX];  // created-row bitmaps (nullptr: untracked)
+  const PushRt* rt;
+  unsigned* err;
+  int nseg, ns, shard_shift, slot;
 };
 
 __device__ __forceinline__ float ld_f1(const float* p) {
@@ -63,34 +67,18 @@ __device__ __forceinline__ int flat_seg_of(const long long* prefix, int nseg, lo
   return lo;
 }
 
-template <bool PUSH>
-__device__ __forceinline__ void flat_prologue(const GroupView& gv, const SegBatch& sb, const FlatMeta* fm, FlatShared& fs) {
-  const int nseg = sb.nseg, ns = gv.n_shards;
+// Block prologue: live lane-items of every segment (device-side counts) -> exclusive prefix.
+template <int NSMAX>
+__device__ __forceinline__ void flat_prefix(const FlatArgs<NSMAX>& p, long long* prefix) {
+  const int nseg = p.nseg;
   for (int s = threadIdx.x; s < nseg; s += blockDim.x) {
-    const b200ps_seg_t& sg = sb.seg[s];
-    const TableView& tv = gv.tables[sg.table];
-    const int dim = tv.dim;
-    const int lpr = PUSH ? dim : (fm->vec[s] ? dim / 4 : dim);
-    fs.lpr[s] = lpr;
-    fs.shift[s] = (lpr & (lpr - 1)) == 0 ? 31 - __clz(lpr) : -1;
-    fs.dim[s] = dim;
-    fs.owner[s] = tv.owner;
-    fs.rows_cap[s] = tv.rows;
-    fs.stride[s] = tv.row_stride;
-#pragma unroll
-    for (int k = 0; k <= kMaxSlots; ++k) fs.soff[s][k] = tv.slot_off[k];
-    fs.prefix[s + 1] = (long long)seg_count(sg) * lpr;  // count for now, scanned below
-  }
-  for (int i = threadIdx.x; i < nseg * ns; i += blockDim.x) {
-    const int s = i / ns, sh = i - s * ns;
-    const TableView& tv = gv.tables[sb.seg[s].table];
-    fs.base[s][sh] = tv.base[sh];
-    fs.present[s][sh] = tv.present[sh];
-  }
-  if (PUSH && threadIdx.x < ns) {
-    fs.lr[threadIdx.x] = gv.rt->lr[threadIdx.x];
-    fs.alpha[threadIdx.x] = gv.rt->alpha[threadIdx.x];
-    fs.l2adj[threadIdx.x] = gv.rt->l2adj[threadIdx.x];
+    int n = p.seg[s].n;
+    const int32_t* nd = p.seg[s].n_dev;
+    if (nd != nullptr) {
+      const int live = *nd;
+      n = live < n ? live : n;
+    }
+    prefix[s + 1] = (long long)n * p.seg[s].lpr;  // count for now, scanned below
   }
   __syncthreads();
   if (threadIdx.x < 32) {  // exclusive scan of <= 96 counts: three per lane
@@ -100,7 +88,7 @@ __device__ __forceinline__ void flat_prologue(const GroupView& gv, const SegBatc
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
       const int idx = lane * PER + j;
-      v[j] = idx < nseg ? fs.prefix[idx + 1] : 0;
+      v[j] = idx < nseg ? prefix[idx + 1] : 0;
       sum += v[j];
     }
     long long incl = sum;
@@ -114,46 +102,54 @@ __device__ __forceinline__ void flat_prologue(const GroupView& gv, const SegBatc
     for (int j = 0; j < PER; ++j) {
       const int idx = lane * PER + j;
       run += v[j];
-      if (idx < nseg) fs.prefix[idx + 1] = run;
+      if (idx < nseg) prefix[idx + 1] = run;
     }
-    if (lane == 0) fs.prefix[0] = 0;
+    if (lane == 0) prefix[0] = 0;
   }
   __syncthreads();
 }
 
 struct FlatLoc {
   float* rec;
-  long long slot;
+  uint32_t* pres;  // bitmap word of this row (nullptr: untracked)
+  uint32_t bit;
   int shard;
   bool ok;
 };
 
-__device__ __forceinline__ FlatLoc flat_locate(const GroupView& gv, const FlatShared& fs, int seg, long long id) {
+template <int NSMAX>
+__device__ __forceinline__ FlatLoc flat_locate(const FlatArgs<NSMAX>& p, int seg, long long id) {
+  const FlatSegP& sp = p.seg[seg];
   FlatLoc r;
   const bool nonneg = id >= 0;
   const long long uid = nonneg ? id : 0;
-  if (fs.owner[seg] >= 0) {
-    r.shard = fs.owner[seg];
-    r.slot = uid;
-  } else if (gv.shard_shift >= 0) {
-    r.shard = (int)(uid & (long long)(gv.n_shards - 1));
-    r.slot = uid >> gv.shard_shift;
+  long long slot;
+  if (NSMAX == 1) {
+    r.shard = 0;
+    slot = uid;
+  } else if (sp.owner >= 0) {
+    r.shard = sp.owner;
+    slot = uid;
+  } else if (p.shard_shift >= 0) {
+    r.shard = (int)(uid & (long long)(p.ns - 1));
+    slot = uid >> p.shard_shift;
   } else {
-    r.slot = uid / gv.n_shards;
-    r.shard = (int)(uid - r.slot * gv.n_shards);
+    slot = uid / p.ns;
+    r.shard = (int)(uid - slot * p.ns);
   }
-  r.ok = nonneg && r.slot < fs.rows_cap[seg];
-  if (!r.ok) r.slot = 0;
-  r.rec = fs.base[seg][r.shard] + r.slot * fs.stride[seg];
+  r.ok = nonneg && slot < sp.rows_cap;
+  if (!r.ok) slot = 0;
+  const int at = NSMAX == 1 ? seg : seg * p.ns + r.shard;
+  r.rec = p.base[at] + slot * sp.stride;
+  uint32_t* bm = p.present[at];
+  r.pres = bm ? bm + (slot >> 5) : nullptr;
+  r.bit = 1u << (slot & 31);
   return r;
 }
 
-__device__ __forceinline__ void flat_mark_present(const FlatShared& fs, int seg, const FlatLoc& r) {
-  uint32_t* bm = fs.present[seg][r.shard];
-  if (bm == nullptr) return;
-  uint32_t* w = bm + (r.slot >> 5);
-  const uint32_t bit = 1u << (r.slot & 31);
-  if (!(*(volatile uint32_t*)w & bit)) atomicOr_system(w, bit);
+__device__ __forceinline__ void flat_mark_present(const FlatLoc& r) {
+  if (r.pres == nullptr) return;
+  if (!(*(volatile uint32_t*)r.pres & r.bit)) atomicOr_system(r.pres, r.bit);  // the shard may be a peer GPU
 }
 
 // item w of the flat space -> (segment, row, column); `seg` is a running hint (items of one thread ascend)
@@ -162,16 +158,18 @@ struct FlatItem {
   int seg, col;
   bool live;
 };
-__device__ __forceinline__ FlatItem flat_item(const FlatShared& fs, long long w, long long total, int& seg) {
+template <int NSMAX>
+__device__ __forceinline__ FlatItem flat_item(const FlatArgs<NSMAX>& p, const long long* prefix, long long w, long long total,
+                                              int& seg) {
   FlatItem it;
   it.live = w < total;
   if (it.live)
-    while (w >= fs.prefix[seg + 1]) ++seg;
+    while (w >= prefix[seg + 1]) ++seg;
   it.seg = seg;
-  const long long local = it.live ? w - fs.prefix[seg] : 0;
-  const int sh = fs.shift[seg];
-  it.row = sh >= 0 ? local >> sh : local / fs.lpr[seg];
-  it.col = (int)(local - it.row * fs.lpr[seg]);
+  const long long local = it.live ? w - prefix[seg] : 0;
+  const int sh = p.seg[seg].shift, lpr = p.seg[seg].lpr;
+  it.row = sh >= 0 ? local >> sh : local / lpr;
+  it.col = (int)(local - it.row * lpr);
   return it;
 }
 
@@ -179,24 +177,24 @@ __device__ __forceinline__ FlatItem flat_item(const FlatShared& fs, long long w,
 // pull (WRITE = false, PullEmbeddingVectors) / set (WRITE = true, SetEmbeddingVectors / slot access):
 // item = (row, 16 B chunk) when the segment is vectorisable, else (row, float).
 // ---------------------------------------------------------------------------
-template <bool WRITE, int U>
-__global__ void __launch_bounds__(256) k_copy_flat(GroupView gv, SegBatch sb, FlatMeta fm, int slot) {
-  __shared__ FlatShared fs;
-  flat_prologue<false>(gv, sb, &fm, fs);
-  const int nseg = sb.nseg;
-  const long long total = fs.prefix[nseg];
+template <bool WRITE, int U, int NSMAX>
+__global__ void __launch_bounds__(256) k_copy_flat(const __grid_constant__ FlatArgs<NSMAX> p) {
+  __shared__ long long prefix[kMaxSegs + 1];
+  flat_prefix(p, prefix);
+  const int nseg = p.nseg;
+  const long long total = prefix[nseg];
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long wb = warp * (32 * U); wb < total; wb += nwarp * (32 * U)) {
     const long long w0 = wb + lane;
-    int seg = flat_seg_of(fs.prefix, nseg, w0 < total ? w0 : total - 1);
+    int seg = flat_seg_of(prefix, nseg, w0 < total ? w0 : total - 1);
     FlatItem it[U];
     long long id[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      it[k] = flat_item(fs, wb + k * 32 + lane, total, seg);
-      id[k] = it[k].live ? sb.seg[it[k].seg].ids_dev[it[k].row] : 0;
+      it[k] = flat_item(p, prefix, wb + k * 32 + lane, total, seg);
+      id[k] = it[k].live ? p.seg[it[k].seg].ids[it[k].row] : 0;
     }
     FlatLoc loc[U];
     float4 x[U];
@@ -205,17 +203,18 @@ __global__ void __launch_bounds__(256) k_copy_flat(GroupView gv, SegBatch sb, Fl
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       dst[k] = nullptr;
+      vec[k] = false;
       if (!it[k].live) continue;
-      const int s = it[k].seg;
-      loc[k] = flat_locate(gv, fs, s, id[k]);
+      const FlatSegP& sp = p.seg[it[k].seg];
+      loc[k] = flat_locate(p, it[k].seg, id[k]);
       if (!loc[k].ok) {
-        if (it[k].col == 0) atomicOr(gv.err, kErrRange);
+        if (it[k].col == 0) atomicOr(p.err, kErrRange);
         continue;
       }
-      vec[k] = fs.lpr[s] != fs.dim[s];
+      vec[k] = sp.vec != 0;
       const int off = vec[k] ? 4 * it[k].col : it[k].col;
-      float* rec = loc[k].rec + fs.soff[s][slot] + off;
-      float* user = sb.seg[s].rows_dev + it[k].row * fs.dim[s] + off;
+      float* rec = loc[k].rec + sp.soff[p.slot] + off;
+      float* user = sp.rows + it[k].row * sp.dim + off;
       const float* src = WRITE ? user : rec;
       dst[k] = WRITE ? rec : user;
       if (vec[k]) x[k] = ld_f4(src);
@@ -223,7 +222,7 @@ __global__ void __launch_bounds__(256) k_copy_flat(GroupView gv, SegBatch sb, Fl
     }
 #pragma unroll
     for (int k = 0; k < U; ++k)
-      if (dst[k] != nullptr && it[k].col == 0) flat_mark_present(fs, it[k].seg, loc[k]);
+      if (dst[k] != nullptr && it[k].col == 0) flat_mark_present(loc[k]);
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       if (dst[k] == nullptr) continue;
@@ -237,70 +236,78 @@ __global__ void __launch_bounds__(256) k_copy_flat(GroupView gv, SegBatch sb, Fl
 // push: lane = (row, column).  dim-1 tables whose record is one float4 [p, s0, s1, s2] keep the
 // single 16 B access.
 // ---------------------------------------------------------------------------
-template <int OPT, int U>
-__global__ void __launch_bounds__(256) k_push_flat(GroupView gv, SegBatch sb, OptParams o) {
+template <int OPT, int U, int NSMAX>
+__global__ void __launch_bounds__(256) k_push_flat(const __grid_constant__ FlatArgs<NSMAX> p, const OptParams o) {
   constexpr int S = opt_slots(OPT);
-  __shared__ FlatShared fs;
-  flat_prologue<true>(gv, sb, nullptr, fs);
-  const int nseg = sb.nseg;
-  const long long total = fs.prefix[nseg];
+  __shared__ long long prefix[kMaxSegs + 1];
+  __shared__ float s_lr[kMaxShards], s_alpha[kMaxShards], s_l2[kMaxShards];
+  if (threadIdx.x < p.ns) {  // this push's effective lr / Adam alpha / FTRL l2 per shard (k_push_begin)
+    s_lr[threadIdx.x] = p.rt->lr[threadIdx.x];
+    s_alpha[threadIdx.x] = p.rt->alpha[threadIdx.x];
+    s_l2[threadIdx.x] = p.rt->l2adj[threadIdx.x];
+  }
+  flat_prefix(p, prefix);
+  const int nseg = p.nseg;
+  const long long total = prefix[nseg];
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long wb = warp * (32 * U); wb < total; wb += nwarp * (32 * U)) {
     const long long w0 = wb + lane;
-    int seg = flat_seg_of(fs.prefix, nseg, w0 < total ? w0 : total - 1);
+    int seg = flat_seg_of(prefix, nseg, w0 < total ? w0 : total - 1);
     FlatItem it[U];
     long long id[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      it[k] = flat_item(fs, wb + k * 32 + lane, total, seg);
-      id[k] = it[k].live ? sb.seg[it[k].seg].ids_dev[it[k].row] : 0;
+      it[k] = flat_item(p, prefix, wb + k * 32 + lane, total, seg);
+      id[k] = it[k].live ? p.seg[it[k].seg].ids[it[k].row] : 0;
     }
     FlatLoc loc[U];
-    float g[U], p[U], s0[U], s1[U], s2[U];
+    float g[U], pv[U], s0[U], s1[U], s2[U];
     float* rp[U];
     bool rec4[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       rp[k] = nullptr;
+      rec4[k] = false;
       s0[k] = s1[k] = s2[k] = 0.f;
       if (!it[k].live) continue;
-      const int s = it[k].seg;
-      loc[k] = flat_locate(gv, fs, s, id[k]);
+      const FlatSegP& sp = p.seg[it[k].seg];
+      loc[k] = flat_locate(p, it[k].seg, id[k]);
       if (!loc[k].ok) {
-        if (it[k].col == 0) atomicOr(gv.err, kErrRange);
+        if (it[k].col == 0) atomicOr(p.err, kErrRange);
         continue;
       }
-      const int dim = fs.dim[s];
-      g[k] = ld_f1(sb.seg[s].rows_dev + it[k].row * dim + it[k].col);
+      const int dim = sp.dim;
+      g[k] = ld_f1(sp.rows + it[k].row * dim + it[k].col);
       rp[k] = loc[k].rec + it[k].col;
-      rec4[k] = S > 0 && dim == 1 && fs.stride[s] == 4 && fs.soff[s][1] == 1;
+      rec4[k] = S > 0 && dim == 1 && sp.stride == 4 && sp.soff[1] == 1;
       if (rec4[k]) {
         const float4 r = ld_f4(rp[k]);
-        p[k] = r.x; s0[k] = r.y; s1[k] = r.z; s2[k] = r.w;
+        pv[k] = r.x; s0[k] = r.y; s1[k] = r.z; s2[k] = r.w;
       } else {
-        p[k] = ld_f1(rp[k]);
-        if (S > 0) s0[k] = ld_f1(rp[k] + fs.soff[s][1]);
-        if (S > 1) s1[k] = ld_f1(rp[k] + fs.soff[s][2]);
-        if (S > 2) s2[k] = ld_f1(rp[k] + fs.soff[s][3]);
+        pv[k] = ld_f1(rp[k]);
+        if (S > 0) s0[k] = ld_f1(rp[k] + sp.soff[1]);
+        if (S > 1) s1[k] = ld_f1(rp[k] + sp.soff[2]);
+        if (S > 2) s2[k] = ld_f1(rp[k] + sp.soff[3]);
       }
     }
 #pragma unroll
     for (int k = 0; k < U; ++k)
-      if (rp[k] != nullptr && it[k].col == 0) flat_mark_present(fs, it[k].seg, loc[k]);
+      if (rp[k] != nullptr && it[k].col == 0) flat_mark_present(loc[k]);
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       if (rp[k] == nullptr) continue;
-      const int s = it[k].seg, sh = loc[k].shard;
-      opt_update<OPT>(g[k], p[k], s0[k], s1[k], s2[k], fs.lr[sh], fs.alpha[sh], fs.l2adj[sh], o);
+      const FlatSegP& sp = p.seg[it[k].seg];
+      const int sh = loc[k].shard;
+      opt_update<OPT>(g[k], pv[k], s0[k], s1[k], s2[k], s_lr[sh], s_alpha[sh], s_l2[sh], o);
       if (rec4[k]) {
-        st_f4(rp[k], make_float4(p[k], s0[k], s1[k], s2[k]));
+        st_f4(rp[k], make_float4(pv[k], s0[k], s1[k], s2[k]));
       } else {
-        st_f1(rp[k], p[k]);
-        if (S > 0) st_f1(rp[k] + fs.soff[s][1], s0[k]);
-        if (S > 1) st_f1(rp[k] + fs.soff[s][2], s1[k]);
-        if (S > 2) st_f1(rp[k] + fs.soff[s][3], s2[k]);
+        st_f1(rp[k], pv[k]);
+        if (S > 0) st_f1(rp[k] + sp.soff[1], s0[k]);
+        if (S > 1) st_f1(rp[k] + sp.soff[2], s1[k]);
+        if (S > 2) st_f1(rp[k] + sp.soff[3], s2[k]);
       }
     }
   }

@@ -2,10 +2,10 @@
 // persistent kernel (round 1: seven launches, 48 us at 38 x 32768 ids).
 //
 //   phase 0  (only when something must be cleared) hash keys / position arrays
-//   phase A  insert: position array entry of every id <- min(position), chunk-major so the heads of
-//            all segments go first; lanes of a warp holding the same id elect one writer
+//   phase A  insert: position array entry of every id <- min(position); all id loads, then all probes,
+//            then the atomics; lanes of a warp that would write the same entry elect one writer
 //   ---- grid barrier ----
-//   phase B  per 1024-position tile: first-occurrence flags, block scan, decoupled look-back over
+//   phase B  per tile (256 x PPT positions, coalesced): first-occurrence flags, ballot ranks, decoupled look-back over
 //            the tile aggregates of the segment (single pass: no scan kernel), global ranks,
 //            unique ids written in rank order, n_unique by the last tile of each segment
 //   ---- grid barrier ----
@@ -24,9 +24,7 @@
 namespace b200ps_impl {
 
 constexpr long long kEmptyKey = (long long)0x8000000000000000ULL;
-constexpr int kUTile = 1024;   // positions per tile (256 threads x 4 consecutive positions)
 constexpr int kUThreads = 256;
-constexpr int kUChunkShiftMax = 11;  // insert order: <= 2048-position chunks, chunk-major over the segments
 constexpr long long kUSpins = 1LL << 22;
 constexpr unsigned kErrUnique = 16u;
 
@@ -56,7 +54,7 @@ struct UArgs {
   unsigned long long* hdr;
   unsigned long long magic;
   int cap, ntiles, tagged, use_bounds, n_direct, n_hashed;
-  int chunk_shift;              // log2 of the insert chunk (>= 5: whole warps)
+  int ppt;                      // positions per thread of a tile (4, 8, 12 or 16)
   UniqueBounds ub;
   int64_t* uniq;
   int* inv;
@@ -99,9 +97,16 @@ __device__ __forceinline__ unsigned long long u_word(unsigned tag, unsigned flag
   return ((unsigned long long)((tag << 2) | flag) << 32) | value;
 }
 
-__global__ void __launch_bounds__(kUThreads) k_unique(UArgs a) {
-  __shared__ int s_warp[kUThreads / 32];
-  __shared__ int s_excl;
+// PPT = positions per thread of a tile (tile = 256 * PPT positions of one segment; thread tid owns the
+// positions q*256 + tid, so every global access of a warp is coalesced).  The host picks the smallest
+// PPT for which the launch is a single pass (tiles <= resident blocks): every phase is then ONE
+// dependent chain with PPT independent loads in flight per thread.
+template <int PPT>
+__global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
+  constexpr int NW = kUThreads / 32;
+  constexpr int TILE = kUThreads * PPT;
+  __shared__ int s_cnt[PPT * NW];  // first-occurrence counts per (q, warp), then their exclusive prefix
+  __shared__ int s_excl, s_tot;
   // header snapshot: stable until block 0 rewrites it after the last barrier
   const bool fresh = a.hdr[0] != a.magic;
   const unsigned long long epoch64 = fresh ? 0ULL : a.hdr[1];
@@ -115,90 +120,115 @@ __global__ void __launch_bounds__(kUThreads) k_unique(UArgs a) {
   const long long gsz = (long long)gridDim.x * kUThreads;
   const long long gtid = (long long)blockIdx.x * kUThreads + threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const long long k = a.k;
   const int T = a.T;
+  const long long tiles = (long long)T * a.ntiles;
 
   // ---- phase 0: clear what this call cannot read as empty ----
   const bool clear_direct = a.n_direct > 0 && (!a.tagged || stale_cycle);
   if (a.n_hashed > 0 || clear_direct || fresh) {
     if (fresh) {  // descriptors of a foreign layout could carry this call's tag
-      const long long n = (long long)T * a.ntiles;
-      for (long long i = gtid; i < n; i += gsz) a.status[i] = 0ULL;
+      for (long long i = gtid; i < tiles; i += gsz) a.status[i] = 0ULL;
     }
     if (a.n_hashed > 0 || clear_direct) {
-    if (!a.use_bounds) {
-      const long long n = (long long)T * a.cap;
-      for (long long i = gtid; i < n; i += gsz) {
-        a.keys[i] = kEmptyKey;
-        a.minpos[i] = 0x7fffffff;
-      }
-    } else {
-      for (int t = 0; t < T; ++t) {
-        if (a.ub.bound[t] > 0) {
-          if (!clear_direct) continue;
-          int* dp = a.ub.dpos + a.ub.off[t];
-          for (long long i = gtid; i < a.ub.bound[t]; i += gsz) dp[i] = 0x7fffffff;
-        } else {
-          long long* keys = a.keys + (long long)t * a.cap;
-          int* mp = a.minpos + (long long)t * a.cap;
-          for (long long i = gtid; i < a.cap; i += gsz) {
-            keys[i] = kEmptyKey;
-            mp[i] = 0x7fffffff;
+      if (!a.use_bounds) {
+        const long long n = (long long)T * a.cap;
+        for (long long i = gtid; i < n; i += gsz) {
+          a.keys[i] = kEmptyKey;
+          a.minpos[i] = 0x7fffffff;
+        }
+      } else {
+        for (int t = 0; t < T; ++t) {
+          if (a.ub.bound[t] > 0) {
+            if (!clear_direct) continue;
+            int* dp = a.ub.dpos + a.ub.off[t];
+            for (long long i = gtid; i < a.ub.bound[t]; i += gsz) dp[i] = 0x7fffffff;
+          } else {
+            long long* keys = a.keys + (long long)t * a.cap;
+            int* mp = a.minpos + (long long)t * a.cap;
+            for (long long i = gtid; i < a.cap; i += gsz) {
+              keys[i] = kEmptyKey;
+              mp[i] = 0x7fffffff;
+            }
           }
         }
       }
-    }
     }
     target += gridDim.x;
     u_grid_barrier(bar, target, a.err);
   }
 
-  // ---- phase A: insert ----
-  {
-    const long long nchunk = (k + (1LL << a.chunk_shift) - 1) >> a.chunk_shift;
-    const long long per_chunk = (long long)T << a.chunk_shift;
-    const long long items = nchunk * per_chunk;  // multiple of 32: warps stay whole
-    for (long long w = gtid; w < items; w += gsz) {
-      const long long c = w / per_chunk;
-      const long long rem = w - c * per_chunk;
-      const int t = (int)(rem >> a.chunk_shift);
-      const long long i = (c << a.chunk_shift) + (rem & ((1LL << a.chunk_shift) - 1));
-      const bool live = i < k;
-      long long id = live ? u_id(a, (long long)t * k + i) : 0;
-      const bool direct = a.use_bounds && a.ub.bound[t] > 0;  // warp-uniform (a chunk is one segment)
-      const unsigned livem = __ballot_sync(0xffffffffu, live);   // dead lanes (tail of the last chunk) never match
-      if (direct) {
-        if (id < 0 || id >= a.ub.bound[t]) id = 0;  // out-of-range ids are reported by the table kernels
-        // warp-level id dedup: equal ids elect their lowest lane = smallest position
-        const unsigned peers = __match_any_sync(0xffffffffu, id) & livem;
-        if (live) {
-          if ((__ffs(peers) - 1) == lane) {
-            int* mp = a.ub.dpos + a.ub.off[t] + id;
-            const int v = prefix | (int)i;
-            if (*(volatile int*)mp > v) atomicMin(mp, v);
-          }
-          a.fp[(long long)t * k + i] = (int)id;
+  // ---- phase A: insert.  position array entry of every id <- min(position) ----
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int t = (int)(tile / a.ntiles);
+    const long long base = (tile - (long long)t * a.ntiles) * TILE;
+    const bool direct = a.use_bounds && a.ub.bound[t] > 0;
+    int* fp = a.fp + (long long)t * k;
+    if (direct) {
+      int* dp = a.ub.dpos + a.ub.off[t];
+      const int bound = a.ub.bound[t];
+      int id[PPT], cur[PPT];  // bounded ids fit 32 bits
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {  // all id loads first
+        const long long i = base + q * kUThreads + threadIdx.x;
+        const long long v = i < k ? u_id(a, (long long)t * k + i) : 0;
+        id[q] = (v < 0 || v >= bound) ? 0 : (int)v;  // out-of-range ids are reported by the table kernels
+      }
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {  // then all probes of the position array
+        const long long i = base + q * kUThreads + threadIdx.x;
+        cur[q] = i < k ? *(volatile int*)(dp + id[q]) : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        const long long i = base + q * kUThreads + threadIdx.x;
+        const bool live = i < k;
+        const int v = prefix | (int)i;
+        // warp-level id dedup among the lanes that would write: equal ids elect their lowest lane
+        // (= smallest position); after the first few occurrences the recorded position already wins
+        const bool want = live && cur[q] > v;
+        const unsigned wm = __ballot_sync(0xffffffffu, want);
+        if (wm) {
+          const unsigned peers = __match_any_sync(0xffffffffu, want ? id[q] : -1 - lane) & wm;
+          if (want && (__ffs(peers) - 1) == lane) atomicMin(dp + id[q], v);
         }
-      } else {
-        const unsigned peers = __match_any_sync(0xffffffffu, id) & livem;
-        const int leader = live ? __ffs(peers) - 1 : lane;
-        unsigned s = 0;
-        if (live && lane == leader) {
-          unsigned long long* keys = reinterpret_cast<unsigned long long*>(a.keys + (long long)t * a.cap);
-          int* mp = a.minpos + (long long)t * a.cap;
-          const unsigned mask = a.cap - 1;
-          s = (unsigned)mix64((uint64_t)id) & mask;
-          while (true) {
-            unsigned long long prev = keys[s];
-            if (prev == (unsigned long long)kEmptyKey)
-              prev = atomicCAS(&keys[s], (unsigned long long)kEmptyKey, (unsigned long long)id);
-            if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)id) break;
-            s = (s + 1) & mask;
-          }
-          if (*(volatile int*)&mp[s] > (int)i) atomicMin(&mp[s], (int)i);
+        if (live) fp[i] = id[q];
+      }
+    } else {
+      unsigned long long* keys = reinterpret_cast<unsigned long long*>(a.keys + (long long)t * a.cap);
+      int* mp = a.minpos + (long long)t * a.cap;
+      const unsigned mask = a.cap - 1;
+#pragma unroll 1
+      for (int q0 = 0; q0 < PPT; q0 += 4) {
+        long long id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long i = base + (q0 + u) * kUThreads + threadIdx.x;
+          id[u] = i < k ? u_id(a, (long long)t * k + i) : 0;
         }
-        s = __shfl_sync(0xffffffffu, s, leader);
-        if (live) a.fp[(long long)t * k + i] = (int)s;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long i = base + (q0 + u) * kUThreads + threadIdx.x;
+          const bool live = i < k;
+          const unsigned livem = __ballot_sync(0xffffffffu, live);  // dead lanes (ragged tail) never match
+          const unsigned peers = __match_any_sync(0xffffffffu, id[u]) & livem;
+          const int leader = live ? __ffs(peers) - 1 : lane;
+          unsigned sl = 0;
+          if (live && lane == leader) {
+            sl = (unsigned)mix64((uint64_t)id[u]) & mask;
+            while (true) {
+              unsigned long long prev = keys[sl];
+              if (prev == (unsigned long long)kEmptyKey)
+                prev = atomicCAS(&keys[sl], (unsigned long long)kEmptyKey, (unsigned long long)id[u]);
+              if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)id[u]) break;
+              sl = (sl + 1) & mask;
+            }
+            if (*(volatile int*)&mp[sl] > (int)i) atomicMin(&mp[sl], (int)i);
+          }
+          sl = __shfl_sync(0xffffffffu, sl, leader);
+          if (live) fp[i] = (int)sl;
+        }
       }
     }
   }
@@ -206,54 +236,71 @@ __global__ void __launch_bounds__(kUThreads) k_unique(UArgs a) {
   u_grid_barrier(bar, target, a.err);
 
   // ---- phase B: flags, single-pass scan over the tiles of each segment, ranks, unique ids ----
-  const long long tiles = (long long)T * a.ntiles;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int t = (int)(tile / a.ntiles);
     const long long j = tile - (long long)t * a.ntiles;
+    const long long base = j * TILE;
     const bool direct = a.use_bounds && a.ub.bound[t] > 0;
     const int* mp = direct ? a.ub.dpos + a.ub.off[t] : a.minpos + (long long)t * a.cap;
     const int pm = direct ? pos_mask : 0x7fffffff;
     int* fp = a.fp + (long long)t * k;
-    const long long i0 = j * kUTile + threadIdx.x * 4;  // 4 CONSECUTIVE positions: ranks follow position order
-    int f[4], c = 0;
+    int v[PPT];  // slot / id of position q, then the first position of that id
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const long long i = i0 + q;
-      f[q] = 0;
-      if (i < k) {
-        const int first = mp[fp[i]] & pm;
-        fp[i] = first;
-        f[q] = first == (int)i;
-      }
-      c += f[q];
+    for (int q = 0; q < PPT; ++q) {
+      const long long i = base + q * kUThreads + threadIdx.x;
+      v[q] = i < k ? fp[i] : 0;
     }
-    int x = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+    for (int q = 0; q < PPT; ++q) {
+      const long long i = base + q * kUThreads + threadIdx.x;
+      v[q] = i < k ? (mp[v[q]] & pm) : -1;
     }
-    if (lane == 31) s_warp[wid] = x;
+    unsigned fmask = 0;                   // bit q: position q*256 + tid is a first occurrence
+    unsigned long long wr[2] = {0ULL, 0ULL};  // 5 bits per q: first occurrences among the lower lanes, same q
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const long long i = base + q * kUThreads + threadIdx.x;
+      const bool f = i < k && v[q] == (int)i;
+      if (i < k) fp[i] = v[q];
+      const unsigned bal = __ballot_sync(0xffffffffu, f);
+      wr[q / 12] |= (unsigned long long)__popc(bal & lt_mask) << (5 * (q % 12));
+      if (f) fmask |= 1u << q;
+      if (lane == 0) s_cnt[q * NW + wid] = __popc(bal);
+    }
     __syncthreads();
-    int wbase = 0, tot = 0;
+    if (wid == 0) {  // exclusive scan of the PPT*NW counts (position order = q major, warp minor)
+      constexpr int PER = (PPT * NW + 31) / 32;
+      int cv[PER], sum = 0;
 #pragma unroll
-    for (int w = 0; w < kUThreads / 32; ++w) {
-      const int v = s_warp[w];
-      if (w < wid) wbase += v;
-      tot += v;
-    }
-    if (wid == 0) {
+      for (int e = 0; e < PER; ++e) {
+        const int idx = lane * PER + e;
+        cv[e] = idx < PPT * NW ? s_cnt[idx] : 0;
+        sum += cv[e];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      int run = incl - sum;
+#pragma unroll
+      for (int e = 0; e < PER; ++e) {
+        const int idx = lane * PER + e;
+        if (idx < PPT * NW) s_cnt[idx] = run;
+        run += cv[e];
+      }
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
       if (lane == 0) u_stv(&a.status[tile], u_word(tag, j == 0 ? kUFlagP : kUFlagA, (unsigned)tot));
       int excl = 0;
       long long look = j - 1;  // predecessor tiles of this segment, nearest first, 32 at a time
       long long spins = 0;
       while (look >= 0) {
         const long long idx = look - lane;
-        unsigned long long wv = 0;
         bool valid = true;  // lanes before the segment start count as an exclusive prefix of 0
         unsigned flag = kUFlagP, val = 0;
         if (idx >= 0) {
-          wv = u_ldv(&a.status[(long long)t * a.ntiles + idx]);
+          const unsigned long long wv = u_ldv(&a.status[(long long)t * a.ntiles + idx]);
           const unsigned hi = (unsigned)(wv >> 32);
           valid = (hi >> 2) == tag && (hi & 3u) != 0;
           flag = hi & 3u;
@@ -278,23 +325,24 @@ __global__ void __launch_bounds__(kUThreads) k_unique(UArgs a) {
       }
       if (lane == 0) {
         s_excl = excl;
+        s_tot = tot;
         if (j > 0) u_stv(&a.status[tile], u_word(tag, kUFlagP, (unsigned)(excl + tot)));
         if (j == a.ntiles - 1) a.n_unique[t] = excl + tot;
       }
     }
     __syncthreads();
-    int r = s_excl + wbase + x - c;
+    const int excl = s_excl;
     int* rank_at = a.rank_at + (long long)t * k;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (f[q]) {
-        const long long i = i0 + q;
+    for (int q = 0; q < PPT; ++q) {
+      if (fmask >> q & 1u) {
+        const long long i = base + q * kUThreads + threadIdx.x;
+        const int r = excl + s_cnt[q * NW + wid] + (int)(wr[q / 12] >> (5 * (q % 12)) & 31ULL);
         rank_at[i] = r;
         a.uniq[(long long)t * k + r] = u_id(a, (long long)t * k + i);
-        ++r;
       }
     }
-    __syncthreads();  // s_warp / s_excl are reused by the next tile
+    __syncthreads();  // s_cnt / s_excl are reused by the next tile
   }
   target += gridDim.x;
   u_grid_barrier(bar, target, a.err);
@@ -302,14 +350,20 @@ __global__ void __launch_bounds__(kUThreads) k_unique(UArgs a) {
   // ---- phase C: inverse index ----
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int t = (int)(tile / a.ntiles);
-    const long long j = tile - (long long)t * a.ntiles;
+    const long long base = (tile - (long long)t * a.ntiles) * TILE;
     const int* fp = a.fp + (long long)t * k;
     const int* rank_at = a.rank_at + (long long)t * k;
     int* inv = a.inv + (long long)t * k;
+    int f[PPT];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const long long i = j * kUTile + q * kUThreads + threadIdx.x;
-      if (i < k) inv[i] = rank_at[fp[i]];
+    for (int q = 0; q < PPT; ++q) {
+      const long long i = base + q * kUThreads + threadIdx.x;
+      f[q] = i < k ? fp[i] : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const long long i = base + q * kUThreads + threadIdx.x;
+      if (i < k) inv[i] = rank_at[f[q]];
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // every block took its header snapshot before barrier 1

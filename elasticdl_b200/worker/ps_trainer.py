@@ -164,6 +164,47 @@ class ParameterServerTrainer(object):
         self._optimizer.zero_grad(set_to_none=True)
         self._non_embed_grads = None
 
+    # ------------------------------------------------------------------ the worker's training loop
+    def train_loop(self, batches, max_minibatch_retry_num=64, on_step=None):
+        """The training loop of elasticdl/python/worker/worker.py:338-370 around train_minibatch, with its
+        `get_model_steps` logic (SSP, docs/designs/async_sgd.md:129-157): the dense model is pulled from the
+        PS only every `get_model_steps` minibatches (and after a failed one); in between the worker trains
+        with its LOCAL model, which `_update_local_model` advances with the gradients it just pushed
+        (dense variables only -- embedding rows are always pulled fresh).  A minibatch whose push is not
+        accepted is retried up to `max_minibatch_retry_num` times (worker.py:181-234: "Worker got stuck").
+        batches: iterable of (features, labels).  Returns [(version, loss)] per minibatch."""
+        local_update_count = self._get_model_steps
+        last_training_minibatch_failed = False
+        out = []
+        for features, labels in batches:
+            if last_training_minibatch_failed or local_update_count >= self._get_model_steps:
+                local_update_count = 0
+                train_with_local_model = False
+            else:
+                train_with_local_model = True
+            err_msg = ""
+            try:  # _safe_process_minibatch (worker.py:274-300)
+                for _ in range(max_minibatch_retry_num):
+                    accepted, version, loss = self.train_minibatch(features, labels, train_with_local_model)
+                    if accepted:
+                        break
+                else:
+                    raise RuntimeError("Worker got stuck")
+            except RuntimeError as err:
+                err_msg = str(err)
+            local_update_count += 1
+            if err_msg:
+                last_training_minibatch_failed = True
+                out.append((None, None))
+            else:
+                last_training_minibatch_failed = False
+                if local_update_count < self._get_model_steps:
+                    self._update_local_model()
+                out.append((version, loss))
+            if on_step is not None:
+                on_step(train_with_local_model, err_msg)
+        return out
+
     # ------------------------------------------------------------------ eval / misc
     def get_model_version(self):
         return self._model_version

@@ -126,6 +126,62 @@ def test_trainer_equals_local_training_worker_ps_interaction_test_py_203(n_shard
     group.close()
 
 
+@pytest.mark.parametrize("get_model_steps", [1, 3])
+def test_train_loop_get_model_steps_worker_py_346(get_model_steps):
+    """The worker loop of worker.py:338-370: the dense model is pulled every `get_model_steps` minibatches,
+    in between the worker trains on its local model advanced by _update_local_model (ps_trainer.py:139-147).
+    With one worker and SGD on both sides the local model tracks the PS exactly, so the run must equal plain
+    local torch training -- and _get_model must have run only at minibatches 0, 3, 6."""
+    import types
+
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+    from elasticdl_b200.worker.ps_trainer import ParameterServerTrainer
+
+    torch.manual_seed(0)
+    model = TinyModel().cuda()
+    group = PSGroup(2, *SGD, device=0)
+    client = PSClient(group)
+    client.dense_output = "torch"
+    trainer = ParameterServerTrainer(model, client, args=types.SimpleNamespace(get_model_steps=get_model_steps))
+    rows, dim, steps = 50, 8, 7
+    init = torch.randn(rows, dim, device="cuda") * 0.1
+    group.set_rows([("tiny_emb/embeddings:0", torch.arange(rows), init)])
+    table = init.clone().requires_grad_(True)
+    fc = torch.nn.Linear(3 * dim, 1).cuda()
+    fc.load_state_dict(model.fc.state_dict())
+    opt = torch.optim.SGD([table] + list(fc.parameters()), lr=0.1)
+    gen = torch.Generator().manual_seed(1)
+    batches = [(torch.randint(0, rows, (16, 3), generator=gen).cuda(), torch.randn(16, generator=gen).cuda())
+               for _ in range(steps)]
+    pulls, flags = [], []
+    orig = trainer._get_model
+
+    def counting_get_model():
+        pulls.append(len(flags))
+        orig()
+
+    trainer._get_model = counting_get_model
+    out = trainer.train_loop(batches, on_step=lambda local, err: flags.append((local, err)))
+    assert [f[1] for f in flags] == [""] * steps
+    assert pulls == list(range(0, steps, get_model_steps))
+    assert [f[0] for f in flags] == [i % get_model_steps != 0 for i in range(steps)]
+    for (ids, labels), (version, loss) in zip(batches, out):
+        opt.zero_grad()
+        l2 = ((fc(table[ids].reshape(16, -1)).squeeze(1) - labels) ** 2).mean()
+        l2.backward()
+        opt.step()
+        assert abs(float(loss) - float(l2)) < 1e-5
+    assert [v for v, _ in out] == list(range(1, steps + 1))
+    params, _ = client.pull_dense_parameters([0, 1], [-1, -1])
+    assert torch.allclose(params["fc.weight"], fc.weight.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(params["fc.bias"], fc.bias.detach(), rtol=1e-5, atol=1e-6)
+    # the worker's local copy after the last local update equals the PS too (single worker, SGD both sides)
+    if get_model_steps > 1 and steps % get_model_steps != 0:
+        assert torch.allclose(model.fc.weight.detach(), fc.weight.detach(), rtol=1e-5, atol=1e-6)
+    group.close()
+
+
 def _torch_reference_grads(eng, tower, wide0, deep0, ids, dense, labels):
     rows_n = len(wide0)
     wt = [w.clone().requires_grad_(True) for w in wide0]
