@@ -1388,9 +1388,12 @@ size_t b200ps_unique_workspace(int T, int64_t k) {
          align256((size_t)T * ntiles * 8) + 256;
 }
 
+static long long* g_dbg_buf = nullptr;  // b200ps_debug_buffer: per-block phase time stamps (profiling aid)
+static size_t g_dbg_bytes = 0;
+
 static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int64_t k, const int64_t* bounds,
                        int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
-                       size_t workspace_bytes, void* stream) {
+                       size_t workspace_bytes, void* stream, int blocks_per_sm = 0) {
   if (T < 1 || T > 65535 || k < 1 || k > (1LL << 29)) return fail(B200PS_EINVAL, "bad unique shape");
   if (!ids_dev || !uniq_dev || !inv_dev || !n_unique_dev || !workspace_dev) return fail(B200PS_EINVAL, "null argument");
   if (workspace_bytes < b200ps_unique_workspace(T, k)) return fail(B200PS_EINVAL, "unique workspace too small");
@@ -1414,7 +1417,10 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
     occ[dev] = o < 1 ? 1 : (o > 4 ? 4 : o);
     sms[dev] = n < 1 ? 1 : n;
   }
-  const long long max_blocks = dev < 64 ? (long long)occ[dev] * sms[dev] : 132;
+  long long max_blocks = dev < 64 ? (long long)occ[dev] * sms[dev] : 132;
+  // a caller that overlaps the dedup with other kernels (lookahead pipeline) asks for a thin grid: the
+  // persistent blocks hold their registers for the whole call, including the time spent at the grid barriers
+  if (blocks_per_sm > 0 && dev < 64 && (long long)blocks_per_sm * sms[dev] < max_blocks) max_blocks = (long long)blocks_per_sm * sms[dev];
   // smallest tile for which every phase is a single pass over the grid
   int ppt = 16;
   for (int cand : {4, 8, 12}) {
@@ -1449,6 +1455,7 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   a.inv = inv_dev;
   a.n_unique = n_unique_dev;
   a.err = ps ? ps->d_err : nullptr;
+  a.dbg = (g_dbg_buf && g_dbg_bytes >= (size_t)max_blocks * 64) ? g_dbg_buf : nullptr;
   const long long tiles = (long long)T * a.ntiles;
   long long blocks = tiles < max_blocks ? tiles : max_blocks;
   if (blocks < 1) blocks = 1;
@@ -1482,6 +1489,19 @@ int b200ps_unique_bounded_i32(b200ps_t* ps, const int32_t* ids32_dev, int T, int
                               size_t workspace_bytes, void* stream) {
   return unique_impl(ps, ids32_dev, 1, T, k, bounds, uniq_dev, inv_dev, n_unique_dev, workspace_dev, workspace_bytes,
                      stream);
+}
+
+int b200ps_unique_bounded_ex(b200ps_t* ps, const void* ids_dev, int ids_are_int32, int T, int64_t k, const int64_t* bounds,
+                             int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
+                             size_t workspace_bytes, int blocks_per_sm, void* stream) {
+  return unique_impl(ps, ids_dev, ids_are_int32 ? 1 : 0, T, k, bounds, uniq_dev, inv_dev, n_unique_dev, workspace_dev,
+                     workspace_bytes, stream, blocks_per_sm);
+}
+
+int b200ps_debug_buffer(void* dev_ptr, size_t bytes) {
+  g_dbg_buf = (long long*)dev_ptr;
+  g_dbg_bytes = dev_ptr ? bytes : 0;
+  return B200PS_OK;
 }
 
 static int dim_class(int dim, const void* a, const void* b) {

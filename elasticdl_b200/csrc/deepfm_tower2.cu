@@ -14,8 +14,9 @@
 //                         per-sample MLP tail (it needs dh1 / dz / FM sums in registers for B1 anyway)
 //   B1 embedding grads    warp = its 5 groups, lane = sample; equal rows of a warp combine up a tree
 //                         (warp-level id dedup), one vector red per distinct row
-//   B2 parameter grads    thread = 2 tile columns x 16 hidden units, accumulated in registers across
-//                         the CTA's tiles, one atomic per output per CTA at the end
+//   B2 parameter grads    thread = tile column t x 16 hidden units + a quarter of one of the last 64 columns
+//                         (all 8 warps busy), accumulated in registers across the CTA's tiles, one atomic
+//                         per output per CTA at the end
 // W1 is presented in TILE COLUMN ORDER (W1x[c][j]: deep columns first, then dense, then b1 as the weight
 // of the constant-1 column) by the prep kernel, so the bias needs no special case and every CTA loads it
 // with straight 16-byte copies.  fp32 SIMT: the step has 1 GFLOP of first-layer work -- the kernel is
@@ -135,11 +136,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
     if (t < H2) { s_b2[t] = a.params[l.o_b2 + t]; s_w3[t] = a.params[l.o_w3 + t]; }
     if (t < ND) s_wd[t] = a.params[l.o_wd + t];
   }
-  // B2 accumulators, persistent over the CTA's tiles: thread t < 160 owns tile columns t and t + 160
-  float acc0[H1], acc1[H1];
-  float sacc[3] = {0.f, 0.f, 0.f};  // warp 5: small outputs lane + 32*i (dW2 64 | db2 4 | dw3 4 | dwd 13)
+  // B2 accumulators, persistent over the CTA's tiles, all 8 warps busy: thread t owns tile column t (16 hidden
+  // units) and, of the remaining 64 columns, column 256 + t/4 x hidden units 4*(t%4) .. +3
+  float acc0[H1], acc1[4];
+  float sacc = 0.f;  // threads t < 85: one small output each (dW2 64 | db2 4 | dw3 4 | dwd 13)
 #pragma unroll
-  for (int j = 0; j < H1; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+  for (int j = 0; j < H1; ++j) acc0[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc1[j] = 0.f;
   float loss_acc = 0.f;
   __syncthreads();
 
@@ -150,9 +154,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
     {
       const int npair = G * TS;
       constexpr int NP = (MAXG * TS + THREADS - 1) / THREADS;  // 5 (group, sample) pairs per thread
+      constexpr int NFILL = (TS * 16 + THREADS - 1) / THREADS;  // dense | 1 | 0 0 columns: 2 per thread
       int rk[NP];
+      float wv[NP], dv[NFILL];
+      // every global load is issued before anything waits on one (the SM issues in order: a store of a
+      // loaded value in the middle of the loop would serialise the five gather chains)
 #pragma unroll
-      for (int jj = 0; jj < NP; ++jj) {  // all rank loads first, then all row copies: independent chains in flight
+      for (int jj = 0; jj < NP; ++jj) {
         const int i = t + THREADS * jj;
         rk[jj] = 0;
         if (i < npair) {
@@ -162,26 +170,45 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
         }
       }
 #pragma unroll
+      for (int jj = 0; jj < NFILL; ++jj) {  // tile columns 304..319 of sample s: dense 13 | 1 | 0 | 0
+        const int i = t + THREADS * jj;
+        const int s = i >> 4, c = i & 15;
+        long long b = b0 + s;
+        if (b >= B) b = B - 1;
+        float v = c == ND ? 1.0f : 0.f;
+        if (i < TS * 16 && c < ND) v = a.dense[b * ND + c];
+        dv[jj] = v;
+      }
+#pragma unroll
       for (int jj = 0; jj < NP; ++jj) {
         const int i = t + THREADS * jj;
+        wv[jj] = 0.f;
         if (i < npair) {
-          const int g = i >> 5, s = i & 31, r = rk[jj];
-          R[g * TS + s] = r;
-          const float* row = a.bet_deep + ((long long)g * B + r) * D;
+          const int g = i >> 5, s = i & 31;
+          const float* row = a.bet_deep + ((long long)g * B + rk[jj]) * D;
           float* dst = X + s * XS + g * D;
           cp_async16(dst, row);
           cp_async16(dst + 4, row + 4);
-          X[s * XS + XW + g] = a.bet_wide[(long long)g * B + r];
+          wv[jj] = a.bet_wide[(long long)g * B + rk[jj]];
         }
       }
-      for (int i = t; i < TS * (NCOL - G * D); i += THREADS) {  // columns G*8 .. 319: zero, dense, 1, 0, 0
-        const int s = i / (NCOL - G * D), c = G * D + i % (NCOL - G * D);
-        long long b = b0 + s;
-        if (b >= B) b = B - 1;
-        float v = 0.f;
-        if (c >= MAXG * D && c < MAXG * D + ND) v = a.dense[b * ND + (c - MAXG * D)];
-        else if (c == MAXG * D + ND) v = 1.0f;
-        X[s * XS + c] = v;
+#pragma unroll
+      for (int jj = 0; jj < NP; ++jj) {
+        const int i = t + THREADS * jj;
+        if (i < npair) {
+          const int g = i >> 5, s = i & 31;
+          R[g * TS + s] = rk[jj];
+          X[s * XS + XW + g] = wv[jj];
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < NFILL; ++jj) {
+        const int i = t + THREADS * jj;
+        if (i < TS * 16) X[(i >> 4) * XS + MAXG * D + (i & 15)] = dv[jj];
+      }
+      for (int i = t; i < TS * (MAXG - G) * D; i += THREADS) {  // unused group columns (G < 38): zeros
+        const int s = i / ((MAXG - G) * D), c = G * D + i % ((MAXG - G) * D);
+        X[s * XS + c] = 0.f;
       }
       cp_async_wait_all();
     }
@@ -363,31 +390,32 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
       }
       __syncthreads();  // Mst complete
       // ---------------- B2: parameter gradients, accumulated over the CTA's tiles ----------------
-      if (t < NCOL / 2) {
+      {
+        const int c1 = 256 + (t >> 2), jq = (t & 3) * 4;
 #pragma unroll 4
         for (int s = 0; s < TS; ++s) {
           const float4* d4 = reinterpret_cast<const float4*>(Mst + s * MS);
           const float4 q0 = d4[0], q1 = d4[1], q2 = d4[2], q3 = d4[3];
           const float dh[H1] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-          const float x0 = X[s * XS + t], x1 = X[s * XS + t + NCOL / 2];
+          const float x0 = X[s * XS + t], x1 = X[s * XS + c1];
+          const float4 dq = *reinterpret_cast<const float4*>(Mst + s * MS + jq);
 #pragma unroll
-          for (int j = 0; j < H1; ++j) {
-            acc0[j] = fmaf(dh[j], x0, acc0[j]);
-            acc1[j] = fmaf(dh[j], x1, acc1[j]);
-          }
+          for (int j = 0; j < H1; ++j) acc0[j] = fmaf(dh[j], x0, acc0[j]);
+          acc1[0] = fmaf(dq.x, x1, acc1[0]);
+          acc1[1] = fmaf(dq.y, x1, acc1[1]);
+          acc1[2] = fmaf(dq.z, x1, acc1[2]);
+          acc1[3] = fmaf(dq.w, x1, acc1[3]);
         }
-      } else if (warp == 5) {
-        for (int s = 0; s < TS; ++s) {
-          const float* m = Mst + s * MS;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int o = lane + 32 * i;
-            float v = 0.f;
+        if (t < H2 * H1 + 2 * H2 + ND) {
+          const int o = t;
+          for (int s = 0; s < TS; ++s) {
+            const float* m = Mst + s * MS;
+            float v;
             if (o < H2 * H1) v = m[32 + o / H1] * m[16 + o % H1];                         // dh2[k] * a1[j]
             else if (o < H2 * H1 + H2) v = m[32 + o - H2 * H1];                            // dh2[k]
             else if (o < H2 * H1 + 2 * H2) v = m[40] * m[36 + o - H2 * H1 - H2];           // dz * h2[k]
-            else if (o < H2 * H1 + 2 * H2 + ND) v = m[40] * X[s * XS + MAXG * D + o - H2 * H1 - 2 * H2];  // dz * dense[e]
-            sacc[i] += v;
+            else v = m[40] * X[s * XS + MAXG * D + o - H2 * H1 - 2 * H2];                  // dz * dense[e]
+            sacc += v;
           }
         }
       }
@@ -395,27 +423,24 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
     __syncthreads();  // X / R / P are rewritten by the next tile's gather
   }
   if (BACKWARD) {
-    if (t < NCOL / 2) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int c = t + half * (NCOL / 2);
+    for (int j = 0; j < H1; ++j) {
+      const int dst = w1x_src(l, G, t, j);
+      if (dst >= 0) atomicAdd(a.grads + dst, acc0[j]);
+    }
 #pragma unroll
-        for (int j = 0; j < H1; ++j) {
-          const int dst = w1x_src(l, G, c, j);
-          if (dst >= 0) atomicAdd(a.grads + dst, half ? acc1[j] : acc0[j]);
-        }
-      }
-    } else if (warp == 5) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int o = lane + 32 * i;
-        int off = -1;
-        if (o < H2 * H1) off = l.o_w2 + o;
-        else if (o < H2 * H1 + H2) off = l.o_b2 + o - H2 * H1;
-        else if (o < H2 * H1 + 2 * H2) off = l.o_w3 + o - H2 * H1 - H2;
-        else if (o < H2 * H1 + 2 * H2 + ND) off = l.o_wd + o - H2 * H1 - 2 * H2;
-        if (off >= 0) atomicAdd(a.grads + off, sacc[i]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const int dst = w1x_src(l, G, 256 + (t >> 2), (t & 3) * 4 + j);
+      if (dst >= 0) atomicAdd(a.grads + dst, acc1[j]);
+    }
+    if (t < H2 * H1 + 2 * H2 + ND) {
+      const int o = t;
+      int off;
+      if (o < H2 * H1) off = l.o_w2 + o;
+      else if (o < H2 * H1 + H2) off = l.o_b2 + o - H2 * H1;
+      else if (o < H2 * H1 + 2 * H2) off = l.o_w3 + o - H2 * H1 - H2;
+      else off = l.o_wd + o - H2 * H1 - 2 * H2;
+      atomicAdd(a.grads + off, sacc);
     }
     if (warp == 0) {
       for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, o);

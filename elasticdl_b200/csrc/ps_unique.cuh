@@ -60,6 +60,7 @@ struct UArgs {
   int* inv;
   int* n_unique;
   unsigned* err;
+  long long* dbg;               // optional [blocks][8] globaltimer stamps per phase (profiling aid)
 };
 
 __device__ __forceinline__ long long u_id(const UArgs& a, long long idx) {
@@ -73,6 +74,13 @@ __device__ __forceinline__ unsigned long long u_ldv(const unsigned long long* p)
 __device__ __forceinline__ void u_stv(unsigned long long* p, unsigned long long v) {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+
+__device__ __forceinline__ long long u_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define U_STAMP(slot) do { if (a.dbg && threadIdx.x == 0) a.dbg[(long long)blockIdx.x * 8 + (slot)] = u_now(); } while (0)
 
 __device__ __forceinline__ void u_grid_barrier(unsigned* bar, unsigned target, unsigned* err) {
   __syncthreads();
@@ -159,6 +167,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
     u_grid_barrier(bar, target, a.err);
   }
 
+  U_STAMP(0);
   // ---- phase A: insert.  position array entry of every id <- min(position) ----
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int t = (int)(tile / a.ntiles);
@@ -168,33 +177,44 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
     if (direct) {
       int* dp = a.ub.dpos + a.ub.off[t];
       const int bound = a.ub.bound[t];
-      int id[PPT], cur[PPT];  // bounded ids fit 32 bits
+      int id[PPT];  // bounded ids fit 32 bits
 #pragma unroll
       for (int q = 0; q < PPT; ++q) {  // all id loads first
         const long long i = base + q * kUThreads + threadIdx.x;
         const long long v = i < k ? u_id(a, (long long)t * k + i) : 0;
         id[q] = (v < 0 || v >= bound) ? 0 : (int)v;  // out-of-range ids are reported by the table kernels
+        if (i < k) fp[i] = id[q];
       }
+      // probes, then atomics, in three rounds (positions q = 0 | 1..3 | the rest): a hot id (small tables,
+      // Zipf heads) occurs in every warp of every tile, and only a probe issued AFTER an earlier, smaller
+      // position has landed can skip its atomic -- with all probes up front every occurrence queued on
+      // the same address (ncu: the slowest block's queue was a third of the kernel).
+      auto round = [&](const int q0, const int q1) {
+        int cur[PPT];
 #pragma unroll
-      for (int q = 0; q < PPT; ++q) {  // then all probes of the position array
-        const long long i = base + q * kUThreads + threadIdx.x;
-        cur[q] = i < k ? *(volatile int*)(dp + id[q]) : 0;
-      }
-#pragma unroll
-      for (int q = 0; q < PPT; ++q) {
-        const long long i = base + q * kUThreads + threadIdx.x;
-        const bool live = i < k;
-        const int v = prefix | (int)i;
-        // warp-level id dedup among the lanes that would write: equal ids elect their lowest lane
-        // (= smallest position); after the first few occurrences the recorded position already wins
-        const bool want = live && cur[q] > v;
-        const unsigned wm = __ballot_sync(0xffffffffu, want);
-        if (wm) {
-          const unsigned peers = __match_any_sync(0xffffffffu, want ? id[q] : -1 - lane) & wm;
-          if (want && (__ffs(peers) - 1) == lane) atomicMin(dp + id[q], v);
+        for (int q = 0; q < PPT; ++q) {
+          if (q < q0 || q >= q1) continue;
+          const long long i = base + q * kUThreads + threadIdx.x;
+          cur[q] = i < k ? *(volatile int*)(dp + id[q]) : 0;
         }
-        if (live) fp[i] = id[q];
-      }
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+          if (q < q0 || q >= q1) continue;
+          const long long i = base + q * kUThreads + threadIdx.x;
+          const int v = prefix | (int)i;
+          // warp-level id dedup among the lanes that would write: equal ids elect their lowest lane
+          // (= smallest position)
+          const bool want = i < k && cur[q] > v;
+          const unsigned wm = __ballot_sync(0xffffffffu, want);
+          if (wm) {
+            const unsigned peers = __match_any_sync(0xffffffffu, want ? id[q] : -1 - lane) & wm;
+            if (want && (__ffs(peers) - 1) == lane) atomicMin(dp + id[q], v);
+          }
+        }
+      };
+      round(0, 1);
+      round(1, PPT < 4 ? PPT : 4);
+      if (PPT > 4) round(4, PPT);
     } else {
       unsigned long long* keys = reinterpret_cast<unsigned long long*>(a.keys + (long long)t * a.cap);
       int* mp = a.minpos + (long long)t * a.cap;
@@ -232,8 +252,10 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
       }
     }
   }
+  U_STAMP(1);
   target += gridDim.x;
   u_grid_barrier(bar, target, a.err);
+  U_STAMP(2);
 
   // ---- phase B: flags, single-pass scan over the tiles of each segment, ranks, unique ids ----
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -344,8 +366,10 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
     }
     __syncthreads();  // s_cnt / s_excl are reused by the next tile
   }
+  U_STAMP(3);
   target += gridDim.x;
   u_grid_barrier(bar, target, a.err);
+  U_STAMP(4);
 
   // ---- phase C: inverse index ----
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -366,6 +390,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
       if (i < k) inv[i] = rank_at[f[q]];
     }
   }
+  U_STAMP(5);
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // every block took its header snapshot before barrier 1
     if (a.tagged) a.hdr[2] = epoch64 / kUniqEpochs;  // the position arrays are valid for this cycle
     else if (fresh) a.hdr[2] = ~0ULL;

@@ -277,6 +277,9 @@ class DeepFMPSEngine:
         self.bounds = (_ctb.c_int64 * G)(*[int(r) for r in group_rows])  # id ranges: dedup by direct address
         self.ws = torch.zeros(group.lib.b200ps_unique_bounded_workspace(G, B, self.bounds), dtype=torch.uint8, device=dev)
         self._predict_state = None  # predict() dedups into its own workspace / plan (lazy)
+        import os as _os
+
+        self.lookahead_blocks_per_sm = int(_os.environ.get("B200_LOOKAHEAD_UNIQUE_BLOCKS", "1"))
         self.bet_w = torch.zeros((G * B, 1), **f32)
         self.bet_d = torch.zeros((G * B, D), **f32)
         self.act_w = torch.empty((G * B, 1), **f32)
@@ -446,12 +449,14 @@ class DeepFMPSEngine:
         self.steps += 1
         return loss.detach().reshape(())
 
-    def _unique_into(self, ids):
-        """tf.unique per id group into the current plan, on the current stream."""
+    def _unique_into(self, ids, blocks_per_sm=0):
+        """tf.unique per id group into the current plan, on the current stream.  blocks_per_sm > 0: a thin
+        persistent grid (the lookahead pipeline runs the dedup beside the training kernels)."""
         g = self.group
-        fn = g.lib.b200ps_unique_bounded_i32 if ids.dtype == torch.int32 else g.lib.b200ps_unique_bounded
-        check(fn(g._h, ids.data_ptr(), self.G, self.B, self.bounds, self.uniq.data_ptr(), self.inv.data_ptr(),
-                 self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(), g._stream()))
+        check(g.lib.b200ps_unique_bounded_ex(g._h, ids.data_ptr(), 1 if ids.dtype == torch.int32 else 0, self.G, self.B,
+                                             self.bounds, self.uniq.data_ptr(), self.inv.data_ptr(),
+                                             self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                                             int(blocks_per_sm), g._stream()))
 
     # ------------------------------------------------------------------ lookahead pipeline
     def _ensure_plans(self):
@@ -479,7 +484,7 @@ class DeepFMPSEngine:
         self.side.wait_stream(main)  # fork: the other plan's buffers were last read by the previous step
         self._use(1 - p)
         with torch.cuda.stream(self.side):
-            self._unique_into(next_ids)
+            self._unique_into(next_ids, blocks_per_sm=self.lookahead_blocks_per_sm)
         self._use(p)
         loss = self.step(None, dense, labels, ev=ev)
         main.wait_stream(self.side)  # join

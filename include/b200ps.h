@@ -239,6 +239,15 @@ int b200ps_unique(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, int64_
 int b200ps_unique_bounded_i32(b200ps_t* ps, const int32_t* ids32_dev, int T, int64_t k, const int64_t* bounds,
                               int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
                               size_t workspace_bytes, void* stream);
+/* The general form: ids int64 or int32; blocks_per_sm > 0 caps the persistent grid (a caller that overlaps
+ * the dedup with other kernels on a second stream asks for a thin grid, 1 block per SM: the blocks keep
+ * their registers for the whole call); 0 = as many as fit. */
+int b200ps_unique_bounded_ex(b200ps_t* ps, const void* ids_dev, int ids_are_int32, int T, int64_t k, const int64_t* bounds,
+                             int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
+                             size_t workspace_bytes, int blocks_per_sm, void* stream);
+/* Profiling aid: a device buffer (>= 64 B per resident block) that the persistent kernels fill with
+ * %globaltimer stamps per block and phase; NULL switches it off. */
+int b200ps_debug_buffer(void* dev_ptr, size_t bytes);
 /* deduplicate_indexed_slices' sum (tensor_utils.py:39-60) / gather backward:
  * out[t][inv[t][i], :] += values[t][i, :] with warp-level id dedup; out is
  * zeroed first for rows < k. */
