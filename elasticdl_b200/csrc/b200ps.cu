@@ -943,13 +943,14 @@ int b200ps_slot_dense(b200ps_t* ps, int slot, int write, const b200ps_seg_t* seg
   return dense_copy(ps, segs, nseg, stream, write != 0, slot);
 }
 
-static int push_begin_impl(b200ps_t* ps, float lr, const int32_t* mv, void* stream, int bump_only) {
+static int push_begin_impl(b200ps_t* ps, float lr, const int32_t* mv, void* stream, int bump_only, int only_shard = -1) {
   int rc = ready(ps);
   if (rc) return rc;
+  if (only_shard >= ps->n_shards) return fail(B200PS_EINVAL, "bad shard id");
   DeviceGuard g(ps->client_device);
   VersionsIn v{};
   for (int s = 0; s < ps->n_shards; ++s) v.v[s] = mv ? mv[s] : 0;
-  k_push_begin<<<1, 32, 0, (cudaStream_t)stream>>>(group_view(ps), ps->opt, lr, v, ps->staleness, bump_only);
+  k_push_begin<<<1, 32, 0, (cudaStream_t)stream>>>(group_view(ps), ps->opt, lr, v, ps->staleness, bump_only, only_shard);
   ps->launches++;
   CUDA_OK(cudaGetLastError());
   return B200PS_OK;
@@ -959,6 +960,10 @@ int b200ps_push_begin(b200ps_t* ps, float learning_rate, const int32_t* model_ve
   return push_begin_impl(ps, learning_rate, model_versions, stream, 0);
 }
 int b200ps_bump_step(b200ps_t* ps, void* stream) { return push_begin_impl(ps, 0.f, nullptr, stream, 1); }
+int b200ps_push_begin_shard(b200ps_t* ps, int shard, float learning_rate, void* stream) {
+  if (shard < 0) return fail(B200PS_EINVAL, "bad shard id");
+  return push_begin_impl(ps, learning_rate, nullptr, stream, 0, shard);
+}
 
 #define DISPATCH_OPT(KIND, ...)                        \
   switch (KIND) {                                       \
@@ -1218,6 +1223,48 @@ int b200ps_xchg_profile(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_
   return B200PS_OK;
 }
 
+// ---- raw peer-visible buffers + device-side barrier (the allreduce controller's data path) ----
+int b200ps_raw_register(b200ps_t* ps, const char* name, size_t bytes) {
+  if (!ps || !name || bytes < 1) return fail(B200PS_EINVAL, "bad raw buffer definition");
+  std::lock_guard<std::mutex> lk(ps->mu);
+  auto it = ps->by_name.find(name);
+  if (it != ps->by_name.end()) return it->second;
+  Table t;
+  t.name = name;
+  t.dim = 1;
+  t.owner = -1;
+  t.raw = true;
+  t.rows = (int64_t)((bytes + 3) / 4);
+  t.row_stride = 1;
+  t.bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);  // IPC-exportable whole blocks
+  return register_common(ps, std::move(t));
+}
+
+int b200ps_raw_ptr(b200ps_t* ps, int table, int shard, void** ptr, size_t* bytes) {
+  if (!ps || table < 0 || table >= (int)ps->tables.size() || shard < 0 || shard >= ps->n_shards || !ptr)
+    return fail(B200PS_EINVAL, "bad argument");
+  const Table& t = ps->tables[table];
+  if (!t.raw) return fail(B200PS_EINVAL, t.name + " is not a raw buffer");
+  if (!t.alloc[shard].ptr) return fail(B200PS_ESTATE, "shard not attached (sync peers after registering)");
+  *ptr = t.alloc[shard].ptr;
+  if (bytes) *bytes = t.alloc[shard].bytes;
+  return B200PS_OK;
+}
+
+int b200ps_barrier(b200ps_t* ps, void* stream) {
+  int rc = ready(ps);
+  if (rc) return rc;
+  int me = -1, n_local = 0;
+  for (int s = 0; s < ps->n_shards; ++s)
+    if (ps->shard[s].local) { me = s; ++n_local; }
+  if (n_local != 1) return fail(B200PS_ESTATE, "b200ps_barrier needs exactly one local shard per process (rank-per-GPU)");
+  DeviceGuard g(ps->client_device);
+  k_group_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(group_view(ps), me, ps->d_err);
+  ps->launches++;
+  CUDA_OK(cudaGetLastError());
+  return B200PS_OK;
+}
+
 int b200ps_push_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* stream) {
   int rc = ready(ps);
   if (rc) return rc;
@@ -1278,12 +1325,20 @@ int b200ps_push_dense_reduce(b200ps_t* ps, int dense_id, const float* const* gra
   return B200PS_OK;
 }
 
+static int push_end_impl(b200ps_t* ps, int32_t* versions_out_host, void* stream, int only_shard);
 int b200ps_push_end(b200ps_t* ps, int32_t* versions_out_host, void* stream) {
+  return push_end_impl(ps, versions_out_host, stream, -1);
+}
+int b200ps_push_end_shard(b200ps_t* ps, int shard, void* stream) {
+  if (!ps || shard < 0 || shard >= ps->n_shards) return fail(B200PS_EINVAL, "bad shard id");
+  return push_end_impl(ps, nullptr, stream, shard);
+}
+static int push_end_impl(b200ps_t* ps, int32_t* versions_out_host, void* stream, int only_shard) {
   int rc = ready(ps);
   if (rc) return rc;
   DeviceGuard g(ps->client_device);
   cudaStream_t st = (cudaStream_t)stream;
-  k_push_end<<<1, 32, 0, st>>>(group_view(ps), ps->d_versions);
+  k_push_end<<<1, 32, 0, st>>>(group_view(ps), ps->d_versions, only_shard);
   ps->launches++;
   CUDA_OK(cudaGetLastError());
   if (versions_out_host)
@@ -1378,7 +1433,7 @@ size_t b200ps_unique_bounded_workspace(int T, int64_t k, const int64_t* bounds) 
 }
 
 // Look-back descriptors are sized for the smallest tile (256 x 4 positions).
-constexpr int kUMinTile = kUThreads * 4;
+constexpr int kUMinTile = kUUnit;
 
 size_t b200ps_unique_workspace(int T, int64_t k) {
   if (T < 1 || k < 1) return 256;
@@ -1412,7 +1467,7 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   static int sms[64] = {0};
   if (dev < 64 && occ[dev] == 0) {
     int o = 0, n = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_unique<16>, kUThreads, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_unique, kUThreads, 0));
     CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     occ[dev] = o < 1 ? 1 : (o > 4 ? 4 : o);
     sms[dev] = n < 1 ? 1 : n;
@@ -1421,14 +1476,7 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   // a caller that overlaps the dedup with other kernels (lookahead pipeline) asks for a thin grid: the
   // persistent blocks hold their registers for the whole call, including the time spent at the grid barriers
   if (blocks_per_sm > 0 && dev < 64 && (long long)blocks_per_sm * sms[dev] < max_blocks) max_blocks = (long long)blocks_per_sm * sms[dev];
-  // smallest tile for which every phase is a single pass over the grid
-  int ppt = 16;
-  for (int cand : {4, 8, 12}) {
-    const long long tl = (k + (long long)kUThreads * cand - 1) / ((long long)kUThreads * cand);
-    if ((long long)T * tl <= max_blocks) { ppt = cand; break; }
-  }
-  a.ppt = ppt;
-  a.ntiles = (int)((k + (long long)kUThreads * ppt - 1) / ((long long)kUThreads * ppt));
+  a.ntiles = (int)((k + kUUnit - 1) / kUUnit);  // units per segment
   char* p = (char*)workspace_dev;
   a.keys = (long long*)p; p += align256((size_t)T * a.cap * 8);
   a.minpos = (int*)p; p += align256((size_t)T * a.cap * 4);
@@ -1456,16 +1504,37 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   a.n_unique = n_unique_dev;
   a.err = ps ? ps->d_err : nullptr;
   a.dbg = (g_dbg_buf && g_dbg_bytes >= (size_t)max_blocks * 64) ? g_dbg_buf : nullptr;
-  const long long tiles = (long long)T * a.ntiles;
-  long long blocks = tiles < max_blocks ? tiles : max_blocks;
+  // block -> run of units: sparse / hashed segments (an atomic and two uncached sector reads per position) one
+  // unit per block, segments with a tiny id range (cache-resident, mostly duplicates) four times as many
+  URuns ur{};
+  const long long ups = a.ntiles;
+  long long blocks = 0;
+  if (T <= kMaxSegs) {
+    ur.per_seg = 1;
+    for (long long rh = 1;; rh += (rh < 8 ? 1 : rh / 4)) {
+      const long long rl = rh * 4;
+      blocks = 0;
+      for (int t = 0; t < T; ++t) {
+        const bool light = a.use_bounds && a.ub.bound[t] > 0 && (long long)a.ub.bound[t] * 2 < k;
+        long long r = light ? rl : rh;
+        if (r > ups) r = ups;
+        ur.run[t] = (int)r;
+        ur.blk_prefix[t] = (int)blocks;
+        blocks += (ups + r - 1) / r;
+      }
+      ur.blk_prefix[T] = (int)blocks;
+      if (blocks <= max_blocks || rh >= ups) break;
+    }
+  } else {
+    ur.per_seg = 0;
+    const long long units = (long long)T * ups;
+    ur.uniform_run = (int)((units + max_blocks - 1) / max_blocks);
+    if (ur.uniform_run < 1) ur.uniform_run = 1;
+    blocks = (units + ur.uniform_run - 1) / ur.uniform_run;
+  }
   if (blocks < 1) blocks = 1;
   CUDA_OK(cudaMemsetAsync(a.hdr + 4, 0, 8, st));  // the grid-barrier counter
-  switch (ppt) {
-    case 4: k_unique<4><<<(unsigned)blocks, kUThreads, 0, st>>>(a); break;
-    case 8: k_unique<8><<<(unsigned)blocks, kUThreads, 0, st>>>(a); break;
-    case 12: k_unique<12><<<(unsigned)blocks, kUThreads, 0, st>>>(a); break;
-    default: k_unique<16><<<(unsigned)blocks, kUThreads, 0, st>>>(a); break;
-  }
+  k_unique<<<(unsigned)blocks, kUThreads, 0, st>>>(a, ur);
   count_launch(ps, 1);
   CUDA_OK(cudaGetLastError());
   return B200PS_OK;

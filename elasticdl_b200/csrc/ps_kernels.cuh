@@ -634,9 +634,10 @@ struct VersionsIn {
 };
 
 __global__ void k_push_begin(GroupView gv, OptParams o, float learning_rate, VersionsIn mv,
-                             int staleness_modulation, int bump_only) {
+                             int staleness_modulation, int bump_only, int only_shard) {
   int s = threadIdx.x;
   if (s >= gv.n_shards) return;
+  if (only_shard >= 0 && s != only_shard) return;  // an ApplyGradients that reaches one shard only
   ShardCtl* ctl = gv.ctl[s];
   long long step = (long long)atomicAdd_system((unsigned long long*)&ctl->step, 1ULL) + 1;  // optimizer.go:44
   if (bump_only) return;
@@ -653,9 +654,13 @@ __global__ void k_push_begin(GroupView gv, OptParams o, float learning_rate, Ver
   rt->l2adj[s] = o.beta != 0.0f ? add(o.l2, fdiv(o.beta, mul(2.0f, lr))) : o.l2;
 }
 
-__global__ void k_push_end(GroupView gv, int* versions_out) {
+__global__ void k_push_end(GroupView gv, int* versions_out, int only_shard) {
   int s = threadIdx.x;
   if (s >= gv.n_shards) return;
+  if (only_shard >= 0 && s != only_shard) {
+    if (versions_out) versions_out[s] = *(volatile int*)&gv.ctl[s]->version;
+    return;
+  }
   int v = atomicAdd_system(&gv.ctl[s]->version, 1) + 1;  // server.go:196-199
   gv.rt->version[s] = v;
   if (versions_out) versions_out[s] = v;
@@ -668,6 +673,30 @@ __global__ void k_snapshot(GroupView gv, long long* out) {
   out[3 * s + 0] = c->version;
   out[3 * s + 1] = c->step;
   out[3 * s + 2] = c->initialized == 1 ? 1 : 0;
+}
+
+// Device-side barrier of a rank-per-GPU group: every rank adds 1 to the counter in EVERY shard's control
+// block (system-scope atomics over NVLink) and waits until its own counter shows all N arrivals of this
+// epoch.  Kernels launched before it on the stream have completed (their writes are in the owner's L2,
+// where peer reads are served), kernels after it see every peer's pre-barrier writes.  Bounded spin.
+__global__ void k_group_barrier(GroupView gv, int me, unsigned* err) {
+  __shared__ int s_epoch;
+  if (threadIdx.x == 0) s_epoch = ++gv.ctl[me]->bar_epoch;
+  __syncwarp();
+  __threadfence_system();
+  if ((int)threadIdx.x < gv.n_shards) atomicAdd_system(&gv.ctl[threadIdx.x]->bar_count, 1);
+  if (threadIdx.x == 0) {
+    const int target = s_epoch * gv.n_shards;
+    long long spins = 0;
+    while (*(volatile int*)&gv.ctl[me]->bar_count < target) {
+      __nanosleep(100);
+      if (++spins > (1LL << 24)) {
+        atomicOr(err, 8u /* kErrTimeout */);
+        break;
+      }
+    }
+  }
+  __threadfence_system();
 }
 
 // initialized: 0 = no, 2 = a writer holds the claim, 1 = yes (server.go:209-221)

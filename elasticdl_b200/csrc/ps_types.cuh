@@ -60,7 +60,9 @@ struct ShardCtl {
   int version;
   int initialized;
   unsigned err;
-  int pad[11];
+  int bar_count;  // b200ps_barrier: arrivals (every rank adds 1 to every shard's counter per barrier)
+  int bar_epoch;  // b200ps_barrier: barriers this shard's owner has entered
+  int pad[9];
 };
 
 // Per-push values produced by k_push_begin, consumed by the update kernels.

@@ -54,7 +54,6 @@ struct UArgs {
   unsigned long long* hdr;
   unsigned long long magic;
   int cap, ntiles, tagged, use_bounds, n_direct, n_hashed;
-  int ppt;                      // positions per thread of a tile (4, 8, 12 or 16)
   UniqueBounds ub;
   int64_t* uniq;
   int* inv;
@@ -105,16 +104,28 @@ __device__ __forceinline__ unsigned long long u_word(unsigned tag, unsigned flag
   return ((unsigned long long)((tag << 2) | flag) << 32) | value;
 }
 
-// PPT = positions per thread of a tile (tile = 256 * PPT positions of one segment; thread tid owns the
-// positions q*256 + tid, so every global access of a warp is coalesced).  The host picks the smallest
-// PPT for which the launch is a single pass (tiles <= resident blocks): every phase is then ONE
-// dependent chain with PPT independent loads in flight per thread.
-template <int PPT>
-__global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
+// Work unit = 1024 consecutive positions of one segment (256 threads x 4; thread tid owns positions
+// q*256 + tid, so every global access of a warp is coalesced).  A block takes a RUN of consecutive units of
+// one segment (host-built map): segments whose ids are mostly distinct -- large tables: every position
+// costs an atomic and two uncached 32 B sector reads -- get one unit per block, segments with tiny id
+// ranges -- cache-resident position arrays, almost every position a duplicate -- several, so that all
+// blocks of a phase finish together (timeline, profiles/r2_04: with equal tiles the large-table blocks
+// took 2.4x the median and every other block waited at the grid barrier).
+constexpr int kUPPT = 4;
+constexpr int kUUnit = kUThreads * kUPPT;  // 1024
+
+struct URuns {                     // block -> run of units
+  int blk_prefix[kMaxSegs + 1];    // per-segment map (T <= kMaxSegs): first block of segment t
+  int run[kMaxSegs];               // units per block of segment t
+  int per_seg;                     // 1: the map above; 0: every block takes `uniform_run` units of the flat unit space
+  int uniform_run;
+};
+
+__global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
   constexpr int NW = kUThreads / 32;
-  constexpr int TILE = kUThreads * PPT;
+  constexpr int PPT = kUPPT;
   __shared__ int s_cnt[PPT * NW];  // first-occurrence counts per (q, warp), then their exclusive prefix
-  __shared__ int s_excl, s_tot;
+  __shared__ int s_excl;
   // header snapshot: stable until block 0 rewrites it after the last barrier
   const bool fresh = a.hdr[0] != a.magic;
   const unsigned long long epoch64 = fresh ? 0ULL : a.hdr[1];
@@ -131,13 +142,33 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
   const unsigned lt_mask = (1u << lane) - 1u;
   const long long k = a.k;
   const int T = a.T;
-  const long long tiles = (long long)T * a.ntiles;
+  const int ups = a.ntiles;  // units per segment
+  const long long units = (long long)T * ups;
+
+  // this block's run of units [g0, g0 + gcnt) in the flat unit space (g = t * ups + u)
+  long long g0;
+  int gcnt;
+  if (ur.per_seg) {
+    int lo = 0, hi = T;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (ur.blk_prefix[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    const int r = ur.run[lo];
+    const int u0 = ((int)blockIdx.x - ur.blk_prefix[lo]) * r;
+    g0 = (long long)lo * ups + u0;
+    gcnt = u0 < ups ? (ups - u0 < r ? ups - u0 : r) : 0;
+  } else {
+    g0 = (long long)blockIdx.x * ur.uniform_run;
+    const long long left = units - g0;
+    gcnt = left <= 0 ? 0 : (left < ur.uniform_run ? (int)left : ur.uniform_run);
+  }
 
   // ---- phase 0: clear what this call cannot read as empty ----
   const bool clear_direct = a.n_direct > 0 && (!a.tagged || stale_cycle);
   if (a.n_hashed > 0 || clear_direct || fresh) {
     if (fresh) {  // descriptors of a foreign layout could carry this call's tag
-      for (long long i = gtid; i < tiles; i += gsz) a.status[i] = 0ULL;
+      for (long long i = gtid; i < units; i += gsz) a.status[i] = 0ULL;
     }
     if (a.n_hashed > 0 || clear_direct) {
       if (!a.use_bounds) {
@@ -166,18 +197,22 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
     target += gridDim.x;
     u_grid_barrier(bar, target, a.err);
   }
-
   U_STAMP(0);
+
   // ---- phase A: insert.  position array entry of every id <- min(position) ----
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int t = (int)(tile / a.ntiles);
-    const long long base = (tile - (long long)t * a.ntiles) * TILE;
+  for (int gi = 0; gi < gcnt; ++gi) {
+    const long long g = g0 + gi;
+    const int t = (int)(g / ups);
+    const long long base = (g - (long long)t * ups) * kUUnit;
     const bool direct = a.use_bounds && a.ub.bound[t] > 0;
     int* fp = a.fp + (long long)t * k;
     if (direct) {
       int* dp = a.ub.dpos + a.ub.off[t];
       const int bound = a.ub.bound[t];
-      int id[PPT];  // bounded ids fit 32 bits
+      // probing first only pays when most positions are duplicates (small id range); for sparse segments
+      // the probe is one more uncached sector read per position and almost never saves the atomic
+      const bool probe = (long long)bound * 2 < k;
+      int id[PPT], cur[PPT];  // bounded ids fit 32 bits
 #pragma unroll
       for (int q = 0; q < PPT; ++q) {  // all id loads first
         const long long i = base + q * kUThreads + threadIdx.x;
@@ -185,70 +220,55 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
         id[q] = (v < 0 || v >= bound) ? 0 : (int)v;  // out-of-range ids are reported by the table kernels
         if (i < k) fp[i] = id[q];
       }
-      // probes, then atomics, in three rounds (positions q = 0 | 1..3 | the rest): a hot id (small tables,
-      // Zipf heads) occurs in every warp of every tile, and only a probe issued AFTER an earlier, smaller
-      // position has landed can skip its atomic -- with all probes up front every occurrence queued on
-      // the same address (ncu: the slowest block's queue was a third of the kernel).
-      auto round = [&](const int q0, const int q1) {
-        int cur[PPT];
 #pragma unroll
-        for (int q = 0; q < PPT; ++q) {
-          if (q < q0 || q >= q1) continue;
-          const long long i = base + q * kUThreads + threadIdx.x;
-          cur[q] = i < k ? *(volatile int*)(dp + id[q]) : 0;
-        }
+      for (int q = 0; q < PPT; ++q) {
+        const long long i = base + q * kUThreads + threadIdx.x;
+        cur[q] = (probe && i < k) ? *(volatile int*)(dp + id[q]) : 0x7fffffff;
+      }
 #pragma unroll
-        for (int q = 0; q < PPT; ++q) {
-          if (q < q0 || q >= q1) continue;
-          const long long i = base + q * kUThreads + threadIdx.x;
-          const int v = prefix | (int)i;
-          // warp-level id dedup among the lanes that would write: equal ids elect their lowest lane
-          // (= smallest position)
-          const bool want = i < k && cur[q] > v;
-          const unsigned wm = __ballot_sync(0xffffffffu, want);
-          if (wm) {
-            const unsigned peers = __match_any_sync(0xffffffffu, want ? id[q] : -1 - lane) & wm;
-            if (want && (__ffs(peers) - 1) == lane) atomicMin(dp + id[q], v);
-          }
+      for (int q = 0; q < PPT; ++q) {
+        const long long i = base + q * kUThreads + threadIdx.x;
+        const int v = prefix | (int)i;
+        // warp-level id dedup among the lanes that would write: equal ids elect their lowest lane
+        // (= smallest position); later units of this block see what the earlier ones recorded
+        const bool want = i < k && cur[q] > v;
+        const unsigned wm = __ballot_sync(0xffffffffu, want);
+        if (wm) {
+          const unsigned peers = __match_any_sync(0xffffffffu, want ? id[q] : -1 - lane) & wm;
+          if (want && (__ffs(peers) - 1) == lane) atomicMin(dp + id[q], v);
         }
-      };
-      round(0, 1);
-      round(1, PPT < 4 ? PPT : 4);
-      if (PPT > 4) round(4, PPT);
+      }
     } else {
       unsigned long long* keys = reinterpret_cast<unsigned long long*>(a.keys + (long long)t * a.cap);
       int* mp = a.minpos + (long long)t * a.cap;
       const unsigned mask = a.cap - 1;
-#pragma unroll 1
-      for (int q0 = 0; q0 < PPT; q0 += 4) {
-        long long id[4];
+      long long id[PPT];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const long long i = base + (q0 + u) * kUThreads + threadIdx.x;
-          id[u] = i < k ? u_id(a, (long long)t * k + i) : 0;
-        }
+      for (int q = 0; q < PPT; ++q) {
+        const long long i = base + q * kUThreads + threadIdx.x;
+        id[q] = i < k ? u_id(a, (long long)t * k + i) : 0;
+      }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const long long i = base + (q0 + u) * kUThreads + threadIdx.x;
-          const bool live = i < k;
-          const unsigned livem = __ballot_sync(0xffffffffu, live);  // dead lanes (ragged tail) never match
-          const unsigned peers = __match_any_sync(0xffffffffu, id[u]) & livem;
-          const int leader = live ? __ffs(peers) - 1 : lane;
-          unsigned sl = 0;
-          if (live && lane == leader) {
-            sl = (unsigned)mix64((uint64_t)id[u]) & mask;
-            while (true) {
-              unsigned long long prev = keys[sl];
-              if (prev == (unsigned long long)kEmptyKey)
-                prev = atomicCAS(&keys[sl], (unsigned long long)kEmptyKey, (unsigned long long)id[u]);
-              if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)id[u]) break;
-              sl = (sl + 1) & mask;
-            }
-            if (*(volatile int*)&mp[sl] > (int)i) atomicMin(&mp[sl], (int)i);
+      for (int q = 0; q < PPT; ++q) {
+        const long long i = base + q * kUThreads + threadIdx.x;
+        const bool live = i < k;
+        const unsigned livem = __ballot_sync(0xffffffffu, live);  // dead lanes (ragged tail) never match
+        const unsigned peers = __match_any_sync(0xffffffffu, id[q]) & livem;
+        const int leader = live ? __ffs(peers) - 1 : lane;
+        unsigned sl = 0;
+        if (live && lane == leader) {
+          sl = (unsigned)mix64((uint64_t)id[q]) & mask;
+          while (true) {
+            unsigned long long prev = keys[sl];
+            if (prev == (unsigned long long)kEmptyKey)
+              prev = atomicCAS(&keys[sl], (unsigned long long)kEmptyKey, (unsigned long long)id[q]);
+            if (prev == (unsigned long long)kEmptyKey || prev == (unsigned long long)id[q]) break;
+            sl = (sl + 1) & mask;
           }
-          sl = __shfl_sync(0xffffffffu, sl, leader);
-          if (live) fp[i] = (int)sl;
+          if (*(volatile int*)&mp[sl] > (int)i) atomicMin(&mp[sl], (int)i);
         }
+        sl = __shfl_sync(0xffffffffu, sl, leader);
+        if (live) fp[i] = (int)sl;
       }
     }
   }
@@ -257,11 +277,12 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
   u_grid_barrier(bar, target, a.err);
   U_STAMP(2);
 
-  // ---- phase B: flags, single-pass scan over the tiles of each segment, ranks, unique ids ----
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int t = (int)(tile / a.ntiles);
-    const long long j = tile - (long long)t * a.ntiles;
-    const long long base = j * TILE;
+  // ---- phase B: flags, single-pass scan over the units of each segment, ranks, unique ids ----
+  for (int gi = 0; gi < gcnt; ++gi) {
+    const long long g = g0 + gi;
+    const int t = (int)(g / ups);
+    const long long j = g - (long long)t * ups;
+    const long long base = j * kUUnit;
     const bool direct = a.use_bounds && a.ub.bound[t] > 0;
     const int* mp = direct ? a.ub.dpos + a.ub.off[t] : a.minpos + (long long)t * a.cap;
     const int pm = direct ? pos_mask : 0x7fffffff;
@@ -277,52 +298,41 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
       const long long i = base + q * kUThreads + threadIdx.x;
       v[q] = i < k ? (mp[v[q]] & pm) : -1;
     }
-    unsigned fmask = 0;                   // bit q: position q*256 + tid is a first occurrence
-    unsigned long long wr[2] = {0ULL, 0ULL};  // 5 bits per q: first occurrences among the lower lanes, same q
+    unsigned fmask = 0;  // bit q: position q*256 + tid is a first occurrence
+    int wrank[PPT];      // first occurrences among the lower lanes of the warp, same q
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
       const long long i = base + q * kUThreads + threadIdx.x;
       const bool f = i < k && v[q] == (int)i;
-      if (i < k) fp[i] = v[q];
+      // duplicates keep the first position of their id (phase C looks its rank up); first occurrences
+      // get their inverse index right here and are marked done
+      if (i < k && !f) fp[i] = v[q];
       const unsigned bal = __ballot_sync(0xffffffffu, f);
-      wr[q / 12] |= (unsigned long long)__popc(bal & lt_mask) << (5 * (q % 12));
+      wrank[q] = __popc(bal & lt_mask);
       if (f) fmask |= 1u << q;
       if (lane == 0) s_cnt[q * NW + wid] = __popc(bal);
     }
     __syncthreads();
-    if (wid == 0) {  // exclusive scan of the PPT*NW counts (position order = q major, warp minor)
-      constexpr int PER = (PPT * NW + 31) / 32;
-      int cv[PER], sum = 0;
-#pragma unroll
-      for (int e = 0; e < PER; ++e) {
-        const int idx = lane * PER + e;
-        cv[e] = idx < PPT * NW ? s_cnt[idx] : 0;
-        sum += cv[e];
-      }
-      int incl = sum;
+    if (wid == 0) {  // exclusive scan of the PPT*NW = 32 counts (position order = q major, warp minor)
+      const int c = s_cnt[lane];
+      int incl = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int y = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += y;
       }
-      int run = incl - sum;
-#pragma unroll
-      for (int e = 0; e < PER; ++e) {
-        const int idx = lane * PER + e;
-        if (idx < PPT * NW) s_cnt[idx] = run;
-        run += cv[e];
-      }
+      s_cnt[lane] = incl - c;
       const int tot = __shfl_sync(0xffffffffu, incl, 31);
-      if (lane == 0) u_stv(&a.status[tile], u_word(tag, j == 0 ? kUFlagP : kUFlagA, (unsigned)tot));
+      if (lane == 0) u_stv(&a.status[g], u_word(tag, j == 0 ? kUFlagP : kUFlagA, (unsigned)tot));
       int excl = 0;
-      long long look = j - 1;  // predecessor tiles of this segment, nearest first, 32 at a time
+      long long look = j - 1;  // predecessor units of this segment, nearest first, 32 at a time
       long long spins = 0;
       while (look >= 0) {
         const long long idx = look - lane;
         bool valid = true;  // lanes before the segment start count as an exclusive prefix of 0
         unsigned flag = kUFlagP, val = 0;
         if (idx >= 0) {
-          const unsigned long long wv = u_ldv(&a.status[(long long)t * a.ntiles + idx]);
+          const unsigned long long wv = u_ldv(&a.status[(long long)t * ups + idx]);
           const unsigned hi = (unsigned)(wv >> 32);
           valid = (hi >> 2) == tag && (hi & 3u) != 0;
           flag = hi & 3u;
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
           continue;
         }
         const unsigned pmask = __ballot_sync(0xffffffffu, flag == kUFlagP);
-        const int stop = pmask ? __ffs(pmask) - 1 : 31;  // nearest tile that already knows its inclusive prefix
+        const int stop = pmask ? __ffs(pmask) - 1 : 31;  // nearest unit that already knows its inclusive prefix
         int contrib = lane <= stop ? (int)val : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
@@ -347,34 +357,37 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
       }
       if (lane == 0) {
         s_excl = excl;
-        s_tot = tot;
-        if (j > 0) u_stv(&a.status[tile], u_word(tag, kUFlagP, (unsigned)(excl + tot)));
-        if (j == a.ntiles - 1) a.n_unique[t] = excl + tot;
+        if (j > 0) u_stv(&a.status[g], u_word(tag, kUFlagP, (unsigned)(excl + tot)));
+        if (j == ups - 1) a.n_unique[t] = excl + tot;
       }
     }
     __syncthreads();
     const int excl = s_excl;
     int* rank_at = a.rank_at + (long long)t * k;
+    int* inv = a.inv + (long long)t * k;
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
       if (fmask >> q & 1u) {
         const long long i = base + q * kUThreads + threadIdx.x;
-        const int r = excl + s_cnt[q * NW + wid] + (int)(wr[q / 12] >> (5 * (q % 12)) & 31ULL);
+        const int r = excl + s_cnt[q * NW + wid] + wrank[q];
         rank_at[i] = r;
+        inv[i] = r;
+        fp[i] = -1;  // done: phase C skips it
         a.uniq[(long long)t * k + r] = u_id(a, (long long)t * k + i);
       }
     }
-    __syncthreads();  // s_cnt / s_excl are reused by the next tile
+    __syncthreads();  // s_cnt / s_excl are reused by the next unit
   }
   U_STAMP(3);
   target += gridDim.x;
   u_grid_barrier(bar, target, a.err);
   U_STAMP(4);
 
-  // ---- phase C: inverse index ----
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int t = (int)(tile / a.ntiles);
-    const long long base = (tile - (long long)t * a.ntiles) * TILE;
+  // ---- phase C: inverse index of the duplicates = rank of their id's first occurrence ----
+  for (int gi = 0; gi < gcnt; ++gi) {
+    const long long g = g0 + gi;
+    const int t = (int)(g / ups);
+    const long long base = (g - (long long)t * ups) * kUUnit;
     const int* fp = a.fp + (long long)t * k;
     const int* rank_at = a.rank_at + (long long)t * k;
     int* inv = a.inv + (long long)t * k;
@@ -382,12 +395,12 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a) {
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
       const long long i = base + q * kUThreads + threadIdx.x;
-      f[q] = i < k ? fp[i] : 0;
+      f[q] = i < k ? fp[i] : -1;
     }
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
       const long long i = base + q * kUThreads + threadIdx.x;
-      if (i < k) inv[i] = rank_at[f[q]];
+      if (f[q] >= 0) inv[i] = rank_at[f[q]];
     }
   }
   U_STAMP(5);

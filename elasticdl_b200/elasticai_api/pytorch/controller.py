@@ -55,15 +55,33 @@ def broadcast_object(obj, root_rank=0, name=None):
 
 
 def broadcast_optimizer_state(optimizer, root_rank=0):
-    """Tensors of the optimizer state are broadcast flat; scalars (step counts, lr ...) as an object."""
+    """Tensors of the optimizer state are broadcast flat; scalars (step counts, lr ...) as an object.
+    A rank whose optimizer holds no (or less) state than the root -- an elastic joiner, or a rank whose
+    warm-up call did not step -- first materialises the root's entries (the Horovod original does the
+    same before broadcasting), so every rank enters the same collectives."""
     if comm_size() <= 1:
         return
     sd = optimizer.state_dict()
-    meta = broadcast_object({"param_groups": sd["param_groups"],
-                             "keys": {k: sorted(v.keys(), key=str) for k, v in sd["state"].items()}}, root_rank)
+    layout = {pid: {k: ((tuple(v.shape), str(v.dtype).replace("torch.", "")) if isinstance(v, torch.Tensor) else None)
+                    for k, v in st.items()} for pid, st in sd["state"].items()}
+    meta = broadcast_object({"param_groups": sd["param_groups"], "layout": layout}, root_rank)
+    if comm_rank() != root_rank:
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        for pid, entries in meta["layout"].items():
+            st = sd["state"].setdefault(pid, {})
+            dev = params[pid].device if isinstance(pid, int) and pid < len(params) else torch.device("cpu")
+            for k, spec in entries.items():
+                if spec is not None and not isinstance(st.get(k), torch.Tensor):
+                    st[k] = torch.zeros(spec[0], dtype=getattr(torch, spec[1]), device=dev)
+                elif spec is None:
+                    st.setdefault(k, None)
+        for pid in [q for q in sd["state"] if q not in meta["layout"]]:
+            del sd["state"][pid]
     tensors, scalars = [], {}
-    for pid, st in sd["state"].items():
-        for k, v in st.items():
+    for pid in sorted(sd["state"], key=str):
+        st = sd["state"][pid]
+        for k in sorted(st, key=str):
+            v = st[k]
             if isinstance(v, torch.Tensor):
                 tensors.append(v)
             else:
@@ -106,6 +124,9 @@ class PyTorchAllReduceController(AllReduceController):
     def broadcast(self):  # controller.py:126-131
         broadcast_parameters(self._model.state_dict(), root_rank=0)
         broadcast_optimizer_state(self._optimizer, root_rank=0)
+        ps = getattr(self._optimizer, "_ps", None)
+        if ps is not None:  # fused mode: the master copy of the parameters lives on the PS shards
+            ps.load_params()
         self.global_completed_batch_num = broadcast_object(self.global_completed_batch_num,
                                                            name="GlobalCompletedBatchNum")
 

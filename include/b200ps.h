@@ -198,6 +198,23 @@ int b200ps_push_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* st
 int b200ps_push_dense_reduce(b200ps_t* ps, int dense_id, const float* const* grads_dev,
                              int n_replicas, float scale, void* stream);
 int b200ps_push_end(b200ps_t* ps, int32_t* versions_out_host, void* stream);
+/* begin / end that reach ONE shard only: the owner-side ApplyGradients of the allreduce controller's fused
+ * reduce + update (every rank updates the slice it owns exactly once per step). */
+int b200ps_push_begin_shard(b200ps_t* ps, int shard, float learning_rate, void* stream);
+int b200ps_push_end_shard(b200ps_t* ps, int shard, void* stream);
+
+/* ---- the dense allreduce controller's data path (rank-per-GPU groups) ----------------------------
+ * Replaces the Horovod collectives of elasticai_api/pytorch/optimizer.py:141-168 + the wrapped optimizer's
+ * step: every rank keeps its flat gradient bucket in a RAW buffer that the peers map (CUDA IPC); the owner
+ * of parameter slice s runs b200ps_push_dense_reduce with the N peer pointers -- the reduce-scatter, the
+ * averaging and the in-place optimizer update are ONE kernel that reads the peers' gradients over NVLink --
+ * and every rank then reads the updated slices back with b200ps_pull_dense (the all-gather).  b200ps_barrier
+ * orders the phases on the device (flags in the peer-mapped shard control blocks; no host round trip, no NCCL).
+ * raw_register: a zero-filled allocation of `bytes` on every local shard, exported with the shard; returns its
+ * id (shares the table id space).  raw_ptr: its address on `shard` as mapped on the client device. */
+int b200ps_raw_register(b200ps_t* ps, const char* name, size_t bytes);
+int b200ps_raw_ptr(b200ps_t* ps, int table, int shard, void** ptr, size_t* bytes);
+int b200ps_barrier(b200ps_t* ps, void* stream);
 /* step++ only (a failed ApplyGradients still bumps it, quirk Q2). */
 int b200ps_bump_step(b200ps_t* ps, void* stream);
 

@@ -66,6 +66,36 @@ def main():
         dist.all_reduce(mean)
         mean /= world
         assert torch.allclose(p1.detach(), p0 - 0.1 * mean, atol=1e-6), "averaged gradient != mean over ranks"
+    # ---- fused mode: reduce-scatter + averaging + momentum update in one kernel over peer memory ----------
+    import numpy as np
+
+    from oracle import ps_oracle as O
+
+    torch.manual_seed(77)  # same initial model on every rank
+    fmodel = torch.nn.Sequential(torch.nn.Linear(40, 33), torch.nn.Tanh(), torch.nn.Linear(33, 3)).to(dev)
+    fopt = DistributedOptimizer(torch.optim.SGD(fmodel.parameters(), lr=0.05, momentum=0.9, nesterov=True),
+                                named_parameters=fmodel.named_parameters(), fused=True)
+    assert fopt._ps is not None, "fused backend was not selected"
+    want_p = [p.detach().cpu().numpy().copy() for p in fmodel.parameters()]
+    want_v = [np.zeros_like(w) for w in want_p]
+    for step in range(3):
+        gx = torch.Generator(device=dev).manual_seed(900 + 10 * step + rank)
+        xb, yb = torch.randn(8, 40, device=dev, generator=gx), torch.randn(8, 3, device=dev, generator=gx)
+        fopt.zero_grad()
+        ((fmodel(xb) - yb) ** 2).mean().backward()
+        mine = [p.grad.detach().clone() for p in fmodel.parameters()]
+        fopt.step()
+        for i, gl in enumerate(mine):
+            allg = [torch.empty_like(gl) for _ in range(world)]
+            dist.all_gather(allg, gl)
+            acc = allg[0].cpu().numpy().astype(np.float32).copy()
+            for r in range(1, world):  # the kernel sums the ranks in rank order
+                acc = (acc + allg[r].cpu().numpy()).astype(np.float32)
+            g_avg = (acc * np.float32(1.0 / world)).astype(np.float32)
+            O.np_momentum(g_avg.reshape(-1), want_p[i].reshape(-1), want_v[i].reshape(-1), 0.9, True, 0.05)
+        for w, p in zip(want_p, fmodel.parameters()):
+            assert np.array_equal(w, p.detach().cpu().numpy()), "fused reduce+update differs from the oracle (step %d)" % step
+    fopt._ps.group.check()
     # ---- config 4 timing: one-bucket allreduce of ResNet-50-sized gradients + fused momentum update ----
     shapes = resnet50_like_shapes()
     params = [torch.nn.Parameter(torch.zeros(s, device=dev)) for s in shapes]

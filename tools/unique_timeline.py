@@ -51,6 +51,12 @@ def main():
             for j, nm in enumerate(names):
                 col = (t[:, j] - t0) / 1e3
                 out[nm] = [round(float(col.min()), 1), round(float(np.median(col)), 1), round(float(col.max()), 1)]
+            # which blocks are the slow ones: blocks are laid out segment by segment
+            dur = (t[:, 1] - t[:, 0]) / 1e3
+            order = np.argsort(-dur)[:5]
+            out["slowest_A_blocks"] = [[int(i), round(float(dur[i]), 1)] for i in order]
+            durb = (t[:, 3] - t[:, 2]) / 1e3
+            out["slowest_B_blocks"] = [[int(i), round(float(durb[i]), 1)] for i in np.argsort(-durb)[:5]]
             print(json.dumps(out))
 
 
