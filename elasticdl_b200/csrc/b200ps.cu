@@ -1526,12 +1526,17 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
       if (blocks <= max_blocks || rh >= ups) break;
     }
   } else {
+    // many segments: equal runs; once there are more segments than resident blocks, one slot per segment
     ur.per_seg = 0;
-    const long long units = (long long)T * ups;
-    ur.uniform_run = (int)((units + max_blocks - 1) / max_blocks);
-    if (ur.uniform_run < 1) ur.uniform_run = 1;
-    blocks = (units + ur.uniform_run - 1) / ur.uniform_run;
+    long long r = 1;
+    while (r < ups && (long long)T * ((ups + r - 1) / r) > max_blocks) r += (r < 8 ? 1 : r / 4);
+    if (r > ups) r = ups;
+    ur.uniform_run = (int)r;
+    ur.bps = (int)((ups + r - 1) / r);
+    blocks = (long long)T * ur.bps;
   }
+  ur.nslots = (int)blocks;
+  if (blocks > max_blocks) blocks = max_blocks;  // the grid walks the slots (slot = block, block + grid, ...)
   if (blocks < 1) blocks = 1;
   CUDA_OK(cudaMemsetAsync(a.hdr + 4, 0, 8, st));  // the grid-barrier counter
   k_unique<<<(unsigned)blocks, kUThreads, 0, st>>>(a, ur);

@@ -4,8 +4,8 @@
 // kernel) with one dependent global gather chain per lane at ~20 % occupancy: 113 us of a 198 us
 // step.  Here a CTA owns a tile of 32 samples and gathers the tile's 38 x 32 rows ONCE, with
 // cp.async (16 B, L2 -> shared memory, no registers held while in flight), into
-//     X[s] = [ deep 38 x 8 | dense 13 | 1 (bias column) | 0 0 | wide 38 | pad ]     (row stride 364 floats:
-//            91 x 16 B, odd, so a warp's 32 rows are bank-conflict free for 128-bit reads)
+//     X[s] = [ deep 38 x 8 | dense 13 | 1 (bias column) | 0 0 | pad ]     (row stride 324 floats = 81 x 16 B,
+//            odd, so a warp's 32 rows are bank-conflict free for 128-bit reads; wide values in WV[g][s])
 // and everything else -- H1 = X W1x, the FM sums, the per-sample middle, dX = dH1 W1x^T + FM term with the
 // per-unique-id reduction, dW1x += dH1^T X and the small gradients -- runs out of shared memory:
 //   G  gather             5 (group, sample) pairs per thread: rank load, 2 cp.async + 1 wide load
@@ -38,8 +38,8 @@ constexpr int THREADS = 256;  // 8 warps
 constexpr int NKP = 8;        // column parts (warps) of phases F / B1
 constexpr int KPC = 40;       // tile columns per part = 5 id groups
 constexpr int NCOL = 320;     // deep 304 | dense 13 | 1 | 0 0   (G <= 38)
-constexpr int XS = 364;       // row stride: 320 + wide 38 + pad, = 91 * 4
-constexpr int XW = 320;       // offset of the wide values inside a row
+constexpr int XS = 324;       // row stride: 320 + pad = 81 * 4 (odd number of 16 B quads: conflict-free 128-bit row reads)
+constexpr int RS = 39;        // rank row stride (odd): Rt[s][g]
 constexpr int RW = H1 + D + 2;  // partial record: h[16] | s[8] | q | lin
 constexpr int MS = 44;        // per-sample backward state: dh1 16 | a1 16 | dh2 4 | h2 4 | dz | pad 3
 constexpr int MAXG = 38;
@@ -67,13 +67,18 @@ thread_local std::string g_msg;
 constexpr int SM_W1X = NCOL * H1;          // 5120
 constexpr int SM_X = TS * XS;              // 11648
 constexpr int SM_P = NKP * RW * TS;        // 6656   partial records [kp][r][s]; reused as T[r][s] + M[s][MS]
-constexpr int SM_R = MAXG * TS;            // 1216   ranks [g][s]
+constexpr int SM_R = TS * RS;              // 1248   ranks Rt[s][g]
+constexpr int SM_WV = MAXG * TS;           // 1216   wide values WV[g][s]
 constexpr int SM_SMALL = 128;              // b... w2 64 | b2 4 | w3 4 | wd 16
-constexpr size_t SMEM_BYTES = (size_t)(SM_W1X + SM_X + SM_P + SM_R + SM_SMALL) * sizeof(float);
+constexpr size_t SMEM_BYTES = (size_t)(SM_W1X + SM_X + SM_P + SM_R + SM_WV + SM_SMALL) * sizeof(float);
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -116,8 +121,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
   float* W1x = smem;                 // [NCOL][16]
   float* X = W1x + SM_W1X;           // [TS][XS]
   float* P = X + SM_X;               // [NKP][RW][TS], later T[RW][TS] and Mst[TS][MS]
-  int* R = reinterpret_cast<int*>(P + SM_P);  // [G][TS]
-  float* small = reinterpret_cast<float*>(R + SM_R);
+  int* Rt = reinterpret_cast<int*>(P + SM_P);  // [TS][RS] ranks
+  float* WV = reinterpret_cast<float*>(Rt + SM_R);  // [G][TS] wide values
+  float* small = WV + SM_WV;
   float* s_w2 = small;        // [H2][H1]
   float* s_b2 = small + 64;   // [H2]
   float* s_w3 = small + 68;   // [H2]
@@ -138,12 +144,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
   }
   // B2 accumulators, persistent over the CTA's tiles, all 8 warps busy: thread t owns tile column t (16 hidden
   // units) and, of the remaining 64 columns, column 256 + t/4 x hidden units 4*(t%4) .. +3
-  float acc0[H1], acc1[4];
+  float2 acc0[H1 / 2], acc1[2];
   float sacc = 0.f;  // threads t < 85: one small output each (dW2 64 | db2 4 | dw3 4 | dwd 13)
 #pragma unroll
-  for (int j = 0; j < H1; ++j) acc0[j] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) acc1[j] = 0.f;
+  for (int j = 0; j < H1 / 2; ++j) acc0[j] = make_float2(0.f, 0.f);
+  acc1[0] = acc1[1] = make_float2(0.f, 0.f);
   float loss_acc = 0.f;
   __syncthreads();
 
@@ -151,14 +156,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
   for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const long long b0 = tile * TS;
     // ---------------- G: gather the tile once ----------------
+    // step 1: ranks (coalesced: 32 consecutive samples of one group per warp) -> Rt[s][g]; dense columns.
+    // step 2: the rows, lane = consecutive 16 B chunk of ONE sample's row, so that a warp's cp.async
+    //         destinations are contiguous in shared memory (lane = sample put every lane's 16 B into its
+    //         own wavefront: 32-way, 2560 of the tile's 13.3 K shared-memory wavefronts -- ncu, profiles/r2_04).
     {
       const int npair = G * TS;
       constexpr int NP = (MAXG * TS + THREADS - 1) / THREADS;  // 5 (group, sample) pairs per thread
       constexpr int NFILL = (TS * 16 + THREADS - 1) / THREADS;  // dense | 1 | 0 0 columns: 2 per thread
       int rk[NP];
-      float wv[NP], dv[NFILL];
-      // every global load is issued before anything waits on one (the SM issues in order: a store of a
-      // loaded value in the middle of the loop would serialise the five gather chains)
+      float dv[NFILL];
 #pragma unroll
       for (int jj = 0; jj < NP; ++jj) {
         const int i = t + THREADS * jj;
@@ -182,24 +189,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
 #pragma unroll
       for (int jj = 0; jj < NP; ++jj) {
         const int i = t + THREADS * jj;
-        wv[jj] = 0.f;
-        if (i < npair) {
-          const int g = i >> 5, s = i & 31;
-          const float* row = a.bet_deep + ((long long)g * B + rk[jj]) * D;
-          float* dst = X + s * XS + g * D;
-          cp_async16(dst, row);
-          cp_async16(dst + 4, row + 4);
-          wv[jj] = a.bet_wide[(long long)g * B + rk[jj]];
-        }
-      }
-#pragma unroll
-      for (int jj = 0; jj < NP; ++jj) {
-        const int i = t + THREADS * jj;
-        if (i < npair) {
-          const int g = i >> 5, s = i & 31;
-          R[g * TS + s] = rk[jj];
-          X[s * XS + XW + g] = wv[jj];
-        }
+        if (i < npair) Rt[(i & 31) * RS + (i >> 5)] = rk[jj];
       }
 #pragma unroll
       for (int jj = 0; jj < NFILL; ++jj) {
@@ -210,15 +200,27 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
         const int s = i / ((MAXG - G) * D), c = G * D + i % ((MAXG - G) * D);
         X[s * XS + c] = 0.f;
       }
+      __syncthreads();
+      const int nchunk = G * 2;  // 16 B chunks per sample row
+      for (int i = t; i < TS * nchunk; i += THREADS) {
+        const int s = i / nchunk, ch = i - s * nchunk;
+        const int g = ch >> 1;
+        const int r = Rt[s * RS + g];
+        cp_async16(X + s * XS + ch * 4, a.bet_deep + ((long long)g * B + r) * D + (ch & 1) * 4);
+      }
+      for (int i = t; i < npair; i += THREADS) {  // wide values: lane = sample
+        const int g = i >> 5, s = i & 31;
+        cp_async4(WV + g * TS + s, a.bet_wide + (long long)g * B + Rt[s * RS + g]);
+      }
       cp_async_wait_all();
     }
     __syncthreads();
     const bool live = b0 + lane < B;
     // ---------------- F: partial H1 / FM sums over this warp's 40 columns ----------------
     {
-      float h[H1];
+      float2 h2[H1 / 2];
 #pragma unroll
-      for (int j = 0; j < H1; ++j) h[j] = 0.f;
+      for (int j = 0; j < H1 / 2; ++j) h2[j] = make_float2(0.f, 0.f);
       float sd[D], q = 0.f, lin = 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) sd[d] = 0.f;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
         if (g < G) {  // an embedding group: FM sums + the wide value
 #pragma unroll
           for (int d = 0; d < D; ++d) { sd[d] += xv[d]; q = fmaf(xv[d], xv[d], q); }
-          lin += xrow[XW + g];
+          lin += WV[g * TS + lane];
         } else if (c == MAXG * D) {  // dense columns 304..311 and (next chunk) 312..316: the linear part
 #pragma unroll
           for (int d = 0; d < D; ++d) lin = fmaf(s_wd[d], xv[d], lin);
@@ -245,19 +247,21 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           const float4* w4 = reinterpret_cast<const float4*>(W1x + (c + d) * H1);
+          const float2 xx = make_float2(xv[d], xv[d]);
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
+          for (int qd = 0; qd < 4; ++qd) {  // packed fp32 FMA (FFMA2, sm_100): two hidden units per instruction
             const float4 w = w4[qd];
-            h[4 * qd + 0] = fmaf(w.x, xv[d], h[4 * qd + 0]);
-            h[4 * qd + 1] = fmaf(w.y, xv[d], h[4 * qd + 1]);
-            h[4 * qd + 2] = fmaf(w.z, xv[d], h[4 * qd + 2]);
-            h[4 * qd + 3] = fmaf(w.w, xv[d], h[4 * qd + 3]);
+            h2[2 * qd] = __ffma2_rn(make_float2(w.x, w.y), xx, h2[2 * qd]);
+            h2[2 * qd + 1] = __ffma2_rn(make_float2(w.z, w.w), xx, h2[2 * qd + 1]);
           }
         }
       }
       float* mine = P + (warp * RW) * TS + lane;
 #pragma unroll
-      for (int j = 0; j < H1; ++j) mine[j * TS] = h[j];
+      for (int j = 0; j < H1 / 2; ++j) {
+        mine[(2 * j) * TS] = h2[j].x;
+        mine[(2 * j + 1) * TS] = h2[j].y;
+      }
 #pragma unroll
       for (int d = 0; d < D; ++d) mine[(H1 + d) * TS] = sd[d];
       mine[(H1 + D) * TS] = q;
@@ -349,21 +353,19 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           const float4* w4 = reinterpret_cast<const float4*>(W1x + (c + d) * H1);
-          float dt = 0.f;
+          float2 dt2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
             const float4 w = w4[qd];
-            dt = fmaf(w.x, dh1[4 * qd + 0], dt);
-            dt = fmaf(w.y, dh1[4 * qd + 1], dt);
-            dt = fmaf(w.z, dh1[4 * qd + 2], dt);
-            dt = fmaf(w.w, dh1[4 * qd + 3], dt);
+            dt2 = __ffma2_rn(make_float2(w.x, w.y), make_float2(dh1[4 * qd + 0], dh1[4 * qd + 1]), dt2);
+            dt2 = __ffma2_rn(make_float2(w.z, w.w), make_float2(dh1[4 * qd + 2], dh1[4 * qd + 3]), dt2);
           }
-          x[d] = fmaf(dz, sd[d] - ev[d], dt);
+          x[d] = fmaf(dz, sd[d] - ev[d], dt2.x + dt2.y);
         }
         x[D] = dz;  // wide row gradient
         // warp-level id dedup: lanes hitting the same row combine pairwise up a tree threaded through the
         // peer mask (pointer doubling): ceil(log2(max multiplicity)) rounds for the whole warp
-        const int r = R[g * TS + lane];
+        const int r = Rt[lane * RS + g];
         const int key = live ? r : -1 - lane;
         const unsigned peers = __match_any_sync(0xffffffffu, key);
         const int rank = __popc(peers & ((1u << lane) - 1));
@@ -399,12 +401,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
           const float dh[H1] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
           const float x0 = X[s * XS + t], x1 = X[s * XS + c1];
           const float4 dq = *reinterpret_cast<const float4*>(Mst + s * MS + jq);
+          const float2 xx0 = make_float2(x0, x0), xx1 = make_float2(x1, x1);
 #pragma unroll
-          for (int j = 0; j < H1; ++j) acc0[j] = fmaf(dh[j], x0, acc0[j]);
-          acc1[0] = fmaf(dq.x, x1, acc1[0]);
-          acc1[1] = fmaf(dq.y, x1, acc1[1]);
-          acc1[2] = fmaf(dq.z, x1, acc1[2]);
-          acc1[3] = fmaf(dq.w, x1, acc1[3]);
+          for (int j = 0; j < H1 / 2; ++j) acc0[j] = __ffma2_rn(make_float2(dh[2 * j], dh[2 * j + 1]), xx0, acc0[j]);
+          acc1[0] = __ffma2_rn(make_float2(dq.x, dq.y), xx1, acc1[0]);
+          acc1[1] = __ffma2_rn(make_float2(dq.z, dq.w), xx1, acc1[1]);
         }
         if (t < H2 * H1 + 2 * H2 + ND) {
           const int o = t;
@@ -426,12 +427,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
 #pragma unroll
     for (int j = 0; j < H1; ++j) {
       const int dst = w1x_src(l, G, t, j);
-      if (dst >= 0) atomicAdd(a.grads + dst, acc0[j]);
+      if (dst >= 0) atomicAdd(a.grads + dst, (j & 1) ? acc0[j >> 1].y : acc0[j >> 1].x);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int dst = w1x_src(l, G, 256 + (t >> 2), (t & 3) * 4 + j);
-      if (dst >= 0) atomicAdd(a.grads + dst, acc1[j]);
+      if (dst >= 0) atomicAdd(a.grads + dst, (j & 1) ? acc1[j >> 1].y : acc1[j >> 1].x);
     }
     if (t < H2 * H1 + 2 * H2 + ND) {
       const int o = t;

@@ -114,11 +114,12 @@ __device__ __forceinline__ unsigned long long u_word(unsigned tag, unsigned flag
 constexpr int kUPPT = 4;
 constexpr int kUUnit = kUThreads * kUPPT;  // 1024
 
-struct URuns {                     // block -> run of units
-  int blk_prefix[kMaxSegs + 1];    // per-segment map (T <= kMaxSegs): first block of segment t
-  int run[kMaxSegs];               // units per block of segment t
-  int per_seg;                     // 1: the map above; 0: every block takes `uniform_run` units of the flat unit space
-  int uniform_run;
+struct URuns {                     // run slot -> (segment, first unit, units); a block takes slots b, b + grid, ...
+  int blk_prefix[kMaxSegs + 1];    // per-segment map (T <= kMaxSegs): first slot of segment t
+  int run[kMaxSegs];               // units per slot of segment t
+  int per_seg;                     // 1: the map above; 0: `bps` slots of `uniform_run` units per segment
+  int uniform_run, bps;
+  int nslots;
 };
 
 __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
@@ -143,26 +144,29 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
   const long long k = a.k;
   const int T = a.T;
   const int ups = a.ntiles;  // units per segment
-  const long long units = (long long)T * ups;
+  const long long units = (long long)T * ups;  // descriptors are sized for one per unit (>= run slots)
 
-  // this block's run of units [g0, g0 + gcnt) in the flat unit space (g = t * ups + u)
-  long long g0;
-  int gcnt;
-  if (ur.per_seg) {
-    int lo = 0, hi = T;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (ur.blk_prefix[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+  // run slot -> segment t, first unit j0 (inside the segment), number of units
+  auto slot_of = [&](const int slot, int& t, long long& j0, int& cnt) {
+    int r, u0;
+    if (ur.per_seg) {
+      int lo = 0, hi = T;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (ur.blk_prefix[mid] <= slot) lo = mid; else hi = mid;
+      }
+      t = lo;
+      r = ur.run[lo];
+      u0 = (slot - ur.blk_prefix[lo]) * r;
+    } else {
+      t = slot / ur.bps;
+      r = ur.uniform_run;
+      u0 = (slot - t * ur.bps) * r;
     }
-    const int r = ur.run[lo];
-    const int u0 = ((int)blockIdx.x - ur.blk_prefix[lo]) * r;
-    g0 = (long long)lo * ups + u0;
-    gcnt = u0 < ups ? (ups - u0 < r ? ups - u0 : r) : 0;
-  } else {
-    g0 = (long long)blockIdx.x * ur.uniform_run;
-    const long long left = units - g0;
-    gcnt = left <= 0 ? 0 : (left < ur.uniform_run ? (int)left : ur.uniform_run);
-  }
+    j0 = u0;
+    cnt = u0 < ups ? (ups - u0 < r ? ups - u0 : r) : 0;
+  };
+  const int nslots = ur.nslots;
 
   // ---- phase 0: clear what this call cannot read as empty ----
   const bool clear_direct = a.n_direct > 0 && (!a.tagged || stale_cycle);
@@ -200,10 +204,12 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
   U_STAMP(0);
 
   // ---- phase A: insert.  position array entry of every id <- min(position) ----
-  for (int gi = 0; gi < gcnt; ++gi) {
-    const long long g = g0 + gi;
-    const int t = (int)(g / ups);
-    const long long base = (g - (long long)t * ups) * kUUnit;
+  for (int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+   int t, gcnt;
+   long long j0;
+   slot_of(slot, t, j0, gcnt);
+   for (int gi = 0; gi < gcnt; ++gi) {
+    const long long base = (j0 + gi) * kUUnit;
     const bool direct = a.use_bounds && a.ub.bound[t] > 0;
     int* fp = a.fp + (long long)t * k;
     if (direct) {
@@ -271,68 +277,75 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
         if (live) fp[i] = (int)sl;
       }
     }
+   }
   }
   U_STAMP(1);
   target += gridDim.x;
   u_grid_barrier(bar, target, a.err);
   U_STAMP(2);
 
-  // ---- phase B: flags, single-pass scan over the units of each segment, ranks, unique ids ----
-  for (int gi = 0; gi < gcnt; ++gi) {
-    const long long g = g0 + gi;
-    const int t = (int)(g / ups);
-    const long long j = g - (long long)t * ups;
-    const long long base = j * kUUnit;
+  // ---- phase B: flags, single-pass scan over the RUNS of each segment, ranks, unique ids ----
+  // The look-back works on whole runs: pass 1 counts the first occurrences of all the block's units and
+  // publishes ONE aggregate, then looks back over the predecessor runs of the segment; pass 2 assigns the
+  // ranks.  (Per-unit descriptors made a block's first unit wait for the previous block's LAST unit, which
+  // itself sat behind that block's earlier look-backs: the segment was processed serially -- timeline,
+  // profiles/r2_05.)
+  for (int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+    int t, gcnt;
+    long long j0;  // first unit of the run inside its segment
+    slot_of(slot, t, j0, gcnt);
+    if (gcnt == 0) continue;  // block-uniform
+    __syncthreads();          // s_cnt / s_excl of the previous slot have been consumed
     const bool direct = a.use_bounds && a.ub.bound[t] > 0;
     const int* mp = direct ? a.ub.dpos + a.ub.off[t] : a.minpos + (long long)t * a.cap;
     const int pm = direct ? pos_mask : 0x7fffffff;
     int* fp = a.fp + (long long)t * k;
-    int v[PPT];  // slot / id of position q, then the first position of that id
+    // pass 1: first position of every id, per-thread count of first occurrences over the run
+    int mine = 0;
+    for (int gi = 0; gi < gcnt; ++gi) {
+      const long long base = (j0 + gi) * kUUnit;
+      int v[PPT];
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-      const long long i = base + q * kUThreads + threadIdx.x;
-      v[q] = i < k ? fp[i] : 0;
-    }
-#pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-      const long long i = base + q * kUThreads + threadIdx.x;
-      v[q] = i < k ? (mp[v[q]] & pm) : -1;
-    }
-    unsigned fmask = 0;  // bit q: position q*256 + tid is a first occurrence
-    int wrank[PPT];      // first occurrences among the lower lanes of the warp, same q
-#pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-      const long long i = base + q * kUThreads + threadIdx.x;
-      const bool f = i < k && v[q] == (int)i;
-      // duplicates keep the first position of their id (phase C looks its rank up); first occurrences
-      // get their inverse index right here and are marked done
-      if (i < k && !f) fp[i] = v[q];
-      const unsigned bal = __ballot_sync(0xffffffffu, f);
-      wrank[q] = __popc(bal & lt_mask);
-      if (f) fmask |= 1u << q;
-      if (lane == 0) s_cnt[q * NW + wid] = __popc(bal);
-    }
-    __syncthreads();
-    if (wid == 0) {  // exclusive scan of the PPT*NW = 32 counts (position order = q major, warp minor)
-      const int c = s_cnt[lane];
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
+      for (int q = 0; q < PPT; ++q) {
+        const long long i = base + q * kUThreads + threadIdx.x;
+        v[q] = i < k ? fp[i] : 0;
       }
-      s_cnt[lane] = incl - c;
-      const int tot = __shfl_sync(0xffffffffu, incl, 31);
-      if (lane == 0) u_stv(&a.status[g], u_word(tag, j == 0 ? kUFlagP : kUFlagA, (unsigned)tot));
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        const long long i = base + q * kUThreads + threadIdx.x;
+        v[q] = i < k ? (mp[v[q]] & pm) : -1;
+      }
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        const long long i = base + q * kUThreads + threadIdx.x;
+        if (i < k) {
+          fp[i] = v[q];  // pass 2 and phase C read the first position from here (coalesced)
+          mine += v[q] == (int)i;
+        }
+      }
+    }
+    // run total -> descriptor of this block's run; look back over the predecessor runs of the segment
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) s_cnt[wid] = mine;
+    __syncthreads();
+    if (wid == 0) {
+      int tot = lane < NW ? s_cnt[lane] : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      // the runs of one segment are consecutive slots: first_slot .. slot - 1 precede this one
+      const int first_slot = ur.per_seg ? ur.blk_prefix[t] : t * ur.bps;
+      const long long jr = (long long)slot - first_slot;  // index of this run inside its segment
+      if (lane == 0) u_stv(&a.status[slot], u_word(tag, jr == 0 ? kUFlagP : kUFlagA, (unsigned)tot));
       int excl = 0;
-      long long look = j - 1;  // predecessor units of this segment, nearest first, 32 at a time
+      long long look = jr - 1;
       long long spins = 0;
       while (look >= 0) {
         const long long idx = look - lane;
         bool valid = true;  // lanes before the segment start count as an exclusive prefix of 0
         unsigned flag = kUFlagP, val = 0;
         if (idx >= 0) {
-          const unsigned long long wv = u_ldv(&a.status[(long long)t * ups + idx]);
+          const unsigned long long wv = u_ldv(&a.status[first_slot + idx]);
           const unsigned hi = (unsigned)(wv >> 32);
           valid = (hi >> 2) == tag && (hi & 3u) != 0;
           flag = hi & 3u;
@@ -347,7 +360,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
           continue;
         }
         const unsigned pmask = __ballot_sync(0xffffffffu, flag == kUFlagP);
-        const int stop = pmask ? __ffs(pmask) - 1 : 31;  // nearest unit that already knows its inclusive prefix
+        const int stop = pmask ? __ffs(pmask) - 1 : 31;  // nearest run that already knows its inclusive prefix
         int contrib = lane <= stop ? (int)val : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
@@ -357,26 +370,61 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
       }
       if (lane == 0) {
         s_excl = excl;
-        if (j > 0) u_stv(&a.status[g], u_word(tag, kUFlagP, (unsigned)(excl + tot)));
-        if (j == ups - 1) a.n_unique[t] = excl + tot;
+        if (jr > 0) u_stv(&a.status[slot], u_word(tag, kUFlagP, (unsigned)(excl + tot)));
+        if (j0 + gcnt == ups) a.n_unique[t] = excl + tot;  // the run that ends the segment
       }
     }
     __syncthreads();
-    const int excl = s_excl;
+    // pass 2: ranks in position order (unit by unit, q major, warp minor), unique ids, inverse of the firsts
+    int run_base = s_excl;
     int* rank_at = a.rank_at + (long long)t * k;
     int* inv = a.inv + (long long)t * k;
+    for (int gi = 0; gi < gcnt; ++gi) {
+      const long long base = (j0 + gi) * kUUnit;
+      int v[PPT];
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-      if (fmask >> q & 1u) {
+      for (int q = 0; q < PPT; ++q) {
         const long long i = base + q * kUThreads + threadIdx.x;
-        const int r = excl + s_cnt[q * NW + wid] + wrank[q];
-        rank_at[i] = r;
-        inv[i] = r;
-        fp[i] = -1;  // done: phase C skips it
-        a.uniq[(long long)t * k + r] = u_id(a, (long long)t * k + i);
+        v[q] = i < k ? fp[i] : -1;
       }
+      __syncthreads();  // s_cnt of the previous unit (or of the run total) has been consumed
+      unsigned fmask = 0;
+      int wrank[PPT];
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        const long long i = base + q * kUThreads + threadIdx.x;
+        const bool f = i < k && v[q] == (int)i;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        wrank[q] = __popc(bal & lt_mask);
+        if (f) fmask |= 1u << q;
+        if (lane == 0) s_cnt[q * NW + wid] = __popc(bal);
+      }
+      __syncthreads();
+      if (wid == 0) {  // exclusive scan of the PPT*NW = 32 counts
+        const int c = s_cnt[lane];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += y;
+        }
+        s_cnt[lane] = incl - c;
+        if (lane == 31) s_excl = incl;  // this unit's total (the run's exclusive prefix was copied to run_base)
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        if (fmask >> q & 1u) {
+          const long long i = base + q * kUThreads + threadIdx.x;
+          const int r = run_base + s_cnt[q * NW + wid] + wrank[q];
+          rank_at[i] = r;
+          inv[i] = r;
+          fp[i] = -1;  // done: phase C skips it
+          a.uniq[(long long)t * k + r] = u_id(a, (long long)t * k + i);
+        }
+      }
+      run_base += s_excl;
     }
-    __syncthreads();  // s_cnt / s_excl are reused by the next unit
   }
   U_STAMP(3);
   target += gridDim.x;
@@ -384,10 +432,12 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
   U_STAMP(4);
 
   // ---- phase C: inverse index of the duplicates = rank of their id's first occurrence ----
-  for (int gi = 0; gi < gcnt; ++gi) {
-    const long long g = g0 + gi;
-    const int t = (int)(g / ups);
-    const long long base = (g - (long long)t * ups) * kUUnit;
+  for (int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+   int t, gcnt;
+   long long j0;
+   slot_of(slot, t, j0, gcnt);
+   for (int gi = 0; gi < gcnt; ++gi) {
+    const long long base = (j0 + gi) * kUUnit;
     const int* fp = a.fp + (long long)t * k;
     const int* rank_at = a.rank_at + (long long)t * k;
     int* inv = a.inv + (long long)t * k;
@@ -402,6 +452,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
       const long long i = base + q * kUThreads + threadIdx.x;
       if (f[q] >= 0) inv[i] = rank_at[f[q]];
     }
+   }
   }
   U_STAMP(5);
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // every block took its header snapshot before barrier 1
