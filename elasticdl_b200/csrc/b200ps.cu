@@ -358,10 +358,10 @@ int split_segs(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, bool want_dense
     }
     int c;
     long long work;
-    if (want_dense) {
+    if (want_dense) {  // one launch for all of them: the kernels pick the 128-bit path per segment
       long long numel = t.rows * t.dim;
-      c = (numel % 4 == 0 && aligned16(sg.rows_dev)) ? 1 : 0;
-      work = c ? numel / 4 : numel;
+      c = 1;
+      work = (numel % 4 == 0 && aligned16(sg.rows_dev)) ? numel / 4 : numel;
     } else {
       c = legacy_class(t, sg.rows_dev);
       int W = c == 0 ? 1 : 4 * c;
@@ -918,14 +918,9 @@ static int dense_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* st
   if (rc) return rc;
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
-  return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
-    if (write) {
-      if (c) k_dense_copy<4, true><<<grid, 256, 0, st>>>(gv, b, slot);
-      else k_dense_copy<1, true><<<grid, 256, 0, st>>>(gv, b, slot);
-    } else {
-      if (c) k_dense_copy<4, false><<<grid, 256, 0, st>>>(gv, b, slot);
-      else k_dense_copy<1, false><<<grid, 256, 0, st>>>(gv, b, slot);
-    }
+  return for_each_class(ps, sp, [&](int, dim3 grid, const SegBatch& b) {
+    if (write) k_dense_copy<true><<<grid, 256, 0, st>>>(gv, b, slot);
+    else k_dense_copy<false><<<grid, 256, 0, st>>>(gv, b, slot);
   });
 }
 
@@ -1276,16 +1271,12 @@ int b200ps_push_dense(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* st
   cudaStream_t st = (cudaStream_t)stream;
   OptParams o = ps->opt;
   const bool twice = (ps->flags & 1u) && o.kind == kAMSGrad;
-  return for_each_class(ps, sp, [&](int c, dim3 grid, const SegBatch& b) {
+  return for_each_class(ps, sp, [&](int, dim3 grid, const SegBatch& b) {
     if (twice) {
-      if (c) k_push_dense<kAMSGrad, 4, true><<<grid, 256, 0, st>>>(gv, b, o);
-      else k_push_dense<kAMSGrad, 1, true><<<grid, 256, 0, st>>>(gv, b, o);
+      k_push_dense<kAMSGrad, true><<<grid, 256, 0, st>>>(gv, b, o);
       return;
     }
-    DISPATCH_OPT(o.kind, {
-      if (c) k_push_dense<OPT, 4, false><<<grid, 256, 0, st>>>(gv, b, o);
-      else k_push_dense<OPT, 1, false><<<grid, 256, 0, st>>>(gv, b, o);
-    });
+    DISPATCH_OPT(o.kind, k_push_dense<OPT, false><<<grid, 256, 0, st>>>(gv, b, o));
   });
 }
 

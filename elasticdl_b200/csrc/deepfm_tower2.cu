@@ -14,7 +14,7 @@
 //                         per-sample MLP tail (it needs dh1 / dz / FM sums in registers for B1 anyway)
 //   B1 embedding grads    warp = its 5 groups, lane = sample; equal rows of a warp combine up a tree
 //                         (warp-level id dedup), one vector red per distinct row
-//   B2 parameter grads    thread = tile column t x 16 hidden units + a quarter of one of the last 64 columns
+//   B2 parameter grads    thread = tile column t x 16 hidden units + 4 hidden units of column 256 + t % 64
 //                         (all 8 warps busy), accumulated in registers across the CTA's tiles, one atomic
 //                         per output per CTA at the end
 // W1 is presented in TILE COLUMN ORDER (W1x[c][j]: deep columns first, then dense, then b1 as the weight
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
     if (t < ND) s_wd[t] = a.params[l.o_wd + t];
   }
   // B2 accumulators, persistent over the CTA's tiles, all 8 warps busy: thread t owns tile column t (16 hidden
-  // units) and, of the remaining 64 columns, column 256 + t/4 x hidden units 4*(t%4) .. +3
+  // units) and, of the remaining 64 columns, column 256 + t%64 x hidden units 4*(t/64) .. +3
   float2 acc0[H1 / 2], acc1[2];
   float sacc = 0.f;  // threads t < 85: one small output each (dW2 64 | db2 4 | dw3 4 | dwd 13)
 #pragma unroll
@@ -393,14 +393,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
       __syncthreads();  // Mst complete
       // ---------------- B2: parameter gradients, accumulated over the CTA's tiles ----------------
       {
-        const int c1 = 256 + (t >> 2), jq = (t & 3) * 4;
+        // second column: 256 + t % 64, hidden units 4*(t/64) .. +3 -- warp-uniform, so its dh1 quad is one of the
+        // four broadcast loads above (a per-lane quad cost four shared-memory wavefronts per load)
+        const int c1 = 256 + (t & 63), jsel = t >> 6;
 #pragma unroll 4
         for (int s = 0; s < TS; ++s) {
           const float4* d4 = reinterpret_cast<const float4*>(Mst + s * MS);
           const float4 q0 = d4[0], q1 = d4[1], q2 = d4[2], q3 = d4[3];
           const float dh[H1] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
           const float x0 = X[s * XS + t], x1 = X[s * XS + c1];
-          const float4 dq = *reinterpret_cast<const float4*>(Mst + s * MS + jq);
+          const float4 dq = jsel == 0 ? q0 : (jsel == 1 ? q1 : (jsel == 2 ? q2 : q3));
           const float2 xx0 = make_float2(x0, x0), xx1 = make_float2(x1, x1);
 #pragma unroll
           for (int j = 0; j < H1 / 2; ++j) acc0[j] = __ffma2_rn(make_float2(dh[2 * j], dh[2 * j + 1]), xx0, acc0[j]);
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int dst = w1x_src(l, G, 256 + (t >> 2), (t & 3) * 4 + j);
+      const int dst = w1x_src(l, G, 256 + (t & 63), (t >> 6) * 4 + j);
       if (dst >= 0) atomicAdd(a.grads + dst, (j & 1) ? acc1[j >> 1].y : acc1[j >> 1].x);
     }
     if (t < H2 * H1 + 2 * H2 + ND) {

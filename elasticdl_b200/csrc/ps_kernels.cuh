@@ -554,7 +554,9 @@ __device__ __forceinline__ void dense_update_range(const GroupView& gv, const Ta
   }
 }
 
-template <int OPT, int VEC, bool TWICE>
+// One launch for all dense gradients of a push, whatever their sizes: a segment whose element count is a
+// multiple of 4 and whose gradient is 16 B aligned takes the 128-bit path (block-uniform branch).
+template <int OPT, bool TWICE>
 __global__ void __launch_bounds__(256) k_push_dense(GroupView gv, SegBatch sb, OptParams o) {
   const b200ps_seg_t& sg = sb.seg[blockIdx.y];
   const TableView& tv = gv.tables[sg.table];
@@ -562,7 +564,9 @@ __global__ void __launch_bounds__(256) k_push_dense(GroupView gv, SegBatch sb, O
   rg.g[0] = sg.rows_dev;
   rg.n = 1;
   rg.scale = 1.0f;
-  dense_update_range<OPT, VEC, TWICE>(gv, tv, rg, o);
+  const bool vec = ((tv.rows * tv.dim) & 3) == 0 && ((uintptr_t)sg.rows_dev & 15u) == 0;
+  if (vec) dense_update_range<OPT, 4, TWICE>(gv, tv, rg, o);
+  else dense_update_range<OPT, 1, TWICE>(gv, tv, rg, o);
 }
 
 template <int OPT, int VEC, bool TWICE>
@@ -609,18 +613,21 @@ __global__ void __launch_bounds__(256) k_raw_dense(const float* __restrict__ G, 
 }
 
 // pull_dense / set_dense: whole-parameter copy owner shard <-> caller buffer.
-template <int VEC, bool WRITE>
+template <bool WRITE>
 __global__ void __launch_bounds__(256) k_dense_copy(GroupView gv, SegBatch sb, int slot) {
   const b200ps_seg_t& sg = sb.seg[blockIdx.y];
   const TableView& tv = gv.tables[sg.table];
   float* P = tv.base[tv.owner] + tv.slot_off[slot];
   float* U = sg.rows_dev;
-  const long long nvec = tv.rows * tv.dim / VEC;
+  const long long numel = tv.rows * tv.dim;
+  const bool vec = (numel & 3) == 0 && ((uintptr_t)U & 15u) == 0;  // block-uniform: one launch for all sizes
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    if (VEC == 4) {
+  if (vec) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel / 4; i += stride) {
       if (WRITE) st_f4(P + 4 * i, ld_f4(U + 4 * i)); else st_f4(U + 4 * i, ld_f4(P + 4 * i));
-    } else {
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
       if (WRITE) P[i] = U[i]; else U[i] = P[i];
     }
   }

@@ -187,13 +187,15 @@ class HostFeeder:
 
 class DeepFMPSEngine:
     def __init__(self, group, batch, lr=1e-3, init_std=0.01, seed=7, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM,
-                 init_rows=True, tower="fused", paired=None, exchange=None):
+                 init_rows=True, tower="tile", paired=None, exchange=None):
         """tower="tile": rows of 32 samples gathered once into shared memory, forward / backward / parameter
         gradients from the tile (csrc/deepfm_tower2.cu);
         tower="fused": round 1's hand-written CUDA tower (csrc/deepfm_tower.cu, three row gathers);
         tower="mma": its tensor-core variant (csrc/deepfm_tower_mma.cu, rows gathered once, 3xTF32 mma.sync);
         tower="torch": torch autograd over library kernels (kept for A/B measurements and tests)."""
         assert tower in ("tile", "fused", "mma", "torch")
+        if tower == "tile" and len(group_rows) > 38:
+            tower = "fused"  # the tile tower holds at most 38 id groups in its shared-memory row
         self.tower_kind = tower
         # paired=True: the deep (dim 8) and wide (dim 1) tables of an id group share one record
         # per id, so one request per id serves both (ps_kernels.cuh "Paired tables")
