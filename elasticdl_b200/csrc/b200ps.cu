@@ -1084,7 +1084,7 @@ int b200ps_xchg_create(b200ps_t* ps, int G, int B, const int32_t* deep_tables, c
   ps->x_cap = (long long)G * B;
   const long long n = ps->n_shards;
   ps->x_off_ids = 4096;
-  ps->x_off_resp = ps->x_off_ids + ps->x_cap * kXIdEntry;
+  ps->x_off_resp = ps->x_off_ids + n * ps->x_cap * kXIdEntry;  // one id bucket per owner
   ps->x_off_upd = ps->x_off_resp + n * ps->x_cap * kXResp;
   ps->x_off_served = ps->x_off_upd + n * ps->x_cap * kXUpd;
   const long long bytes = ps->x_off_served + n * ps->x_cap * kXServed;

@@ -5,10 +5,13 @@
 // Measured on this box (tools/mgpu_probe.py): scattered 32 B accesses to a peer GPU -- reads AND
 // writes -- run at ~130-160 GB/s (a few G sectors/s, independent of request size), coalesced peer
 // traffic at the link rate.  So nothing scattered crosses NVLink:
-//   pull  k_x_post      requester compacts its unique ids into its exchange buffer as {id, slot}
-//         k_x_serve     every OWNER streams every requester's list over NVLink (coalesced reads),
-//                       keeps the ids it owns (id % N), gathers those rows from its own HBM and
-//                       appends {row, slot} CONTIGUOUSLY to the requester's response region; it
+//   pull  k_x_post      requester buckets its unique ids BY OWNER (id % N) into its exchange buffer as
+//                       {id, slot} words: block-level histogram in shared memory, one cursor
+//                       reservation per (block, owner), the per-owner counts travel with the flag
+//         k_x_serve     every OWNER streams ITS bucket of every requester's list over NVLink (coalesced
+//                       reads of exactly the ids it owns: an all-to-all-v -- round 1 had every owner read
+//                       every whole list, N x the bytes), gathers those rows from its own HBM and writes
+//                       {row, slot} to the same index of the requester's response region; it
 //                       remembers (id, group) of what it served, in order
 //         k_x_unscatter requester copies the rows of each owner's region to bet[slot]
 //   push  k_x_send_upd  requester walks each owner's response region again (its order == the owner's
@@ -35,7 +38,6 @@ constexpr int kXIdEntry = 16;  // bytes: {int64 id; int32 slot; int32 tag}
 constexpr int kXResp = 64;     // bytes: {d0 d1 d2 tag}{d3 d4 d5 tag}{d6 d7 wide tag}{slot 0 0 tag}
 constexpr int kXUpd = 48;      // bytes: {g0 g1 g2 tag}{g3 g4 g5 tag}{g6 g7 gwide tag}
 constexpr int kXServed = 16;   // bytes: {int64 id; int32 grp; int32 pad}   (owner-local)
-constexpr int kXChunk = 512;   // ids scanned per block iteration in k_x_serve (256 threads x 2)
 
 struct XHeader {  // first page of every rank's exchange buffer
   // written by source ranks into the OWNER's header (self-validating words)
@@ -46,7 +48,8 @@ struct XHeader {  // first page of every rank's exchange buffer
   int applied[kMaxShards];  // [owner] tag: that owner has applied my updates
   // local
   int epoch;
-  int cursor[kMaxShards];      // owner: rows served so far to each source (this epoch)
+  int post_cursor[kMaxShards]; // requester: ids bucketed so far for each owner (this epoch)
+  int cursor[kMaxShards];      // (unused since the ids arrive bucketed)
   int served_cnt[kMaxShards];  // owner: rows served to each source by the last pull
   unsigned done_blocks;
   unsigned done_src[kMaxShards];
@@ -62,7 +65,10 @@ struct XView {
 };
 
 __device__ __forceinline__ XHeader* xhdr(const XView& x, int r) { return reinterpret_cast<XHeader*>(x.buf[r]); }
-__device__ __forceinline__ char* xids(const XView& x, int r) { return x.buf[r] + x.off_ids; }
+// bucket of the ids requester r wants from owner o (cap entries each)
+__device__ __forceinline__ char* xids(const XView& x, int r, int o) {
+  return x.buf[r] + x.off_ids + ((long long)o * x.cap) * kXIdEntry;
+}
 __device__ __forceinline__ char* xresp(const XView& x, int requester, int owner) {
   return x.buf[requester] + x.off_resp + ((long long)owner * x.cap) * kXResp;
 }
@@ -134,13 +140,16 @@ __device__ __forceinline__ int group_of(const int* prefix, int G, int w) {
   return lo;
 }
 
-// Requester: open a new epoch and publish this step's unique ids, compacted over the groups, as
-// tagged {id, slot} words in its own exchange buffer; the owners are told how many there are.
+// Requester: open a new epoch and publish this step's unique ids, bucketed by owner, as tagged {id, slot}
+// words in its own exchange buffer; every owner is told how many of them are its own.
+constexpr int kXPostPer = 4;  // ids per thread per block iteration
 __global__ void __launch_bounds__(256) k_x_post(XView x, const int64_t* __restrict__ uniq, const int* __restrict__ n_unique) {
   XHeader* h = xhdr(x, x.me);
-  char* ids = xids(x, x.me);
   __shared__ int s_prefix[kMaxSegs + 1];
   __shared__ int s_u[kMaxSegs];
+  __shared__ int s_hist[kMaxShards];           // ids of this chunk per owner
+  __shared__ int s_wbase[8][kMaxShards];       // per warp: its offset inside the block's range of that owner
+  __shared__ int s_base[kMaxShards];           // the block's reservation in each owner's bucket
   const int epoch = *(volatile int*)&h->epoch + 1;  // every block reads it before the last one bumps it
   if (threadIdx.x < x.G) {
     const int u = n_unique[threadIdx.x];
@@ -157,142 +166,144 @@ __global__ void __launch_bounds__(256) k_x_post(XView x, const int64_t* __restri
   }
   __syncthreads();
   const int total = s_prefix[x.G];
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
-    const int g = group_of(s_prefix, x.G, w);
-    const int slot = g * x.B + (w - s_prefix[g]);
-    const long long id = uniq[slot];
-    st_word16(ids + (long long)w * kXIdEntry, (int)(id & 0xffffffffLL), (int)(id >> 32), slot, epoch);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool pow2 = (x.n & (x.n - 1)) == 0;
+  constexpr int kChunk = 256 * kXPostPer;
+  for (int chunk = blockIdx.x * kChunk; chunk < total; chunk += gridDim.x * kChunk) {
+    long long id[kXPostPer];
+    int slot[kXPostPer], own[kXPostPer], rk[kXPostPer];
+    if (threadIdx.x < x.n) s_hist[threadIdx.x] = 0;
+#pragma unroll
+    for (int j = 0; j < kXPostPer; ++j) {
+      const int w = chunk + j * 256 + threadIdx.x;
+      own[j] = -1;
+      slot[j] = 0;
+      id[j] = 0;
+      if (w < total) {
+        const int g = group_of(s_prefix, x.G, w);
+        slot[j] = g * x.B + (w - s_prefix[g]);
+        id[j] = uniq[slot[j]];
+        own[j] = pow2 ? (int)(id[j] & (x.n - 1)) : (int)(((id[j] % x.n) + x.n) % x.n);
+      }
+    }
+    __syncthreads();
+    // per warp and owner: how many ids, and each lane's rank among them (ballots, no atomics).
+    // lane o (< n) keeps the warp's running count of owner o over the rounds.
+    int cnt_prev = 0;
+#pragma unroll
+    for (int j = 0; j < kXPostPer; ++j) {
+      rk[j] = 0;
+      int addv = 0;
+      for (int o = 0; o < x.n; ++o) {
+        const unsigned m = __ballot_sync(0xffffffffu, own[j] == o);
+        const int before = __shfl_sync(0xffffffffu, cnt_prev, o);
+        if (own[j] == o) rk[j] = before + __popc(m & ((1u << lane) - 1));
+        if (lane == o) addv = __popc(m);
+      }
+      cnt_prev += addv;
+    }
+    if (lane < x.n) s_wbase[wid][lane] = atomicAdd(&s_hist[lane], cnt_prev);  // warp's offset inside the block's range
+    __syncthreads();
+    if (threadIdx.x < x.n) s_base[threadIdx.x] = s_hist[threadIdx.x] ? atomicAdd(&h->post_cursor[threadIdx.x], s_hist[threadIdx.x]) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kXPostPer; ++j) {
+      if (own[j] < 0) continue;
+      const int at = s_base[own[j]] + s_wbase[wid][own[j]] + rk[j];
+      st_word16(xids(x, x.me, own[j]) + (long long)at * kXIdEntry, (int)(id[j] & 0xffffffffLL), (int)(id[j] >> 32), slot[j], epoch);
+    }
+    __syncthreads();  // s_hist / s_wbase / s_base are rewritten by the next chunk
   }
   __shared__ bool last;
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(&h->done_blocks, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!last) return;
+  __threadfence();
+  if (threadIdx.x < x.n) {  // tell every owner how many of my ids are its own
+    const int cnt = *(volatile int*)&h->post_cursor[threadIdx.x];
+    st_word8(&xhdr(x, threadIdx.x)->req[x.me], cnt, epoch);
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     h->epoch = epoch;
     h->done_blocks = 0;
   }
   if (threadIdx.x < kMaxShards) {
-    h->cursor[threadIdx.x] = 0;
+    h->post_cursor[threadIdx.x] = 0;
     h->done_src[threadIdx.x] = 0;
   }
-  if (threadIdx.x < x.n) st_word8(&xhdr(x, threadIdx.x)->req[x.me], total, epoch);
 }
 
 __device__ __forceinline__ long long id_of(int lo, int hi) {
   return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
 }
 
-// Owner: stream source blockIdx.y's id list, keep the ids this shard owns, gather and return the rows.
+// Owner: stream MY bucket of source blockIdx.y's id list, gather the rows, return them at the same index.
 __global__ void __launch_bounds__(256) k_x_serve(XView x, GroupView gv) {
-  constexpr int PER = kXChunk / 256;
   const int src = blockIdx.y;
   XHeader* h = xhdr(x, x.me);
-  __shared__ int s_epoch, s_total, s_n, s_base;
-  __shared__ long long s_id[kXChunk];
-  __shared__ int s_slot[kXChunk];
+  __shared__ int s_epoch, s_total;
   if (threadIdx.x == 0) {
     s_epoch = h->epoch;
     s_total = poll8(&h->req[src], s_epoch, gv.err).x;
-    s_n = 0;
   }
   __syncthreads();
   const int epoch = s_epoch, total = s_total;
-  const char* ids = xids(x, src);    // the source's list (remote unless src == me), read coalesced
-  char* resp = xresp(x, src, x.me);  // remote, appended contiguously
+  const char* ids = xids(x, src, x.me);  // the ids source `src` wants from me (remote unless src == me), read coalesced
+  char* resp = xresp(x, src, x.me);      // remote, written contiguously: entry i answers id i
   char* served = xserved(x, x.me, src);
   const int lane = threadIdx.x & 31, lane4 = threadIdx.x & 3;
-  const bool pow2 = (x.n & (x.n - 1)) == 0;
-  int4 nxt[PER];
-  auto fetch = [&](int chunk) {  // issue the (remote) loads of a chunk; consumed one iteration later
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const int w = chunk + j * 256 + threadIdx.x;
-      nxt[j] = make_int4(0, 0, -1, epoch);
-      if (w < total) nxt[j] = ld_word16(ids + (long long)w * kXIdEntry);
-    }
-  };
-  int chunk = blockIdx.x * kXChunk;
-  if (chunk < total) fetch(chunk);
-  for (; chunk < total; chunk += gridDim.x * kXChunk) {
-    // pass 1: compact the ids this shard owns into shared memory
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      int4 e = nxt[j];
-      if (e.w != epoch) e = poll16(ids + (long long)(chunk + j * 256 + threadIdx.x) * kXIdEntry, epoch, gv.err);
-      const long long id = id_of(e.x, e.y);
-      const int slot = e.z;
-      const int owner = pow2 ? (int)(id & (x.n - 1)) : (int)(((id % x.n) + x.n) % x.n);
-      const bool mine = slot >= 0 && e.w == epoch && owner == x.me;
-      const unsigned m = __ballot_sync(0xffffffffu, mine);
-      int base = 0;
-      if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (mine) {
-        const int p = base + __popc(m & ((1u << lane) - 1));
-        s_id[p] = id;
-        s_slot[p] = slot;
+  const unsigned gm = 0xfu << (lane & 28);
+  const long long stride = (long long)gridDim.x * blockDim.x / 4;
+  // four lanes per id -- they load {deep lo, deep hi, wide, -} and store one tagged word each
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i < total; i += stride) {
+    int4 e = make_int4(0, 0, 0, 0);
+    if (lane4 == 0) e = poll16(ids + i * kXIdEntry, epoch, gv.err);  // one remote 16 B read per id
+    e.x = __shfl_sync(gm, e.x, 0, 4);
+    e.y = __shfl_sync(gm, e.y, 0, 4);
+    e.z = __shfl_sync(gm, e.z, 0, 4);
+    const long long id = id_of(e.x, e.y);
+    const int slot = e.z;
+    const int g = slot / x.B;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane4 < 2) {
+      const TableView& td = gv.tables[x.deep_tab[g]];
+      RowLoc loc = locate(gv, td, id);
+      if (loc.ok) {
+        v = ld_f4(loc.rec + 4 * lane4);
+        if (lane4 == 0) mark_present(td, loc);
+      } else if (lane4 == 0) {
+        atomicOr(gv.err, kErrRange);
+      }
+    } else if (lane4 == 2) {
+      const TableView& tw = gv.tables[x.wide_tab[g]];
+      RowLoc lw = locate(gv, tw, id);
+      if (lw.ok) {
+        v.x = *lw.rec;
+        mark_present(tw, lw);
       }
     }
-    const int next = chunk + gridDim.x * kXChunk;
-    if (next < total) fetch(next);
-    __syncthreads();
-    const int n = s_n;
-    if (threadIdx.x == 0) s_base = n ? atomicAdd(&h->cursor[src], n) : 0;
-    __syncthreads();
-    const int base = s_base;
-    // pass 2: four lanes per kept id -- they load {deep lo, deep hi, wide, -} and store one tagged word each
-    const int n4 = (n + 63) & ~63;  // whole 4-lane groups stay converged for the shuffles
-    for (int e = threadIdx.x >> 2; e < n4; e += 64) {
-      const bool live = e < n;
-      const long long id = live ? s_id[e] : 0;
-      const int slot = live ? s_slot[e] : 0;
-      const int g = slot / x.B;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live && lane4 < 2) {
-        const TableView& td = gv.tables[x.deep_tab[g]];
-        RowLoc loc = locate(gv, td, id);
-        if (loc.ok) {
-          v = ld_f4(loc.rec + 4 * lane4);
-          if (lane4 == 0) mark_present(td, loc);
-        } else if (lane4 == 0) {
-          atomicOr(gv.err, kErrRange);
-        }
-      } else if (live && lane4 == 2) {
-        const TableView& tw = gv.tables[x.wide_tab[g]];
-        RowLoc lw = locate(gv, tw, id);
-        if (lw.ok) {
-          v.x = *lw.rec;
-          mark_present(tw, lw);
-        }
-      }
-      const unsigned gm = 0xfu << (lane & 28);
-      const float d3 = __shfl_sync(gm, v.w, 0, 4), d6 = __shfl_sync(gm, v.z, 1, 4), d7 = __shfl_sync(gm, v.w, 1, 4);
-      if (!live) continue;
-      char* out = resp + (long long)(base + e) * kXResp + 16 * lane4;
-      if (lane4 == 0) st_word16(out, __float_as_int(v.x), __float_as_int(v.y), __float_as_int(v.z), epoch);
-      else if (lane4 == 1) st_word16(out, __float_as_int(d3), __float_as_int(v.x), __float_as_int(v.y), epoch);
-      else if (lane4 == 2) st_word16(out, __float_as_int(d6), __float_as_int(d7), __float_as_int(v.x), epoch);
-      else {
-        st_word16(out, slot, 0, 0, epoch);
-        int4 rec = make_int4((int)(id & 0xffffffffLL), (int)(id >> 32), g, 0);
-        *reinterpret_cast<int4*>(served + (long long)(base + e) * kXServed) = rec;
-      }
+    const float d3 = __shfl_sync(gm, v.w, 0, 4), d6 = __shfl_sync(gm, v.z, 1, 4), d7 = __shfl_sync(gm, v.w, 1, 4);
+    char* out = resp + i * kXResp + 16 * lane4;
+    if (lane4 == 0) st_word16(out, __float_as_int(v.x), __float_as_int(v.y), __float_as_int(v.z), epoch);
+    else if (lane4 == 1) st_word16(out, __float_as_int(d3), __float_as_int(v.x), __float_as_int(v.y), epoch);
+    else if (lane4 == 2) st_word16(out, __float_as_int(d6), __float_as_int(d7), __float_as_int(v.x), epoch);
+    else {
+      st_word16(out, slot, 0, 0, epoch);
+      int4 rec = make_int4((int)(id & 0xffffffffLL), (int)(id >> 32), g, 0);
+      *reinterpret_cast<int4*>(served + i * kXServed) = rec;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
   }
   __shared__ bool last;
-  __threadfence();  // cursor / served records: local, read by this GPU's later kernels and the last block
+  __threadfence();  // served records: local, read by this GPU's later kernels
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(&h->done_src[src], 1u) == gridDim.x - 1;
   __syncthreads();
   if (last && threadIdx.x == 0) {
-    __threadfence();
-    const int cnt = *(volatile int*)&h->cursor[src];
-    h->served_cnt[src] = cnt;
-    st_word8(&xhdr(x, src)->resp[x.me], cnt, epoch);
+    h->served_cnt[src] = total;
+    st_word8(&xhdr(x, src)->resp[x.me], total, epoch);
     h->done_src[src] = 0;
   }
 }
