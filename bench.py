@@ -298,6 +298,8 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "owner", "direct"],
                     help="multi-GPU row exchange: owner-computes bulk exchange (default for N>1) or direct peer access")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the post-timing N>1 parity self-check")
+    ap.add_argument("--ids", default="narrow", choices=["narrow", "int32"],
+                    help="id transport of the packed batches: 1/2/4 bytes per id by table size, or int32")
     args = ap.parse_args()
     cpu_batch = args.cpu_batch or args.batch
 
@@ -345,15 +347,16 @@ def main():
     group = PSGroup(world, "Adam", ADAM_ARGS, device=local_rank,
                     local_shards=[rank] if world > 1 else None)
     engine = DeepFMPSEngine(group, args.batch, tower=args.tower, paired=args.paired == "on",
-                            exchange=None if args.exchange == "auto" else args.exchange)
+                            exchange=None if args.exchange == "auto" else args.exchange, id_transport=args.ids)
     config["record_layout"] = "paired deep+wide record per id" if engine.paired else "one record slab per table"
     config["exchange"] = engine.exchange
     use_graph = args.tower != "torch" and not args.no_graph
     lookahead = use_graph and args.lookahead == "on"
     config["pipeline"] = ("CUDA graph per step; id dedup of batch i+1 overlapped with step i on a second stream"
                           if lookahead else ("CUDA graph per step" if use_graph else "eager launches"))
-    config["id_transport"] = ("ids cross PCIe / sit in HBM as int32 (all tables < 2^31 rows), widened to int64 "
-                              "inside the dedup kernel; one packed buffer per batch [ids|dense|labels]")
+    config["id_transport"] = (("ids cross PCIe / sit in HBM at 1 / 2 / 4 bytes by table size (<= 256 / <= 65536 / larger rows)"
+                               if args.ids == "narrow" else "ids cross PCIe / sit in HBM as int32 (all tables < 2^31 rows)")
+                              + ", widened to int64 inside the dedup kernel; one packed buffer per batch [ids|dense|labels]")
     if world > 1:
         dist.barrier()
     B = args.batch
@@ -364,8 +367,8 @@ def main():
     for p in range(args.pool):
         ids, dense, labels = synthetic_batch(B, 1234 + p + 1000 * rank, dev, args.dist)
         devb.append((ids, dense, labels))
-        devp.append(pack_batch(ids, dense, labels))
-        host.append(pack_batch(ids.cpu(), dense.cpu(), labels.cpu(), pin=True))
+        devp.append(pack_batch(ids, dense, labels, widths=engine.widths))
+        host.append(pack_batch(ids.cpu(), dense.cpu(), labels.cpu(), pin=True, widths=engine.widths))
     uniq_per_batch = []
     for ids, _, _ in devb:
         _, _, n = group.unique(ids.view(-1), G)
@@ -498,7 +501,7 @@ def main():
         else:
             hb = host[i % args.pool].to(dev, non_blocking=True)
             from elasticdl_b200.workloads.deepfm import packed_views
-            loss = engine.step(*packed_views(hb, G, B))
+            loss = engine.step(*packed_views(hb, G, B, engine.widths))
         loss_pin[i].copy_(loss, non_blocking=True)
     e3.record()
     sync_all()
@@ -525,7 +528,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "h2d_copy_ms_probe": h2d_ms,
                     "h2d_gbs_probe": h2d / h2d_ms / 1e6,
-                    "id_narrowing": "ids int64 -> int32 on the host side of the boundary (packed batch), widened on the device"},
+                    "id_narrowing": "ids int64 -> %s on the host side of the boundary (packed batch), widened on the device" % ("1/2/4-byte" if args.ids == "narrow" else "int32")},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / max(args.steps, 1),
             "launch_mode": "cuda_graph" if use_graph else "eager", "eager_ms_per_step": ms_eager / args.steps,
             "tower": args.tower,

@@ -103,6 +103,9 @@ SYMBOLS = {
     "b200ps_unique_bounded_i32": (_i, [_vp, _vp, _i, _i64, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200ps_unique_bounded_ex": (_i, [_vp, _vp, _i, _i, _i64, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "b200ps_debug_buffer": (_i, [_vp, _sz]),
+    "b200ps_unique_packed": (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_int32), _i, _i64, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp,
+                                  _sz, _i, _vp]),
+    "b200ps_packed_ids_bytes": (_sz, [ctypes.POINTER(ctypes.c_int32), _i, _i64]),
     "b200ps_segment_sum": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp]),
     "b200ps_gather_rows": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp]),
     "b200ps_shard_state": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_int32)]),

@@ -867,7 +867,26 @@ static int rows_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   if (rc) return rc;
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
-  if (sp.flat_n) {
+  // large gathers go through the shared-memory staged kernel (cp.async in, one bulk async copy out per warp):
+  // its bytes in flight are bounded by shared memory, not registers.  Small ones are one latency chain either way.
+  static const long long staged_min = [] { const char* e = getenv("B200_STAGED_MIN"); return e ? atoll(e) : 2000000LL; }();
+  if (sp.flat_n && !write && sp.flat_items >= staged_min) {
+    constexpr int SU = 8;
+    long long blocks = (sp.flat_items + 256LL * SU - 1) / (256LL * SU);
+    const long long cap = (long long)ps->n_sm * 4;
+    if (blocks > cap) blocks = cap;
+    if (ps->n_shards == 1) {
+      FlatArgs<1> fa;
+      fill_flat(ps, sp, false, slot, &fa);
+      k_pull_staged<SU, 1><<<(unsigned)blocks, 256, 0, st>>>(fa);
+    } else {
+      FlatArgs<8> fa;
+      fill_flat(ps, sp, false, slot, &fa);
+      k_pull_staged<SU, 8><<<(unsigned)blocks, 256, 0, st>>>(fa);
+    }
+    ps->launches++;
+    CUDA_OK(cudaGetLastError());
+  } else if (sp.flat_n) {
     int u_rt, grid;
     flat_shape(ps, sp.flat_items, &u_rt, &grid);
     if (ps->n_shards == 1) {
@@ -1439,7 +1458,7 @@ static size_t g_dbg_bytes = 0;
 
 static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int64_t k, const int64_t* bounds,
                        int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
-                       size_t workspace_bytes, void* stream, int blocks_per_sm = 0) {
+                       size_t workspace_bytes, void* stream, int blocks_per_sm = 0, const int32_t* widths = nullptr) {
   if (T < 1 || T > 65535 || k < 1 || k > (1LL << 29)) return fail(B200PS_EINVAL, "bad unique shape");
   if (!ids_dev || !uniq_dev || !inv_dev || !n_unique_dev || !workspace_dev) return fail(B200PS_EINVAL, "null argument");
   if (workspace_bytes < b200ps_unique_workspace(T, k)) return fail(B200PS_EINVAL, "unique workspace too small");
@@ -1530,7 +1549,20 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   if (blocks > max_blocks) blocks = max_blocks;  // the grid walks the slots (slot = block, block + grid, ...)
   if (blocks < 1) blocks = 1;
   CUDA_OK(cudaMemsetAsync(a.hdr + 4, 0, 8, st));  // the grid-barrier counter
-  k_unique<<<(unsigned)blocks, kUThreads, 0, st>>>(a, ur);
+  UIdLayout idl{};
+  if (widths != nullptr) {  // packed ids: segment t holds k elements of widths[t] bytes, segments back to back, 16 B aligned
+    if (T > kMaxSegs) return fail(B200PS_EINVAL, "per-segment id widths need T <= " + std::to_string(kMaxSegs));
+    long long off = 0;
+    for (int t = 0; t < T; ++t) {
+      const int w = widths[t];
+      if (w != 1 && w != 2 && w != 4 && w != 8) return fail(B200PS_EINVAL, "id width must be 1, 2, 4 or 8 bytes");
+      idl.off[t] = off;
+      idl.width[t] = (unsigned char)w;
+      off += ((long long)k * w + 15) / 16 * 16;
+    }
+    a.ids32 = 2;
+  }
+  k_unique<<<(unsigned)blocks, kUThreads, 0, st>>>(a, ur, idl);
   count_launch(ps, 1);
   CUDA_OK(cudaGetLastError());
   return B200PS_OK;
@@ -1561,6 +1593,20 @@ int b200ps_unique_bounded_ex(b200ps_t* ps, const void* ids_dev, int ids_are_int3
                              size_t workspace_bytes, int blocks_per_sm, void* stream) {
   return unique_impl(ps, ids_dev, ids_are_int32 ? 1 : 0, T, k, bounds, uniq_dev, inv_dev, n_unique_dev, workspace_dev,
                      workspace_bytes, stream, blocks_per_sm);
+}
+
+int b200ps_unique_packed(b200ps_t* ps, const void* ids_dev, const int32_t* widths, int T, int64_t k, const int64_t* bounds,
+                         int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
+                         size_t workspace_bytes, int blocks_per_sm, void* stream) {
+  if (!widths) return fail(B200PS_EINVAL, "widths is null");
+  return unique_impl(ps, ids_dev, 2, T, k, bounds, uniq_dev, inv_dev, n_unique_dev, workspace_dev, workspace_bytes, stream,
+                     blocks_per_sm, widths);
+}
+
+size_t b200ps_packed_ids_bytes(const int32_t* widths, int T, int64_t k) {
+  size_t off = 0;
+  for (int t = 0; widths && t < T; ++t) off += ((size_t)k * (size_t)widths[t] + 15) / 16 * 16;
+  return off;
 }
 
 int b200ps_debug_buffer(void* dev_ptr, size_t bytes) {

@@ -67,7 +67,7 @@ thread_local std::string g_msg;
 constexpr int SM_W1X = NCOL * H1;          // 5120
 constexpr int SM_X = TS * XS;              // 11648
 constexpr int SM_P = NKP * RW * TS;        // 6656   partial records [kp][r][s]; reused as T[r][s] + M[s][MS]
-constexpr int SM_R = TS * RS;              // 1248   ranks Rt[s][g]
+constexpr int SM_R = 2 * TS * RS;          // 2496   ranks Rt[buffer][s][g]: this tile's and the prefetched next tile's
 constexpr int SM_WV = MAXG * TS;           // 1216   wide values WV[g][s]
 constexpr int SM_SMALL = 128;              // b... w2 64 | b2 4 | w3 4 | wd 16
 constexpr size_t SMEM_BYTES = (size_t)(SM_W1X + SM_X + SM_P + SM_R + SM_WV + SM_SMALL) * sizeof(float);
@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
   float* W1x = smem;                 // [NCOL][16]
   float* X = W1x + SM_W1X;           // [TS][XS]
   float* P = X + SM_X;               // [NKP][RW][TS], later T[RW][TS] and Mst[TS][MS]
-  int* Rt = reinterpret_cast<int*>(P + SM_P);  // [TS][RS] ranks
-  float* WV = reinterpret_cast<float*>(Rt + SM_R);  // [G][TS] wide values
+  int* Rt0 = reinterpret_cast<int*>(P + SM_P);  // [2][TS][RS] ranks
+  float* WV = reinterpret_cast<float*>(Rt0 + SM_R);  // [G][TS] wide values
   float* small = WV + SM_WV;
   float* s_w2 = small;        // [H2][H1]
   float* s_b2 = small + 64;   // [H2]
@@ -153,29 +153,30 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
   __syncthreads();
 
   const long long ntile = ((long long)B + TS - 1) / TS;
-  for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+  // ranks of a tile: 4-byte cp.async, coalesced reads of inv (32 consecutive samples of one group per warp)
+  auto fetch_ranks = [&](const long long tl, int* dst) {
+    const long long bb0 = tl * TS;
+    for (int i = t; i < G * TS; i += THREADS) {
+      long long b = bb0 + (i & 31);
+      if (b >= B) b = B - 1;  // dead samples replay the last one, their results are masked
+      cp_async4(dst + (i & 31) * RS + (i >> 5), a.inv + (long long)(i >> 5) * B + b);
+    }
+  };
+  int cur = 0;
+  if ((long long)blockIdx.x < ntile) fetch_ranks(blockIdx.x, Rt0);
+  cp_async_wait_all();
+  __syncthreads();
+  for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x, cur ^= 1) {
     const long long b0 = tile * TS;
+    int* Rt = Rt0 + cur * (TS * RS);
     // ---------------- G: gather the tile once ----------------
-    // step 1: ranks (coalesced: 32 consecutive samples of one group per warp) -> Rt[s][g]; dense columns.
-    // step 2: the rows, lane = consecutive 16 B chunk of ONE sample's row, so that a warp's cp.async
-    //         destinations are contiguous in shared memory (lane = sample put every lane's 16 B into its
-    //         own wavefront: 32-way, 2560 of the tile's 13.3 K shared-memory wavefronts -- ncu, profiles/r2_04).
+    // The tile's ranks are already in Rt (prefetched while the previous tile was computed), so the gather is
+    // ONE global round trip: the row copies of this tile and the rank prefetch of the next one fly together.
+    // Rows: lane = consecutive 16 B chunk of ONE sample's row (contiguous shared-memory destinations).
     {
       const int npair = G * TS;
-      constexpr int NP = (MAXG * TS + THREADS - 1) / THREADS;  // 5 (group, sample) pairs per thread
       constexpr int NFILL = (TS * 16 + THREADS - 1) / THREADS;  // dense | 1 | 0 0 columns: 2 per thread
-      int rk[NP];
       float dv[NFILL];
-#pragma unroll
-      for (int jj = 0; jj < NP; ++jj) {
-        const int i = t + THREADS * jj;
-        rk[jj] = 0;
-        if (i < npair) {
-          long long b = b0 + (i & 31);
-          if (b >= B) b = B - 1;  // dead samples replay the last one, their results are masked
-          rk[jj] = a.inv[(long long)(i >> 5) * B + b];
-        }
-      }
 #pragma unroll
       for (int jj = 0; jj < NFILL; ++jj) {  // tile columns 304..319 of sample s: dense 13 | 1 | 0 | 0
         const int i = t + THREADS * jj;
@@ -186,21 +187,6 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
         if (i < TS * 16 && c < ND) v = a.dense[b * ND + c];
         dv[jj] = v;
       }
-#pragma unroll
-      for (int jj = 0; jj < NP; ++jj) {
-        const int i = t + THREADS * jj;
-        if (i < npair) Rt[(i & 31) * RS + (i >> 5)] = rk[jj];
-      }
-#pragma unroll
-      for (int jj = 0; jj < NFILL; ++jj) {
-        const int i = t + THREADS * jj;
-        if (i < TS * 16) X[(i >> 4) * XS + MAXG * D + (i & 15)] = dv[jj];
-      }
-      for (int i = t; i < TS * (MAXG - G) * D; i += THREADS) {  // unused group columns (G < 38): zeros
-        const int s = i / ((MAXG - G) * D), c = G * D + i % ((MAXG - G) * D);
-        X[s * XS + c] = 0.f;
-      }
-      __syncthreads();
       const int nchunk = G * 2;  // 16 B chunks per sample row
       for (int i = t; i < TS * nchunk; i += THREADS) {
         const int s = i / nchunk, ch = i - s * nchunk;
@@ -211,6 +197,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
       for (int i = t; i < npair; i += THREADS) {  // wide values: lane = sample
         const int g = i >> 5, s = i & 31;
         cp_async4(WV + g * TS + s, a.bet_wide + (long long)g * B + Rt[s * RS + g]);
+      }
+      if (tile + gridDim.x < ntile) fetch_ranks(tile + gridDim.x, Rt0 + (cur ^ 1) * (TS * RS));
+#pragma unroll
+      for (int jj = 0; jj < NFILL; ++jj) {
+        const int i = t + THREADS * jj;
+        if (i < TS * 16) X[(i >> 4) * XS + MAXG * D + (i & 15)] = dv[jj];
+      }
+      for (int i = t; i < TS * (MAXG - G) * D; i += THREADS) {  // unused group columns (G < 38): zeros
+        const int s = i / ((MAXG - G) * D), c = G * D + i % ((MAXG - G) * D);
+        X[s * XS + c] = 0.f;
       }
       cp_async_wait_all();
     }

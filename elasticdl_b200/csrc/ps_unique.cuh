@@ -42,10 +42,15 @@ struct UniqueBounds {      // per segment: ids are known to be < bound (0 = unkn
 constexpr int kUniqPosBits = 20;
 constexpr int kUniqEpochs = 2047;  // prefixes 0..2046 keep the value below 0x7fffffff (= empty)
 
+struct UIdLayout {               // ids_kind == 2: every segment has its own element width and byte offset
+  long long off[kMaxSegs];       // byte offset of segment t inside the ids buffer
+  unsigned char width[kMaxSegs]; // 1, 2, 4 (unsigned) or 8 (int64) bytes per id
+};
+
 struct UArgs {
   const void* ids;
   long long k;
-  int T, ids32;
+  int T, ids32;                  // ids32: 0 = int64 [T][k], 1 = int32 [T][k], 2 = per-segment layout (UIdLayout)
   long long* keys;              // [T][cap]   (hashed segments)
   int* minpos;                  // [T][cap]
   int* fp;                      // [T][k]  slot / id, then first position of the id at i
@@ -62,8 +67,15 @@ struct UArgs {
   long long* dbg;               // optional [blocks][8] globaltimer stamps per phase (profiling aid)
 };
 
-__device__ __forceinline__ long long u_id(const UArgs& a, long long idx) {
-  return a.ids32 ? (long long)reinterpret_cast<const int*>(a.ids)[idx] : reinterpret_cast<const long long*>(a.ids)[idx];
+__device__ __forceinline__ long long u_id(const UArgs& a, const UIdLayout& L, int t, long long i) {
+  if (a.ids32 == 0) return reinterpret_cast<const long long*>(a.ids)[(long long)t * a.k + i];
+  if (a.ids32 == 1) return (long long)reinterpret_cast<const int*>(a.ids)[(long long)t * a.k + i];
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(a.ids) + L.off[t];
+  const int w = L.width[t];
+  if (w == 1) return (long long)base[i];
+  if (w == 2) return (long long)reinterpret_cast<const unsigned short*>(base)[i];
+  if (w == 4) return (long long)reinterpret_cast<const unsigned int*>(base)[i];
+  return reinterpret_cast<const long long*>(base)[i];
 }
 __device__ __forceinline__ unsigned long long u_ldv(const unsigned long long* p) {
   unsigned long long v;
@@ -122,7 +134,8 @@ struct URuns {                     // run slot -> (segment, first unit, units); 
   int nslots;
 };
 
-__global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
+__global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__ UArgs a, const __grid_constant__ URuns ur,
+                                                         const __grid_constant__ UIdLayout idl) {
   constexpr int NW = kUThreads / 32;
   constexpr int PPT = kUPPT;
   __shared__ int s_cnt[PPT * NW];  // first-occurrence counts per (q, warp), then their exclusive prefix
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
 #pragma unroll
       for (int q = 0; q < PPT; ++q) {  // all id loads first
         const long long i = base + q * kUThreads + threadIdx.x;
-        const long long v = i < k ? u_id(a, (long long)t * k + i) : 0;
+        const long long v = i < k ? u_id(a, idl, t, i) : 0;
         id[q] = (v < 0 || v >= bound) ? 0 : (int)v;  // out-of-range ids are reported by the table kernels
         if (i < k) fp[i] = id[q];
       }
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
 #pragma unroll
       for (int q = 0; q < PPT; ++q) {
         const long long i = base + q * kUThreads + threadIdx.x;
-        id[q] = i < k ? u_id(a, (long long)t * k + i) : 0;
+        id[q] = i < k ? u_id(a, idl, t, i) : 0;
       }
 #pragma unroll
       for (int q = 0; q < PPT; ++q) {
@@ -420,7 +433,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(UArgs a, URuns ur) {
           rank_at[i] = r;
           inv[i] = r;
           fp[i] = -1;  // done: phase C skips it
-          a.uniq[(long long)t * k + r] = u_id(a, (long long)t * k + i);
+          a.uniq[(long long)t * k + r] = u_id(a, idl, t, i);
         }
       }
       run_base += s_excl;

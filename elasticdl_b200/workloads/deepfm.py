@@ -80,29 +80,59 @@ def synthetic_batch(batch, seed, device, dist="zipf", zipf_s=1.05, group_rows=GR
     return ids, dense, labels
 
 
-def packed_nbytes(G, B):
-    """One training batch as ONE buffer: [ids int32 G x B | dense fp32 B x 13 | labels fp32 B]."""
-    return 4 * G * B + 4 * B * N_DENSE + 4 * B
+def id_widths(group_rows):
+    """Bytes per id of every group on the wire: a table with at most 256 / 65536 rows needs one / two."""
+    return [1 if r <= 256 else (2 if r <= 65536 else 4) for r in group_rows]
 
 
-def packed_views(buf, G, B):
-    """(ids int32 [G, B], dense fp32 [B, 13], labels fp32 [B]) views of a packed uint8 buffer."""
-    a, b = 4 * G * B, 4 * G * B + 4 * B * N_DENSE
-    return (buf[:a].view(torch.int32).view(G, B), buf[a:b].view(torch.float32).view(B, N_DENSE),
-            buf[b:b + 4 * B].view(torch.float32))
+def _ids_layout(B, widths):
+    """[(byte offset, width)] of the per-group id segments (each padded to 16 bytes) and the total."""
+    off, out = 0, []
+    for w in widths:
+        out.append((off, w))
+        off += (B * w + 15) // 16 * 16
+    return out, off
 
 
-def pack_batch(ids, dense, labels, pin=False):
-    """Pack (ids int64/int32 [G, B], dense [B, 13], labels [B]) into one uint8 buffer on the same
-    device (pin=True: pinned host memory).  ids are narrowed to int32 -- every dac_ctr table has
-    fewer than 2^31 rows; the device widens them again inside the dedup kernel
-    (b200ps_unique_bounded_i32), so the PS sees the same int64 ids."""
+def packed_nbytes(G, B, widths=None):
+    """One training batch as ONE buffer: [ids, group by group at their own width | dense fp32 B x 13 | labels fp32 B].
+    widths=None: int32 ids."""
+    widths = widths or [4] * G
+    return _ids_layout(B, widths)[1] + 4 * B * N_DENSE + 4 * B
+
+
+def packed_views(buf, G, B, widths=None):
+    """(ids, dense fp32 [B, 13], labels fp32 [B]) views of a packed uint8 buffer; ids is an int32 [G, B] view
+    when every width is 4, else the uint8 id region itself (the dedup kernel reads it with the widths)."""
+    widths = widths or [4] * G
+    a = _ids_layout(B, widths)[1]
+    b = a + 4 * B * N_DENSE
+    ids = buf[:a].view(torch.int32).view(G, B) if all(w == 4 for w in widths) else buf[:a]
+    return ids, buf[a:b].view(torch.float32).view(B, N_DENSE), buf[b:b + 4 * B].view(torch.float32)
+
+
+_NP_UINT = {1: torch.uint8, 2: torch.int16, 4: torch.int32}
+
+
+def pack_batch(ids, dense, labels, pin=False, widths=None):
+    """Pack (ids int64/int32 [G, B], dense [B, 13], labels [B]) into one uint8 buffer on the same device
+    (pin=True: pinned host memory).  ids are narrowed to `widths` bytes per group (default int32: every
+    dac_ctr table has fewer than 2^31 rows); the device widens them again inside the dedup kernel
+    (b200ps_unique_bounded_i32 / b200ps_unique_packed), so the PS sees the same int64 ids."""
     G, B = ids.shape
-    buf = torch.empty(packed_nbytes(G, B), dtype=torch.uint8, device="cpu" if pin else ids.device)
+    widths = widths or [4] * G
+    layout, a = _ids_layout(B, widths)
+    buf = torch.zeros(packed_nbytes(G, B, widths), dtype=torch.uint8, device="cpu" if pin else ids.device)
     if pin:
         buf = buf.pin_memory()
-    v_ids, v_dense, v_labels = packed_views(buf, G, B)
-    v_ids.copy_(ids)
+    for g, (off, w) in enumerate(layout):
+        # unsigned narrowing: two's complement of the low bytes (uint16 as int16 bits)
+        seg = buf[off:off + B * w].view(_NP_UINT[w])
+        v = ids[g].to(torch.int64)
+        if w == 2:
+            v = torch.where(v >= 32768, v - 65536, v)
+        seg.copy_(v.to(_NP_UINT[w]))
+    _, v_dense, v_labels = packed_views(buf, G, B, widths)
     v_dense.copy_(dense)
     v_labels.copy_(labels)
     return buf
@@ -143,7 +173,7 @@ class HostFeeder:
         self.e = engine
         dev, G, B = engine.device, engine.G, engine.B
         self.depth = depth
-        self.slots = [torch.empty(packed_nbytes(G, B), dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.slots = [torch.empty(packed_nbytes(G, B, engine.widths), dtype=torch.uint8, device=dev) for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ready = [torch.cuda.Event() for _ in range(depth)]
         self.free = [torch.cuda.Event() for _ in range(depth)]
@@ -159,8 +189,7 @@ class HostFeeder:
             if len(host_batch) == 1:
                 self.slots[k].copy_(host_batch[0], non_blocking=True)
             else:
-                for dst, src in zip(packed_views(self.slots[k], self.e.G, self.e.B), host_batch):
-                    dst.copy_(src, non_blocking=True)
+                self.e._fill(self.slots[k], host_batch)
             self.ready[k].record(self.copy_stream)
         self.head += 1
 
@@ -187,7 +216,7 @@ class HostFeeder:
 
 class DeepFMPSEngine:
     def __init__(self, group, batch, lr=1e-3, init_std=0.01, seed=7, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM,
-                 init_rows=True, tower="tile", paired=None, exchange=None):
+                 init_rows=True, tower="tile", paired=None, exchange=None, id_transport="int32"):
         """tower="tile": rows of 32 samples gathered once into shared memory, forward / backward / parameter
         gradients from the tile (csrc/deepfm_tower2.cu);
         tower="fused": round 1's hand-written CUDA tower (csrc/deepfm_tower.cu, three row gathers);
@@ -279,9 +308,15 @@ class DeepFMPSEngine:
         self.bounds = (_ctb.c_int64 * G)(*[int(r) for r in group_rows])  # id ranges: dedup by direct address
         self.ws = torch.zeros(group.lib.b200ps_unique_bounded_workspace(G, B, self.bounds), dtype=torch.uint8, device=dev)
         self._predict_state = None  # predict() dedups into its own workspace / plan (lazy)
+        # id transport of the packed batches (pack_batch / HostFeeder / captured graphs): "int32" or "narrow"
+        # (1 / 2 / 4 bytes per id by table size -- 72 instead of 152 bytes of ids per dac_ctr sample)
+        self.id_transport = id_transport
+        self.widths = id_widths(group_rows) if id_transport == "narrow" else [4] * G
+        self._c_widths = (_ctb.c_int32 * G)(*self.widths)
         import os as _os
 
-        self.lookahead_blocks_per_sm = int(_os.environ.get("B200_LOOKAHEAD_UNIQUE_BLOCKS", "1"))
+        self.lookahead_blocks_per_sm = int(_os.environ.get("B200_LOOKAHEAD_UNIQUE_BLOCKS", "0"))
+        self.lookahead_fork = _os.environ.get("B200_LOOKAHEAD_FORK", "push")  # "push" | "start" (tuning knob)
         self.bet_w = torch.zeros((G * B, 1), **f32)
         self.bet_d = torch.zeros((G * B, D), **f32)
         self.act_w = torch.empty((G * B, 1), **f32)
@@ -370,7 +405,7 @@ class DeepFMPSEngine:
         a.loss, a.logits, a.scratch = self.loss_buf.data_ptr(), self.logits_buf.data_ptr(), self.scratch.data_ptr()
         self.tower_args = a
 
-    def step(self, ids, dense, labels, ev=None):
+    def step(self, ids, dense, labels, ev=None, after_tower=None):
         """ids int64 [G, B] (group-major), dense fp32 [B, 13], labels fp32 [B] -- all on the device.
         Returns the loss (device scalar).  ev: optional dict name -> list; CUDA-event pairs are
         recorded around the named PS kernels on the launching stream."""
@@ -429,6 +464,8 @@ class DeepFMPSEngine:
             dense_segs = self.push_dense_segs
         else:
             loss, dense_segs = self._torch_tower(dense, labels, mark, done, st)
+        if after_tower is not None:
+            after_tower()  # lookahead pipeline: the next batch's dedup forks here (beside the push)
         # (7) push: one ApplyGradients per shard
         g.push_begin(self.lr, self.zero_versions)
         arr, n = dense_segs
@@ -455,6 +492,11 @@ class DeepFMPSEngine:
         """tf.unique per id group into the current plan, on the current stream.  blocks_per_sm > 0: a thin
         persistent grid (the lookahead pipeline runs the dedup beside the training kernels)."""
         g = self.group
+        if ids.dtype == torch.uint8:  # the id region of a packed batch with per-group widths
+            check(g.lib.b200ps_unique_packed(g._h, ids.data_ptr(), self._c_widths, self.G, self.B, self.bounds,
+                                             self.uniq.data_ptr(), self.inv.data_ptr(), self.n_unique.data_ptr(),
+                                             self.ws.data_ptr(), self.ws.numel(), int(blocks_per_sm), g._stream()))
+            return
         check(g.lib.b200ps_unique_bounded_ex(g._h, ids.data_ptr(), 1 if ids.dtype == torch.int32 else 0, self.G, self.B,
                                              self.bounds, self.uniq.data_ptr(), self.inv.data_ptr(),
                                              self.n_unique.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
@@ -483,12 +525,21 @@ class DeepFMPSEngine:
             raise RuntimeError("call prepare(first_ids) before step_ahead")
         main = torch.cuda.current_stream(self.device)
         p = self.cur
-        self.side.wait_stream(main)  # fork: the other plan's buffers were last read by the previous step
-        self._use(1 - p)
-        with torch.cuda.stream(self.side):
-            self._unique_into(next_ids, blocks_per_sm=self.lookahead_blocks_per_sm)
-        self._use(p)
-        loss = self.step(None, dense, labels, ev=ev)
+
+        def fork():
+            # The dedup of the next batch runs beside the PUSH of this one: the push kernels are light
+            # (48 registers, < 1 KB of shared memory) and share the SMs with the persistent dedup blocks,
+            # whereas the tower's CTAs need the whole register file of an SM and would simply wait for
+            # the dedup to finish (measured: forking at the start of the step hid 11 of its 45 us).
+            self.side.wait_stream(main)  # the other plan's buffers were last read by the previous step
+            self._use(1 - p)
+            with torch.cuda.stream(self.side):
+                self._unique_into(next_ids, blocks_per_sm=self.lookahead_blocks_per_sm)
+            self._use(p)
+
+        if self.lookahead_fork != "push":
+            fork()  # "start": beside the whole step
+        loss = self.step(None, dense, labels, ev=ev, after_tower=fork if self.lookahead_fork == "push" else None)
         main.wait_stream(self.side)  # join
         self._use(1 - p)
         return loss
@@ -501,8 +552,8 @@ class DeepFMPSEngine:
             raise RuntimeError("graph capture needs the fused tower (torch autograd allocates)")
         dev, G, B = self.device, self.G, self.B
         self._ensure_plans()
-        self.s_packed = [torch.zeros(packed_nbytes(G, B), dtype=torch.uint8, device=dev) for _ in range(2)]
-        views = [packed_views(b, G, B) for b in self.s_packed]
+        self.s_packed = [torch.zeros(packed_nbytes(G, B, self.widths), dtype=torch.uint8, device=dev) for _ in range(2)]
+        views = [packed_views(b, G, B, self.widths) for b in self.s_packed]
         torch.cuda.synchronize(dev)
         start, steps = self.cur, self.steps
         self.graphs_ahead = [None, None]
@@ -520,16 +571,20 @@ class DeepFMPSEngine:
         """dst: static packed buffer; batch: (packed,) or (ids, dense, labels) -- device or pinned host."""
         if len(batch) == 1:
             dst.copy_(batch[0], non_blocking=True)
-        else:
+        elif all(w == 4 for w in self.widths):
             for d, src in zip(packed_views(dst, self.G, self.B), batch):
                 d.copy_(src, non_blocking=True)
+        else:  # separate tensors into a narrow layout: pack on the device (compatibility path)
+            ids, dense, labels = batch
+            dst.copy_(pack_batch(ids.to(self.device), dense.to(self.device), labels.to(self.device), widths=self.widths),
+                      non_blocking=True)
 
     def prepare_packed(self, *batch):
         """Lookahead through the captured graphs: load the FIRST batch and deduplicate its ids."""
         if self.graphs_ahead is None:
             self.capture_ahead()
         self._fill(self.s_packed[self.cur], batch)
-        self._unique_into(packed_views(self.s_packed[self.cur], self.G, self.B)[0])
+        self._unique_into(packed_views(self.s_packed[self.cur], self.G, self.B, self.widths)[0])
 
     def step_ahead_graph(self, *next_batch):
         """step_ahead through the captured graphs: trains on the batch loaded by the previous call (or
@@ -549,11 +604,11 @@ class DeepFMPSEngine:
         if self.tower_kind == "torch":
             raise RuntimeError("graph capture needs the fused tower (torch autograd allocates)")
         dev, G, B = self.device, self.G, self.B
-        self.s_one = torch.zeros(packed_nbytes(G, B), dtype=torch.uint8, device=dev)
+        self.s_one = torch.zeros(packed_nbytes(G, B, self.widths), dtype=torch.uint8, device=dev)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.step(*packed_views(self.s_one, G, B))
+            self.step(*packed_views(self.s_one, G, B, self.widths))
         self.steps -= 1  # capture does not execute
         return self.graph
 

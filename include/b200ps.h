@@ -262,6 +262,14 @@ int b200ps_unique_bounded_i32(b200ps_t* ps, const int32_t* ids32_dev, int T, int
 int b200ps_unique_bounded_ex(b200ps_t* ps, const void* ids_dev, int ids_are_int32, int T, int64_t k, const int64_t* bounds,
                              int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
                              size_t workspace_bytes, int blocks_per_sm, void* stream);
+/* Narrowest id transport: segment t of the ids buffer holds k UNSIGNED ids of widths[t] bytes (1, 2 or 4; 8 =
+ * int64), the segments back to back, each padded to 16 bytes (b200ps_packed_ids_bytes gives the total).  A
+ * table with fewer than 256 / 65536 rows needs one / two bytes per id on PCIe and in HBM; the widening to
+ * int64 happens at the dedup kernel's first read, the outputs are those of b200ps_unique_bounded. */
+int b200ps_unique_packed(b200ps_t* ps, const void* ids_dev, const int32_t* widths, int T, int64_t k, const int64_t* bounds,
+                         int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,
+                         size_t workspace_bytes, int blocks_per_sm, void* stream);
+size_t b200ps_packed_ids_bytes(const int32_t* widths, int T, int64_t k);
 /* Profiling aid: a device buffer (>= 64 B per resident block) that the persistent kernels fill with
  * %globaltimer stamps per block and phase; NULL switches it off. */
 int b200ps_debug_buffer(void* dev_ptr, size_t bytes);

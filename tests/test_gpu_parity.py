@@ -946,3 +946,96 @@ def test_flat_launch_mixed_tables_device_counts(opt, n_shards):
     owner = string_to_id(dn, n_shards)
     assert np.array_equal(group.pull_dense([dn])[dn].cpu().numpy(), oc.servers[owner].dense[dn]), "indexed rows of a dense parameter"
     group.close()
+
+
+def test_unique_packed_per_segment_id_widths():
+    """b200ps_unique_packed: every segment of the ids buffer at its own width (1 / 2 / 4 / 8 bytes, unsigned,
+    16 B padded segments) == the int64 dedup of the same ids, bit for bit."""
+    import ctypes
+
+    from elasticdl_b200 import _lib
+
+    group, _, _ = make_pair(1)
+    lib = _lib.lib()
+    rng = np.random.RandomState(21)
+    T, k = 6, 5001
+    bounds_l = [200, 256, 65536, 40000, 10 ** 6, 3]
+    widths_l = [1, 1, 2, 2, 4, 8]
+    ids = np.stack([rng.randint(0, b, size=k) for b in bounds_l]).astype(np.int64)
+    ids[1, :3] = [255, 0, 255]
+    ids[2, :3] = [65535, 32768, 32767]
+    widths = (ctypes.c_int32 * T)(*widths_l)
+    bounds = (ctypes.c_int64 * T)(*bounds_l)
+    nbytes = lib.b200ps_packed_ids_bytes(widths, T, k)
+    buf = np.zeros(nbytes, dtype=np.uint8)
+    off = 0
+    for t, w in enumerate(widths_l):
+        seg = ids[t].astype({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.int64}[w])
+        buf[off:off + k * w] = seg.view(np.uint8)
+        off += (k * w + 15) // 16 * 16
+    assert off == nbytes
+    d_buf = torch.from_numpy(buf).cuda()
+    need = lib.b200ps_unique_bounded_workspace(T, k, bounds)
+    ws = torch.zeros(need, dtype=torch.uint8, device="cuda")
+    uniq = torch.empty(T * k, dtype=torch.int64, device="cuda")
+    inv = torch.empty(T * k, dtype=torch.int32, device="cuda")
+    n = torch.empty(T, dtype=torch.int32, device="cuda")
+    for bps in (0, 1):
+        _lib.check(lib.b200ps_unique_packed(group._h, d_buf.data_ptr(), widths, T, k, bounds, uniq.data_ptr(), inv.data_ptr(),
+                                            n.data_ptr(), ws.data_ptr(), ws.numel(), bps, group._stream()))
+        group.check()
+        u, i, c = uniq.cpu().numpy().reshape(T, k), inv.cpu().numpy().reshape(T, k), n.cpu().numpy()
+        for t in range(T):
+            wu, wi = O.unique_first_occurrence(ids[t])
+            assert c[t] == len(wu) and np.array_equal(u[t, : c[t]], wu) and np.array_equal(i[t], wi), (t, bps)
+    group.close()
+
+
+@pytest.mark.parametrize("n_shards", [1, 2])
+def test_staged_pull_large_gather_bit_exact(n_shards):
+    """The shared-memory staged gather (cp.async in, bulk async copy out; taken above 2 M lane-items) returns
+    exactly the table rows: mixed dims (8, 64 staged; 1, 10 direct) in one launch, ragged warp tails, device-side
+    counts, and an out-of-range id (that warp falls back to per-lane stores, the error is raised)."""
+    from elasticdl_b200 import _lib
+
+    group, client, _ = make_pair(n_shards, "adam")
+    rng = np.random.RandomState(9)
+    dims, caps = [8, 64, 1, 10], [300_000, 200_000, 50_000, 5_000]
+    names = ["s%d" % i for i in range(4)]
+    client.push_embedding_table_infos([info(n, d, capacity=c) for n, d, c in zip(names, dims, caps)])
+    tabs = {}
+    for n_, d, c in zip(names, dims, caps):
+        vals = rng.randn(c, d).astype(F)
+        group.set_rows([(n_, np.arange(c), vals)])
+        tabs[n_] = vals
+    lib, h = group.lib, group._h
+    items, keep = [], []
+    for n_, d, c in zip(names, dims, caps):
+        m = c - 7
+        ids = rng.permutation(c)[:m].astype(np.int64)
+        nl = m - 13
+        t_ids = torch.from_numpy(ids).cuda()
+        n_dev = torch.tensor([nl], dtype=torch.int32, device="cuda")
+        rows = torch.full((m, d), -3.0, dtype=torch.float32, device="cuda")
+        keep.append((ids, nl, rows, t_ids, n_dev))
+        items.append((group.lookup(n_)[0], m, t_ids, n_dev, rows))
+    arr, nseg = group.make_segs(items)
+    _lib.check(lib.b200ps_pull_rows(h, arr, nseg, group._stream()))  # 0.6 M + 3.2 M + ... lane-items: the staged kernel
+    group.check()
+    for (ids, nl, rows, _, _), n_ in zip(keep, names):
+        got = rows.cpu().numpy()
+        assert np.array_equal(got[:nl], tabs[n_][ids[:nl]]), n_
+        assert (got[nl:] == -3.0).all(), n_
+    # one id out of range in the middle of the dim-8 segment: every other row still arrives, the error is reported
+    ids0, nl0, rows0, t_ids0, _ = keep[0]
+    t_ids0[1234] = caps[0] + 5
+    rows0.fill_(-3.0)
+    _lib.check(lib.b200ps_pull_rows(h, arr, nseg, group._stream()))
+    with pytest.raises(ValueError):
+        group.check()
+    got = rows0.cpu().numpy()
+    ok = np.ones(nl0, dtype=bool)
+    ok[1234] = False
+    assert np.array_equal(got[:nl0][ok], tabs[names[0]][ids0[:nl0]][ok])
+    assert (got[1234] == -3.0).all()
+    group.close()
