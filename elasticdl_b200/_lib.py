@@ -87,7 +87,7 @@ SYMBOLS = {
     "b200ps_push_dense_reduce": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _f, _vp]),
     "b200ps_push_end": (_i, [_vp, _vp, _vp]),
     "b200ps_bump_step": (_i, [_vp, _vp]),
-    "b200ps_push_begin_shard": (_i, [_vp, _i, _f, _vp]),
+    "b200ps_push_begin_shard": (_i, [_vp, _i, _f, ctypes.POINTER(ctypes.c_int32), _vp]),
     "b200ps_push_end_shard": (_i, [_vp, _i, _vp]),
     "b200ps_raw_register": (_i, [_vp, ctypes.c_char_p, _sz]),
     "b200ps_raw_ptr": (_i, [_vp, _i, _i, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),

@@ -974,9 +974,9 @@ int b200ps_push_begin(b200ps_t* ps, float learning_rate, const int32_t* model_ve
   return push_begin_impl(ps, learning_rate, model_versions, stream, 0);
 }
 int b200ps_bump_step(b200ps_t* ps, void* stream) { return push_begin_impl(ps, 0.f, nullptr, stream, 1); }
-int b200ps_push_begin_shard(b200ps_t* ps, int shard, float learning_rate, void* stream) {
+int b200ps_push_begin_shard(b200ps_t* ps, int shard, float learning_rate, const int32_t* model_versions, void* stream) {
   if (shard < 0) return fail(B200PS_EINVAL, "bad shard id");
-  return push_begin_impl(ps, learning_rate, nullptr, stream, 0, shard);
+  return push_begin_impl(ps, learning_rate, model_versions, stream, 0, shard);
 }
 
 #define DISPATCH_OPT(KIND, ...)                        \
@@ -1696,6 +1696,7 @@ int b200ps_snapshot_state(b200ps_t* ps, int64_t* out_host, void* stream) {
 int b200ps_try_init(b200ps_t* ps, int shard, int* won) {
   if (!ps || shard < 0 || shard >= ps->n_shards || !ps->shard[shard].attached || !won) return fail(B200PS_EINVAL, "bad shard");
   DeviceGuard g(ps->client_device);
+  CUDA_OK(cudaDeviceSynchronize());  // synchronous query on the legacy stream: order it after the caller's non-blocking streams
   k_try_init<<<1, 1>>>((ShardCtl*)ps->shard[shard].ctl.ptr, (int*)ps->d_count);
   ps->launches++;
   CUDA_OK(cudaGetLastError());
@@ -1720,6 +1721,7 @@ static int present_scan(b200ps_t* ps, int table, int shard, int64_t* ids_dev, in
   if (t.is_dense || (!t.present_off && !t.hashed)) return fail(B200PS_ESTATE, "created rows are not tracked for " + t.name);
   if (!t.alloc[shard].ptr) return fail(B200PS_ESTATE, "shard not attached");
   DeviceGuard g(ps->client_device);
+  CUDA_OK(cudaDeviceSynchronize());  // synchronous query on the legacy stream: order it after the caller's non-blocking streams
   CUDA_OK(cudaMemsetAsync(ps->d_count, 0, 8, 0));
   if (t.hashed) {
     k_key_ids<<<grid_for(ps, t.rows), 256>>>((const long long*)((const char*)t.alloc[shard].ptr + t.keys_off), t.rows, ids_dev,

@@ -147,7 +147,7 @@ class _FusedPSBackend(object):
     def reduce_update_gather(self, lr, scale):
         lib, h, st = self._lib, self.group._h, self._stream()
         self._check(lib.b200ps_barrier(h, st))                      # every rank's gradients are complete
-        self._check(lib.b200ps_push_begin_shard(h, self.rank, float(lr), st))
+        self._check(lib.b200ps_push_begin_shard(h, self.rank, float(lr), None, st))
         self._check(lib.b200ps_push_dense_reduce(h, self.slice_ids[self.rank], self._reduce_ptrs, self.world,
                                                  float(scale), st))   # reduce + scale + update, one kernel
         self._check(lib.b200ps_push_end_shard(h, self.rank, st))

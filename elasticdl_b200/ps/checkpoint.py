@@ -251,7 +251,6 @@ def load(group, client, version_dir):
     if not is_valid_version_dir(version_dir):
         raise ValueError("%s is not a complete checkpoint" % version_dir)
     from elasticdl_b200.common.hash_utils import string_to_id
-    from elasticdl_b200.common.tensor_utils import EmbeddingTableInfo
 
     n = group.n_shards
     version, all_infos, dense, rows = 0, {}, {}, {}
@@ -264,10 +263,14 @@ def load(group, client, version_dir):
         dense.update(d)
         for name, (ids, vals) in t.items():
             rows.setdefault(name, []).append((ids, vals))
-    new_tables = [EmbeddingTableInfo(name, int(dim), init, dtype) for name, dim, init, dtype in all_infos.values()
-                  if name not in group.tables]
-    if new_tables:
-        client.push_embedding_table_infos(new_tables)
+    # restored tables are hashed (the checkpoint does not store a capacity): size the slot pool from the
+    # number of rows actually saved so that the restore itself can never overflow it
+    saved_rows = {name: sum(len(p[0]) for p in parts) for name, parts in rows.items()}
+    for name, dim, init, dtype in all_infos.values():
+        if name not in group.tables:
+            expected = max(2 * saved_rows.get(name, 0), 1 << 16)
+            group.register_table(name, int(dim), init, None, expected_rows=expected)
+    group.commit()
     if dense:
         client.partition_dense_parameters(dense.keys(), shapes={k: v.shape for k, v in dense.items()})
     for name, parts in rows.items():
@@ -276,11 +279,24 @@ def load(group, client, version_dir):
         mine = np.isin(ids % n, group.local_shards)
         if mine.any():
             group.set_rows([(name, ids[mine], vals[mine])])
+            # optimizer slots are not part of a checkpoint (quirk Q9): restored rows start from the slot's
+            # initial value even when the group had trained before
+            dim_ = vals.shape[1] if vals.ndim == 2 else 1
+            for k in (1, 2, 3):
+                init_v = 0.0
+                if group.opt_type == "Ftrl" and k == 1:  # the "accumulator" slot (optimizer_wrapper.py:116-149)
+                    init_v = float(dict(kv.split("=") for kv in group.opt_args.strip(";").split(";"))["initial_accumulator_value"])
+                try:
+                    group.slot_rows(name, ids[mine], k, np.full((int(mine.sum()), dim_), init_v, dtype=np.float32))
+                except ValueError:  # the optimizer has no such slot
+                    break
     by_shard = {}
     for name, v in dense.items():
         by_shard.setdefault(string_to_id(name, n), []).append((name, v))
     for shard in group.local_shards:
         if by_shard.get(shard):
             group.set_dense(by_shard[shard])
+    group.check()  # a restore that overflowed a table or met a bad id fails HERE, before the shards read as initialised
+    for shard in group.local_shards:
         group.set_shard_state(shard, version=version if version >= 1 else -1, initialized=1)
     return version

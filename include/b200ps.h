@@ -199,8 +199,10 @@ int b200ps_push_dense_reduce(b200ps_t* ps, int dense_id, const float* const* gra
                              int n_replicas, float scale, void* stream);
 int b200ps_push_end(b200ps_t* ps, int32_t* versions_out_host, void* stream);
 /* begin / end that reach ONE shard only: the owner-side ApplyGradients of the allreduce controller's fused
- * reduce + update (every rank updates the slice it owns exactly once per step). */
-int b200ps_push_begin_shard(b200ps_t* ps, int shard, float learning_rate, void* stream);
+ * reduce + update (every rank updates the slice it owns exactly once per step), and of the per-shard gRPC
+ * facade (ps/grpc_server.py: one Pserver = one shard, server.go:176-206). */
+int b200ps_push_begin_shard(b200ps_t* ps, int shard, float learning_rate, const int32_t* model_versions /* [n_shards] or NULL */,
+                            void* stream);
 int b200ps_push_end_shard(b200ps_t* ps, int shard, void* stream);
 
 /* ---- the dense allreduce controller's data path (rank-per-GPU groups) ----------------------------
