@@ -274,6 +274,49 @@ def parity_check_multi(engine, group, rank, world, dev, lr=1e-3):
     return res
 
 
+def api_path_leg(dev, batches, steps, warmup):
+    """The same DeepFM step through the DROP-IN API instead of the engine: ParameterServerTrainer.train_minibatch
+    over 76 elasticdl Embedding layers + PSClient (worker/ps_trainer.py), tower in eager torch.  Timed by wall
+    clock around K steps (device idle on both sides); `batched` = the trainer's batched lookups, `per_layer` = one
+    unique + pull per layer call as embedding_delegate.py:75-106 does."""
+    import time
+    import types
+
+    import torch
+
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+    from elasticdl_b200.worker.ps_trainer import ParameterServerTrainer
+    from elasticdl_b200.workloads.deepfm import DeepFMLayersModel
+
+    out = {}
+    for mode, batched, k in (("batched", True, steps), ("per_layer", False, max(2, steps // 3))):
+        group = PSGroup(1, "Adam", ADAM_ARGS, device=dev.index)
+        client = PSClient(group)
+        client.dense_output = "torch"
+        model = DeepFMLayersModel().to(dev)
+        trainer = ParameterServerTrainer(model, client, args=types.SimpleNamespace(
+            get_model_steps=1, batched_embedding_lookups=batched))
+        feats = [(DeepFMLayersModel.features_of(ids, dense), labels) for ids, dense, labels in batches]
+        for i in range(warmup):
+            trainer.train_minibatch(*feats[i % len(feats)])
+        torch.cuda.synchronize(dev)
+        l0 = group.launch_count
+        t0 = time.perf_counter()
+        for i in range(k):
+            accepted, version, loss = trainer.train_minibatch(*feats[(warmup + i) % len(feats)])
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / k
+        B = batches[0][0].shape[1]
+        out[mode] = {"ms_per_step": dt * 1e3, "samples_per_s": B / dt, "ps_launches_per_step": (group.launch_count - l0) / k,
+                     "steps": k, "final_loss": float(loss)}
+        group.close()
+        del trainer, model, client, group
+    out["what"] = ("ParameterServerTrainer.train_minibatch (pull_dense + 76 Embedding layers + eager torch tower + "
+                   "push_gradients), 1 shard, wall clock; the engine path (`value`) fuses the tower and replays a CUDA graph")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -297,6 +340,8 @@ def main():
                     help="store each group's deep+wide rows as one record per id")
     ap.add_argument("--exchange", default="auto", choices=["auto", "owner", "direct"],
                     help="multi-GPU row exchange: owner-computes bulk exchange (default for N>1) or direct peer access")
+    ap.add_argument("--api-steps", type=int, default=6,
+                    help="steps of the drop-in API path (ParameterServerTrainer) timed after the engine at N=1; 0 = skip")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the post-timing N>1 parity self-check")
     ap.add_argument("--ids", default="narrow", choices=["narrow", "int32"],
                     help="id transport of the packed batches: 1/2/4 bytes per id by table size, or int32")
@@ -557,6 +602,9 @@ def main():
             line["pull_gbs"] = kern[pk]["gbs"]
             line["pull_frac_of_peak"] = kern[pk]["gbs"] / peak
     line["unique_ids_per_step"] = u_mean
+    if world == 1 and args.api_steps > 0 and not args.profile_step:
+        line["api_path"] = api_path_leg(dev, devb, args.api_steps, 3)
+        line["api_path"]["engine_over_batched_api"] = line["api_path"]["batched"]["ms_per_step"] / (ms / args.steps)
     if not args.no_cpu_baseline and world == 1:
         sps, T, desc = cpu_reference(cpu_batch, args.cpu_steps, 1, args.dist)
         line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": T, "kind": "port", "sample": desc,

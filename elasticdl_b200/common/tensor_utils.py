@@ -11,6 +11,12 @@ class UniqueTensor(Tensor):
     __slots__ = ()
 
 
+# Unique ids whose COUNT stays on the device: `ids` is a padded int64 device array, `n_dev` a
+# one-element int32 device tensor holding how many leading entries are live.  Lets the
+# pull / push of a batch run without reading the count back to the host.
+DeviceIds = namedtuple("DeviceIds", ("ids", "n_dev"))
+
+
 # The reference's EmbeddingTableInfo is (name, dim, initializer, dtype).  The HBM
 # tables are direct-indexed, so the number of ids (the layer's input_dim) travels
 # with it as an optional fifth field.

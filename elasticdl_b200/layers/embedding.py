@@ -54,6 +54,11 @@ class Embedding(torch.nn.Module):
         self._lookup_embedding_func = None
         self._embedding_and_ids = []
         self.tape = None
+        # batched lookups (worker/ps_trainer.py): which input object this layer was called with in the
+        # current step, and -- when the trainer looked all layers up in one launch before the forward
+        # pass -- (that input object, this layer's rows of the batched result)
+        self._inputs_seen = []
+        self._prefetched = None
 
     @property
     def name(self):
@@ -74,6 +79,8 @@ class Embedding(torch.nn.Module):
     def reset(self):
         self.tape = None
         self._embedding_and_ids = []
+        self._inputs_seen = []
+        self._prefetched = None
 
     @property
     def embedding_and_ids(self):
@@ -121,6 +128,11 @@ class Embedding(torch.nn.Module):
         return bet, inv
 
     def forward(self, ids):
+        self._inputs_seen.append(ids)
+        if self._prefetched is not None and self._prefetched[0] is ids:
+            rows = self._prefetched[1]  # looked up with every other layer of the model before the forward pass
+            self._prefetched = None
+            return rows.reshape(tuple(ids.shape) + (self.output_dim,))
         if isinstance(ids, torch.Tensor) and ids.is_sparse:
             return self._sparse_input_call(ids)
         ids = torch.as_tensor(ids)

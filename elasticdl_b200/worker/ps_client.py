@@ -15,7 +15,7 @@ import torch
 
 from elasticdl_b200 import _lib
 from elasticdl_b200.common.hash_utils import string_to_id
-from elasticdl_b200.common.tensor_utils import Tensor, UniqueTensor  # noqa: F401  (Tensor re-exported as the reference module does)
+from elasticdl_b200.common.tensor_utils import DeviceIds, Tensor, UniqueTensor  # noqa: F401  (Tensor re-exported as the reference module does)
 from elasticdl_b200.ps.group import PSGroup
 
 
@@ -63,6 +63,17 @@ class PSClient(object):
         tensors in, device tensors out).  No reference counterpart: the reference
         issues one RPC per (layer, shard)."""
         return self.group.pull_rows(requests)
+
+    def pull_embedding_vectors_into(self, requests):
+        """[(layer_name, ids int64 device [k], n_dev int32 device [1] | None, out float32 device [k, dim])]:
+        the first n_dev[0] (or k) ids of every request are looked up into `out`, all requests in one
+        launch and without a host read of the counts (rows past the count are left untouched)."""
+        g = self.group
+        items = []
+        for name, ids, n_dev, out in requests:
+            tid, dim, _, _ = g.lookup(name)
+            items.append((tid, ids.numel(), ids, n_dev, out))
+        g._run_segs(g.lib.b200ps_pull_rows, items)
 
     def push_embedding_table_infos(self, infos):
         """ps_client.py:289-301 -> every shard creates the tables + slot tables."""
@@ -201,9 +212,15 @@ class PSClient(object):
                     if width != dim:
                         raise ValueError("grad width is not equal to embedding dim")
                     if is_edl and already_unique.get(name) and len(vl) == 1:
-                        ids_t = g._ids(il[0])
-                        row_items.append((tid, ids_t.numel(), ids_t, None, g._f32(vl[0]).reshape(-1, dim)))
+                        n_dev = None
+                        if isinstance(il[0], DeviceIds):  # count stays on the device
+                            ids_t, n_dev = il[0].ids, il[0].n_dev
+                        else:
+                            ids_t = g._ids(il[0])
+                        row_items.append((tid, ids_t.numel(), ids_t, n_dev, g._f32(vl[0]).reshape(-1, dim)))
                         continue
+                    if any(isinstance(i, DeviceIds) for i in il):
+                        raise ValueError("DeviceIds gradients of %s cannot be merged with others" % name)
                     uniq, n_unique, gsum, k = self._dedup(name, vl, il, dim)
                     row_items.append((tid, k, uniq, n_unique, gsum))
         except (_lib.PSNotFound, ValueError):

@@ -15,7 +15,8 @@ restated over torch autograd:
 import numpy as np
 import torch
 
-from elasticdl_b200.common.tensor_utils import DT_FLOAT, EmbeddingTableInfo, Tensor, UniqueTensor
+from elasticdl_b200 import ops
+from elasticdl_b200.common.tensor_utils import DT_FLOAT, DeviceIds, EmbeddingTableInfo, Tensor, UniqueTensor
 from elasticdl_b200.layers.embedding import Embedding
 
 
@@ -49,6 +50,11 @@ class ParameterServerTrainer(object):
         self._evaluation_result = {}
         self._var_created = False
         self._model_version = -1
+        # batched embedding lookups: None = not learnt yet, False = this model does not qualify,
+        # else [(k, dim, [(layer, feature key)])] (see _learn_lookup_plan)
+        self._batched_lookups = getattr(args, "batched_embedding_lookups", True) if args is not None else True
+        self._lookup_plan = None if self._batched_lookups else False
+        self._group_bets = []
         self._init_embeddings()
 
     # ------------------------------------------------------------------ embeddings
@@ -73,6 +79,88 @@ class ParameterServerTrainer(object):
     def _reset_embedding(self):
         for layer in self._embedding_layers:
             layer.reset()
+        self._group_bets = []
+
+    # ------------------------------------------------------------------ batched lookups
+    # The reference issues one lookup RPC per Embedding layer call (embedding_delegate.py:75-106), each one
+    # a unique + pull of its own.  On one device that is ~6 launches and, for the exact [U, dim] BET shape,
+    # two host reads per layer -- 76 layers of DeepFM make the step host-bound.  The trainer therefore
+    # learns, during its first minibatch, which entry of `features` every Embedding layer is called with
+    # (by object identity), and from the second minibatch on looks ALL layers up before the forward pass:
+    # one unique launch and one gather per group of same-shaped layers, ONE pull launch for all tables,
+    # the unique counts never leaving the device (DeviceIds).  A layer whose input is not the recorded
+    # object simply takes its own per-layer path, and the plan is learnt again.
+    @staticmethod
+    def _feature_items(features):
+        if isinstance(features, torch.Tensor):
+            return [(None, features)]
+        if isinstance(features, dict):
+            return list(features.items())
+        if isinstance(features, (list, tuple)):
+            return list(enumerate(features))
+        return []
+
+    @staticmethod
+    def _feature_at(features, key):
+        return features if key is None else features[key]
+
+    def _learn_lookup_plan(self, features):
+        by_obj = {id(v): k for k, v in self._feature_items(features)}
+        groups = {}
+        for layer in self._embedding_layers:
+            seen = layer._inputs_seen
+            if len(seen) != 1 or id(seen[0]) not in by_obj:
+                return False  # called twice, or on a tensor derived from the features: keep per-layer lookups
+            src = seen[0]
+            if not (isinstance(src, torch.Tensor) and src.is_cuda and not src.is_sparse
+                    and src.dtype == torch.int64 and src.numel() > 0):
+                return False
+            groups.setdefault((src.numel(), layer.output_dim), []).append((layer, by_obj[id(src)]))
+        return [(k, dim, members) for (k, dim), members in groups.items()] or False
+
+    def _prefetch_embeddings(self, features):
+        """Look every Embedding layer of the plan up now.  Returns False (nothing done) when the features
+        no longer match the plan."""
+        g = self._ps_client.group
+        work = []
+        for k, dim, members in self._lookup_plan:
+            srcs = []
+            for layer, key in members:
+                try:
+                    src = self._feature_at(features, key)
+                except (KeyError, IndexError, TypeError):
+                    return False
+                if not (isinstance(src, torch.Tensor) and src.is_cuda and src.dtype == torch.int64
+                        and not src.is_sparse and src.numel() == k):
+                    return False
+                srcs.append(src)
+            work.append((k, dim, members, srcs))
+        requests, staged = [], []
+        for k, dim, members, srcs in work:
+            T = len(members)
+            flat = [s.reshape(-1) for s in srcs]
+            step = k * 8
+            if all(f.is_contiguous() for f in flat) and all(
+                    flat[t].data_ptr() == flat[0].data_ptr() + t * step for t in range(T)) and T > 1 \
+                    and flat[0]._base is not None and flat[0]._base is flat[-1]._base:
+                ids = torch.as_strided(flat[0], (T * k,), (1,))  # the features are rows of one [T, k] array
+            else:
+                ids = flat[0] if T == 1 else torch.cat(flat)
+            uniq, inv, n_dev = g.unique(ids, T)
+            bet = torch.zeros((T * k, dim), dtype=torch.float32, device=ids.device)
+            for t, (layer, _) in enumerate(members):
+                requests.append((layer.embedding_weight_name, uniq[t * k:(t + 1) * k], n_dev[t:t + 1],
+                                 bet[t * k:(t + 1) * k]))
+            staged.append((k, dim, members, srcs, uniq, inv, n_dev, bet))
+        self._ps_client.pull_embedding_vectors_into(requests)
+        for k, dim, members, srcs, uniq, inv, n_dev, bet in staged:
+            T = len(members)
+            bet.requires_grad_(True)
+            rows = ops.GatherRows.apply(bet, inv, T, k, dim).view(T, k, dim).unbind(0)
+            for t, (layer, _) in enumerate(members):
+                layer._prefetched = (srcs[t], rows[t])
+            self._group_bets.append((bet, uniq, n_dev, k, members))
+        return True
 
     # ------------------------------------------------------------------ model pull
     def _get_model(self):  # ps_trainer.py:149-184
@@ -103,7 +191,7 @@ class ParameterServerTrainer(object):
         self._var_created = True
 
     def get_trainable_items(self):
-        bets = []
+        bets = [bet for (bet, _, _, _, _) in self._group_bets]
         for layer in self._embedding_layers:
             bets.extend(bet for (bet, _) in layer.embedding_and_ids)
         return list(self._non_embed_vars.values()) + bets
@@ -118,7 +206,15 @@ class ParameterServerTrainer(object):
 
     def _training_process_eagerly(self, features, labels):  # ps_trainer.py:391-400
         self._set_tape_for_embedding(True)
+        prefetched = bool(self._lookup_plan) and self._prefetch_embeddings(features)
         outputs = self._model(features)
+        if self._batched_lookups:
+            stale = [layer for layer in self._embedding_layers if layer._prefetched is not None]
+            if stale:  # a prefetched layer was not called with the recorded object (or not called at all)
+                raise RuntimeError("batched embedding lookup of %s was not consumed by the model; construct the "
+                                   "trainer with args.batched_embedding_lookups=False" % stale[0].name)
+            if not prefetched:
+                self._lookup_plan = self._learn_lookup_plan(features)
         loss = self._loss(labels, outputs)
         grads = torch.autograd.grad(loss, self.get_trainable_items(), allow_unused=True)
         return loss.detach(), grads
@@ -134,6 +230,14 @@ class ParameterServerTrainer(object):
         edl_grads = []
         bet_number = 0
         edl_embedding_grads = gradients[len(names):]
+        for (bet, uniq, n_dev, k, members) in self._group_bets:  # batched lookups: one BET per layer group
+            g_bet = edl_embedding_grads[bet_number]
+            for t, (layer, _) in enumerate(members):
+                edl_grads.append(UniqueTensor(layer.embedding_weight_name, g_bet[t * k:(t + 1) * k],
+                                              DeviceIds(uniq[t * k:(t + 1) * k], n_dev[t:t + 1])))
+            bet_number += 1
+        edl_embedding_grads = edl_embedding_grads[bet_number:]
+        bet_number = 0
         for layer in self._embedding_layers:
             for i, (_, batch_ids) in enumerate(layer.embedding_and_ids):
                 edl_grads.append(UniqueTensor(layer.embedding_weight_name,

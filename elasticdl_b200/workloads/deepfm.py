@@ -721,3 +721,42 @@ class DeepFMPSEngine:
         pull = sum(n_unique_total * (8 + 8 * d) for d in (1, deep_dim))
         push = sum(n_unique_total * (8 + 4 * d + (1 + opt_slots) * 8 * d) for d in (1, deep_dim))
         return pull, push
+
+
+class DeepFMLayersModel(torch.nn.Module):
+    """The model a model_zoo job runs through the drop-in API (model_zoo/dac_ctr/deepfm_model.py:33-109):
+    one elasticdl Embedding layer per feature group and family -- G deep layers (dim 8) and G wide layers
+    (dim 1), each looked up with its own id tensor -- in front of DeepFMTower in eager torch.
+    forward(features): features = {"dense": [B, 13] float32, "ids_0" .. "ids_{G-1}": [B] int64}.
+    Carries `.optimizer` / `.loss` as ParameterServerTrainer expects (worker/ps_trainer.py)."""
+
+    def __init__(self, group_rows=GROUP_ROWS, deep_dim=DEEP_DIM, lr=1e-3, initializer="zero"):
+        super().__init__()
+        from elasticdl_b200.layers import Embedding
+
+        G = len(group_rows)
+        self.deep = torch.nn.ModuleList(
+            [Embedding(deep_dim, input_dim=r, embeddings_initializer=initializer, name="deep_%d" % g)
+             for g, r in enumerate(group_rows)])
+        self.wide = torch.nn.ModuleList(
+            [Embedding(1, input_dim=r, embeddings_initializer=initializer, name="wide_%d" % g)
+             for g, r in enumerate(group_rows)])
+        self.tower = DeepFMTower(G, deep_dim)
+        self.optimizer = torch.optim.Adam(self.tower.parameters(), lr=lr)
+        bce = torch.nn.BCEWithLogitsLoss()
+        self.loss = lambda labels, logits: bce(logits, labels)
+
+    @staticmethod
+    def features_of(ids, dense):
+        """ids [G, B] int64 -> the per-feature dict (row views of the one array, as a dataset's
+        feature columns are)."""
+        f = {"dense": dense}
+        for g in range(ids.shape[0]):
+            f["ids_%d" % g] = ids[g]
+        return f
+
+    def forward(self, features):
+        G = len(self.deep)
+        deep = torch.stack([self.deep[g](features["ids_%d" % g]) for g in range(G)], 1)  # [B, G, D]
+        wide = torch.cat([self.wide[g](features["ids_%d" % g]) for g in range(G)], 1)    # [B, G]
+        return self.tower(features["dense"], wide, deep)

@@ -349,3 +349,65 @@ def test_multi_gpu_exchange_and_allreduce_via_torchrun(script, token):
                           "--master-addr", "127.0.0.1", "--master-port", "29534",
                           os.path.join(root, "tests", script)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and token in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("n_shards,views", [(1, True), (2, False)])
+def test_trainer_batched_lookups_equal_per_layer_lookups(n_shards, views):
+    """The trainer's batched lookups (one unique + one gather per layer group, ONE pull launch, counts kept
+    on the device) train exactly like the per-layer path of embedding_delegate.py:75-106: same losses, same
+    tables and dense parameters after 4 Adam minibatches of a 2 x 5-layer DeepFM -- with far fewer launches and
+    no per-layer host reads.  Feature tensors are row views of one array, or separately allocated."""
+    import types
+
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+    from elasticdl_b200.worker.ps_trainer import ParameterServerTrainer
+    from elasticdl_b200.workloads.deepfm import DeepFMLayersModel
+
+    rows = [7, 300, 5000, 40, 1200]
+    B = 512
+
+    def run(batched):
+        torch.manual_seed(3)
+        model = DeepFMLayersModel(rows, lr=0.01, initializer="uniform").cuda()
+        group = PSGroup(n_shards, *ADAM, device=0, seed=11)
+        client = PSClient(group)
+        client.dense_output = "torch"
+        trainer = ParameterServerTrainer(model, client, args=types.SimpleNamespace(
+            get_model_steps=1, batched_embedding_lookups=batched))
+        gen = torch.Generator().manual_seed(5)
+        losses, launches = [], []
+        for step in range(4):
+            ids = torch.stack([torch.randint(0, r, (B,), generator=gen) for r in rows]).cuda()
+            dense = torch.randn(B, 13, generator=gen).cuda()
+            labels = (torch.rand(B, generator=gen) < 0.3).float().cuda()
+            feats = DeepFMLayersModel.features_of(ids if views else ids.clone(), dense)
+            if not views:
+                feats.update({"ids_%d" % g: ids[g].clone() for g in range(len(rows))})
+            before = group.launch_count
+            accepted, version, loss = trainer.train_minibatch(feats, labels)
+            launches.append(group.launch_count - before)
+            assert accepted and version == step + 1
+            losses.append(float(loss))
+        tabs = {}
+        for g, r in enumerate(rows):
+            for fam in ("deep", "wide"):
+                name = "%s_%d/embeddings:0" % (fam, g)
+                tabs[name] = client.pull_embedding_vectors(name, torch.arange(r).cuda()).cpu()
+        params, _ = client.pull_dense_parameters(list(range(n_shards)), [-1] * n_shards)
+        params = {k: v.cpu() for k, v in params.items()}
+        plan = trainer._lookup_plan
+        group.close()
+        return losses, tabs, params, launches, plan
+
+    l_b, t_b, p_b, n_b, plan = run(True)
+    l_p, t_p, p_p, n_p, plan_p = run(False)
+    assert plan and plan_p is False
+    assert sorted((k, dim, len(m)) for k, dim, m in plan) == [(B, 1, 5), (B, 8, 5)]
+    assert np.allclose(l_b, l_p, rtol=1e-6, atol=1e-7)
+    for name in t_p:
+        assert torch.allclose(t_b[name], t_p[name], rtol=1e-5, atol=1e-7), name
+    for name in p_p:
+        assert torch.allclose(p_b[name], p_p[name], rtol=1e-5, atol=1e-7), name
+    assert n_b[0] == n_p[0]          # the first minibatch learns the plan on the per-layer path
+    assert n_b[-1] * 3 < n_p[-1]     # afterwards: a handful of launches instead of ~6 per layer
