@@ -126,6 +126,8 @@ SYMBOLS = {
     "b200_deepfm_launch_count": (_i64, []),
     "b200_deepfm_fwd_bwd_tile": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
     "b200_deepfm_forward_tile": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
+    "b200_deepfm_tile_prologue": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
+    "b200_deepfm_tile_main": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
     "b200_deepfm_tile_launch_count": (_i64, []),
     "b200_deepfm_tile_last_error": (ctypes.c_char_p, []),
     # include/b200_features.h

@@ -459,8 +459,9 @@ int check_args(const b200_deepfm_args_t* a, bool backward) {
   return 0;
 }
 
+// what: 1 = prologue only (k_tile_prep), 2 = tile kernel only, 3 = both
 template <bool BACKWARD>
-int launch(const b200_deepfm_args_t* args, void* stream) {
+int launch(const b200_deepfm_args_t* args, void* stream, int what = 3) {
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
@@ -473,13 +474,21 @@ int launch(const b200_deepfm_args_t* args, void* stream) {
   b200_deepfm_args_t a = *args;
   if (!BACKWARD) { a.grads = nullptr; a.gsum_deep = nullptr; a.gsum_wide = nullptr; a.loss = nullptr; }
   float* w1x = a.scratch;  // NCOL*16 floats at the start of the scratch buffer
-  k_tile_prep<<<dim3(4, BACKWARD ? a.G : 1), 256, 0, st>>>(a, layout(a.G).total, w1x);
+  if (what & 1) {
+    k_tile_prep<<<dim3(4, BACKWARD ? a.G : 1), 256, 0, st>>>(a, layout(a.G).total, w1x);
+    g_launches += 1;
+  }
+  if (!(what & 2)) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_msg = cudaGetErrorString(e); return -2; }
+    return 0;
+  }
   const long long ntile = ((long long)a.B + TS - 1) / TS;
   static const int per_sm = [] { const char* e = getenv("B200_TILE_CTAS"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
   long long grid = (long long)n_sm * per_sm;
   if (grid > ntile) grid = ntile;
   k_tower_tile<BACKWARD><<<(unsigned)grid, THREADS, SMEM_BYTES, st>>>(*args, w1x);
-  g_launches += 2;
+  g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_msg = cudaGetErrorString(e); return -2; }
   return 0;
@@ -495,6 +504,16 @@ const char* b200_deepfm_tile_last_error(void) { return g_msg.c_str(); }
 int b200_deepfm_fwd_bwd_tile(const b200_deepfm_args_t* args, void* stream) {
   if (check_args(args, true)) return -1;
   return launch<true>(args, stream);
+}
+
+int b200_deepfm_tile_prologue(const b200_deepfm_args_t* args, void* stream) {
+  if (check_args(args, true)) return -1;
+  return launch<true>(args, stream, 1);
+}
+
+int b200_deepfm_tile_main(const b200_deepfm_args_t* args, void* stream) {
+  if (check_args(args, true)) return -1;
+  return launch<true>(args, stream, 2);
 }
 
 int b200_deepfm_forward_tile(const b200_deepfm_args_t* args, void* stream) {

@@ -334,6 +334,8 @@ class DeepFMPSEngine:
         self.plans = [self._make_plan()]
         self.cur = 0
         self.side = None
+        self.aux = None  # second stream of the branched step (see step())
+        self.branch = _os.environ.get("B200_STEP_BRANCHES", "1") != "0"
         self.graph = None
         self.graphs_ahead = None
         if self.exchange == "owner":
@@ -424,14 +426,39 @@ class DeepFMPSEngine:
         def done(e):
             if e is not None:
                 e[1].record()
-        # (1) pull dense parameters straight into the tower's tensors
-        arr, n = self.pull_dense_segs
-        check(lib.b200ps_pull_dense(h, arr, n, st))
+        import ctypes as _ct
+
+        # Branches: the step has six launch-bound kernels (pull_dense, tower prologue, push_begin, push_dense,
+        # push_end; 4-8 us each, ncu profiles/r2_*) that do not depend on the row kernels beside them.  With
+        # `branch` they run on a second stream -- inside a captured graph these become parallel branches --
+        # while the main stream carries unique -> pull -> tower -> push rows:
+        #   aux:  pull_dense -> push_begin -> tower prologue  | joined before the tower
+        #   aux:  push_dense                                   | beside the row push, joined before push_end
+        branch = self.branch and self.tower_kind == "tile" and ev is None
+        main = torch.cuda.current_stream(self.device)
+        if branch:
+            if self.aux is None:
+                self.aux = torch.cuda.Stream(device=self.device)
+            a = self.tower_args
+            a.dense, a.labels = dense.data_ptr(), labels.data_ptr()
         # (2) unique ids per group; wide and deep tables of a group share them
         if ids is not None:
             e = mark("unique")
             self._unique_into(ids)
             done(e)
+        # (1) pull dense parameters straight into the tower's tensors
+        if branch:
+            self.aux.wait_stream(main)  # n_unique of this batch, parameters of the previous step
+            with torch.cuda.stream(self.aux):
+                arr, n = self.pull_dense_segs
+                check(lib.b200ps_pull_dense(h, arr, n, g._stream()))
+                g.push_begin(self.lr, self.zero_versions)
+                rc = lib.b200_deepfm_tile_prologue(_ct.byref(a), g._stream())
+                if rc:
+                    raise RuntimeError("b200_deepfm_tile_prologue failed (%d)" % rc)
+        else:
+            arr, n = self.pull_dense_segs
+            check(lib.b200ps_pull_dense(h, arr, n, st))
         # (3) pull the unique rows of all 76 tables
         if self.exchange == "owner":
             e = mark("pull_exchange")
@@ -448,12 +475,18 @@ class DeepFMPSEngine:
                 e = mark(name)
                 check(lib.b200ps_pull_rows(h, arr, n, st))
                 done(e)
-        if self.tower_kind in ("tile", "fused", "mma"):
+        if branch:
+            main.wait_stream(self.aux)
+            rc = lib.b200_deepfm_tile_main(_ct.byref(a), st)
+            if rc:
+                raise RuntimeError("b200_deepfm_tile_main failed (%d)" % rc)
+            loss = self.loss_buf
+            dense_segs = self.push_dense_segs
+        elif self.tower_kind in ("tile", "fused", "mma"):
             # (4-6) gather + tower forward/backward + per-unique-id gradient sums: three launches
             e_t = mark("tower_fwd_bwd")
             a = self.tower_args
             a.dense, a.labels = dense.data_ptr(), labels.data_ptr()
-            import ctypes as _ct
 
             fn = {"mma": lib.b200_deepfm_fwd_bwd_mma, "tile": lib.b200_deepfm_fwd_bwd_tile}.get(self.tower_kind, lib.b200_deepfm_fwd_bwd)
             rc = fn(_ct.byref(a), st)
@@ -467,9 +500,15 @@ class DeepFMPSEngine:
         if after_tower is not None:
             after_tower()  # lookahead pipeline: the next batch's dedup forks here (beside the push)
         # (7) push: one ApplyGradients per shard
-        g.push_begin(self.lr, self.zero_versions)
-        arr, n = dense_segs
-        check(lib.b200ps_push_dense(h, arr, n, st))
+        if branch:
+            self.aux.wait_stream(main)
+            with torch.cuda.stream(self.aux):
+                arr, n = dense_segs
+                check(lib.b200ps_push_dense(h, arr, n, g._stream()))
+        else:
+            g.push_begin(self.lr, self.zero_versions)
+            arr, n = dense_segs
+            check(lib.b200ps_push_dense(h, arr, n, st))
         if self.exchange == "owner":
             e = mark("push_exchange")
             check(lib.b200ps_xchg_push(h, self.gsum_d.data_ptr(), self.gsum_w.data_ptr(), st))
@@ -484,6 +523,8 @@ class DeepFMPSEngine:
                 e = mark(name)
                 check(lib.b200ps_push_rows(h, arr, n, st))
                 done(e)
+        if branch:
+            main.wait_stream(self.aux)
         g.push_end(sync=False)
         self.steps += 1
         return loss.detach().reshape(())

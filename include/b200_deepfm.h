@@ -63,6 +63,11 @@ int64_t b200_deepfm_mma_launch_count(void);
  * 320*16 floats (W1 in tile column order); at most 38 id groups. */
 int b200_deepfm_fwd_bwd_tile(const b200_deepfm_args_t* args, void* stream);
 int b200_deepfm_forward_tile(const b200_deepfm_args_t* args, void* stream);
+/* b200_deepfm_fwd_bwd_tile in its two halves, so that a caller can put the prologue on another stream, beside
+ * the row pull: the prologue (W1 into tile order; zero the gradient buffers, the loss and the live rows of the
+ * per-unique-id sums) reads only `params` and `n_unique`; the main kernel needs the prologue and the pulled rows. */
+int b200_deepfm_tile_prologue(const b200_deepfm_args_t* args, void* stream);
+int b200_deepfm_tile_main(const b200_deepfm_args_t* args, void* stream);
 int64_t b200_deepfm_tile_launch_count(void);
 const char* b200_deepfm_tile_last_error(void);
 /* forward only (logits), for evaluation. */

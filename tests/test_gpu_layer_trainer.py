@@ -384,9 +384,10 @@ def test_trainer_batched_lookups_equal_per_layer_lookups(n_shards, views):
             feats = DeepFMLayersModel.features_of(ids if views else ids.clone(), dense)
             if not views:
                 feats.update({"ids_%d" % g: ids[g].clone() for g in range(len(rows))})
-            before = group.launch_count
+            count = lambda: group.launch_count + int(group.lib.b200ps_launch_count(None))  # noqa: E731
+            before = count()
             accepted, version, loss = trainer.train_minibatch(feats, labels)
-            launches.append(group.launch_count - before)
+            launches.append(count() - before)
             assert accepted and version == step + 1
             losses.append(float(loss))
         tabs = {}
@@ -410,4 +411,4 @@ def test_trainer_batched_lookups_equal_per_layer_lookups(n_shards, views):
     for name in p_p:
         assert torch.allclose(p_b[name], p_p[name], rtol=1e-5, atol=1e-7), name
     assert n_b[0] == n_p[0]          # the first minibatch learns the plan on the per-layer path
-    assert n_b[-1] * 3 < n_p[-1]     # afterwards: a handful of launches instead of ~6 per layer
+    assert n_b[-1] * 2 < n_p[-1]     # afterwards: a handful of launches instead of several per layer
