@@ -432,12 +432,13 @@ int for_each_class(b200ps_t* ps, Split& sp, F&& launch) {
 }
 
 // Persistent grid of the flat kernels: U rows in flight per thread once the work fills the machine.
-void flat_shape(b200ps_t* ps, long long items, int* U, int* grid) {
+void flat_shape(b200ps_t* ps, long long items, int* U, int* grid, bool copy = false) {
   static const int force_u = [] { const char* e = getenv("B200_FLAT_U"); return e ? atoi(e) : 0; }();      // tuning knobs
   static const int per_sm = [] { const char* e = getenv("B200_FLAT_BLOCKS"); return e ? atoi(e) : 0; }();
   const long long cap = (long long)ps->n_sm * (per_sm > 0 ? per_sm : 8);
   *U = items >= cap * 256 * 2 ? 2 : 1;
-  if (force_u == 1 || force_u == 2) *U = force_u;
+  if (copy && items >= cap * 256 * 16) *U = 4;
+  if (force_u == 1 || force_u == 2 || (copy && force_u == 4)) *U = force_u;
   long long blocks = (items + 256LL * *U - 1) / (256LL * *U);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -446,6 +447,14 @@ void flat_shape(b200ps_t* ps, long long items, int* U, int* grid) {
 
 #define DISPATCH_U(UVAL, ...)                          \
   switch (UVAL) {                                       \
+    case 2: { constexpr int U = 2; __VA_ARGS__; } break; \
+    default: { constexpr int U = 1; __VA_ARGS__; } break; \
+  }
+// the copy kernels also come with four rows in flight per thread (wide rows of big gathers: the bare-gather
+// probe reaches 81 % of the copy peak with one 256 B row chunk in flight per lane and 95 % with four)
+#define DISPATCH_UC(UVAL, ...)                         \
+  switch (UVAL) {                                       \
+    case 4: { constexpr int U = 4; __VA_ARGS__; } break; \
     case 2: { constexpr int U = 2; __VA_ARGS__; } break; \
     default: { constexpr int U = 1; __VA_ARGS__; } break; \
   }
@@ -867,9 +876,13 @@ static int rows_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
   if (rc) return rc;
   GroupView gv = group_view(ps);
   cudaStream_t st = (cudaStream_t)stream;
-  // large gathers go through the shared-memory staged kernel (cp.async in, one bulk async copy out per warp):
-  // its bytes in flight are bounded by shared memory, not registers.  Small ones are one latency chain either way.
-  static const long long staged_min = [] { const char* e = getenv("B200_STAGED_MIN"); return e ? atoll(e) : 2000000LL; }();
+  // The shared-memory staged gather (cp.async in, one bulk async copy out per warp: bytes in flight bounded by
+  // shared memory instead of registers) is OPT-IN (B200_STAGED_MIN = lane-items from which it is taken): measured
+  // at 4 M random dim-8 rows it reaches 28 % of the copy peak where the register path reaches 35 % and the bare
+  // gather probe (tools/probes/gather_roof.cu) 37 % -- random 32 B sectors are bound by the memory system's
+  // request rate, not by bytes in flight, so the extra shared-memory round trip only costs.
+  const char* staged_env = getenv("B200_STAGED_MIN");
+  const long long staged_min = staged_env ? atoll(staged_env) : (1LL << 62);
   if (sp.flat_n && !write && sp.flat_items >= staged_min) {
     constexpr int SU = 8;
     long long blocks = (sp.flat_items + 256LL * SU - 1) / (256LL * SU);
@@ -888,18 +901,18 @@ static int rows_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
     CUDA_OK(cudaGetLastError());
   } else if (sp.flat_n) {
     int u_rt, grid;
-    flat_shape(ps, sp.flat_items, &u_rt, &grid);
+    flat_shape(ps, sp.flat_items, &u_rt, &grid, true);
     if (ps->n_shards == 1) {
       FlatArgs<1> fa;
       fill_flat(ps, sp, false, slot, &fa);
-      DISPATCH_U(u_rt, {
+      DISPATCH_UC(u_rt, {
         if (write) k_copy_flat<true, U, 1><<<grid, 256, 0, st>>>(fa);
         else k_copy_flat<false, U, 1><<<grid, 256, 0, st>>>(fa);
       });
     } else {
       FlatArgs<8> fa;
       fill_flat(ps, sp, false, slot, &fa);
-      DISPATCH_U(u_rt, {
+      DISPATCH_UC(u_rt, {
         if (write) k_copy_flat<true, U, 8><<<grid, 256, 0, st>>>(fa);
         else k_copy_flat<false, U, 8><<<grid, 256, 0, st>>>(fa);
       });

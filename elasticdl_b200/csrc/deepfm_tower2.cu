@@ -91,10 +91,11 @@ __host__ __device__ inline int w1x_src(const Layout& l, int G, int c, int j) {
   return -1;
 }
 
-__global__ void __launch_bounds__(256) k_tile_prep(b200_deepfm_args_t a, int n_params, float* w1x) {
+__global__ void __launch_bounds__(256) k_tile_prep(b200_deepfm_args_t a, int n_params, float* w1x, int main_grid) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid == 0 && a.loss) *a.loss = 0.f;
+  if (tid == 0 && blockIdx.y == 0) reinterpret_cast<int*>(w1x + NCOL * H1)[0] = main_grid;  // dynamic tile counter
   if (blockIdx.y == 0) {
     if (a.grads)
       for (long long i = tid; i < n_params; i += stride) a.grads[i] = 0.f;
@@ -162,12 +163,24 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
       cp_async4(dst + (i & 31) * RS + (i >> 5), a.inv + (long long)(i >> 5) * B + b);
     }
   };
+  // Tiles are handed out dynamically (one atomic per tile on a counter the prologue set to gridDim.x): with
+  // 1024 tiles on 296 resident CTAs a static round-robin leaves SMs with 8 tiles next to SMs with 6.  A CTA
+  // needs the index of its NEXT tile while it gathers the current one (rank prefetch), so two slots rotate:
+  // s_tile[k & 1] = tile of iteration k, written during iteration k - 2 (slot reuse) by thread 0.
+  __shared__ int s_tile[2];
+  int* tile_counter = reinterpret_cast<int*>(const_cast<float*>(w1x_g) + SM_W1X);
+  if (t == 0) {
+    s_tile[0] = (int)blockIdx.x;
+    s_tile[1] = atomicAdd(tile_counter, 1);
+  }
   int cur = 0;
   if ((long long)blockIdx.x < ntile) fetch_ranks(blockIdx.x, Rt0);
   cp_async_wait_all();
   __syncthreads();
-  for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x, cur ^= 1) {
-    const long long b0 = tile * TS;
+  for (int iter = 0;; ++iter, cur ^= 1) {
+    const int tile = s_tile[iter & 1], tile_next = s_tile[(iter + 1) & 1];
+    if (tile >= ntile) break;
+    const long long b0 = (long long)tile * TS;
     int* Rt = Rt0 + cur * (TS * RS);
     // ---------------- G: gather the tile once ----------------
     // The tile's ranks are already in Rt (prefetched while the previous tile was computed), so the gather is
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
         const int g = i >> 5, s = i & 31;
         cp_async4(WV + g * TS + s, a.bet_wide + (long long)g * B + Rt[s * RS + g]);
       }
-      if (tile + gridDim.x < ntile) fetch_ranks(tile + gridDim.x, Rt0 + (cur ^ 1) * (TS * RS));
+      if (tile_next < ntile) fetch_ranks(tile_next, Rt0 + (cur ^ 1) * (TS * RS));
 #pragma unroll
       for (int jj = 0; jj < NFILL; ++jj) {
         const int i = t + THREADS * jj;
@@ -211,6 +224,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
       cp_async_wait_all();
     }
     __syncthreads();
+    if (t == 0) s_tile[iter & 1] = atomicAdd(tile_counter, 1);  // tile of iteration iter + 2
     const bool live = b0 + lane < B;
     // ---------------- F: partial H1 / FM sums over this warp's 40 columns ----------------
     {
@@ -473,9 +487,13 @@ int launch(const b200_deepfm_args_t* args, void* stream, int what = 3) {
   }
   b200_deepfm_args_t a = *args;
   if (!BACKWARD) { a.grads = nullptr; a.gsum_deep = nullptr; a.gsum_wide = nullptr; a.loss = nullptr; }
-  float* w1x = a.scratch;  // NCOL*16 floats at the start of the scratch buffer
+  float* w1x = a.scratch;  // NCOL*16 floats at the start of the scratch buffer, then the tile counter
+  const long long ntile = ((long long)a.B + TS - 1) / TS;
+  static const int per_sm = [] { const char* e = getenv("B200_TILE_CTAS"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+  long long grid = (long long)n_sm * per_sm;
+  if (grid > ntile) grid = ntile;
   if (what & 1) {
-    k_tile_prep<<<dim3(4, BACKWARD ? a.G : 1), 256, 0, st>>>(a, layout(a.G).total, w1x);
+    k_tile_prep<<<dim3(4, BACKWARD ? a.G : 1), 256, 0, st>>>(a, layout(a.G).total, w1x, (int)grid);
     g_launches += 1;
   }
   if (!(what & 2)) {
@@ -483,10 +501,6 @@ int launch(const b200_deepfm_args_t* args, void* stream, int what = 3) {
     if (e != cudaSuccess) { g_msg = cudaGetErrorString(e); return -2; }
     return 0;
   }
-  const long long ntile = ((long long)a.B + TS - 1) / TS;
-  static const int per_sm = [] { const char* e = getenv("B200_TILE_CTAS"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
-  long long grid = (long long)n_sm * per_sm;
-  if (grid > ntile) grid = ntile;
   k_tower_tile<BACKWARD><<<(unsigned)grid, THREADS, SMEM_BYTES, st>>>(*args, w1x);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();

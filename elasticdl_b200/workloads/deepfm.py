@@ -323,7 +323,7 @@ class DeepFMPSEngine:
         self.act_d = torch.empty((G * B, D), **f32)
         self.gsum_w = torch.zeros((G * B, 1), **f32)
         self.gsum_d = torch.zeros((G * B, D), **f32)
-        self.scratch = torch.empty(B * 44 + 16 * (N_DENSE + D * G), **f32)  # b200_deepfm.h: backward state + W1^T
+        self.scratch = torch.empty(max(B * 44 + 16 * (N_DENSE + D * G), 320 * 16 + 16), **f32)  # b200_deepfm.h: backward state + W1^T | tile tower: W1 tile + counter
         self.loss_buf = torch.zeros(1, **f32)
         self.logits_buf = torch.empty(B, **f32)
         self.zero_versions = [0] * group.n_shards

@@ -60,7 +60,7 @@ int64_t b200_deepfm_mma_launch_count(void);
 /* Same contract, computed by the TILE tower (csrc/deepfm_tower2.cu, round 2, the default): a CTA gathers the
  * rows of 32 samples once into shared memory (cp.async) and runs forward, backward and the
  * parameter-gradient contraction from that tile -- two launches (prep + tile kernel).  `scratch` needs
- * 320*16 floats (W1 in tile column order); at most 38 id groups. */
+ * 320*16 + 16 floats (W1 in tile column order, then the dynamic tile counter); at most 38 id groups. */
 int b200_deepfm_fwd_bwd_tile(const b200_deepfm_args_t* args, void* stream);
 int b200_deepfm_forward_tile(const b200_deepfm_args_t* args, void* stream);
 /* b200_deepfm_fwd_bwd_tile in its two halves, so that a caller can put the prologue on another stream, beside

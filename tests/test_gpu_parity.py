@@ -992,12 +992,13 @@ def test_unique_packed_per_segment_id_widths():
 
 
 @pytest.mark.parametrize("n_shards", [1, 2])
-def test_staged_pull_large_gather_bit_exact(n_shards):
-    """The shared-memory staged gather (cp.async in, bulk async copy out; taken above 2 M lane-items) returns
+def test_staged_pull_large_gather_bit_exact(n_shards, monkeypatch):
+    """The shared-memory staged gather (cp.async in, bulk async copy out; opt-in through B200_STAGED_MIN) returns
     exactly the table rows: mixed dims (8, 64 staged; 1, 10 direct) in one launch, ragged warp tails, device-side
     counts, and an out-of-range id (that warp falls back to per-lane stores, the error is raised)."""
     from elasticdl_b200 import _lib
 
+    monkeypatch.setenv("B200_STAGED_MIN", "100000")
     group, client, _ = make_pair(n_shards, "adam")
     rng = np.random.RandomState(9)
     dims, caps = [8, 64, 1, 10], [300_000, 200_000, 50_000, 5_000]
@@ -1038,4 +1039,29 @@ def test_staged_pull_large_gather_bit_exact(n_shards):
     ok[1234] = False
     assert np.array_equal(got[:nl0][ok], tabs[names[0]][ids0[:nl0]][ok])
     assert (got[1234] == -3.0).all()
+    group.close()
+
+
+@pytest.mark.parametrize("n_shards", [1, 2])
+def test_wide_rows_big_gather_four_rows_in_flight(n_shards):
+    """Gathers / sets above ~4.8 M lane-items take the copy kernel with four rows in flight per thread
+    (csrc/b200ps.cu flat_shape): 320 K dim-64 rows set, pulled back in random order with a device-side
+    count and a ragged tail -- bit-exact (embedding_table.go:61-77)."""
+    group, client, _ = make_pair(n_shards, "sgd")
+    rng = np.random.RandomState(21)
+    rows, dim = 320_000, 64
+    client.push_embedding_table_infos([info("w64", dim, capacity=rows)])
+    vals = rng.randn(rows, dim).astype(F)
+    group.set_rows([("w64", np.arange(rows), vals)])  # 5.1 M lane-items: the U = 4 write path
+    ids = rng.permutation(rows).astype(np.int64)
+    m = rows - 3
+    live = m - 11
+    t_ids = torch.from_numpy(ids[:m]).cuda()
+    n_dev = torch.tensor([live], dtype=torch.int32, device="cuda")
+    out = torch.full((m, dim), -7.0, dtype=torch.float32, device="cuda")
+    group._run_segs(group.lib.b200ps_pull_rows, [(group.lookup("w64")[0], m, t_ids, n_dev, out)])
+    group.check()
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:live], vals[ids[:live]])
+    assert (got[live:] == -7.0).all()
     group.close()
