@@ -51,6 +51,7 @@ def main():
     rows = 5_549_416
     out = []
     only = os.environ.get("BK_ONLY", "")  # e.g. "adam:8" -> one optimizer / dim (tuning sweeps)
+    sizes = [int(x) for x in os.environ.get("BK_SIZES", "122000,1000000,4000000").split(",")]  # unique ids per launch
     for opt_name, opt, S in (("adam", ADAM, 2), ("sgd", SGD, 0)):
         if only and not only.startswith(opt_name):
             continue
@@ -61,7 +62,7 @@ def main():
             name = "t%d" % dim
             tid = group.register_table(name, dim, "zero", rows)
             group.commit()
-            for U in (122_000, 1_000_000, 4_000_000):
+            for U in sizes:
                 pools = []
                 for p in range(3):  # rotate id sets so consecutive launches touch different rows
                     ids = torch.randperm(rows, device=dev)[:U].contiguous()

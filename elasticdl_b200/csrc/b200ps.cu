@@ -437,7 +437,8 @@ void flat_shape(b200ps_t* ps, long long items, int* U, int* grid, bool copy = fa
   static const int per_sm = [] { const char* e = getenv("B200_FLAT_BLOCKS"); return e ? atoi(e) : 0; }();
   const long long cap = (long long)ps->n_sm * (per_sm > 0 ? per_sm : 8);
   *U = items >= cap * 256 * 2 ? 2 : 1;
-  if (copy && items >= cap * 256 * 16) *U = 4;
+  // (U = 4 is reachable through B200_FLAT_U only: measured on 1 M / 4 M dim-64 rows it LOSES to U = 2 --
+  //  41 % vs 49-51 % of the copy peak -- its 80 registers cost more resident warps than the unroll adds.)
   if (force_u == 1 || force_u == 2 || (copy && force_u == 4)) *U = force_u;
   long long blocks = (items + 256LL * *U - 1) / (256LL * *U);
   if (blocks > cap) blocks = cap;
@@ -450,8 +451,7 @@ void flat_shape(b200ps_t* ps, long long items, int* U, int* grid, bool copy = fa
     case 2: { constexpr int U = 2; __VA_ARGS__; } break; \
     default: { constexpr int U = 1; __VA_ARGS__; } break; \
   }
-// the copy kernels also come with four rows in flight per thread (wide rows of big gathers: the bare-gather
-// probe reaches 81 % of the copy peak with one 256 B row chunk in flight per lane and 95 % with four)
+// the copy kernels also come with four rows in flight per thread (tuning knob B200_FLAT_U=4)
 #define DISPATCH_UC(UVAL, ...)                         \
   switch (UVAL) {                                       \
     case 4: { constexpr int U = 4; __VA_ARGS__; } break; \

@@ -151,6 +151,14 @@ __device__ __forceinline__ void flat_mark_present(const FlatLoc& r) {
   if (r.pres == nullptr) return;
   if (!(*(volatile uint32_t*)r.pres & r.bit)) atomicOr_system(r.pres, r.bit);  // the shard may be a peer GPU
 }
+// The same in two halves: the bitmap word is LOADED together with the row's record (it arrives with it) and
+// tested after the stores, so the test never adds a dependent round trip of its own.
+__device__ __forceinline__ uint32_t flat_present_word(const FlatLoc& r) {
+  return r.pres ? *(volatile uint32_t*)r.pres : 0xffffffffu;
+}
+__device__ __forceinline__ void flat_mark_present(const FlatLoc& r, uint32_t word) {
+  if (!(word & r.bit)) atomicOr_system(r.pres, r.bit);
+}
 
 // item w of the flat space -> (segment, row, column); `seg` is a running hint (items of one thread ascend)
 struct FlatItem {
@@ -200,10 +208,12 @@ __global__ void __launch_bounds__(256) k_copy_flat(const __grid_constant__ FlatA
     float4 x[U];
     float* dst[U];
     bool vec[U];
+    uint32_t pw[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       dst[k] = nullptr;
       vec[k] = false;
+      pw[k] = 0xffffffffu;
       if (!it[k].live) continue;
       const FlatSegP& sp = p.seg[it[k].seg];
       loc[k] = flat_locate(p, it[k].seg, id[k]);
@@ -219,16 +229,17 @@ __global__ void __launch_bounds__(256) k_copy_flat(const __grid_constant__ FlatA
       dst[k] = WRITE ? rec : user;
       if (vec[k]) x[k] = ld_f4(src);
       else x[k].x = ld_f1(src);
+      if (it[k].col == 0) pw[k] = flat_present_word(loc[k]);
     }
-#pragma unroll
-    for (int k = 0; k < U; ++k)
-      if (dst[k] != nullptr && it[k].col == 0) flat_mark_present(loc[k]);
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       if (dst[k] == nullptr) continue;
       if (vec[k]) st_f4(dst[k], x[k]);
       else st_f1(dst[k], x[k].x);
     }
+#pragma unroll
+    for (int k = 0; k < U; ++k)
+      if (dst[k] != nullptr) flat_mark_present(loc[k], pw[k]);
   }
 }
 
@@ -368,10 +379,12 @@ __global__ void __launch_bounds__(256) k_push_flat(const __grid_constant__ FlatA
     float g[U], pv[U], s0[U], s1[U], s2[U];
     float* rp[U];
     bool rec4[U];
+    uint32_t pw[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       rp[k] = nullptr;
       rec4[k] = false;
+      pw[k] = 0xffffffffu;
       s0[k] = s1[k] = s2[k] = 0.f;
       if (!it[k].live) continue;
       const FlatSegP& sp = p.seg[it[k].seg];
@@ -393,10 +406,8 @@ __global__ void __launch_bounds__(256) k_push_flat(const __grid_constant__ FlatA
         if (S > 1) s1[k] = ld_f1(rp[k] + sp.soff[2]);
         if (S > 2) s2[k] = ld_f1(rp[k] + sp.soff[3]);
       }
+      if (it[k].col == 0) pw[k] = flat_present_word(loc[k]);
     }
-#pragma unroll
-    for (int k = 0; k < U; ++k)
-      if (rp[k] != nullptr && it[k].col == 0) flat_mark_present(loc[k]);
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       if (rp[k] == nullptr) continue;
@@ -412,6 +423,9 @@ __global__ void __launch_bounds__(256) k_push_flat(const __grid_constant__ FlatA
         if (S > 2) st_f1(rp[k] + sp.soff[3], s2[k]);
       }
     }
+#pragma unroll
+    for (int k = 0; k < U; ++k)
+      if (rp[k] != nullptr) flat_mark_present(loc[k], pw[k]);
   }
 }
 

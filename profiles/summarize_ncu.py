@@ -18,9 +18,20 @@ METRICS = [
     ("launch__registers_per_thread", "regs"),
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
-    ("smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "stall long_sb %"),
-    ("smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "stall lg_throttle %"),
-    ("smsp__warp_issue_stalled_barrier_per_warp_active.pct", "stall barrier %"),
+    ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue active %"),
+    ("smsp__average_warp_latency_per_inst_issued.ratio", "cycles / issued inst (per warp)"),
+    # warp-state stall reasons: average number of warps per scheduler in that state per issue-active cycle
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall lg_throttle"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_scoreboard"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall mio_throttle"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
+    ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "stall membar"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
+    ("smsp__inst_executed.sum", "warp instructions"),
 ]
 
 

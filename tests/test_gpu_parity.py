@@ -1043,16 +1043,16 @@ def test_staged_pull_large_gather_bit_exact(n_shards, monkeypatch):
 
 
 @pytest.mark.parametrize("n_shards", [1, 2])
-def test_wide_rows_big_gather_four_rows_in_flight(n_shards):
-    """Gathers / sets above ~4.8 M lane-items take the copy kernel with four rows in flight per thread
-    (csrc/b200ps.cu flat_shape): 320 K dim-64 rows set, pulled back in random order with a device-side
-    count and a ragged tail -- bit-exact (embedding_table.go:61-77)."""
+def test_wide_rows_big_gather(n_shards):
+    """A big gather / set of wide rows (5.1 M lane-items: the persistent grid loops ~8 times with two rows in
+    flight per thread): 320 K dim-64 rows set, pulled back in random order with a device-side count and a
+    ragged tail -- bit-exact (embedding_table.go:61-77)."""
     group, client, _ = make_pair(n_shards, "sgd")
     rng = np.random.RandomState(21)
     rows, dim = 320_000, 64
     client.push_embedding_table_infos([info("w64", dim, capacity=rows)])
     vals = rng.randn(rows, dim).astype(F)
-    group.set_rows([("w64", np.arange(rows), vals)])  # 5.1 M lane-items: the U = 4 write path
+    group.set_rows([("w64", np.arange(rows), vals)])  # 5.1 M lane-items
     ids = rng.permutation(rows).astype(np.int64)
     m = rows - 3
     live = m - 11
