@@ -531,23 +531,26 @@ def main():
         p1.record(cs)
     sync_all()
     h2d_ms = min(h2d_ms, p0.elapsed_time(p1) / 8)
-    e2.record()
+    # W warm-up steps run through the feeder (untimed, like the device-resident arm's warm-up) and leave its
+    # prefetch window full; then EXACTLY K steps are timed between two barrier + synchronize points: every timed
+    # step enqueues the H2D copy of one batch from pinned host memory (the batch `ahead` steps in front of it,
+    # like the reference's dataset.prefetch), runs one dedup + one train pass, and copies its loss D2H.
+    n_e2e = args.warmup + args.steps
     if feeder is not None:
-        for j in range(min(ahead, args.steps)):
+        for j in range(ahead):
             feeder.submit(host[j % args.pool])
-    for i in range(args.steps):
+    for i in range(n_e2e):
+        if i == args.warmup:
+            sync_all()  # barrier + synchronize: the prefetched batches have landed, nothing is in flight
+            e2.record()
         if feeder is not None:
-            # every step's inputs come from pinned host memory (ONE packed copy per batch); the copies of
-            # the next batches (side stream) overlap the kernels of batch i, like the reference's
-            # dataset.prefetch(1)
-            if i + ahead < args.steps:
-                feeder.submit(host[(i + ahead) % args.pool])
+            feeder.submit(host[(i + ahead) % args.pool])
             loss = feeder.run_next()
         else:
             hb = host[i % args.pool].to(dev, non_blocking=True)
             from elasticdl_b200.workloads.deepfm import packed_views
             loss = engine.step(*packed_views(hb, G, B, engine.widths))
-        loss_pin[i].copy_(loss, non_blocking=True)
+        loss_pin[i % loss_pin.numel()].copy_(loss, non_blocking=True)
     e3.record()
     sync_all()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
@@ -577,7 +580,7 @@ def main():
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / max(args.steps, 1),
             "launch_mode": "cuda_graph" if use_graph else "eager", "eager_ms_per_step": ms_eager / args.steps,
             "tower": args.tower,
-            "final_loss": float(loss_pin[args.steps - 1])}
+            "final_loss": float(loss_pin[(args.warmup + args.steps - 1) % loss_pin.numel()])}
     if parity is not None:
         line["parity_check"] = parity
     if kern:

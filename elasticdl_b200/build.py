@@ -15,11 +15,26 @@ NVCC_FLAGS = [
 ]
 
 
+STAMP = LIB + ".sources.sha256"
+
+
+def _sources_digest():
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read() + b"\0")
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB):
+    """The library is current iff the digest of the sources it was built from (a sidecar file that travels
+    with it) equals the digest of the sources in the tree -- file times do not survive a snapshot / checkout."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    with open(STAMP) as fh:
+        return fh.read().strip() != _sources_digest()
 
 
 def build(force=False, verbose=False):
@@ -39,8 +54,12 @@ def build(force=False, verbose=False):
                 return LIB
             tmp = LIB + ".tmp.%d" % os.getpid()
             cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+            digest = _sources_digest()
             subprocess.check_call(cmd, cwd=CSRC)
             os.replace(tmp, LIB)
+            with open(STAMP + ".tmp", "w") as fh:
+                fh.write(digest + "\n")
+            os.replace(STAMP + ".tmp", STAMP)
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB

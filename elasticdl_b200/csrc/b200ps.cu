@@ -126,6 +126,7 @@ struct b200ps {
   bool x_pulled = false;
   int* d_x_deep = nullptr;
   int* d_x_wide = nullptr;
+  std::vector<int> x_deep_host, x_wide_host;
   std::mutex mu;
 };
 
@@ -1140,6 +1141,8 @@ int b200ps_xchg_create(b200ps_t* ps, int G, int B, const int32_t* deep_tables, c
   CUDA_OK(cudaMalloc(&ps->d_x_wide, sizeof(int) * G));
   CUDA_OK(cudaMemcpy(ps->d_x_deep, deep_tables, sizeof(int) * G, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(ps->d_x_wide, wide_tables, sizeof(int) * G, cudaMemcpyHostToDevice));
+  ps->x_deep_host.assign(deep_tables, deep_tables + G);
+  ps->x_wide_host.assign(wide_tables, wide_tables + G);
   return B200PS_OK;
 }
 
@@ -1166,6 +1169,39 @@ static int xview(b200ps_t* ps, XView* x) {
   return B200PS_OK;
 }
 
+// The owner-side constants of the exchanged table pairs on MY shard, for the fast exchange kernels.  false: some
+// table is hashed / owned by one shard / not allocated here -> the generic kernels run instead.
+static bool xtabs(b200ps_t* ps, XTabs* t) {
+  static const bool off = [] { const char* e = getenv("B200_XCHG_FAST"); return e && atoi(e) == 0; }();
+  if (off || ps->x_G > kXMaxG) return false;
+  const int me = ps->x_me;
+  t->shard_shift = -1;
+  if ((ps->n_shards & (ps->n_shards - 1)) == 0) {
+    int sh = 0;
+    while ((1 << sh) < ps->n_shards) ++sh;
+    t->shard_shift = sh;
+  }
+  for (int g = 0; g < ps->x_G; ++g) {
+    const Table& d = ps->tables[ps->x_deep_host[g]];
+    const Table& w = ps->tables[ps->x_wide_host[g]];
+    if (d.hashed || w.hashed || d.owner >= 0 || w.owner >= 0 || d.is_dense || w.is_dense) return false;
+    if (!d.alloc[me].ptr || !w.alloc[me].ptr) return false;
+    t->deep[g] = (float*)((char*)d.alloc[me].ptr + d.base_off);
+    t->wide[g] = (float*)((char*)w.alloc[me].ptr + w.base_off);
+    t->deep_pres[g] = d.present_off ? (uint32_t*)((char*)d.alloc[me].ptr + d.present_off) : nullptr;
+    t->wide_pres[g] = w.present_off ? (uint32_t*)((char*)w.alloc[me].ptr + w.present_off) : nullptr;
+    t->deep_rows[g] = d.rows;
+    t->wide_rows[g] = w.rows;
+    t->deep_stride[g] = (int)d.row_stride;
+    t->wide_stride[g] = (int)w.row_stride;
+    for (int j = 0; j <= kMaxSlots; ++j) {
+      if (g == 0) { t->deep_soff[j] = (int)d.slot_off[j]; t->wide_soff[j] = (int)w.slot_off[j]; }
+      else if (t->deep_soff[j] != (int)d.slot_off[j] || t->wide_soff[j] != (int)w.slot_off[j]) return false;
+    }
+  }
+  return true;
+}
+
 // grid.x per peer
 static int xchg_per_peer(b200ps_t* ps) {
   static const int mult = [] {
@@ -1187,8 +1223,14 @@ int b200ps_xchg_pull(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_uni
   GroupView gv = group_view(ps);
   dim3 grid(xchg_per_peer(ps), ps->n_shards);
   k_x_post<<<ps->n_sm, 256, 0, st>>>(x, uniq_dev, n_unique_dev);
-  k_x_serve<<<grid, 256, 0, st>>>(x, gv);
-  k_x_unscatter<<<grid, 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
+  XTabs xt;
+  if (xtabs(ps, &xt)) {
+    k_x_serve2<4><<<grid, 256, 0, st>>>(x, xt, gv.err);
+    k_x_unscatter2<4><<<grid, 256, 0, st>>>(x, gv.err, bet_deep_dev, bet_wide_dev);
+  } else {
+    k_x_serve<<<grid, 256, 0, st>>>(x, gv);
+    k_x_unscatter<<<grid, 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
+  }
   ps->launches += 3;
   ps->x_pulled = true;
   CUDA_OK(cudaGetLastError());
@@ -1206,8 +1248,14 @@ int b200ps_xchg_push(b200ps_t* ps, const float* gsum_deep_dev, const float* gsum
   GroupView gv = group_view(ps);
   OptParams o = ps->opt;
   dim3 grid(xchg_per_peer(ps), ps->n_shards);
-  k_x_send_upd<<<grid, 256, 0, st>>>(x, gv, gsum_deep_dev, gsum_wide_dev);
-  DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
+  XTabs xt;
+  if (xtabs(ps, &xt)) {
+    k_x_send_upd2<4><<<grid, 256, 0, st>>>(x, gv.rt, gsum_deep_dev, gsum_wide_dev);
+    DISPATCH_OPT(o.kind, k_x_apply2<OPT, 2><<<grid, 256, 0, st>>>(x, xt, gv.err, o));
+  } else {
+    k_x_send_upd<<<grid, 256, 0, st>>>(x, gv, gsum_deep_dev, gsum_wide_dev);
+    DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
+  }
   k_x_wait_applied<<<1, 32, 0, st>>>(x, gv);
   ps->launches += 3;
   CUDA_OK(cudaGetLastError());
@@ -1230,15 +1278,21 @@ int b200ps_xchg_profile(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_
   cudaEvent_t ev[7];
   for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
   cudaEventRecord(ev[0], st);
+  XTabs xt;
+  const bool fast = xtabs(ps, &xt);
   k_x_post<<<ps->n_sm, 256, 0, st>>>(x, uniq_dev, n_unique_dev);
   cudaEventRecord(ev[1], st);
-  k_x_serve<<<grid, 256, 0, st>>>(x, gv);
+  if (fast) k_x_serve2<4><<<grid, 256, 0, st>>>(x, xt, gv.err);
+  else k_x_serve<<<grid, 256, 0, st>>>(x, gv);
   cudaEventRecord(ev[2], st);
-  k_x_unscatter<<<grid, 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
+  if (fast) k_x_unscatter2<4><<<grid, 256, 0, st>>>(x, gv.err, bet_deep_dev, bet_wide_dev);
+  else k_x_unscatter<<<grid, 256, 0, st>>>(x, gv, bet_deep_dev, bet_wide_dev);
   cudaEventRecord(ev[3], st);
-  k_x_send_upd<<<grid, 256, 0, st>>>(x, gv, gsum_deep_dev, gsum_wide_dev);
+  if (fast) k_x_send_upd2<4><<<grid, 256, 0, st>>>(x, gv.rt, gsum_deep_dev, gsum_wide_dev);
+  else k_x_send_upd<<<grid, 256, 0, st>>>(x, gv, gsum_deep_dev, gsum_wide_dev);
   cudaEventRecord(ev[4], st);
-  DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
+  if (fast) { DISPATCH_OPT(o.kind, k_x_apply2<OPT, 2><<<grid, 256, 0, st>>>(x, xt, gv.err, o)); }
+  else { DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o)); }
   cudaEventRecord(ev[5], st);
   k_x_wait_applied<<<1, 32, 0, st>>>(x, gv);
   cudaEventRecord(ev[6], st);

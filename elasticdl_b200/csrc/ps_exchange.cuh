@@ -447,6 +447,316 @@ __global__ void __launch_bounds__(256) k_x_apply(XView x, GroupView gv, OptParam
   }
 }
 
+// =============================================================================
+// Fast variants (round 2): the same protocol and the same words on the wire as the four kernels above, with
+//   * the owner's table constants resolved on the HOST (XTabs, a __grid_constant__ parameter): base pointer,
+//     bitmap, stride and row count of each of the G (deep, wide) pairs on MY shard -- no dependent loads of a
+//     table directory between an id and its record;
+//   * XU entries in flight per 4-lane group: all remote / inbox words of an iteration are loaded before the
+//     first one is used, then all records, then the stores.  Every pass of these kernels is a chain of two to
+//     four dependent round trips (NVLink word -> HBM record -> NVLink store); round 1 ran 3-4 passes of one
+//     entry per lane group, now one pass covers the list.
+// Used when every exchanged table is direct-indexed and striped (the hashed / dense-owner cases keep the generic
+// kernels above).
+// =============================================================================
+constexpr int kXMaxG = kMaxSegs / 2;
+struct XTabs {
+  float* deep[kXMaxG];
+  float* wide[kXMaxG];
+  uint32_t* deep_pres[kXMaxG];
+  uint32_t* wide_pres[kXMaxG];
+  long long deep_rows[kXMaxG], wide_rows[kXMaxG];  // rows on my shard
+  int deep_stride[kXMaxG], wide_stride[kXMaxG];    // floats
+  int deep_soff[kMaxSlots + 1], wide_soff[kMaxSlots + 1];
+  int shard_shift;  // log2(n) or -1
+};
+
+__device__ __forceinline__ long long xslot_of(const XView& x, const XTabs& t, long long id) {
+  return t.shard_shift >= 0 ? id >> t.shard_shift : id / x.n;
+}
+
+template <int XU>
+__global__ void __launch_bounds__(256) k_x_serve2(const __grid_constant__ XView x, const __grid_constant__ XTabs t, unsigned* err) {
+  const int src = blockIdx.y;
+  XHeader* h = xhdr(x, x.me);
+  __shared__ int s_epoch, s_total;
+  if (threadIdx.x == 0) {
+    s_epoch = h->epoch;
+    s_total = poll8(&h->req[src], s_epoch, err).x;
+  }
+  __syncthreads();
+  const int epoch = s_epoch, total = s_total;
+  const char* ids = xids(x, src, x.me);
+  char* resp = xresp(x, src, x.me);
+  char* served = xserved(x, x.me, src);
+  const int lane = threadIdx.x & 31, lane4 = threadIdx.x & 3;
+  const unsigned gm = 0xfu << (lane & 28);
+  const long long stride = (long long)gridDim.x * blockDim.x / 4;
+  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i0 < total; i0 += stride * XU) {
+    int4 e[XU];
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {  // all remote id words of this iteration
+      const long long i = i0 + k * stride;
+      e[k] = make_int4(0, 0, 0, epoch);
+      if (lane4 == 0 && i < total) e[k] = ld_word16(ids + i * kXIdEntry);
+    }
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {
+      const long long i = i0 + k * stride;
+      if (lane4 == 0 && i < total && e[k].w != epoch) e[k] = poll16(ids + i * kXIdEntry, epoch, err);
+      e[k].x = __shfl_sync(gm, e[k].x, 0, 4);
+      e[k].y = __shfl_sync(gm, e[k].y, 0, 4);
+      e[k].z = __shfl_sync(gm, e[k].z, 0, 4);
+    }
+    float4 v[XU];
+    uint32_t* pres[XU];
+    uint32_t word[XU], bit[XU];
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {  // all records (and their created-row bitmap words)
+      const long long i = i0 + k * stride;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pres[k] = nullptr;
+      word[k] = 0xffffffffu;
+      bit[k] = 0;
+      if (i >= total) continue;
+      const long long id = id_of(e[k].x, e[k].y);
+      const int g = e[k].z / x.B;
+      const long long sl = xslot_of(x, t, id);
+      if (lane4 < 2) {
+        const bool ok = id >= 0 && sl < t.deep_rows[g];
+        if (ok) {
+          v[k] = ld_f4(t.deep[g] + sl * t.deep_stride[g] + 4 * lane4);
+          if (lane4 == 0 && t.deep_pres[g]) { pres[k] = t.deep_pres[g] + (sl >> 5); bit[k] = 1u << (sl & 31); }
+        } else if (lane4 == 0) {
+          atomicOr(err, kErrRange);
+        }
+      } else if (lane4 == 2) {
+        if (id >= 0 && sl < t.wide_rows[g]) {
+          v[k].x = *(t.wide[g] + sl * t.wide_stride[g]);
+          if (t.wide_pres[g]) { pres[k] = t.wide_pres[g] + (sl >> 5); bit[k] = 1u << (sl & 31); }
+        }
+      }
+      if (pres[k]) word[k] = *(volatile uint32_t*)pres[k];
+    }
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {  // responses: entry i answers id i
+      const long long i = i0 + k * stride;
+      if (i >= total) continue;
+      const float d3 = __shfl_sync(gm, v[k].w, 0, 4), d6 = __shfl_sync(gm, v[k].z, 1, 4), d7 = __shfl_sync(gm, v[k].w, 1, 4);
+      char* out = resp + i * kXResp + 16 * lane4;
+      if (lane4 == 0) st_word16(out, __float_as_int(v[k].x), __float_as_int(v[k].y), __float_as_int(v[k].z), epoch);
+      else if (lane4 == 1) st_word16(out, __float_as_int(d3), __float_as_int(v[k].x), __float_as_int(v[k].y), epoch);
+      else if (lane4 == 2) st_word16(out, __float_as_int(d6), __float_as_int(d7), __float_as_int(v[k].x), epoch);
+      else {
+        st_word16(out, e[k].z, 0, 0, epoch);
+        *reinterpret_cast<int4*>(served + i * kXServed) = make_int4(e[k].x, e[k].y, e[k].z / x.B, 0);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < XU; ++k)
+      if (pres[k] && !(word[k] & bit[k])) atomicOr(pres[k], bit[k]);
+  }
+  __shared__ bool last;
+  __threadfence();  // served records: local, read by this GPU's later kernels
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&h->done_src[src], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    h->served_cnt[src] = total;
+    st_word8(&xhdr(x, src)->resp[x.me], total, epoch);
+    h->done_src[src] = 0;
+  }
+}
+
+template <int XU>
+__global__ void __launch_bounds__(256) k_x_unscatter2(const __grid_constant__ XView x, unsigned* err, float* bet_d, float* bet_w) {
+  const int owner = blockIdx.y;
+  XHeader* h = xhdr(x, x.me);
+  __shared__ int s_cnt, s_epoch;
+  if (threadIdx.x == 0) {
+    s_epoch = h->epoch;
+    s_cnt = poll8(&h->resp[owner], s_epoch, err).x;
+  }
+  __syncthreads();
+  const int cnt = s_cnt, epoch = s_epoch;
+  const char* resp = xresp(x, x.me, owner);
+  const int lane = threadIdx.x & 31, lane4 = threadIdx.x & 3;
+  const unsigned gm = 0xfu << (lane & 28);
+  const long long stride = (long long)gridDim.x * blockDim.x / 4;
+  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i0 < cnt; i0 += stride * XU) {
+    int4 p[XU];
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {
+      const long long i = i0 + k * stride;
+      p[k] = make_int4(0, 0, 0, epoch);
+      if (i < cnt) p[k] = ld_word16(resp + i * kXResp + 16 * lane4);
+    }
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {
+      const long long i = i0 + k * stride;
+      if (i < cnt && p[k].w != epoch) p[k] = poll16(resp + i * kXResp + 16 * lane4, epoch, err);
+      const int slot = __shfl_sync(gm, p[k].x, 3, 4);
+      if (i >= cnt) continue;
+      float* row = bet_d + (long long)slot * 8;
+      if (lane4 == 0) {
+        row[0] = __int_as_float(p[k].x); row[1] = __int_as_float(p[k].y); row[2] = __int_as_float(p[k].z);
+      } else if (lane4 == 1) {
+        row[3] = __int_as_float(p[k].x); row[4] = __int_as_float(p[k].y); row[5] = __int_as_float(p[k].z);
+      } else if (lane4 == 2) {
+        row[6] = __int_as_float(p[k].x); row[7] = __int_as_float(p[k].y);
+        bet_w[slot] = __int_as_float(p[k].z);
+      }
+    }
+  }
+}
+
+template <int XU>
+__global__ void __launch_bounds__(256) k_x_send_upd2(const __grid_constant__ XView x, const PushRt* rt, const float* __restrict__ gsum_d,
+                                                     const float* __restrict__ gsum_w) {
+  const int owner = blockIdx.y;
+  XHeader* h = xhdr(x, x.me);
+  const int epoch = h->epoch;
+  const int cnt = ld_word8(&h->resp[owner]).x;  // validated by this step's unscatter
+  const char* resp = xresp(x, x.me, owner);
+  char* upd = xupd(x, owner, x.me);  // remote, contiguous
+  const int lane = threadIdx.x & 31, lane4 = threadIdx.x & 3;
+  const unsigned gm = 0xfu << (lane & 28);
+  if (blockIdx.x == 0 && threadIdx.x == 0)  // this push's lr / Adam alpha / l2 for that shard (k_push_begin)
+    st_word16(&xhdr(x, owner)->updh[x.me], __float_as_int(rt->lr[owner]), __float_as_int(rt->alpha[owner]),
+              __float_as_int(rt->l2adj[owner]), epoch);
+  const long long stride = (long long)gridDim.x * blockDim.x / 4;
+  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i0 < cnt; i0 += stride * XU) {
+    int slot[XU];
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {
+      const long long i = i0 + k * stride;
+      slot[k] = 0;
+      if (i < cnt) slot[k] = ld_word16(resp + i * kXResp + 48).x;
+    }
+    float4 v[XU];
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {
+      const long long i = i0 + k * stride;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i >= cnt) continue;
+      if (lane4 < 2) v[k] = *reinterpret_cast<const float4*>(gsum_d + (long long)slot[k] * 8 + 4 * lane4);
+      else if (lane4 == 2) v[k].x = gsum_w[slot[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {
+      const long long i = i0 + k * stride;
+      if (i >= cnt) continue;
+      const float g3 = __shfl_sync(gm, v[k].w, 0, 4), g6 = __shfl_sync(gm, v[k].z, 1, 4), g7 = __shfl_sync(gm, v[k].w, 1, 4);
+      char* out = upd + i * kXUpd + 16 * lane4;
+      if (lane4 == 0) st_word16(out, __float_as_int(v[k].x), __float_as_int(v[k].y), __float_as_int(v[k].z), epoch);
+      else if (lane4 == 1) st_word16(out, __float_as_int(g3), __float_as_int(v[k].x), __float_as_int(v[k].y), epoch);
+      else if (lane4 == 2) st_word16(out, __float_as_int(g6), __float_as_int(g7), __float_as_int(v[k].x), epoch);
+    }
+  }
+}
+
+template <int OPT, int XU>
+__global__ void __launch_bounds__(256) k_x_apply2(const __grid_constant__ XView x, const __grid_constant__ XTabs t, unsigned* err,
+                                                  const OptParams o) {
+  constexpr int S = opt_slots(OPT);
+  const int src = blockIdx.y;
+  XHeader* h = xhdr(x, x.me);
+  __shared__ int s_epoch, s_cnt;
+  __shared__ float s_lr, s_alpha, s_l2;
+  if (threadIdx.x == 0) {
+    s_epoch = h->epoch;
+    const int4 hd = poll16(&h->updh[src], s_epoch, err);
+    s_cnt = h->served_cnt[src];
+    s_lr = __int_as_float(hd.x);
+    s_alpha = __int_as_float(hd.y);
+    s_l2 = __int_as_float(hd.z);
+  }
+  __syncthreads();
+  const int cnt = s_cnt, epoch = s_epoch;
+  const float lr = s_lr, alpha = s_alpha, l2adj = s_l2;
+  const char* upd = xupd(x, x.me, src);
+  const char* served = xserved(x, x.me, src);
+  const int lane = threadIdx.x & 31, lane4 = threadIdx.x & 3;  // deep lo, deep hi, wide, idle
+  const unsigned gm = 0xfu << (lane & 28);
+  const long long stride = (long long)gridDim.x * blockDim.x / 4;
+  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 4; i0 < cnt; i0 += stride * XU) {
+    int4 e[XU], p[XU];
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {  // what I served as entry i (local) and its update words (inbox, written by the peer)
+      const long long i = i0 + k * stride;
+      e[k] = make_int4(0, 0, 0, 0);
+      p[k] = make_int4(0, 0, 0, epoch);
+      if (i >= cnt) continue;
+      e[k] = *reinterpret_cast<const int4*>(served + i * kXServed);
+      if (lane4 < 3) p[k] = ld_word16(upd + i * kXUpd + 16 * lane4);
+    }
+    float* rec[XU];
+    float4 pr[XU], s0[XU], s1[XU], s2[XU], g[XU];
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {
+      const long long i = i0 + k * stride;
+      rec[k] = nullptr;
+      if (i < cnt && lane4 < 3 && p[k].w != epoch) p[k] = poll16(upd + i * kXUpd + 16 * lane4, epoch, err);
+      // words {g0 g1 g2}{g3 g4 g5}{g6 g7 gw} -> lane 0: g0..g3, lane 1: g4..g7, lane 2: gw
+      const int q1x = __shfl_sync(gm, p[k].x, 1, 4), q2x = __shfl_sync(gm, p[k].x, 2, 4), q2y = __shfl_sync(gm, p[k].y, 2, 4);
+      if (i >= cnt) continue;
+      const long long id = id_of(e[k].x, e[k].y);
+      const int gi = e[k].z;
+      const long long sl = xslot_of(x, t, id);
+      if (lane4 < 2) {
+        if (!(id >= 0 && sl < t.deep_rows[gi])) continue;  // already reported by the serving pass
+        g[k] = lane4 == 0 ? make_float4(__int_as_float(p[k].x), __int_as_float(p[k].y), __int_as_float(p[k].z), __int_as_float(q1x))
+                          : make_float4(__int_as_float(p[k].y), __int_as_float(p[k].z), __int_as_float(q2x), __int_as_float(q2y));
+        rec[k] = t.deep[gi] + sl * t.deep_stride[gi] + 4 * lane4;
+        pr[k] = ld_f4(rec[k]);
+        if (S > 0) s0[k] = ld_f4(rec[k] + t.deep_soff[1]);
+        if (S > 1) s1[k] = ld_f4(rec[k] + t.deep_soff[2]);
+        if (S > 2) s2[k] = ld_f4(rec[k] + t.deep_soff[3]);
+      } else if (lane4 == 2) {
+        if (!(id >= 0 && sl < t.wide_rows[gi])) continue;
+        g[k].x = __int_as_float(p[k].z);
+        rec[k] = t.wide[gi] + sl * t.wide_stride[gi];
+        pr[k].x = *rec[k];
+        if (S > 0) s0[k].x = rec[k][t.wide_soff[1]];
+        if (S > 1) s1[k].x = rec[k][t.wide_soff[2]];
+        if (S > 2) s2[k].x = rec[k][t.wide_soff[3]];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < XU; ++k) {
+      if (rec[k] == nullptr) continue;
+      if (lane4 < 2) {
+        float* gf = reinterpret_cast<float*>(&g[k]);
+        float* pf = reinterpret_cast<float*>(&pr[k]);
+        float* af = reinterpret_cast<float*>(&s0[k]);
+        float* bf = reinterpret_cast<float*>(&s1[k]);
+        float* cf = reinterpret_cast<float*>(&s2[k]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) opt_update<OPT>(gf[c], pf[c], af[c], bf[c], cf[c], lr, alpha, l2adj, o);
+        st_f4(rec[k], pr[k]);
+        if (S > 0) st_f4(rec[k] + t.deep_soff[1], s0[k]);
+        if (S > 1) st_f4(rec[k] + t.deep_soff[2], s1[k]);
+        if (S > 2) st_f4(rec[k] + t.deep_soff[3], s2[k]);
+      } else {
+        opt_update<OPT>(g[k].x, pr[k].x, s0[k].x, s1[k].x, s2[k].x, lr, alpha, l2adj, o);
+        *rec[k] = pr[k].x;
+        if (S > 0) rec[k][t.wide_soff[1]] = s0[k].x;
+        if (S > 1) rec[k][t.wide_soff[2]] = s1[k].x;
+        if (S > 2) rec[k][t.wide_soff[3]] = s2[k].x;
+      }
+    }
+  }
+  __shared__ bool last;
+  __threadfence();  // rows are local: this GPU's later kernels (its next serve) read them in stream order
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&h->done_src[src], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(&xhdr(x, src)->applied[x.me]), "r"(epoch) : "memory");
+    h->done_src[src] = 0;
+  }
+}
+
 // Requester: all owners have applied my updates (push_end bumps the versions after this).
 __global__ void k_x_wait_applied(XView x, GroupView gv) {
   XHeader* h = xhdr(x, x.me);
