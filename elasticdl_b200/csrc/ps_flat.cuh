@@ -20,12 +20,14 @@
 //   * the update is "lane = (row, column)": the 8 lanes of a dim-8 row read 32 contiguous bytes of
 //     param, of each slot and of the gradient -- one full sector per array per row, no shuffles --
 //     and every lane executes exactly one element update (the d8 kernel ran four on 2 of 8 lanes).
+// Measured and rejected (git history, commit "flat kernels: warp-uniform segment fast path"): specialising the
+// loop body for warp-iterations that lie inside one segment (segment constants loaded once, no per-item search)
+// cut instructions but cost 12-16 registers -- 4 M-row pull 35.5 % vs 36.2 % of the copy peak, dim-64 57-59 % vs
+// 58-60 %, step 191-192 vs 189-190 us: these kernels are bound by memory round trips, not by issue slots.
 // Arithmetic is opt_update<> of ps_kernels.cuh: results stay bit-identical to the oracle.
 // Replaces go/pkg/kernel/kernel.go:35-199 (Sparse* / Indexed* row loops) and
 // go/pkg/common/embedding_table.go:61-77 (Get / SetEmbeddingVectors).
 #pragma once
-#include <type_traits>
-
 #include "ps_kernels.cuh"
 
 namespace b200ps_impl {
@@ -183,40 +185,12 @@ __device__ __forceinline__ FlatItem flat_item(const FlatArgs<NSMAX>& p, const lo
   return it;
 }
 
-// The same when the whole warp-iteration lies inside ONE segment (the common case: a warp only straddles a
-// boundary once per segment): the segment's constants are loaded once, nothing is searched per item.
-struct FlatSegU {
-  long long p0;  // prefix of the segment
-  int seg, shift, lpr;
-};
-__device__ __forceinline__ FlatItem flat_item_u(const FlatSegU& u, long long w, long long total) {
-  FlatItem it;
-  it.live = w < total;
-  it.seg = u.seg;
-  const long long local = it.live ? w - u.p0 : 0;
-  it.row = u.shift >= 0 ? local >> u.shift : local / u.lpr;
-  it.col = (int)(local - it.row * u.lpr);
-  return it;
-}
-// wb: first item of the warp-iteration (warp-uniform).  Returns true when items [wb, wb + n) lie in one segment.
-template <int NSMAX>
-__device__ __forceinline__ bool flat_uniform(const FlatArgs<NSMAX>& p, const long long* prefix, long long wb, int n, long long total,
-                                             FlatSegU* u) {
-  const int seg = flat_seg_of(prefix, p.nseg, wb);
-  const long long wend = wb + n < total ? wb + n : total;
-  u->seg = seg;
-  u->p0 = prefix[seg];
-  u->shift = p.seg[seg].shift;
-  u->lpr = p.seg[seg].lpr;
-  return prefix[seg + 1] >= wend;
-}
-
 // ---------------------------------------------------------------------------
 // pull (WRITE = false, PullEmbeddingVectors) / set (WRITE = true, SetEmbeddingVectors / slot access):
 // item = (row, 16 B chunk) when the segment is vectorisable, else (row, float).
 // ---------------------------------------------------------------------------
 template <bool WRITE, int U, int NSMAX>
-__global__ void __launch_bounds__(256, 5) k_copy_flat(const __grid_constant__ FlatArgs<NSMAX> p) {
+__global__ void __launch_bounds__(256) k_copy_flat(const __grid_constant__ FlatArgs<NSMAX> p) {
   __shared__ long long prefix[kMaxSegs + 1];
   flat_prefix(p, prefix);
   const int nseg = p.nseg;
@@ -225,29 +199,14 @@ __global__ void __launch_bounds__(256, 5) k_copy_flat(const __grid_constant__ Fl
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long wb = warp * (32 * U); wb < total; wb += nwarp * (32 * U)) {
-    FlatSegU su;
-    const bool uniform = flat_uniform(p, prefix, wb, 32 * U, total, &su);
-    // the body twice: UNI = the whole warp-iteration lies in segment su.seg (its constants are loaded once and
-    // nothing is searched per item), or the general case
-    auto body = [&](auto uni_c) {
-    constexpr bool UNI = decltype(uni_c)::value;
+    const long long w0 = wb + lane;
+    int seg = flat_seg_of(prefix, nseg, w0 < total ? w0 : total - 1);
     FlatItem it[U];
     long long id[U];
-    if (UNI) {
-      const int64_t* ids = p.seg[su.seg].ids;
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        it[k] = flat_item_u(su, wb + k * 32 + lane, total);
-        id[k] = it[k].live ? ids[it[k].row] : 0;
-      }
-    } else {
-      const long long w0 = wb + lane;
-      int seg = flat_seg_of(prefix, nseg, w0 < total ? w0 : total - 1);
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        it[k] = flat_item(p, prefix, wb + k * 32 + lane, total, seg);
-        id[k] = it[k].live ? p.seg[it[k].seg].ids[it[k].row] : 0;
-      }
+    for (int k = 0; k < U; ++k) {
+      it[k] = flat_item(p, prefix, wb + k * 32 + lane, total, seg);
+      id[k] = it[k].live ? p.seg[it[k].seg].ids[it[k].row] : 0;
     }
     FlatLoc loc[U];
     float4 x[U];
@@ -260,9 +219,8 @@ __global__ void __launch_bounds__(256, 5) k_copy_flat(const __grid_constant__ Fl
       vec[k] = false;
       pw[k] = 0xffffffffu;
       if (!it[k].live) continue;
-      const int sg = UNI ? su.seg : it[k].seg;
-      const FlatSegP& sp = p.seg[sg];
-      loc[k] = flat_locate(p, sg, id[k]);
+      const FlatSegP& sp = p.seg[it[k].seg];
+      loc[k] = flat_locate(p, it[k].seg, id[k]);
       if (!loc[k].ok) {
         if (it[k].col == 0) atomicOr(p.err, kErrRange);
         continue;
@@ -286,8 +244,6 @@ __global__ void __launch_bounds__(256, 5) k_copy_flat(const __grid_constant__ Fl
 #pragma unroll
     for (int k = 0; k < U; ++k)
       if (dst[k] != nullptr) flat_mark_present(loc[k], pw[k]);
-    };
-    if (uniform) body(std::true_type{}); else body(std::false_type{});
   }
 }
 
@@ -398,7 +354,7 @@ __global__ void __launch_bounds__(256) k_pull_staged(const __grid_constant__ Fla
 // single 16 B access.
 // ---------------------------------------------------------------------------
 template <int OPT, int U, int NSMAX>
-__global__ void __launch_bounds__(256, 5) k_push_flat(const __grid_constant__ FlatArgs<NSMAX> p, const OptParams o) {
+__global__ void __launch_bounds__(256) k_push_flat(const __grid_constant__ FlatArgs<NSMAX> p, const OptParams o) {
   constexpr int S = opt_slots(OPT);
   __shared__ long long prefix[kMaxSegs + 1];
   __shared__ float s_lr[kMaxShards], s_alpha[kMaxShards], s_l2[kMaxShards];
@@ -414,29 +370,14 @@ __global__ void __launch_bounds__(256, 5) k_push_flat(const __grid_constant__ Fl
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long wb = warp * (32 * U); wb < total; wb += nwarp * (32 * U)) {
-    FlatSegU su;
-    const bool uniform = flat_uniform(p, prefix, wb, 32 * U, total, &su);
-    // the body twice: UNI = the whole warp-iteration lies in segment su.seg (its constants are loaded once and
-    // nothing is searched per item), or the general case
-    auto body = [&](auto uni_c) {
-    constexpr bool UNI = decltype(uni_c)::value;
+    const long long w0 = wb + lane;
+    int seg = flat_seg_of(prefix, nseg, w0 < total ? w0 : total - 1);
     FlatItem it[U];
     long long id[U];
-    if (UNI) {
-      const int64_t* ids = p.seg[su.seg].ids;
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        it[k] = flat_item_u(su, wb + k * 32 + lane, total);
-        id[k] = it[k].live ? ids[it[k].row] : 0;
-      }
-    } else {
-      const long long w0 = wb + lane;
-      int seg = flat_seg_of(prefix, nseg, w0 < total ? w0 : total - 1);
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        it[k] = flat_item(p, prefix, wb + k * 32 + lane, total, seg);
-        id[k] = it[k].live ? p.seg[it[k].seg].ids[it[k].row] : 0;
-      }
+    for (int k = 0; k < U; ++k) {
+      it[k] = flat_item(p, prefix, wb + k * 32 + lane, total, seg);
+      id[k] = it[k].live ? p.seg[it[k].seg].ids[it[k].row] : 0;
     }
     FlatLoc loc[U];
     float g[U], pv[U], s0[U], s1[U], s2[U];
@@ -450,9 +391,8 @@ __global__ void __launch_bounds__(256, 5) k_push_flat(const __grid_constant__ Fl
       pw[k] = 0xffffffffu;
       s0[k] = s1[k] = s2[k] = 0.f;
       if (!it[k].live) continue;
-      const int sg = UNI ? su.seg : it[k].seg;
-      const FlatSegP& sp = p.seg[sg];
-      loc[k] = flat_locate(p, sg, id[k]);
+      const FlatSegP& sp = p.seg[it[k].seg];
+      loc[k] = flat_locate(p, it[k].seg, id[k]);
       if (!loc[k].ok) {
         if (it[k].col == 0) atomicOr(p.err, kErrRange);
         continue;
@@ -475,7 +415,7 @@ __global__ void __launch_bounds__(256, 5) k_push_flat(const __grid_constant__ Fl
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       if (rp[k] == nullptr) continue;
-      const FlatSegP& sp = p.seg[UNI ? su.seg : it[k].seg];
+      const FlatSegP& sp = p.seg[it[k].seg];
       const int sh = loc[k].shard;
       opt_update<OPT>(g[k], pv[k], s0[k], s1[k], s2[k], s_lr[sh], s_alpha[sh], s_l2[sh], o);
       if (rec4[k]) {
@@ -490,8 +430,6 @@ __global__ void __launch_bounds__(256, 5) k_push_flat(const __grid_constant__ Fl
 #pragma unroll
     for (int k = 0; k < U; ++k)
       if (rp[k] != nullptr) flat_mark_present(loc[k], pw[k]);
-    };
-    if (uniform) body(std::true_type{}); else body(std::false_type{});
   }
 }
 
