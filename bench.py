@@ -419,7 +419,6 @@ def main():
         _, _, n = group.unique(ids.view(-1), G)
         uniq_per_batch.append(int(n.sum().item()))
     h2d = host[0].numel()
-    loss_pin = torch.empty(args.steps + args.warmup + 8, dtype=torch.float32).pin_memory()
     u_mean = statistics.mean(uniq_per_batch)
     rows_mb = u_mean * (96 + 16) / 1e6  # Adam records touched per step: 96 B (dim 8) + 16 B (dim 1) per unique id
     config["l2_policy"] = ("pool of %d distinct batches cycled: a batch's rows (%.0f MB of records per step, plus "
@@ -545,12 +544,15 @@ def main():
             e2.record()
         if feeder is not None:
             feeder.submit(host[(i + ahead) % args.pool])
-            loss = feeder.run_next()
+            feeder.run_next()
         else:
             hb = host[i % args.pool].to(dev, non_blocking=True)
             from elasticdl_b200.workloads.deepfm import packed_views
-            loss = engine.step(*packed_views(hb, G, B, engine.widths))
-        loss_pin[i % loss_pin.numel()].copy_(loss, non_blocking=True)
+            engine.step(*packed_views(hb, G, B, engine.widths))
+        # the D2H read of the step's loss: the last kernel of every step stores it into a ring in pinned host
+        # memory (engine.loss_ring, 4 bytes over PCIe per step; b200_deepfm_publish_loss) -- a cudaMemcpyAsync of the
+        # scalar between two graph launches put a copy-engine round trip on the critical path of every step
+        # (tools/e2e_probe.py: 198 us per step without it, 222-237 us with it)
     e3.record()
     sync_all()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
@@ -574,13 +576,15 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "d2h": "the step's loss, stored by the step's last kernel into a ring in pinned host memory",
                     "ms_per_step": ms_e2e / args.steps, "h2d_copy_ms_probe": h2d_ms,
                     "h2d_gbs_probe": h2d / h2d_ms / 1e6,
                     "id_narrowing": "ids int64 -> %s on the host side of the boundary (packed batch), widened on the device" % ("1/2/4-byte" if args.ids == "narrow" else "int32")},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / max(args.steps, 1),
             "launch_mode": "cuda_graph" if use_graph else "eager", "eager_ms_per_step": ms_eager / args.steps,
             "tower": args.tower,
-            "final_loss": float(loss_pin[(args.warmup + args.steps - 1) % loss_pin.numel()])}
+            "final_loss": engine.loss_host(engine.steps - 1),
+            "e2e_losses_read_on_host": [engine.loss_host(engine.steps - 1 - j) for j in range(min(3, args.steps))]}
     if parity is not None:
         line["parity_check"] = parity
     if kern:

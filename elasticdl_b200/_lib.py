@@ -126,6 +126,7 @@ SYMBOLS = {
     "b200_deepfm_launch_count": (_i64, []),
     "b200_deepfm_fwd_bwd_tile": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
     "b200_deepfm_forward_tile": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
+    "b200_deepfm_publish_loss": (_i, [_vp, _vp, _i, _vp, _vp]),
     "b200_deepfm_tile_prologue": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
     "b200_deepfm_tile_main": (_i, [ctypes.POINTER(DeepFMArgs), _vp]),
     "b200_deepfm_tile_launch_count": (_i64, []),

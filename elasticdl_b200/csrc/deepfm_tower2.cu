@@ -462,6 +462,15 @@ __global__ void __launch_bounds__(THREADS, 2) k_tower_tile(b200_deepfm_args_t a,
   }
 }
 
+// The step's loss to the host without a copy-engine operation: one thread stores the value into a ring in
+// MAPPED pinned host memory (a 4-byte write over PCIe) and bumps the ring cursor.  A cudaMemcpyAsync of the
+// scalar between two graph launches costs a copy-engine round trip on the critical path of every step.
+__global__ void k_publish_loss(const float* __restrict__ loss, float* ring, int ring_len, unsigned* cursor) {
+  const unsigned at = *cursor;
+  *reinterpret_cast<volatile float*>(ring + (at % (unsigned)ring_len)) = *loss;
+  *cursor = at + 1;
+}
+
 int check_args(const b200_deepfm_args_t* a, bool backward) {
   if (!a || a->G < 1 || a->B < 1) { g_msg = "bad shape"; return -1; }
   if (a->G > MAXG) { g_msg = "the tile tower holds at most 38 id groups"; return -1; }
@@ -528,6 +537,15 @@ int b200_deepfm_tile_prologue(const b200_deepfm_args_t* args, void* stream) {
 int b200_deepfm_tile_main(const b200_deepfm_args_t* args, void* stream) {
   if (check_args(args, true)) return -1;
   return launch<true>(args, stream, 2);
+}
+
+int b200_deepfm_publish_loss(const float* loss_dev, float* ring_host_mapped, int ring_len, unsigned* cursor_dev, void* stream) {
+  if (!loss_dev || !ring_host_mapped || ring_len < 1 || !cursor_dev) { g_msg = "bad publish_loss arguments"; return -1; }
+  k_publish_loss<<<1, 1, 0, (cudaStream_t)stream>>>(loss_dev, ring_host_mapped, ring_len, cursor_dev);
+  g_launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_msg = cudaGetErrorString(e); return -2; }
+  return 0;
 }
 
 int b200_deepfm_forward_tile(const b200_deepfm_args_t* args, void* stream) {

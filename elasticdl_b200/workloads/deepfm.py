@@ -325,6 +325,11 @@ class DeepFMPSEngine:
         self.gsum_d = torch.zeros((G * B, D), **f32)
         self.scratch = torch.empty(max(B * 44 + 16 * (N_DENSE + D * G), 320 * 16 + 16), **f32)  # b200_deepfm.h: backward state + W1^T | tile tower: W1 tile + counter
         self.loss_buf = torch.zeros(1, **f32)
+        # the loss of every step also lands in a ring of pinned host memory, written by a 1-thread kernel at the end
+        # of the step (b200_deepfm_publish_loss): loss_host(k) reads step k's value after a synchronize, no D2H copy
+        self.LOSS_RING = 256
+        self.loss_ring = torch.zeros(self.LOSS_RING, dtype=torch.float32).pin_memory()
+        self.loss_cursor = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.logits_buf = torch.empty(B, **f32)
         self.zero_versions = [0] * group.n_shards
 
@@ -505,10 +510,12 @@ class DeepFMPSEngine:
             with torch.cuda.stream(self.aux):
                 arr, n = dense_segs
                 check(lib.b200ps_push_dense(h, arr, n, g._stream()))
+                self._publish_loss(loss, g._stream())
         else:
             g.push_begin(self.lr, self.zero_versions)
             arr, n = dense_segs
             check(lib.b200ps_push_dense(h, arr, n, st))
+            self._publish_loss(loss, st)
         if self.exchange == "owner":
             e = mark("push_exchange")
             check(lib.b200ps_xchg_push(h, self.gsum_d.data_ptr(), self.gsum_w.data_ptr(), st))
@@ -528,6 +535,19 @@ class DeepFMPSEngine:
         g.push_end(sync=False)
         self.steps += 1
         return loss.detach().reshape(())
+
+    def _publish_loss(self, loss, st):
+        if loss is not self.loss_buf:  # torch tower: its loss tensor is not persistent
+            self.loss_buf.copy_(loss.detach().reshape(1))
+        rc = self.group.lib.b200_deepfm_publish_loss(self.loss_buf.data_ptr(), self.loss_ring.data_ptr(), self.LOSS_RING,
+                                                     self.loss_cursor.data_ptr(), st)
+        if rc:
+            raise RuntimeError("b200_deepfm_publish_loss failed (%d)" % rc)
+
+    def loss_host(self, step_index):
+        """Loss of step `step_index` (0-based count of steps run by this engine) from the host ring; valid once
+        the device has finished that step (synchronize / event) and for the last LOSS_RING steps."""
+        return float(self.loss_ring[step_index % self.LOSS_RING])
 
     def _unique_into(self, ids, blocks_per_sm=0):
         """tf.unique per id group into the current plan, on the current stream.  blocks_per_sm > 0: a thin

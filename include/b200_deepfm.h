@@ -66,6 +66,9 @@ int b200_deepfm_forward_tile(const b200_deepfm_args_t* args, void* stream);
 /* b200_deepfm_fwd_bwd_tile in its two halves, so that a caller can put the prologue on another stream, beside
  * the row pull: the prologue (W1 into tile order; zero the gradient buffers, the loss and the live rows of the
  * per-unique-id sums) reads only `params` and `n_unique`; the main kernel needs the prologue and the pulled rows. */
+/* The step's loss to the host without a copy-engine operation: ring_host_mapped is pinned host memory as the
+ * device sees it (cudaHostAlloc / UVA); entry cursor % ring_len receives *loss_dev, then the cursor advances. */
+int b200_deepfm_publish_loss(const float* loss_dev, float* ring_host_mapped, int ring_len, unsigned* cursor_dev, void* stream);
 int b200_deepfm_tile_prologue(const b200_deepfm_args_t* args, void* stream);
 int b200_deepfm_tile_main(const b200_deepfm_args_t* args, void* stream);
 int64_t b200_deepfm_tile_launch_count(void);

@@ -38,11 +38,14 @@ def resnet50_like_shapes():
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
+    # B200_SHARED_GPU=1: all ranks are processes on cuda:0, collectives over gloo (see tests/mgpu_check.py)
+    shared = os.environ.get("B200_SHARED_GPU") == "1"
+    local = 0 if shared else int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    controller = create_elastic_controller(batch_size=32, num_epochs=1, dataset_size=3200, backend="nccl")
-    assert dist.get_backend() == "nccl" and dist.get_world_size() == world
+    backend = "gloo" if shared else "nccl"
+    controller = create_elastic_controller(batch_size=32, num_epochs=1, dataset_size=3200, backend=backend)
+    assert dist.get_backend() == backend and dist.get_world_size() == world
     # ---- correctness on a small model -------------------------------------------------
     torch.manual_seed(10 + rank)
     model = torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ReLU(), torch.nn.Linear(64, 1)).to(dev)
@@ -104,12 +107,12 @@ def main():
     flat = next(iter(big._buckets.values()))
     flat.normal_(0, 1e-3)
     n = flat.numel()
-    for _ in range(3):
+    for _ in range(1 if shared else 3):
         big.synchronize()
     torch.cuda.synchronize()
     dist.barrier()
     evs = []
-    for _ in range(10):
+    for _ in range(2 if shared else 10):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         big.synchronize()

@@ -30,10 +30,17 @@ ADAM = ("Adam", "learning_rate=0.001;beta_1=0.9;beta_2=0.999;epsilon=1e-07;amsgr
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
+    # B200_SHARED_GPU=1: every rank is a process on cuda:0 (the shards are still separate allocations mapped
+    # across PROCESSES with CUDA IPC, the kernels of the ranks time-slice the one device) and the host-side
+    # plumbing runs over gloo -- NCCL refuses two ranks on one device.  Lets a 1-GPU box run this check.
+    shared = os.environ.get("B200_SHARED_GPU") == "1"
+    local = 0 if shared else int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if shared:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     group = PSGroup(world, *ADAM, device=local, local_shards=[rank])
     client = PSClient(group)
     cap, dim = 100000, 8

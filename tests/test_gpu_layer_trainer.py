@@ -309,6 +309,10 @@ def test_engine_lookahead_pipeline_matches_plain_steps(use_graph):
                     feeder.submit(*host[i + 2])
                 losses.append(float(feeder.run_next()))
         group.check()
+        # every step also stored its loss into the pinned host ring (b200_deepfm_publish_loss): same values,
+        # read without any D2H copy
+        ring = [eng.loss_host(eng.steps - steps + i) for i in range(steps)]
+        assert ring == losses, (ring, losses)
         results.append((losses, _engine_state(group, eng, rows), [s_[0] for s_ in group.snapshot()]))
         group.close()
     (l0, s0, v0), (l1, s1, v1) = results
@@ -318,36 +322,34 @@ def test_engine_lookahead_pipeline_matches_plain_steps(use_graph):
         assert np.allclose(a, b, rtol=0, atol=2e-4), float(np.abs(a - b).max())
 
 
-def test_multi_gpu_peer_shards_via_torchrun():
-    """Rank-per-GPU group with CUDA-IPC peer shards (needs >= 2 GPUs; skipped on 1)."""
+def _torchrun_two_ranks(script, port):
+    """Two ranks through torchrun: one per GPU when the box has two, otherwise both as processes on cuda:0
+    (B200_SHARED_GPU=1: CUDA IPC between the processes, gloo for the host plumbing -- see tests/mgpu_check.py)."""
     import os
     import subprocess
     import sys
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run: gpurun --gpus 2)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533",
-                          os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if torch.cuda.device_count() < 2:
+        env["B200_SHARED_GPU"] = "1"
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", str(port),
+                           os.path.join(root, "tests", script)], capture_output=True, text=True, timeout=900, env=env)
+
+
+def test_multi_gpu_peer_shards_via_torchrun():
+    """Rank-per-process group with CUDA-IPC peer shards (one rank per GPU, or two processes on one GPU)."""
+    out = _torchrun_two_ranks("mgpu_check.py", 29533)
     assert out.returncode == 0 and "mgpu_check ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
 @pytest.mark.parametrize("script,token", [("mgpu_xchg_check.py", "mgpu_xchg_check ok"),
                                           ("mgpu_allreduce_check.py", "mgpu_allreduce ok")])
 def test_multi_gpu_exchange_and_allreduce_via_torchrun(script, token):
-    """Owner-computes NVLink exchange (pull bit-exact vs direct peer access, push bit-exact vs the
-    oracle) and the allreduce controller over NCCL (needs >= 2 GPUs; skipped on 1)."""
-    import os
-    import subprocess
-    import sys
-
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run: gpurun --gpus 2)")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29534",
-                          os.path.join(root, "tests", script)], capture_output=True, text=True, timeout=600)
+    """Owner-computes exchange (pull bit-exact vs direct peer access, push bit-exact vs the oracle) and the
+    allreduce controller incl. its fused reduce+update (NCCL with two GPUs; on one GPU the two ranks share it)."""
+    out = _torchrun_two_ranks(script, 29534)
     assert out.returncode == 0 and token in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
