@@ -1586,6 +1586,20 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   URuns ur{};
   const long long ups = a.ntiles;
   long long blocks = 0;
+  // segments with a small id range go to k_unique_small: one block each, position array in shared memory
+  static const int small_max = [] { const char* e = getenv("B200_UNIQUE_SMALL"); const int v = e ? atoi(e) : kUSmallMax; return v > kUSmallMax ? kUSmallMax : v; }();
+  USmall us{};
+  bool is_small[kMaxSegs] = {};
+  int small_bound = 0;
+  if (a.use_bounds && T <= kMaxSegs) {
+    for (int t = 0; t < T; ++t) {
+      if (a.ub.bound[t] > 0 && a.ub.bound[t] <= small_max) {
+        is_small[t] = true;
+        us.seg[us.n++] = t;
+        if (a.ub.bound[t] > small_bound) small_bound = a.ub.bound[t];
+      }
+    }
+  }
   if (T <= kMaxSegs) {
     ur.per_seg = 1;
     for (long long rh = 1;; rh += (rh < 8 ? 1 : rh / 4)) {
@@ -1597,7 +1611,7 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
         if (r > ups) r = ups;
         ur.run[t] = (int)r;
         ur.blk_prefix[t] = (int)blocks;
-        blocks += (ups + r - 1) / r;
+        if (!is_small[t]) blocks += (ups + r - 1) / r;  // a small segment has no slots in the grid-wide kernel
       }
       ur.blk_prefix[T] = (int)blocks;
       if (blocks <= max_blocks || rh >= ups) break;
@@ -1613,9 +1627,10 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
     blocks = (long long)T * ur.bps;
   }
   ur.nslots = (int)blocks;
+  const bool any_large = blocks > 0;
   if (blocks > max_blocks) blocks = max_blocks;  // the grid walks the slots (slot = block, block + grid, ...)
   if (blocks < 1) blocks = 1;
-  CUDA_OK(cudaMemsetAsync(a.hdr + 4, 0, 8, st));  // the grid-barrier counter
+  if (any_large) CUDA_OK(cudaMemsetAsync(a.hdr + 4, 0, 8, st));  // the grid-barrier counter
   UIdLayout idl{};
   if (widths != nullptr) {  // packed ids: segment t holds k elements of widths[t] bytes, segments back to back, 16 B aligned
     if (T > kMaxSegs) return fail(B200PS_EINVAL, "per-segment id widths need T <= " + std::to_string(kMaxSegs));
@@ -1629,8 +1644,19 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
     }
     a.ids32 = 2;
   }
-  k_unique<<<(unsigned)blocks, kUThreads, 0, st>>>(a, ur, idl);
-  count_launch(ps, 1);
+  if (us.n > 0) {
+    static bool attr_done[64] = {};
+    if (dev < 64 && !attr_done[dev]) {
+      CUDA_OK(cudaFuncSetAttribute(k_unique_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmallMax * 4));
+      attr_done[dev] = true;
+    }
+    k_unique_small<<<(unsigned)us.n, kUSThreads, (size_t)small_bound * 4, st>>>(a, idl, us);
+    count_launch(ps, 1);
+  }
+  if (any_large) {
+    k_unique<<<(unsigned)blocks, kUThreads, 0, st>>>(a, ur, idl);
+    count_launch(ps, 1);
+  }
   CUDA_OK(cudaGetLastError());
   return B200PS_OK;
 }

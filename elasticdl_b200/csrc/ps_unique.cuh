@@ -476,4 +476,127 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
   }
 }
 
+// =============================================================================
+// Segments with a SMALL id range (bound <= kUSmallMax): the whole segment is deduplicated by ONE block of 1024
+// threads whose position array lives in shared memory -- shared-memory atomics instead of L2 atomics, an
+// in-block scan instead of the decoupled look-back, no grid barrier, nothing read from the workspace.
+// 30 of the 38 id groups of the DeepFM batch qualify (<= 16384 rows); they are 79 % of its ids, and phase A
+// of the grid-wide kernel above is bound by the rate of L2 atomics on scattered addresses.  Same results:
+// first-occurrence order, inverse index, n_unique; out-of-range ids count as id 0 (the table kernels report them).
+//   A  pos[id] <- min(position)                (shared-memory atomicMin, checked first)
+//   B  chunks of 4096 positions in order: first-occurrence flags -> ballot ranks -> block scan -> uniq[rank] = id,
+//      pos[id] <- -(rank + 1)
+//   C  inv[i] = -pos[id_i] - 1
+// =============================================================================
+constexpr int kUSmallMax = 16384;
+constexpr int kUSThreads = 1024;
+struct USmall {
+  int seg[kMaxSegs];
+  int n;
+};
+
+__global__ void __launch_bounds__(kUSThreads, 1) k_unique_small(const __grid_constant__ UArgs a, const __grid_constant__ UIdLayout idl,
+                                                                const __grid_constant__ USmall us) {
+  extern __shared__ int s_pos[];  // [bound]
+  constexpr int NW = kUSThreads / 32, PPT = 4, UB = 8;
+  __shared__ int s_cnt[PPT * NW];
+  __shared__ int s_tot;
+  const int t = us.seg[blockIdx.x];
+  const int bound = a.ub.bound[t];
+  const long long k = a.k;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int i = tid; i < bound; i += kUSThreads) s_pos[i] = 0x7fffffff;
+  __syncthreads();
+  auto get = [&](long long i) {
+    const long long v = u_id(a, idl, t, i);
+    return (v < 0 || v >= bound) ? 0 : (int)v;
+  };
+  // ---- A ----
+  for (long long i0 = tid; i0 < k; i0 += (long long)kUSThreads * UB) {
+    int id[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const long long i = i0 + (long long)u * kUSThreads;
+      id[u] = i < k ? get(i) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const long long i = i0 + (long long)u * kUSThreads;
+      if (id[u] >= 0 && *(volatile int*)&s_pos[id[u]] > (int)i) atomicMin(&s_pos[id[u]], (int)i);
+    }
+  }
+  __syncthreads();
+  // ---- B ----
+  int run_base = 0;
+  int64_t* uniq = a.uniq + (long long)t * k;
+  for (long long base = 0; base < k; base += (long long)kUSThreads * PPT) {
+    int id[PPT], wrank[PPT];
+    unsigned fmask = 0;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const long long i = base + (long long)q * kUSThreads + tid;
+      id[q] = i < k ? get(i) : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const long long i = base + (long long)q * kUSThreads + tid;
+      const bool f = id[q] >= 0 && s_pos[id[q]] == (int)i;
+      const unsigned bal = __ballot_sync(0xffffffffu, f);
+      wrank[q] = __popc(bal & lt_mask);
+      if (f) fmask |= 1u << q;
+      if (lane == 0) s_cnt[q * NW + wid] = __popc(bal);
+    }
+    __syncthreads();
+    if (wid == 0) {  // exclusive scan of the PPT * NW = 128 counts (linear order = q major, warp minor): four per lane
+      int c[4], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c[j] = s_cnt[lane * 4 + j];
+        sum += c[j];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      int run = incl - sum;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s_cnt[lane * 4 + j] = run;
+        run += c[j];
+      }
+      if (lane == 31) s_tot = incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      if (fmask >> q & 1u) {
+        const int r = run_base + s_cnt[q * NW + wid] + wrank[q];
+        uniq[r] = (int64_t)id[q];
+        s_pos[id[q]] = -(r + 1);
+      }
+    }
+    run_base += s_tot;
+    __syncthreads();  // s_cnt / s_tot are rewritten by the next chunk, which must also see the ranks in s_pos
+  }
+  // ---- C ----
+  int* inv = a.inv + (long long)t * k;
+  for (long long i0 = tid; i0 < k; i0 += (long long)kUSThreads * UB) {
+    int id[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const long long i = i0 + (long long)u * kUSThreads;
+      id[u] = i < k ? get(i) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const long long i = i0 + (long long)u * kUSThreads;
+      if (id[u] >= 0) inv[i] = -s_pos[id[u]] - 1;
+    }
+  }
+  if (tid == 0) a.n_unique[t] = run_base;
+}
+
 }  // namespace b200ps_impl
