@@ -1591,7 +1591,7 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   USmall us{};
   bool is_small[kMaxSegs] = {};
   int small_bound = 0;
-  if (a.use_bounds && T <= kMaxSegs) {
+  if (a.use_bounds && T <= kMaxSegs && k <= 32LL * kUSThreads) {
     for (int t = 0; t < T; ++t) {
       if (a.ub.bound[t] > 0 && a.ub.bound[t] <= small_max) {
         is_small[t] = true;
@@ -1647,10 +1647,15 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   if (us.n > 0) {
     static bool attr_done[64] = {};
     if (dev < 64 && !attr_done[dev]) {
-      CUDA_OK(cudaFuncSetAttribute(k_unique_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmallMax * 4));
+      CUDA_OK(cudaFuncSetAttribute(k_unique_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmallMax * 4));
+      CUDA_OK(cudaFuncSetAttribute(k_unique_small<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmallMax * 4));
+      CUDA_OK(cudaFuncSetAttribute(k_unique_small<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmallMax * 4));
       attr_done[dev] = true;
     }
-    k_unique_small<<<(unsigned)us.n, kUSThreads, (size_t)small_bound * 4, st>>>(a, idl, us);
+    const size_t smem = (size_t)small_bound * 4;
+    if (k <= 8LL * kUSThreads) k_unique_small<8><<<(unsigned)us.n, kUSThreads, smem, st>>>(a, idl, us);
+    else if (k <= 16LL * kUSThreads) k_unique_small<16><<<(unsigned)us.n, kUSThreads, smem, st>>>(a, idl, us);
+    else k_unique_small<32><<<(unsigned)us.n, kUSThreads, smem, st>>>(a, idl, us);
     count_launch(ps, 1);
   }
   if (any_large) {

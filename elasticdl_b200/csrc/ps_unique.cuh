@@ -483,6 +483,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
 // 30 of the 38 id groups of the DeepFM batch qualify (<= 16384 rows); they are 79 % of its ids, and phase A
 // of the grid-wide kernel above is bound by the rate of L2 atomics on scattered addresses.  Same results:
 // first-occurrence order, inverse index, n_unique; out-of-range ids count as id 0 (the table kernels report them).
+// Taken when k <= 32768 (the ids of a segment then fit the registers of one block, see below).
 //   A  pos[id] <- min(position)                (shared-memory atomicMin, checked first)
 //   B  chunks of 4096 positions in order: first-occurrence flags -> ballot ranks -> block scan -> uniq[rank] = id,
 //      pos[id] <- -(rank + 1)
@@ -495,10 +496,15 @@ struct USmall {
   int n;
 };
 
+// IPT = ids per thread (k <= IPT * 1024): every id is loaded ONCE, with all of a thread's loads in flight together,
+// and stays in a register through the three passes (a one-block-per-SM kernel has nothing else to hide a load
+// behind: re-reading the ids per pass made it 40 us).  Thread tid owns positions j * 1024 + tid.
+template <int IPT>
 __global__ void __launch_bounds__(kUSThreads, 1) k_unique_small(const __grid_constant__ UArgs a, const __grid_constant__ UIdLayout idl,
                                                                 const __grid_constant__ USmall us) {
   extern __shared__ int s_pos[];  // [bound]
-  constexpr int NW = kUSThreads / 32, PPT = 4, UB = 8;
+  constexpr int NW = kUSThreads / 32, PPT = 4;
+  static_assert(IPT % PPT == 0, "chunks of PPT positions per thread");
   __shared__ int s_cnt[PPT * NW];
   __shared__ int s_tot;
   const int t = us.seg[blockIdx.x];
@@ -506,97 +512,92 @@ __global__ void __launch_bounds__(kUSThreads, 1) k_unique_small(const __grid_con
   const long long k = a.k;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
+  // two ids per register (bound <= 16384 < 0xffff = "no position"): 32 ids in 16 registers
+  unsigned pk[IPT / 2];
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    const long long i = (long long)j * kUSThreads + tid;
+    long long v = i < k ? u_id(a, idl, t, i) : 0xffff;
+    if (i < k && (v < 0 || v >= bound)) v = 0;  // out-of-range ids are reported by the table kernels
+    if (j & 1) pk[j >> 1] |= (unsigned)v << 16;
+    else pk[j >> 1] = (unsigned)v;
+    if ((j & 7) == 7) asm volatile("" ::: "memory");  // at most 8 loads in flight: keeps the kernel inside 64 registers
+  }
+#define US_ID(j) ((int)((pk[(j) >> 1] >> (16 * ((j) & 1))) & 0xffffu))
+#define US_LIVE(j) (US_ID(j) != 0xffff)
   for (int i = tid; i < bound; i += kUSThreads) s_pos[i] = 0x7fffffff;
   __syncthreads();
-  auto get = [&](long long i) {
-    const long long v = u_id(a, idl, t, i);
-    return (v < 0 || v >= bound) ? 0 : (int)v;
-  };
   // ---- A ----
-  for (long long i0 = tid; i0 < k; i0 += (long long)kUSThreads * UB) {
-    int id[UB];
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const long long i = i0 + (long long)u * kUSThreads;
-      id[u] = i < k ? get(i) : -1;
-    }
-#pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const long long i = i0 + (long long)u * kUSThreads;
-      if (id[u] >= 0 && *(volatile int*)&s_pos[id[u]] > (int)i) atomicMin(&s_pos[id[u]], (int)i);
-    }
+  for (int j = 0; j < IPT; ++j) {
+    const int i = j * kUSThreads + tid;
+    if (US_LIVE(j) && *(volatile int*)&s_pos[US_ID(j)] > i) atomicMin(&s_pos[US_ID(j)], i);
   }
   __syncthreads();
   // ---- B ----
   int run_base = 0;
   int64_t* uniq = a.uniq + (long long)t * k;
-  for (long long base = 0; base < k; base += (long long)kUSThreads * PPT) {
-    int id[PPT], wrank[PPT];
-    unsigned fmask = 0;
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-      const long long i = base + (long long)q * kUSThreads + tid;
-      id[q] = i < k ? get(i) : -1;
-    }
+  for (int c = 0; c < IPT / PPT; ++c) {
+    if ((long long)c * PPT * kUSThreads < k) {  // block-uniform
+      int wrank[PPT];
+      unsigned fmask = 0;
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-      const long long i = base + (long long)q * kUSThreads + tid;
-      const bool f = id[q] >= 0 && s_pos[id[q]] == (int)i;
-      const unsigned bal = __ballot_sync(0xffffffffu, f);
-      wrank[q] = __popc(bal & lt_mask);
-      if (f) fmask |= 1u << q;
-      if (lane == 0) s_cnt[q * NW + wid] = __popc(bal);
-    }
-    __syncthreads();
-    if (wid == 0) {  // exclusive scan of the PPT * NW = 128 counts (linear order = q major, warp minor): four per lane
-      int c[4], sum = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        c[j] = s_cnt[lane * 4 + j];
-        sum += c[j];
+      for (int q = 0; q < PPT; ++q) {
+        const int j = c * PPT + q;
+        const int i = j * kUSThreads + tid;
+        const bool f = US_LIVE(j) && s_pos[US_ID(j)] == i;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        wrank[q] = __popc(bal & lt_mask);
+        if (f) fmask |= 1u << q;
+        if (lane == 0) s_cnt[q * NW + wid] = __popc(bal);
       }
-      int incl = sum;
+      __syncthreads();
+      if (wid == 0) {  // exclusive scan of the PPT * NW = 128 counts (linear order = q major, warp minor): four per lane
+        int cc[4], sum = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      int run = incl - sum;
+        for (int x = 0; x < 4; ++x) {
+          cc[x] = s_cnt[lane * 4 + x];
+          sum += cc[x];
+        }
+        int incl = sum;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s_cnt[lane * 4 + j] = run;
-        run += c[j];
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += y;
+        }
+        int run = incl - sum;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          s_cnt[lane * 4 + x] = run;
+          run += cc[x];
+        }
+        if (lane == 31) s_tot = incl;
       }
-      if (lane == 31) s_tot = incl;
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        if (fmask >> q & 1u) {
+          const int j = c * PPT + q;
+          const int r = run_base + s_cnt[q * NW + wid] + wrank[q];
+          uniq[r] = (int64_t)US_ID(j);
+          s_pos[US_ID(j)] = -(r + 1);
+        }
+      }
+      run_base += s_tot;
+      __syncthreads();  // s_cnt / s_tot are rewritten by the next chunk, which must also see the ranks in s_pos
     }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-      if (fmask >> q & 1u) {
-        const int r = run_base + s_cnt[q * NW + wid] + wrank[q];
-        uniq[r] = (int64_t)id[q];
-        s_pos[id[q]] = -(r + 1);
-      }
-    }
-    run_base += s_tot;
-    __syncthreads();  // s_cnt / s_tot are rewritten by the next chunk, which must also see the ranks in s_pos
   }
   // ---- C ----
   int* inv = a.inv + (long long)t * k;
-  for (long long i0 = tid; i0 < k; i0 += (long long)kUSThreads * UB) {
-    int id[UB];
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const long long i = i0 + (long long)u * kUSThreads;
-      id[u] = i < k ? get(i) : -1;
-    }
-#pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const long long i = i0 + (long long)u * kUSThreads;
-      if (id[u] >= 0) inv[i] = -s_pos[id[u]] - 1;
-    }
+  for (int j = 0; j < IPT; ++j) {
+    const long long i = (long long)j * kUSThreads + tid;
+    if (US_LIVE(j)) inv[i] = -s_pos[US_ID(j)] - 1;
   }
   if (tid == 0) a.n_unique[t] = run_base;
+#undef US_ID
+#undef US_LIVE
 }
 
 }  // namespace b200ps_impl
