@@ -1065,3 +1065,43 @@ def test_wide_rows_big_gather(n_shards):
     assert np.array_equal(got[:live], vals[ids[:live]])
     assert (got[live:] == -7.0).all()
     group.close()
+
+
+@pytest.mark.parametrize("k", [700, 9000, 32768])
+def test_unique_small_segments_in_shared_memory(k, monkeypatch):
+    """B200_UNIQUE_SMALL: segments whose id range fits a shared-memory position array are deduplicated by one
+    block each (k_unique_small, ids in registers: 8 / 16 / 32 per thread), the others by the grid-wide kernel --
+    same first-occurrence order, inverse index and counts as tf.unique, over several calls (epochs of the
+    grid-wide kernel) and with out-of-range ids (counted as id 0)."""
+    import ctypes
+
+    from elasticdl_b200 import _lib
+
+    monkeypatch.setenv("B200_UNIQUE_SMALL", "16384")
+    group, _, _ = make_pair(1)
+    lib = _lib.lib()
+    rng = np.random.RandomState(33)
+    bounds_l = [3, 27, 16384, 16385, 1000, 2_000_000, 1, 5000]
+    T = len(bounds_l)
+    bounds = (ctypes.c_int64 * T)(*bounds_l)
+    need = lib.b200ps_unique_bounded_workspace(T, k, bounds)
+    ws = torch.zeros(need, dtype=torch.uint8, device="cuda")
+    uniq = torch.empty(T * k, dtype=torch.int64, device="cuda")
+    inv = torch.empty(T * k, dtype=torch.int32, device="cuda")
+    n = torch.empty(T, dtype=torch.int32, device="cuda")
+    for call in range(3):
+        ids = np.stack([rng.randint(0, b, size=k) for b in bounds_l]).astype(np.int64)
+        if call == 1:
+            ids[1, 5] = 10 ** 9   # out of range: counted as id 0 (the table kernels report it)
+            ids[4, 0] = -7
+        d_ids = torch.from_numpy(ids).cuda()
+        _lib.check(lib.b200ps_unique_bounded(group._h, d_ids.data_ptr(), T, k, bounds, uniq.data_ptr(), inv.data_ptr(),
+                                             n.data_ptr(), ws.data_ptr(), ws.numel(), group._stream()))
+        group.check()
+        u, i, c = uniq.cpu().numpy().reshape(T, k), inv.cpu().numpy().reshape(T, k), n.cpu().numpy()
+        for t in range(T):
+            seen = ids[t].copy()
+            seen[(seen < 0) | (seen >= bounds_l[t])] = 0
+            wu, wi = O.unique_first_occurrence(seen)
+            assert c[t] == len(wu) and np.array_equal(u[t, : c[t]], wu) and np.array_equal(i[t], wi), (t, call)
+    group.close()
