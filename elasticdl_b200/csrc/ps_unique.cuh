@@ -77,6 +77,35 @@ __device__ __forceinline__ long long u_id(const UArgs& a, const UIdLayout& L, in
   if (w == 4) return (long long)reinterpret_cast<const unsigned int*>(base)[i];
   return reinterpret_cast<const long long*>(base)[i];
 }
+// Branch-free id loads for unrolled loops: the element width is a property of the SEGMENT, so it is dispatched
+// once around the loop (U_KIND_SWITCH) and every load inside is one plain instruction.  With u_id() in the loop
+// each load sat behind its own width branch and the loads of a thread ran one after the other (ncu source view of
+// k_unique_small: 32 sequential round trips, 32 of its 39 us).
+template <int W, bool SGN>
+__device__ __forceinline__ long long u_ld(const unsigned char* b, long long i) {
+  if (W == 1) return (long long)b[i];
+  if (W == 2) return (long long)reinterpret_cast<const unsigned short*>(b)[i];
+  if (W == 4) return SGN ? (long long)reinterpret_cast<const int*>(b)[i] : (long long)reinterpret_cast<const unsigned int*>(b)[i];
+  return reinterpret_cast<const long long*>(b)[i];
+}
+// kind: 0 = 1 byte, 1 = 2 bytes, 2 = 4 bytes unsigned, 3 = int32, 4 = int64
+__device__ __forceinline__ int u_seg_kind(const UArgs& a, const UIdLayout& L, int t, const unsigned char** base) {
+  const unsigned char* ids = reinterpret_cast<const unsigned char*>(a.ids);
+  if (a.ids32 == 0) { *base = ids + (long long)t * a.k * 8; return 4; }
+  if (a.ids32 == 1) { *base = ids + (long long)t * a.k * 4; return 3; }
+  *base = ids + L.off[t];
+  const int w = L.width[t];
+  return w == 1 ? 0 : (w == 2 ? 1 : (w == 4 ? 2 : 4));
+}
+#define U_KIND_SWITCH(KIND, ...)                                              \
+  switch (KIND) {                                                             \
+    case 0: { constexpr int W = 1; constexpr bool SG = false; __VA_ARGS__; } break; \
+    case 1: { constexpr int W = 2; constexpr bool SG = false; __VA_ARGS__; } break; \
+    case 2: { constexpr int W = 4; constexpr bool SG = false; __VA_ARGS__; } break; \
+    case 3: { constexpr int W = 4; constexpr bool SG = true; __VA_ARGS__; } break;  \
+    default: { constexpr int W = 8; constexpr bool SG = true; __VA_ARGS__; } break; \
+  }
+
 __device__ __forceinline__ unsigned long long u_ldv(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -232,12 +261,23 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
       // the probe is one more uncached sector read per position and almost never saves the atomic
       const bool probe = (long long)bound * 2 < k;
       int id[PPT], cur[PPT];  // bounded ids fit 32 bits
+      {
+        const unsigned char* sbase;
+        const int kind = u_seg_kind(a, idl, t, &sbase);
+        long long raw[PPT];
+        U_KIND_SWITCH(kind, {
 #pragma unroll
-      for (int q = 0; q < PPT; ++q) {  // all id loads first
-        const long long i = base + q * kUThreads + threadIdx.x;
-        const long long v = i < k ? u_id(a, idl, t, i) : 0;
-        id[q] = (v < 0 || v >= bound) ? 0 : (int)v;  // out-of-range ids are reported by the table kernels
-        if (i < k) fp[i] = id[q];
+          for (int q = 0; q < PPT; ++q) {  // all id loads first, one instruction each
+            const long long i = base + q * kUThreads + threadIdx.x;
+            raw[q] = i < k ? u_ld<W, SG>(sbase, i) : 0;
+          }
+        });
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+          const long long i = base + q * kUThreads + threadIdx.x;
+          id[q] = (raw[q] < 0 || raw[q] >= bound) ? 0 : (int)raw[q];  // out-of-range ids are reported by the table kernels
+          if (i < k) fp[i] = id[q];
+        }
       }
 #pragma unroll
       for (int q = 0; q < PPT; ++q) {
@@ -262,10 +302,16 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
       int* mp = a.minpos + (long long)t * a.cap;
       const unsigned mask = a.cap - 1;
       long long id[PPT];
+      {
+        const unsigned char* sbase;
+        const int kind = u_seg_kind(a, idl, t, &sbase);
+        U_KIND_SWITCH(kind, {
 #pragma unroll
-      for (int q = 0; q < PPT; ++q) {
-        const long long i = base + q * kUThreads + threadIdx.x;
-        id[q] = i < k ? u_id(a, idl, t, i) : 0;
+          for (int q = 0; q < PPT; ++q) {
+            const long long i = base + q * kUThreads + threadIdx.x;
+            id[q] = i < k ? u_ld<W, SG>(sbase, i) : 0;
+          }
+        });
       }
 #pragma unroll
       for (int q = 0; q < PPT; ++q) {
@@ -514,14 +560,19 @@ __global__ void __launch_bounds__(kUSThreads, 1) k_unique_small(const __grid_con
   const unsigned lt_mask = (1u << lane) - 1u;
   // two ids per register (bound <= 16384 < 0xffff = "no position"): 32 ids in 16 registers
   unsigned pk[IPT / 2];
+  {
+    const unsigned char* sbase;
+    const int kind = u_seg_kind(a, idl, t, &sbase);
+    U_KIND_SWITCH(kind, {
 #pragma unroll
-  for (int j = 0; j < IPT; ++j) {
-    const long long i = (long long)j * kUSThreads + tid;
-    long long v = i < k ? u_id(a, idl, t, i) : 0xffff;
-    if (i < k && (v < 0 || v >= bound)) v = 0;  // out-of-range ids are reported by the table kernels
-    if (j & 1) pk[j >> 1] |= (unsigned)v << 16;
-    else pk[j >> 1] = (unsigned)v;
-    if ((j & 7) == 7) asm volatile("" ::: "memory");  // at most 8 loads in flight: keeps the kernel inside 64 registers
+      for (int j = 0; j < IPT; ++j) {
+        const long long i = (long long)j * kUSThreads + tid;
+        long long v = i < k ? u_ld<W, SG>(sbase, i) : 0xffff;
+        if (i < k && (v < 0 || v >= bound)) v = 0;  // out-of-range ids are reported by the table kernels
+        if (j & 1) pk[j >> 1] |= (unsigned)v << 16;
+        else pk[j >> 1] = (unsigned)v;
+      }
+    });
   }
 #define US_ID(j) ((int)((pk[(j) >> 1] >> (16 * ((j) & 1))) & 0xffffu))
 #define US_LIVE(j) (US_ID(j) != 0xffff)
