@@ -127,6 +127,9 @@ struct b200ps {
   int* d_x_deep = nullptr;
   int* d_x_wide = nullptr;
   std::vector<int> x_deep_host, x_wide_host;
+  // the dedup's two kernels (small segments / large segments) run side by side: a second stream + fork / join events
+  cudaStream_t u_side = nullptr;
+  cudaEvent_t u_fork = nullptr, u_join = nullptr;
   std::mutex mu;
 };
 
@@ -529,6 +532,9 @@ int b200ps_destroy(b200ps_t* ps) {
   cudaFree(ps->d_state);
   cudaFree(ps->d_x_deep);
   cudaFree(ps->d_x_wide);
+  if (ps->u_side) cudaStreamDestroy(ps->u_side);
+  if (ps->u_fork) cudaEventDestroy(ps->u_fork);
+  if (ps->u_join) cudaEventDestroy(ps->u_join);
   delete ps;
   return B200PS_OK;
 }
@@ -1587,9 +1593,8 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
   const long long ups = a.ntiles;
   long long blocks = 0;
   // segments with a small id range go to k_unique_small: one block each, position array in shared memory
-  // (opt-in through B200_UNIQUE_SMALL=<largest id range>: measured 35-40 us for the 30 small segments of the DeepFM
-  //  batch against the 20 us the grid-wide kernel needs for the 8 large ones -- the whole dedup 71 us instead of 56)
-  const int small_max = [] { const char* e = getenv("B200_UNIQUE_SMALL"); const int v = e ? atoi(e) : 0; return v > kUSmallMax ? kUSmallMax : v; }();
+  // (B200_UNIQUE_SMALL=<largest id range taken by k_unique_small>, 0 = off)
+  const int small_max = [] { const char* e = getenv("B200_UNIQUE_SMALL"); const int v = e ? atoi(e) : kUSmallMax; return v > kUSmallMax ? kUSmallMax : v; }();
   USmall us{};
   bool is_small[kMaxSegs] = {};
   int small_bound = 0;
@@ -1655,12 +1660,31 @@ static int unique_impl(b200ps_t* ps, const void* ids_dev, int ids32, int T, int6
       attr_done[dev] = true;
     }
     const size_t smem = (size_t)small_bound * 4;
-    if (k <= 8LL * kUSThreads) k_unique_small<8><<<(unsigned)us.n, kUSThreads, smem, st>>>(a, idl, us);
-    else if (k <= 16LL * kUSThreads) k_unique_small<16><<<(unsigned)us.n, kUSThreads, smem, st>>>(a, idl, us);
-    else k_unique_small<32><<<(unsigned)us.n, kUSThreads, smem, st>>>(a, idl, us);
+    // with a handle and work for both kernels the small-segment kernel runs on the handle's side stream, beside
+    // the grid-wide one (fork / join through events: also valid inside a stream capture); they share no output
+    cudaStream_t ss = st;
+    const bool fork = ps != nullptr && any_large;
+    if (fork) {
+      if (!ps->u_side) {
+        CUDA_OK(cudaStreamCreateWithFlags(&ps->u_side, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&ps->u_fork, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&ps->u_join, cudaEventDisableTiming));
+      }
+      ss = ps->u_side;
+      CUDA_OK(cudaEventRecord(ps->u_fork, st));
+      CUDA_OK(cudaStreamWaitEvent(ss, ps->u_fork, 0));
+    }
+    if (k <= 8LL * kUSThreads) k_unique_small<8><<<(unsigned)us.n, kUSThreads, smem, ss>>>(a, idl, us);
+    else if (k <= 16LL * kUSThreads) k_unique_small<16><<<(unsigned)us.n, kUSThreads, smem, ss>>>(a, idl, us);
+    else k_unique_small<32><<<(unsigned)us.n, kUSThreads, smem, ss>>>(a, idl, us);
     count_launch(ps, 1);
-  }
-  if (any_large) {
+    if (fork) CUDA_OK(cudaEventRecord(ps->u_join, ss));
+    if (any_large) {
+      k_unique<<<(unsigned)blocks, kUThreads, 0, st>>>(a, ur, idl);
+      count_launch(ps, 1);
+    }
+    if (fork) CUDA_OK(cudaStreamWaitEvent(st, ps->u_join, 0));
+  } else if (any_large) {
     k_unique<<<(unsigned)blocks, kUThreads, 0, st>>>(a, ur, idl);
     count_launch(ps, 1);
   }
