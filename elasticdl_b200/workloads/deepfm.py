@@ -457,10 +457,14 @@ class DeepFMPSEngine:
             with torch.cuda.stream(self.aux):
                 arr, n = self.pull_dense_segs
                 check(lib.b200ps_pull_dense(h, arr, n, g._stream()))
-                g.push_begin(self.lr, self.zero_versions)
                 rc = lib.b200_deepfm_tile_prologue(_ct.byref(a), g._stream())
                 if rc:
                     raise RuntimeError("b200_deepfm_tile_prologue failed (%d)" % rc)
+                ev_prep = torch.cuda.Event()
+                ev_prep.record(self.aux)  # the tower waits for this, not for push_begin behind it
+                g.push_begin(self.lr, self.zero_versions)
+                ev_begin = torch.cuda.Event()
+                ev_begin.record(self.aux)
         else:
             arr, n = self.pull_dense_segs
             check(lib.b200ps_pull_dense(h, arr, n, st))
@@ -481,7 +485,7 @@ class DeepFMPSEngine:
                 check(lib.b200ps_pull_rows(h, arr, n, st))
                 done(e)
         if branch:
-            main.wait_stream(self.aux)
+            main.wait_event(ev_prep)
             rc = lib.b200_deepfm_tile_main(_ct.byref(a), st)
             if rc:
                 raise RuntimeError("b200_deepfm_tile_main failed (%d)" % rc)
@@ -506,6 +510,7 @@ class DeepFMPSEngine:
             after_tower()  # lookahead pipeline: the next batch's dedup forks here (beside the push)
         # (7) push: one ApplyGradients per shard
         if branch:
+            main.wait_event(ev_begin)  # this push's lr / Adam alpha / step (k_push_begin ran on the second stream)
             self.aux.wait_stream(main)
             with torch.cuda.stream(self.aux):
                 arr, n = dense_segs
