@@ -435,19 +435,44 @@ int for_each_class(b200ps_t* ps, Split& sp, F&& launch) {
   return B200PS_OK;
 }
 
-// Persistent grid of the flat kernels: U rows in flight per thread once the work fills the machine.
+// Persistent grid of the flat kernels.  The grid must not exceed what is RESIDENT at once: a block that waits for
+// a free slot starts after the first wave has finished and pays the block prologue (76 device-side counts ->
+// scan -> barrier) and the launch ramp again.  Sized for 8 blocks per SM the 48-register kernels (5 resident)
+// ran 1.6 waves: push 34.8 -> 29.4 us, pull 20.4 -> 16.4 us, step 168.6 -> 162-164 us once the grid follows
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor of the kernel actually launched (profiles/r2_13_*).
+// U rows in flight per thread only once the work is several times what the resident threads cover.
 void flat_shape(b200ps_t* ps, long long items, int* U, int* grid, bool copy = false) {
   static const int force_u = [] { const char* e = getenv("B200_FLAT_U"); return e ? atoi(e) : 0; }();      // tuning knobs
-  static const int per_sm = [] { const char* e = getenv("B200_FLAT_BLOCKS"); return e ? atoi(e) : 0; }();
-  const long long cap = (long long)ps->n_sm * (per_sm > 0 ? per_sm : 8);
-  *U = items >= cap * 256 * 2 ? 2 : 1;
+  const long long resident1 = (long long)ps->n_sm * 6 * 256;  // about what the U = 1 kernels keep resident
+  *U = items >= resident1 * 8 ? 2 : 1;
   // (U = 4 is reachable through B200_FLAT_U only: measured on 1 M / 4 M dim-64 rows it LOSES to U = 2 --
   //  41 % vs 49-51 % of the copy peak -- its 80 registers cost more resident warps than the unroll adds.)
   if (force_u == 1 || force_u == 2 || (copy && force_u == 4)) *U = force_u;
-  long long blocks = (items + 256LL * *U - 1) / (256LL * *U);
+  *grid = 0;  // set by flat_grid() for the kernel instance that is launched
+}
+
+// blocks of `kern` (256 threads, no dynamic shared memory) resident on the whole device
+template <typename K>
+int flat_grid(b200ps_t* ps, K kern, long long items, int U) {
+  static const int per_sm = [] { const char* e = getenv("B200_FLAT_BLOCKS"); return e ? atoi(e) : 0; }();
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> occ;
+  int o = per_sm;
+  if (o <= 0) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = occ.find((const void*)kern);
+    if (it == occ.end()) {
+      int v = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, 256, 0) != cudaSuccess || v < 1) v = 4;
+      it = occ.emplace((const void*)kern, v).first;
+    }
+    o = it->second;
+  }
+  const long long cap = (long long)ps->n_sm * o;
+  long long blocks = (items + 256LL * U - 1) / (256LL * U);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  *grid = (int)blocks;
+  return (int)blocks;
 }
 
 #define DISPATCH_U(UVAL, ...)                          \
@@ -913,15 +938,15 @@ static int rows_copy(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
       FlatArgs<1> fa;
       fill_flat(ps, sp, false, slot, &fa);
       DISPATCH_UC(u_rt, {
-        if (write) k_copy_flat<true, U, 1><<<grid, 256, 0, st>>>(fa);
-        else k_copy_flat<false, U, 1><<<grid, 256, 0, st>>>(fa);
+        if (write) { grid = flat_grid(ps, k_copy_flat<true, U, 1>, sp.flat_items, U); k_copy_flat<true, U, 1><<<grid, 256, 0, st>>>(fa); }
+        else { grid = flat_grid(ps, k_copy_flat<false, U, 1>, sp.flat_items, U); k_copy_flat<false, U, 1><<<grid, 256, 0, st>>>(fa); }
       });
     } else {
       FlatArgs<8> fa;
       fill_flat(ps, sp, false, slot, &fa);
       DISPATCH_UC(u_rt, {
-        if (write) k_copy_flat<true, U, 8><<<grid, 256, 0, st>>>(fa);
-        else k_copy_flat<false, U, 8><<<grid, 256, 0, st>>>(fa);
+        if (write) { grid = flat_grid(ps, k_copy_flat<true, U, 8>, sp.flat_items, U); k_copy_flat<true, U, 8><<<grid, 256, 0, st>>>(fa); }
+        else { grid = flat_grid(ps, k_copy_flat<false, U, 8>, sp.flat_items, U); k_copy_flat<false, U, 8><<<grid, 256, 0, st>>>(fa); }
       });
     }
     ps->launches++;
@@ -1025,11 +1050,17 @@ int b200ps_push_rows(b200ps_t* ps, const b200ps_seg_t* segs, int nseg, void* str
     if (ps->n_shards == 1) {
       FlatArgs<1> fa;
       fill_flat(ps, sp, true, 0, &fa);
-      DISPATCH_OPT(o.kind, DISPATCH_U(u_rt, { k_push_flat<OPT, U, 1><<<grid, 256, 0, st>>>(fa, o); }));
+      DISPATCH_OPT(o.kind, DISPATCH_U(u_rt, {
+        grid = flat_grid(ps, k_push_flat<OPT, U, 1>, sp.flat_items, U);
+        k_push_flat<OPT, U, 1><<<grid, 256, 0, st>>>(fa, o);
+      }));
     } else {
       FlatArgs<8> fa;
       fill_flat(ps, sp, true, 0, &fa);
-      DISPATCH_OPT(o.kind, DISPATCH_U(u_rt, { k_push_flat<OPT, U, 8><<<grid, 256, 0, st>>>(fa, o); }));
+      DISPATCH_OPT(o.kind, DISPATCH_U(u_rt, {
+        grid = flat_grid(ps, k_push_flat<OPT, U, 8>, sp.flat_items, U);
+        k_push_flat<OPT, U, 8><<<grid, 256, 0, st>>>(fa, o);
+      }));
     }
     ps->launches++;
     CUDA_OK(cudaGetLastError());

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
         const int kind = u_seg_kind(a, idl, t, &sbase);
         long long raw[PPT];
         U_KIND_SWITCH(kind, {
-#pragma unroll
+          _Pragma("unroll")
           for (int q = 0; q < PPT; ++q) {  // all id loads first, one instruction each
             const long long i = base + q * kUThreads + threadIdx.x;
             raw[q] = i < k ? u_ld<W, SG>(sbase, i) : 0;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
         const unsigned char* sbase;
         const int kind = u_seg_kind(a, idl, t, &sbase);
         U_KIND_SWITCH(kind, {
-#pragma unroll
+          _Pragma("unroll")
           for (int q = 0; q < PPT; ++q) {
             const long long i = base + q * kUThreads + threadIdx.x;
             id[q] = i < k ? u_ld<W, SG>(sbase, i) : 0;
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kUSThreads, 1) k_unique_small(const __grid_con
     const unsigned char* sbase;
     const int kind = u_seg_kind(a, idl, t, &sbase);
     U_KIND_SWITCH(kind, {
-#pragma unroll
+      _Pragma("unroll")
       for (int j = 0; j < IPT; ++j) {
         const long long i = (long long)j * kUSThreads + tid;
         long long v = i < k ? u_ld<W, SG>(sbase, i) : 0xffff;
