@@ -1288,7 +1288,9 @@ int b200ps_xchg_push(b200ps_t* ps, const float* gsum_deep_dev, const float* gsum
   XTabs xt;
   if (xtabs(ps, &xt)) {
     k_x_send_upd2<4><<<grid, 256, 0, st>>>(x, gv.rt, gsum_deep_dev, gsum_wide_dev);
-    DISPATCH_OPT(o.kind, k_x_apply2<OPT, 2><<<grid, 256, 0, st>>>(x, xt, gv.err, o));
+    // the apply kernel holds 80 registers: 3 blocks per SM are resident, a 4th would wait for a second wave
+    dim3 grid_apply((unsigned)std::max(2, ps->n_sm * 3 / ps->n_shards), ps->n_shards);
+    DISPATCH_OPT(o.kind, k_x_apply2<OPT, 2><<<grid_apply, 256, 0, st>>>(x, xt, gv.err, o));
   } else {
     k_x_send_upd<<<grid, 256, 0, st>>>(x, gv, gsum_deep_dev, gsum_wide_dev);
     DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o));
@@ -1328,7 +1330,8 @@ int b200ps_xchg_profile(b200ps_t* ps, const int64_t* uniq_dev, const int32_t* n_
   if (fast) k_x_send_upd2<4><<<grid, 256, 0, st>>>(x, gv.rt, gsum_deep_dev, gsum_wide_dev);
   else k_x_send_upd<<<grid, 256, 0, st>>>(x, gv, gsum_deep_dev, gsum_wide_dev);
   cudaEventRecord(ev[4], st);
-  if (fast) { DISPATCH_OPT(o.kind, k_x_apply2<OPT, 2><<<grid, 256, 0, st>>>(x, xt, gv.err, o)); }
+  dim3 grid_apply((unsigned)std::max(2, ps->n_sm * 3 / ps->n_shards), ps->n_shards);
+  if (fast) { DISPATCH_OPT(o.kind, k_x_apply2<OPT, 2><<<grid_apply, 256, 0, st>>>(x, xt, gv.err, o)); }
   else { DISPATCH_OPT(o.kind, k_x_apply<OPT><<<grid, 256, 0, st>>>(x, gv, o)); }
   cudaEventRecord(ev[5], st);
   k_x_wait_applied<<<1, 32, 0, st>>>(x, gv);
