@@ -6,14 +6,18 @@
  * baseline (bench.py cpu_baseline / --impl reference).  Nothing under
  * elasticdl_b200/ may import, link or call this file.
  *
- * The reference's own native code (elasticdl/go/pkg/kernel/capi/kernel_api.cc)
- * cannot be compiled here: it includes <eigen3/Eigen/Dense> (kernel_api.cc:4)
- * and Eigen is not in this image; the Go PS needs go/protoc/grpc which are
- * absent too.  So this file restates the algorithm in plain C with the same
- * operation order, compiled -O2 -ffp-contract=off (the reference is built
- * `g++ -O3 -std=c++11` without -march, elasticdl/Makefile:23-25, i.e. SSE2 and
- * no FMA contraction).  Parity is pinned by the reference's golden vectors,
- * see tests/test_oracle_golden.py.
+ * The reference's own native file (elasticdl/go/pkg/kernel/capi/kernel_api.cc)
+ * includes <eigen3/Eigen/Dense> (kernel_api.cc:4) and Eigen is not in this
+ * image; oracle/Makefile `ref` compiles it UNMODIFIED against a stand-in header
+ * (oracle/eigen_shim) into oracle/_ref/libkernel_api_ref.so, and
+ * tests/test_oracle_vs_ref.py checks that the dense kernels below agree with it
+ * bit for bit (live, and through tests/golden/ref_kernel_vectors.npz which that
+ * library produced).  The Go PS around the kernels needs go/protoc/grpc, absent
+ * here, so the row loops, tables and control logic stay a restatement in plain
+ * C with the same operation order, compiled -O3 -ffp-contract=off (the
+ * reference is built `g++ -O3 -std=c++11` without -march,
+ * elasticdl/Makefile:23-25, i.e. SSE2 and no FMA contraction), pinned by the
+ * reference's golden vectors, see tests/test_oracle_golden.py.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference/elasticdl/).

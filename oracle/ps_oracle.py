@@ -15,8 +15,10 @@ Three layers, each citing the reference file:line it follows (paths relative to
                   go/pkg/ps/{server,optimizer,model}.go and
                   python/worker/ps_client.py composed in-process (no gRPC).
 
-Parity status: pinned by the reference's golden vectors (tests/
-test_oracle_golden.py) for SGD/Momentum/Adam/AMSGrad/Adagrad, table semantics,
+Parity status: the dense kernels equal the reference's own kernel_api.cc
+(compiled unmodified as oracle/_ref, see ref_kernels.py) bit for bit
+(tests/test_oracle_vs_ref.py); everything is pinned by the reference's golden
+vectors (tests/test_oracle_golden.py) for SGD/Momentum/Adam/AMSGrad/Adagrad, table semantics,
 hashing, dedup, version/step logic.  FTRL is PARITY UNPINNED (TF arithmetic is
 not under /root/reference; see ps_oracle.c).
 """

@@ -1105,3 +1105,49 @@ def test_unique_small_segments_in_shared_memory(k, monkeypatch):
             wu, wi = O.unique_first_occurrence(seen)
             assert c[t] == len(wu) and np.array_equal(u[t, : c[t]], wu) and np.array_equal(i[t], wi), (t, call)
     group.close()
+
+
+# ------------------------------------------------------------------ golden vectors produced by the reference's own kernels
+def _ref_kernel_cases():
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import gen_kernel_vectors as G
+
+    return G.cases()
+
+
+@pytest.mark.parametrize("name,kind,hp,n", _ref_kernel_cases(), ids=[c[0] for c in _ref_kernel_cases()])
+def test_raw_kernels_reproduce_reference_kernel_vectors(name, kind, hp, n):
+    """tests/golden/ref_kernel_vectors.npz = outputs of /root/reference's kernel_api.cc compiled unmodified
+    (oracle/_ref, tests/golden/gen_kernel_vectors.py).  The kernel_api.h drop-ins on the GPU reproduce them bit for
+    bit over three successive applications (slots feed back; Adam's double bias correction at steps 1..100002)."""
+    import ctypes
+    import os
+
+    from elasticdl_b200 import _lib
+
+    lib = _lib.lib()
+    vec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_kernel_vectors.npz"))
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g3 = torch.from_numpy(vec[name + "/g"]).cuda()
+    p, s0, s1, s2 = [torch.from_numpy(vec[name + "/in_" + k].copy()).cuda() for k in ("p", "s0", "s1", "s2")]
+    for k in range(3):
+        g = g3[k].contiguous()
+        if kind == "sgd":
+            rc = lib.b200ps_kernel_sgd(g.data_ptr(), p.data_ptr(), hp["lr"], n, st)
+        elif kind == "momentum":
+            rc = lib.b200ps_kernel_momentum(g.data_ptr(), p.data_ptr(), s0.data_ptr(), hp["mu"], hp["nesterov"], hp["lr"],
+                                            n, st)
+        elif kind == "adam":
+            rc = lib.b200ps_kernel_adam(g.data_ptr(), p.data_ptr(), s0.data_ptr(), s1.data_ptr(), hp["lr"], n,
+                                        hp["step"] + k, hp["beta1"], hp["beta2"], hp["eps"],
+                                        s2.data_ptr() if hp["ams"] else None, st)
+        else:
+            rc = lib.b200ps_kernel_adagrad(g.data_ptr(), p.data_ptr(), s0.data_ptr(), hp["lr"], n, hp["eps"], st)
+        _lib.check(rc)
+    for k, t in (("p", p), ("s0", s0), ("s1", s1), ("s2", s2)):
+        got = t.cpu().numpy().view(np.uint32)
+        want = vec[name + "/out_" + k].view(np.uint32)
+        assert np.array_equal(got, want), (name, k, int((got != want).sum()))
