@@ -290,15 +290,16 @@ def api_path_leg(dev, batches, steps, warmup):
     from elasticdl_b200.workloads.deepfm import DeepFMLayersModel
 
     out = {}
-    for mode, batched, k in (("batched", True, steps), ("per_layer", False, max(2, steps // 3))):
+    for mode, batched, graphed, k in (("graphed", True, True, 4 * steps), ("batched", True, False, steps),
+                                      ("per_layer", False, False, max(2, steps // 3))):
         group = PSGroup(1, "Adam", ADAM_ARGS, device=dev.index)
         client = PSClient(group)
         client.dense_output = "torch"
         model = DeepFMLayersModel().to(dev)
         trainer = ParameterServerTrainer(model, client, args=types.SimpleNamespace(
-            get_model_steps=1, batched_embedding_lookups=batched))
+            get_model_steps=1, batched_embedding_lookups=batched, cuda_graph=graphed, cuda_graph_warmup=warmup))
         feats = [(DeepFMLayersModel.features_of(ids, dense), labels) for ids, dense, labels in batches]
-        for i in range(warmup):
+        for i in range(warmup + (2 if graphed else 0)):  # graphed: `warmup` eager minibatches, the capture, one replay
             trainer.train_minibatch(*feats[i % len(feats)])
         torch.cuda.synchronize(dev)
         l0 = group.launch_count
@@ -309,11 +310,17 @@ def api_path_leg(dev, batches, steps, warmup):
         dt = (time.perf_counter() - t0) / k
         B = batches[0][0].shape[1]
         out[mode] = {"ms_per_step": dt * 1e3, "samples_per_s": B / dt, "ps_launches_per_step": (group.launch_count - l0) / k,
-                     "steps": k, "final_loss": float(loss)}
+                     "steps": k, "final_loss": float(loss), "version": int(version)}
+        if graphed:
+            out[mode]["cuda_graph"] = isinstance(trainer._graph_state, dict)
+            out[mode]["graph_fallback_reason"] = trainer.graph_fallback_reason
+            out[mode]["per_step"] = "input copy (1 kernel per dtype) + ONE graph replay + error word / versions read on the host"
         group.close()
         del trainer, model, client, group
-    out["what"] = ("ParameterServerTrainer.train_minibatch (pull_dense + 76 Embedding layers + eager torch tower + "
-                   "push_gradients), 1 shard, wall clock; the engine path (`value`) fuses the tower and replays a CUDA graph")
+    out["what"] = ("ParameterServerTrainer.train_minibatch (pull_dense + 76 Embedding layers + torch tower + push_gradients), "
+                   "1 shard, wall clock: `graphed` = args.cuda_graph (the whole minibatch replayed as one CUDA graph), "
+                   "`batched` = eager with batched lookups, `per_layer` = one lookup per layer call as the reference does; "
+                   "the engine path (`value`) additionally fuses the tower into one hand-written kernel")
     return out
 
 
@@ -610,8 +617,12 @@ def main():
             line["pull_frac_of_peak"] = kern[pk]["gbs"] / peak
     line["unique_ids_per_step"] = u_mean
     if world == 1 and args.api_steps > 0 and not args.profile_step:
-        line["api_path"] = api_path_leg(dev, devb, args.api_steps, 3)
-        line["api_path"]["engine_over_batched_api"] = line["api_path"]["batched"]["ms_per_step"] / (ms / args.steps)
+        try:  # a side leg: it must never cost the run its headline line
+            line["api_path"] = api_path_leg(dev, devb, args.api_steps, 3)
+            line["api_path"]["engine_over_batched_api"] = line["api_path"]["batched"]["ms_per_step"] / (ms / args.steps)
+            line["api_path"]["engine_over_graphed_api"] = line["api_path"]["graphed"]["ms_per_step"] / (ms / args.steps)
+        except Exception as err:
+            line["api_path"] = {"error": "%s: %s" % (type(err).__name__, str(err)[:300])}
     if not args.no_cpu_baseline and world == 1:
         sps, T, desc = cpu_reference(cpu_batch, args.cpu_steps, 1, args.dist)
         line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": T, "kind": "port", "sample": desc,

@@ -76,6 +76,7 @@ class PSGroup:
         self.opt_type, self.opt_args = opt_type, opt_args
         self.process_group = process_group
         self.seed = int(seed)
+        self.lr_staleness_modulation = bool(lr_staleness_modulation)
         # PS-side mode flags (python/ps/parameter_server.py / go/cmd/elasticdl_ps/main.go:32-35).
         # The Go PS is async only (server.go:177); sync-SGD follows python/ps/servicer.py:168-238.
         self.use_async = bool(use_async)
@@ -283,11 +284,20 @@ class PSGroup:
             items.append((tid, ids.numel(), ids, None, vals))
         self._run_segs(self.lib.b200ps_set_rows, items)
 
-    def pull_dense(self, names):
+    def pull_dense(self, names, into=None):
+        """Dense parameters by name -> {name: float32 cuda tensor}.  `into` ({name: tensor}) makes the kernel write
+        straight into the caller's tensors (contiguous float32 on this device, right size) instead of new ones."""
         outs, items = {}, []
         for name in names:
             tid, _, is_dense, shape = self.lookup(name)
-            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+            if into is not None:
+                out = into[name]
+                if not (out.is_cuda and out.device == self.device and out.dtype == torch.float32
+                        and out.is_contiguous() and out.numel() == int(np.prod(shape))):
+                    raise ValueError("pull_dense(into=): %s must be a contiguous float32 tensor of %s on %s"
+                                     % (name, tuple(shape), self.device))
+            else:
+                out = torch.empty(shape, dtype=torch.float32, device=self.device)
             outs[name] = out
             items.append((tid, 0, None, None, out))
         self._run_segs(self.lib.b200ps_pull_dense, items)

@@ -165,14 +165,19 @@ class PSClient(object):
         gsum = g.segment_sum(v, inv, 1, k, dim)
         return uniq, n_unique, gsum, k
 
-    def push_gradients(self, grads, edl_grads, learning_rate, model_versions):
+    def push_gradients(self, grads, edl_grads, learning_rate, model_versions, sync=True):
         """Push gradients to the PS (ps_client.py:190-287).  Two kinds:
          - gradients of normal layers (dense, or IndexedSlices of a dense parameter)
          - sparse gradients of ElasticDL embedding layers
         Every shard applies exactly one ApplyGradients and bumps its version
-        (quirk Q7).  Returns (accepted, max_version)."""
+        (quirk Q7).  Returns (accepted, max_version).
+        sync=False (device tensors only, async PS): nothing is read back -- the new versions land in
+        `group._pinned_versions` when the stream gets there and the caller checks `group.check()` itself;
+        returns (True, None).  This form is legal inside a CUDA-graph capture."""
         g = self.group
         if not getattr(g, "use_async", True):
+            if not sync:
+                raise ValueError("push_gradients(sync=False) needs an async PS group")
             return self._push_gradients_sync(grads, edl_grads, learning_rate, model_versions)
         # 1. group by name; same-name merge (ps_client.py:203-217)
         dense, indexed = {}, {}
@@ -233,7 +238,9 @@ class PSClient(object):
             g.push_dense(dense_items)
         if row_items:
             g.push_rows(row_items)
-        versions = g.push_end(sync=True)
+        versions = g.push_end(sync=sync)
+        if not sync:
+            return True, None
         g.check()
         return True, max(versions)
 

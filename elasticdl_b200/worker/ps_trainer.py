@@ -55,6 +55,13 @@ class ParameterServerTrainer(object):
         self._batched_lookups = getattr(args, "batched_embedding_lookups", True) if args is not None else True
         self._lookup_plan = None if self._batched_lookups else False
         self._group_bets = []
+        # CUDA-graph replay of the whole minibatch (see _train_minibatch_graphed): None = not decided yet,
+        # False = this job does not qualify (stays eager), else the captured state
+        self._use_cuda_graph = bool(getattr(args, "cuda_graph", False)) if args is not None else False
+        self._graph_warmup = max(1, int(getattr(args, "cuda_graph_warmup", 3))) if args is not None else 3
+        self._graph_state = None if self._use_cuda_graph else False
+        self._eager_steps = 0
+        self.graph_fallback_reason = None
         self._init_embeddings()
 
     # ------------------------------------------------------------------ embeddings
@@ -199,10 +206,172 @@ class ParameterServerTrainer(object):
     # ------------------------------------------------------------------ train step
     def train_minibatch(self, features, labels, train_with_local_model=False):  # ps_trainer.py:371-385
         self.init_variables_if_need(features, labels)
+        if self._graph_state is not False and not train_with_local_model:
+            out = self._train_minibatch_graphed(features, labels)
+            if out is not None:
+                return out
         if not train_with_local_model:
             self._get_model()
         loss, grads = self._training_process_eagerly(features, labels)
+        self._eager_steps += 1
         return (*self._update_global_model(grads), loss)
+
+    # ------------------------------------------------------------------ the minibatch as ONE CUDA graph
+    # args.cuda_graph=True.  The reference's step is a chain of RPCs and TF ops the worker drives one by one
+    # (ps_trainer.py:371-414); on one device the same chain is ~300 kernel launches (76 lookups, the eager torch
+    # model forward / backward, the push) and the step is bound by the host issuing them, not by the GPU.  After
+    # `cuda_graph_warmup` eager minibatches (variables created and initialised on the PS, the lookup plan learnt,
+    # every workspace at its final size) the trainer captures ONE minibatch -- pull of the dense parameters
+    # straight into the model's tensors, batched lookups, forward, loss, autograd, push with the counts and the
+    # versions kept on the device -- into a CUDA graph over static copies of (features, labels), and from then
+    # on a minibatch is: copy the inputs in, replay, read the error word and the new versions.  Same kernels,
+    # same order, same results as the eager step (tests/test_gpu_layer_trainer.py).  What does not qualify stays
+    # eager, with the reason in `graph_fallback_reason`: a sync-SGD or staleness-modulated PS (the versions a push
+    # carries would be baked into the graph), get_model_steps > 1, host-side or sparse features, per-layer
+    # lookups (they read counts back), a learning rate or feature signature that keeps changing.
+    @staticmethod
+    def _rebuild_features(features, values):
+        if isinstance(features, torch.Tensor):
+            return values[0]
+        if isinstance(features, dict):
+            return dict(zip(features.keys(), values))
+        return type(features)(values) if isinstance(features, tuple) else list(values)
+
+    def _graph_signature(self, features, labels):
+        items = self._feature_items(features)
+        if not items:
+            return None
+        sig = []
+        for k, v in items + [("__labels__", labels)]:
+            if not (isinstance(v, torch.Tensor) and v.is_cuda and not v.is_sparse):
+                return None
+            sig.append((k, tuple(v.shape), v.dtype, v.device.index))
+        return (type(features).__name__, tuple(sig), float(self._optimizer.param_groups[0]["lr"]))
+
+    @staticmethod
+    def _as_one(tensors):
+        """The flat view covering `tensors` when they are consecutive contiguous pieces of one storage, else None."""
+        t0 = tensors[0]
+        end = t0.data_ptr()
+        for t in tensors:
+            if not t.is_contiguous() or t.dtype != t0.dtype or t.data_ptr() != end \
+                    or t.untyped_storage().data_ptr() != t0.untyped_storage().data_ptr():
+                return None
+            end += t.numel() * t.element_size()
+        total = sum(t.numel() for t in tensors)
+        return torch.as_strided(t0, (total,), (1,))
+
+    @staticmethod
+    def _static_like(tensors):
+        """Static copies of `tensors`; the tensors of one dtype are carved out of ONE buffer in order, so features
+        that were rows of one array stay rows of one array (the batched lookup keeps its zero-copy id view and the
+        per-step input copy is one kernel per dtype)."""
+        by_dtype = {}
+        for i, t in enumerate(tensors):
+            by_dtype.setdefault(t.dtype, []).append(i)
+        out, groups = [None] * len(tensors), []
+        for dt, idx in by_dtype.items():
+            buf = torch.empty(sum(tensors[i].numel() for i in idx), dtype=dt, device=tensors[idx[0]].device)
+            off = 0
+            for i in idx:
+                n = tensors[i].numel()
+                out[i] = buf[off:off + n].view(tensors[i].shape)
+                off += n
+            groups.append((buf, idx))
+        return out, groups
+
+    def _copy_inputs(self, st, srcs):
+        for buf, idx in st["groups"]:
+            one = self._as_one([srcs[i] for i in idx])
+            if one is not None:
+                buf.copy_(one)
+            else:
+                torch._foreach_copy_([st["statics"][i] for i in idx], [srcs[i] for i in idx])
+
+    def _graph_eligible(self):
+        g = self._ps_client.group
+        if not getattr(g, "use_async", True):
+            return "sync-SGD PS group"
+        if getattr(g, "lr_staleness_modulation", False):
+            return "lr staleness modulation needs the pulled versions on every push"
+        if self._get_model_steps > 1:
+            return "get_model_steps > 1"
+        if not self._lookup_plan:
+            return "no batched lookup plan for this model"
+        for name, p in self._non_embed_vars.items():
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and name in g.tables):
+                return "parameter %s is not a contiguous float32 device tensor registered on the PS" % name
+        return None
+
+    def _pull_dense_into_model(self):
+        """_get_model without the version handshake: every dense parameter of every shard, written by the pull
+        kernel straight into the model's own tensors (always the latest values; the Go PS would also resend them,
+        server.go:150, because the version a worker that just pushed holds is never ahead of the shard's)."""
+        c = self._ps_client
+        names = [n for ps_id in sorted(c.ps_to_parameter) for n in c.ps_to_parameter[ps_id] if n in self._non_embed_vars]
+        c.group.pull_dense(names, into={n: self._non_embed_vars[n].data for n in names})
+
+    def _capture_minibatch(self, features, labels, sig):
+        srcs = [v for _, v in self._feature_items(features)] + [labels]
+        statics, groups = self._static_like(srcs)
+        st = {"sig": sig, "statics": statics, "groups": groups}
+        self._copy_inputs(st, srcs)
+        s_features = self._rebuild_features(features, statics[:-1])
+        self._reset_embedding()
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.current_stream().synchronize()
+        with torch.cuda.graph(graph):
+            self._pull_dense_into_model()
+            loss, grads = self._training_process_eagerly(s_features, statics[-1])
+            if not self._group_bets or any(layer.embedding_and_ids for layer in self._embedding_layers):
+                raise RuntimeError("the batched lookup plan did not cover this minibatch")
+            self._report_gradient(grads, sync=False)
+        self._reset_embedding()
+        st.update(graph=graph, loss=loss, grads=grads)
+        return st
+
+    def _train_minibatch_graphed(self, features, labels):
+        """One minibatch by graph replay; None = run this one eagerly."""
+        st = self._graph_state
+        sig = self._graph_signature(features, labels)
+        if st is None or sig != st["sig"]:
+            if self._eager_steps < self._graph_warmup:
+                return None
+            why = "features / labels are not dense device tensors" if sig is None else self._graph_eligible()
+            if why is None and st is not None:
+                st["recaptures"] = st.get("recaptures", 0) + 1
+                if st["recaptures"] > 4:
+                    why = "the learning rate or the feature signature keeps changing"
+            if why is not None:
+                self._graph_state, self.graph_fallback_reason = False, why
+                return None
+            recaptures = 0 if st is None else st["recaptures"]
+            stream = torch.cuda.current_stream()
+            try:
+                st = self._capture_minibatch(features, labels, sig)
+            except Exception as err:  # anything the capture cannot hold (a host read, an allocation outside the pool)
+                torch.cuda.set_stream(stream)  # a failed capture_end leaves torch on the capture stream
+                self._reset_embedding()
+                torch.cuda.synchronize()
+                self._graph_state = False
+                self.graph_fallback_reason = "capture failed: %s: %s" % (type(err).__name__, err)
+                return None
+            st["recaptures"] = recaptures
+            self._graph_state = st
+        else:
+            srcs = [v for _, v in self._feature_items(features)] + [labels]
+            self._copy_inputs(st, srcs)
+        g = self._ps_client.group
+        self._timing.start_record_time("batch_process")
+        st["graph"].replay()
+        loss = st["loss"].clone()
+        g.check()  # device sync + the error word (an id outside its table, ...)
+        versions = g._pinned_versions[: g.n_shards].tolist()
+        self._timing.end_record_time("batch_process")
+        # the model this step trained on was pulled at (or after) the versions known before the step
+        self._model_version = max(max(self._model_versions_from_ps), self._model_version)
+        self._model_versions_from_ps = [int(v) for v in versions]
+        return True, max(self._model_versions_from_ps), loss
 
     def _training_process_eagerly(self, features, labels):  # ps_trainer.py:391-400
         self._set_tape_for_embedding(True)
@@ -219,7 +388,7 @@ class ParameterServerTrainer(object):
         grads = torch.autograd.grad(loss, self.get_trainable_items(), allow_unused=True)
         return loss.detach(), grads
 
-    def _report_gradient(self, gradients):  # ps_trainer.py:239-280
+    def _report_gradient(self, gradients, sync=True):  # ps_trainer.py:239-280
         self._timing.start_record_time("report_gradient")
         grads = []
         names = list(self._non_embed_vars.keys())
@@ -248,7 +417,7 @@ class ParameterServerTrainer(object):
                              "number of its output tensor %d." % (len(edl_embedding_grads), bet_number))
         learning_rate = float(self._optimizer.param_groups[0]["lr"])
         accepted, max_version = self._ps_client.push_gradients(
-            grads, edl_grads, learning_rate, self._model_versions_from_ps)
+            grads, edl_grads, learning_rate, self._model_versions_from_ps, **({} if sync else {"sync": False}))
         self._timing.end_record_time("report_gradient")
         return accepted, max_version
 

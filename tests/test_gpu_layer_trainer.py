@@ -414,3 +414,101 @@ def test_trainer_batched_lookups_equal_per_layer_lookups(n_shards, views):
         assert torch.allclose(p_b[name], p_p[name], rtol=1e-5, atol=1e-7), name
     assert n_b[0] == n_p[0]          # the first minibatch learns the plan on the per-layer path
     assert n_b[-1] * 2 < n_p[-1]     # afterwards: a handful of launches instead of several per layer
+
+
+@pytest.mark.parametrize("n_shards,views", [(1, True), (2, False)])
+def test_trainer_cuda_graph_minibatch_equals_eager(n_shards, views):
+    """args.cuda_graph=True: after the eager warm-up minibatches the whole train_minibatch (dense pull into the
+    model, batched lookups, forward, loss, autograd, push) is ONE CUDA-graph replay over static copies of the
+    inputs.  Same (accepted, version, loss) per minibatch, same tables and dense parameters as the eager trainer
+    after 8 Adam minibatches; an id outside its table still raises (the error word is read after every replay)."""
+    import types
+
+    from elasticdl_b200 import _lib
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+    from elasticdl_b200.worker.ps_trainer import ParameterServerTrainer
+    from elasticdl_b200.workloads.deepfm import DeepFMLayersModel
+
+    rows = [7, 300, 5000, 40, 1200]
+    B = 512
+
+    def batch(gen):
+        ids = torch.stack([torch.randint(0, r, (B,), generator=gen) for r in rows]).cuda()
+        dense = torch.randn(B, 13, generator=gen).cuda()
+        labels = (torch.rand(B, generator=gen) < 0.3).float().cuda()
+        feats = DeepFMLayersModel.features_of(ids if views else ids.clone(), dense)
+        if not views:
+            feats.update({"ids_%d" % g: ids[g].clone() for g in range(len(rows))})
+        return feats, labels
+
+    def run(graphed):
+        torch.manual_seed(3)
+        model = DeepFMLayersModel(rows, lr=0.01, initializer="uniform").cuda()
+        group = PSGroup(n_shards, *ADAM, device=0, seed=11)
+        client = PSClient(group)
+        client.dense_output = "torch"
+        trainer = ParameterServerTrainer(model, client, args=types.SimpleNamespace(
+            get_model_steps=1, batched_embedding_lookups=True, cuda_graph=graphed, cuda_graph_warmup=2))
+        gen = torch.Generator().manual_seed(5)
+        losses, modes = [], []
+        for step in range(8):
+            feats, labels = batch(gen)
+            accepted, version, loss = trainer.train_minibatch(feats, labels)
+            assert accepted and version == step + 1, (step, version)
+            losses.append(float(loss))
+            modes.append(isinstance(trainer._graph_state, dict))
+        assert trainer.get_model_version() == 7
+        tabs = {}
+        for g, r in enumerate(rows):
+            for fam in ("deep", "wide"):
+                name = "%s_%d/embeddings:0" % (fam, g)
+                tabs[name] = client.pull_embedding_vectors(name, torch.arange(r).cuda()).cpu()
+        params, _ = client.pull_dense_parameters(list(range(n_shards)), [-1] * n_shards)
+        params = {k: v.cpu() for k, v in params.items()}
+        local = {k: v.detach().cpu().clone() for k, v in model.named_parameters()}
+        if graphed:
+            assert trainer.graph_fallback_reason is None, trainer.graph_fallback_reason
+            assert modes == [False, False] + [True] * 6, modes
+            feats, labels = batch(gen)
+            feats["ids_1"] = feats["ids_1"] + 10 ** 6  # outside table 1: flagged by the kernels, read after the replay
+            with pytest.raises(_lib.PSError):
+                trainer.train_minibatch(feats, labels)
+        group.close()
+        return losses, tabs, params, local
+
+    l_g, t_g, p_g, m_g = run(True)
+    l_e, t_e, p_e, m_e = run(False)
+    assert np.allclose(l_g, l_e, rtol=1e-5, atol=1e-6), (l_g, l_e)
+    for name in t_e:
+        assert torch.allclose(t_g[name], t_e[name], rtol=1e-5, atol=1e-7), name
+    for name in p_e:
+        assert torch.allclose(p_g[name], p_e[name], rtol=1e-5, atol=1e-7), name
+    for name in m_e:  # the model's own tensors hold what the last pull wrote, in both modes
+        assert torch.allclose(m_g[name], m_e[name], rtol=1e-5, atol=1e-7), name
+
+
+def test_trainer_cuda_graph_falls_back_when_not_eligible():
+    """A staleness-modulated PS (the pulled versions travel with every push) keeps the eager path and says why."""
+    import types
+
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+    from elasticdl_b200.worker.ps_trainer import ParameterServerTrainer
+    from elasticdl_b200.workloads.deepfm import DeepFMLayersModel
+
+    rows = [7, 300]
+    torch.manual_seed(0)
+    model = DeepFMLayersModel(rows, lr=0.01).cuda()
+    group = PSGroup(1, *ADAM, device=0, lr_staleness_modulation=True)
+    client = PSClient(group)
+    client.dense_output = "torch"
+    trainer = ParameterServerTrainer(model, client, args=types.SimpleNamespace(cuda_graph=True, cuda_graph_warmup=1))
+    gen = torch.Generator().manual_seed(5)
+    for step in range(3):
+        ids = torch.stack([torch.randint(0, r, (64,), generator=gen) for r in rows]).cuda()
+        feats = DeepFMLayersModel.features_of(ids, torch.randn(64, 13, generator=gen).cuda())
+        accepted, version, _ = trainer.train_minibatch(feats, (torch.rand(64, generator=gen) < 0.3).float().cuda())
+        assert accepted and version == step + 1
+    assert trainer._graph_state is False and "staleness" in trainer.graph_fallback_reason
+    group.close()
