@@ -275,8 +275,10 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
 #pragma unroll
         for (int q = 0; q < PPT; ++q) {
           const long long i = base + q * kUThreads + threadIdx.x;
-          id[q] = (raw[q] < 0 || raw[q] >= bound) ? 0 : (int)raw[q];  // out-of-range ids are reported by the table kernels
+          const bool bad = raw[q] < 0 || raw[q] >= bound;  // counted as id 0 and reported (kErrRange -> b200ps_check)
+          id[q] = bad ? 0 : (int)raw[q];
           if (i < k) fp[i] = id[q];
+          if (bad && i < k && a.err) atomicOr(a.err, kErrRange);
         }
       }
 #pragma unroll
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
 // in-block scan instead of the decoupled look-back, no grid barrier, nothing read from the workspace.
 // 30 of the 38 id groups of the DeepFM batch qualify (<= 16384 rows); they are 79 % of its ids, and phase A
 // of the grid-wide kernel above is bound by the rate of L2 atomics on scattered addresses.  Same results:
-// first-occurrence order, inverse index, n_unique; out-of-range ids count as id 0 (the table kernels report them).
+// first-occurrence order, inverse index, n_unique; out-of-range ids count as id 0 and set kErrRange in the group's error word (b200ps_check raises).
 // Taken when k <= 32768 (the ids of a segment then fit the registers of one block, see below).
 //   A  pos[id] <- min(position)                (shared-memory atomicMin, checked first)
 //   B  chunks of 4096 positions in order: first-occurrence flags -> ballot ranks -> block scan -> uniq[rank] = id,
@@ -568,7 +570,10 @@ __global__ void __launch_bounds__(kUSThreads, 1) k_unique_small(const __grid_con
       for (int j = 0; j < IPT; ++j) {
         const long long i = (long long)j * kUSThreads + tid;
         long long v = i < k ? u_ld<W, SG>(sbase, i) : 0xffff;
-        if (i < k && (v < 0 || v >= bound)) v = 0;  // out-of-range ids are reported by the table kernels
+        if (i < k && (v < 0 || v >= bound)) {  // counted as id 0 and reported (kErrRange -> b200ps_check)
+          v = 0;
+          if (a.err) atomicOr(a.err, kErrRange);
+        }
         if (j & 1) pk[j >> 1] |= (unsigned)v << 16;
         else pk[j >> 1] = (unsigned)v;
       }

@@ -244,7 +244,9 @@ int b200ps_kernel_adagrad(const float* grad, float* param, float* m, float lr, l
  * but one workspace must not be used by two streams at once. */
 size_t b200ps_unique_workspace(int T, int64_t k);
 /* Same with host-side knowledge of the id range of each segment (bounds[t] = table capacity, 0 =
- * unknown): small-range segments use a direct-address position array instead of the hash table. */
+ * unknown): small-range segments use a direct-address position array instead of the hash table.
+ * An id outside [0, bounds[t]) is counted as id 0 and sets the range bit of the group's error word, so the
+ * next b200ps_check() fails with B200PS_ERANGE (the reference raises for it, embedding_delegate.py:254-264). */
 size_t b200ps_unique_bounded_workspace(int T, int64_t k, const int64_t* bounds);
 int b200ps_unique_bounded(b200ps_t* ps, const int64_t* ids_dev, int T, int64_t k, const int64_t* bounds,
                           int64_t* uniq_dev, int32_t* inv_dev, int32_t* n_unique_dev, void* workspace_dev,

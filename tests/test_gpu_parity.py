@@ -1072,7 +1072,7 @@ def test_unique_small_segments_in_shared_memory(k, monkeypatch):
     """B200_UNIQUE_SMALL: segments whose id range fits a shared-memory position array are deduplicated by one
     block each (k_unique_small, ids in registers: 8 / 16 / 32 per thread), the others by the grid-wide kernel --
     same first-occurrence order, inverse index and counts as tf.unique, over several calls (epochs of the
-    grid-wide kernel) and with out-of-range ids (counted as id 0)."""
+    grid-wide kernel) and with out-of-range ids (counted as id 0 AND reported through the group's error word)."""
     import ctypes
 
     from elasticdl_b200 import _lib
@@ -1092,11 +1092,14 @@ def test_unique_small_segments_in_shared_memory(k, monkeypatch):
     for call in range(3):
         ids = np.stack([rng.randint(0, b, size=k) for b in bounds_l]).astype(np.int64)
         if call == 1:
-            ids[1, 5] = 10 ** 9   # out of range: counted as id 0 (the table kernels report it)
+            ids[1, 5] = 10 ** 9   # out of range: counted as id 0, and b200ps_check raises
             ids[4, 0] = -7
         d_ids = torch.from_numpy(ids).cuda()
         _lib.check(lib.b200ps_unique_bounded(group._h, d_ids.data_ptr(), T, k, bounds, uniq.data_ptr(), inv.data_ptr(),
                                              n.data_ptr(), ws.data_ptr(), ws.numel(), group._stream()))
+        if call == 1:
+            with pytest.raises(_lib.PSRangeError):
+                group.check()
         group.check()
         u, i, c = uniq.cpu().numpy().reshape(T, k), inv.cpu().numpy().reshape(T, k), n.cpu().numpy()
         for t in range(T):
