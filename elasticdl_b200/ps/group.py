@@ -123,7 +123,7 @@ class PSGroup:
         """A second client view of the same shards for another worker thread / stream of this
         process (b200ps_clone_view).  Register every table on the owning group first."""
         view = object.__new__(PSGroup)
-        view.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_h", "_ws")})
+        view.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_h", "_ws", "_ws_bounded")})
         view._h = None
         dev = self.device if device is None else torch.device("cuda", device)
         h = ctypes.c_void_p()
@@ -359,21 +359,43 @@ class PSGroup:
         return None
 
     # ------------------------------------------------------------------ dedup
-    def unique(self, ids, T=1):
+    def unique(self, ids, T=1, bounds=None):
         """tf.unique over T equal-length segments.  ids: int64 cuda [T*k].
-        Returns (uniq [T*k] padded, inv int32 [T*k], n_unique int32 [T]) -- all on device."""
+        Returns (uniq [T*k] padded, inv int32 [T*k], n_unique int32 [T]) -- all on device.
+        bounds (optional, one int per segment = the table capacity / the layer's input_dim, 0 = unknown): segments
+        with a known id range are deduplicated through a direct-address position array (b200ps_unique_bounded) --
+        several times faster than hashing; an id outside [0, bound) is counted as id 0 and makes check() raise."""
         ids = self._ids(ids)
         k = ids.numel() // T
-        need = self.lib.b200ps_unique_workspace(T, k)
-        if self._ws is None or self._ws.numel() < need:
-            if self._ws is not None:
-                self._ws.record_stream(torch.cuda.current_stream(self.device))
-            self._ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        if bounds is not None and (T > _lib.MAX_SEGS or len(bounds) != T or not any(int(b) > 0 for b in bounds)):
+            bounds = None
+        key = None if bounds is None else (T, k, tuple(int(b) for b in bounds))
+        if key is None:
+            need = self.lib.b200ps_unique_workspace(T, k)
+            if self._ws is None or self._ws.numel() < need:
+                if self._ws is not None:
+                    self._ws.record_stream(torch.cuda.current_stream(self.device))
+                self._ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+            ws = self._ws
+        else:  # one workspace per (T, k, bounds): the direct-address arrays are laid out by the bounds
+            cache = self.__dict__.setdefault("_ws_bounded", {})
+            if key not in cache:
+                if len(cache) >= 8:  # a job addresses a handful of layer groups; do not hoard beyond that
+                    _, (old, _) = cache.popitem()
+                    old.record_stream(torch.cuda.current_stream(self.device))
+                barr = (ctypes.c_int64 * T)(*key[2])
+                cache[key] = (torch.zeros(self.lib.b200ps_unique_bounded_workspace(T, k, barr), dtype=torch.uint8,
+                                          device=self.device), barr)
+            ws, barr = cache[key]
         uniq = torch.empty(T * k, dtype=torch.int64, device=self.device)
         inv = torch.empty(T * k, dtype=torch.int32, device=self.device)
         n_unique = torch.empty(T, dtype=torch.int32, device=self.device)
-        check(self.lib.b200ps_unique(self._h, ids.data_ptr(), T, k, uniq.data_ptr(), inv.data_ptr(),
-                                     n_unique.data_ptr(), self._ws.data_ptr(), self._ws.numel(), self._stream()))
+        if key is None:
+            check(self.lib.b200ps_unique(self._h, ids.data_ptr(), T, k, uniq.data_ptr(), inv.data_ptr(),
+                                         n_unique.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
+        else:
+            check(self.lib.b200ps_unique_bounded(self._h, ids.data_ptr(), T, k, barr, uniq.data_ptr(), inv.data_ptr(),
+                                                 n_unique.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
         return uniq, inv, n_unique
 
     def segment_sum(self, values, inv, T, k, dim, out=None):

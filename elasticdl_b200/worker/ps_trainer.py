@@ -143,18 +143,24 @@ class ParameterServerTrainer(object):
                 srcs.append(src)
             work.append((k, dim, members, srcs))
         requests, staged = [], []
+        dedups = {}  # layer groups looked up with the SAME feature tensors (DeepFM's deep and wide families) share one dedup
         for k, dim, members, srcs in work:
             T = len(members)
-            flat = [s.reshape(-1) for s in srcs]
-            step = k * 8
-            if all(f.is_contiguous() for f in flat) and all(
-                    flat[t].data_ptr() == flat[0].data_ptr() + t * step for t in range(T)) and T > 1 \
-                    and flat[0]._base is not None and flat[0]._base is flat[-1]._base:
-                ids = torch.as_strided(flat[0], (T * k,), (1,))  # the features are rows of one [T, k] array
-            else:
-                ids = flat[0] if T == 1 else torch.cat(flat)
-            uniq, inv, n_dev = g.unique(ids, T)
-            bet = torch.zeros((T * k, dim), dtype=torch.float32, device=ids.device)
+            # the layers' input_dim bounds the ids of each segment: direct-address dedup instead of hashing
+            bounds = tuple(int(layer.input_dim or 0) for layer, _ in members)
+            dkey = (k, tuple(id(s) for s in srcs), bounds)
+            if dkey not in dedups:
+                flat = [s.reshape(-1) for s in srcs]
+                step = k * 8
+                if all(f.is_contiguous() for f in flat) and all(
+                        flat[t].data_ptr() == flat[0].data_ptr() + t * step for t in range(T)) and T > 1 \
+                        and flat[0]._base is not None and flat[0]._base is flat[-1]._base:
+                    ids = torch.as_strided(flat[0], (T * k,), (1,))  # the features are rows of one [T, k] array
+                else:
+                    ids = flat[0] if T == 1 else torch.cat(flat)
+                dedups[dkey] = g.unique(ids, T, bounds=bounds if all(bounds) else None)
+            uniq, inv, n_dev = dedups[dkey]
+            bet = torch.zeros((T * k, dim), dtype=torch.float32, device=srcs[0].device)
             for t, (layer, _) in enumerate(members):
                 requests.append((layer.embedding_weight_name, uniq[t * k:(t + 1) * k], n_dev[t:t + 1],
                                  bet[t * k:(t + 1) * k]))
@@ -280,9 +286,10 @@ class ParameterServerTrainer(object):
             groups.append((buf, idx))
         return out, groups
 
-    def _copy_inputs(self, st, srcs):
+    @staticmethod
+    def _copy_inputs(st, srcs):
         for buf, idx in st["groups"]:
-            one = self._as_one([srcs[i] for i in idx])
+            one = ParameterServerTrainer._as_one([srcs[i] for i in idx])
             if one is not None:
                 buf.copy_(one)
             else:

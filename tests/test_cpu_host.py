@@ -173,3 +173,45 @@ def test_exchange_blobs_single_process():
     assert exchange_blobs({0: b"a", 1: b"b"}, 2) == {0: b"a", 1: b"b"}
     with pytest.raises(RuntimeError):
         exchange_blobs({0: b"a"}, 2)
+
+
+def test_trainer_graph_input_staging_helpers():
+    """Host logic of the trainer's CUDA-graph mode (worker/ps_trainer.py): static input buffers keep the features of
+    one dtype consecutive in ONE buffer (so rows-of-one-array features stay one zero-copy id array), the per-step
+    copy is a single copy when the sources are consecutive pieces of one array and a multi-tensor copy otherwise,
+    and the capture signature changes with shapes / dtypes / learning rate."""
+    import types
+
+    import torch
+
+    from elasticdl_b200.worker.ps_trainer import ParameterServerTrainer as T
+
+    ids = torch.arange(5 * 16, dtype=torch.int64).reshape(5, 16)
+    dense = torch.randn(16, 13)
+    labels = torch.rand(16)
+    feats = {"dense": dense}
+    feats.update({"ids_%d" % g: ids[g] for g in range(5)})
+    srcs = [v for _, v in T._feature_items(feats)] + [labels]
+    statics, groups = T._static_like(srcs)
+    assert [tuple(s.shape) for s in statics] == [tuple(s.shape) for s in srcs]
+    assert sorted(str(b.dtype) for b, _ in groups) == ["torch.float32", "torch.int64"]
+    id_statics = statics[1:6]
+    one = T._as_one(id_statics)
+    assert one is not None and one.numel() == 5 * 16 and one.data_ptr() == id_statics[0].data_ptr()
+    assert all(s.reshape(-1)._base is id_statics[0].reshape(-1)._base for s in id_statics)
+    assert T._as_one([ids[0], ids[2]]) is None and T._as_one([ids[0].clone(), ids[1].clone()]) is None
+    assert T._as_one([ids[g] for g in range(5)]) is not None
+    st = {"statics": statics, "groups": groups}
+    T._copy_inputs(st, srcs)
+    assert all(torch.equal(a, b) for a, b in zip(statics, srcs))
+    scattered = [s.clone() + 1 for s in srcs]  # separately allocated sources: the multi-tensor copy
+    T._copy_inputs(st, scattered)
+    assert all(torch.equal(a, b) for a, b in zip(statics, scattered))
+    rebuilt = T._rebuild_features(feats, statics[:-1])
+    assert list(rebuilt) == list(feats) and rebuilt["ids_3"] is statics[4]
+    assert T._rebuild_features(dense, [statics[0]]) is statics[0]
+    assert isinstance(T._rebuild_features((dense, ids[0]), statics[:2]), tuple)
+    # the signature needs device tensors: host features never qualify for the graph
+    fake = types.SimpleNamespace(_feature_items=T._feature_items,
+                                 _optimizer=types.SimpleNamespace(param_groups=[{"lr": 0.1}]))
+    assert T._graph_signature(fake, feats, labels) is None
