@@ -303,7 +303,7 @@ class ParameterServerTrainer(object):
             return "lr staleness modulation needs the pulled versions on every push"
         if self._get_model_steps > 1:
             return "get_model_steps > 1"
-        if not self._lookup_plan:
+        if self._embedding_layers and not self._lookup_plan:
             return "no batched lookup plan for this model"
         for name, p in self._non_embed_vars.items():
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and name in g.tables):
@@ -330,7 +330,8 @@ class ParameterServerTrainer(object):
         with torch.cuda.graph(graph):
             self._pull_dense_into_model()
             loss, grads = self._training_process_eagerly(s_features, statics[-1])
-            if not self._group_bets or any(layer.embedding_and_ids for layer in self._embedding_layers):
+            if self._embedding_layers and (not self._group_bets
+                                           or any(layer.embedding_and_ids for layer in self._embedding_layers)):
                 raise RuntimeError("the batched lookup plan did not cover this minibatch")
             self._report_gradient(grads, sync=False)
         self._reset_embedding()

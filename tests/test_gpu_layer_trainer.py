@@ -512,3 +512,70 @@ def test_trainer_cuda_graph_falls_back_when_not_eligible():
         assert accepted and version == step + 1
     assert trainer._graph_state is False and "staleness" in trainer.graph_fallback_reason
     group.close()
+
+
+class MnistFunctional(torch.nn.Module):
+    """model_zoo/mnist/mnist_functional_api.py:21-31 in torch (BASELINE configs[0]): conv 3x3x1x32, conv 3x3x32x64,
+    BatchNorm(64), max-pool 2x2, dense 9216 -> 10 (the Dropout(0.25) is left out: two runs must be comparable)."""
+
+    def __init__(self, lr=0.01):
+        super().__init__()
+        self.c1 = torch.nn.Conv2d(1, 32, 3)
+        self.c2 = torch.nn.Conv2d(32, 64, 3)
+        self.bn = torch.nn.BatchNorm2d(64)
+        self.fc = torch.nn.Linear(9216, 10)
+        self.optimizer = torch.optim.SGD(self.parameters(), lr=lr)  # mnist_functional_api.py:66-67
+        ce = torch.nn.CrossEntropyLoss()
+        self.loss = lambda labels, logits: ce(logits, labels.reshape(-1))  # :57-63
+
+    def forward(self, image):
+        x = torch.relu(self.c1(image.reshape(-1, 1, 28, 28)))
+        x = torch.relu(self.c2(x))
+        x = torch.nn.functional.max_pool2d(self.bn(x), 2)
+        return self.fc(x.flatten(1))
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_trainer_mnist_functional_one_ps_one_worker_config1(graphed):
+    """BASELINE configs[0] (the reference's own CPU-runnable case, here on the device: there is no CPU path): MNIST
+    functional model, 1 PS + 1 worker, SGD 0.01, batch 64, uniform[0,1) images, seed 0.  Dense parameters only:
+    init handshake (the worker's initial values become the PS's, server.go:209-221), one version per minibatch, and
+    PS training == local torch SGD on the same data -- eagerly and as one CUDA graph per minibatch."""
+    import types
+
+    from elasticdl_b200.ps import PSGroup
+    from elasticdl_b200.worker.ps_client import PSClient
+    from elasticdl_b200.worker.ps_trainer import ParameterServerTrainer
+
+    torch.manual_seed(0)
+    model = MnistFunctional().cuda()
+    twin = MnistFunctional().cuda()
+    twin.load_state_dict(model.state_dict())
+    n_params = sum(p.numel() for p in model.parameters())
+    assert n_params == 32 * 9 + 32 + 64 * 32 * 9 + 64 + 2 * 64 + 9216 * 10 + 10  # ~111 K fp32 (SURVEY 8d item 1)
+    group = PSGroup(1, "SGD", "learning_rate=0.01;momentum=0.0;nesterov=false;", device=0)
+    client = PSClient(group)
+    client.dense_output = "torch"
+    trainer = ParameterServerTrainer(model, client, args=types.SimpleNamespace(
+        get_model_steps=1, cuda_graph=graphed, cuda_graph_warmup=2))
+    gen = torch.Generator().manual_seed(0)
+    for step in range(6):
+        image = torch.rand(64, 28, 28, generator=gen).cuda()
+        label = torch.randint(0, 10, (64,), generator=gen).cuda()
+        accepted, version, loss = trainer.train_minibatch(image, label)
+        assert accepted and version == step + 1
+        twin.optimizer.zero_grad()
+        l2 = twin.loss(label, twin(image))
+        l2.backward()
+        twin.optimizer.step()
+        assert abs(float(loss) - float(l2)) < 2e-4 * max(1.0, abs(float(l2))), (step, float(loss), float(l2))
+    if graphed:
+        assert isinstance(trainer._graph_state, dict), trainer.graph_fallback_reason
+    params, _ = client.pull_dense_parameters([0], [-1])
+    want = dict(twin.named_parameters())
+    assert set(params) == set(want)
+    for name, v in params.items():
+        assert torch.allclose(v.reshape(want[name].shape), want[name].detach(), rtol=1e-3, atol=2e-5), name
+    snap = group.snapshot()
+    assert snap[0][0] == 6 and snap[0][2]  # version 6, initialised
+    group.close()
