@@ -261,6 +261,8 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
       // the probe is one more uncached sector read per position and almost never saves the atomic
       const bool probe = (long long)bound * 2 < k;
       int id[PPT], cur[PPT];  // bounded ids fit 32 bits
+      bool any_bad = false;    // reported once per unit, after the loads and probes are in flight (a memory
+                               // operation between them would serialise the loads behind it)
       {
         const unsigned char* sbase;
         const int kind = u_seg_kind(a, idl, t, &sbase);
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
           const bool bad = raw[q] < 0 || raw[q] >= bound;  // counted as id 0 and reported (kErrRange -> b200ps_check)
           id[q] = bad ? 0 : (int)raw[q];
           if (i < k) fp[i] = id[q];
-          if (bad && i < k && a.err) atomicOr(a.err, kErrRange);
+          any_bad |= bad && i < k;
         }
       }
 #pragma unroll
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(kUThreads, 4) k_unique(const __grid_constant__
           if (want && (__ffs(peers) - 1) == lane) atomicMin(dp + id[q], v);
         }
       }
+      if (any_bad && a.err) atomicOr(a.err, kErrRange);
     } else {
       unsigned long long* keys = reinterpret_cast<unsigned long long*>(a.keys + (long long)t * a.cap);
       int* mp = a.minpos + (long long)t * a.cap;
@@ -562,6 +565,7 @@ __global__ void __launch_bounds__(kUSThreads, 1) k_unique_small(const __grid_con
   const unsigned lt_mask = (1u << lane) - 1u;
   // two ids per register (bound <= 16384 < 0xffff = "no position"): 32 ids in 16 registers
   unsigned pk[IPT / 2];
+  bool any_bad = false;
   {
     const unsigned char* sbase;
     const int kind = u_seg_kind(a, idl, t, &sbase);
@@ -570,10 +574,9 @@ __global__ void __launch_bounds__(kUSThreads, 1) k_unique_small(const __grid_con
       for (int j = 0; j < IPT; ++j) {
         const long long i = (long long)j * kUSThreads + tid;
         long long v = i < k ? u_ld<W, SG>(sbase, i) : 0xffff;
-        if (i < k && (v < 0 || v >= bound)) {  // counted as id 0 and reported (kErrRange -> b200ps_check)
-          v = 0;
-          if (a.err) atomicOr(a.err, kErrRange);
-        }
+        const bool bad = i < k && (v < 0 || v >= bound);  // counted as id 0 and reported (kErrRange -> b200ps_check)
+        if (bad) v = 0;
+        any_bad |= bad;  // reported once, after the loads (a memory operation in this loop would serialise them)
         if (j & 1) pk[j >> 1] |= (unsigned)v << 16;
         else pk[j >> 1] = (unsigned)v;
       }
@@ -583,6 +586,7 @@ __global__ void __launch_bounds__(kUSThreads, 1) k_unique_small(const __grid_con
 #define US_LIVE(j) (US_ID(j) != 0xffff)
   for (int i = tid; i < bound; i += kUSThreads) s_pos[i] = 0x7fffffff;
   __syncthreads();
+  if (any_bad && a.err) atomicOr(a.err, kErrRange);
   // ---- A ----
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
