@@ -379,10 +379,7 @@ class PSGroup:
             ws = self._ws
         else:  # one workspace per (T, k, bounds): the direct-address arrays are laid out by the bounds
             cache = self.__dict__.setdefault("_ws_bounded", {})
-            if key not in cache:
-                if len(cache) >= 8:  # a job addresses a handful of layer groups; do not hoard beyond that
-                    _, (old, _) = cache.popitem()
-                    old.record_stream(torch.cuda.current_stream(self.device))
+            if key not in cache:  # never evicted: a captured CUDA graph may hold the address (a job has a handful of keys)
                 barr = (ctypes.c_int64 * T)(*key[2])
                 cache[key] = (torch.zeros(self.lib.b200ps_unique_bounded_workspace(T, k, barr), dtype=torch.uint8,
                                           device=self.device), barr)

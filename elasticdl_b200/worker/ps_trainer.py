@@ -342,18 +342,25 @@ class ParameterServerTrainer(object):
         """One minibatch by graph replay; None = run this one eagerly."""
         st = self._graph_state
         sig = self._graph_signature(features, labels)
-        if st is None or sig != st["sig"]:
-            if self._eager_steps < self._graph_warmup:
+        if isinstance(st, dict) and sig == st["sig"]:
+            self._pending_sig = None
+            self._copy_inputs(st, [v for _, v in self._feature_items(features)] + [labels])
+        else:
+            if sig is None or self._eager_steps < self._graph_warmup:
+                return None  # host-side / sparse inputs cannot be staged; or still warming up
+            if isinstance(st, dict) and sig != getattr(self, "_pending_sig", None):
+                # a one-off (the short last batch of an epoch) runs eagerly and the graph is kept; the same new
+                # signature twice in a row (a new learning rate, a new batch size) is captured again
+                self._pending_sig = sig
                 return None
-            why = "features / labels are not dense device tensors" if sig is None else self._graph_eligible()
-            if why is None and st is not None:
-                st["recaptures"] = st.get("recaptures", 0) + 1
-                if st["recaptures"] > 4:
-                    why = "the learning rate or the feature signature keeps changing"
+            self._pending_sig = None
+            why = self._graph_eligible()
+            recaptures = st["recaptures"] + 1 if isinstance(st, dict) else 0
+            if why is None and recaptures > 4:
+                why = "the learning rate or the feature signature keeps changing"
             if why is not None:
                 self._graph_state, self.graph_fallback_reason = False, why
                 return None
-            recaptures = 0 if st is None else st["recaptures"]
             stream = torch.cuda.current_stream()
             try:
                 st = self._capture_minibatch(features, labels, sig)
@@ -366,9 +373,6 @@ class ParameterServerTrainer(object):
                 return None
             st["recaptures"] = recaptures
             self._graph_state = st
-        else:
-            srcs = [v for _, v in self._feature_items(features)] + [labels]
-            self._copy_inputs(st, srcs)
         g = self._ps_client.group
         self._timing.start_record_time("batch_process")
         st["graph"].replay()

@@ -470,7 +470,20 @@ def test_trainer_cuda_graph_minibatch_equals_eager(n_shards, views):
         if graphed:
             assert trainer.graph_fallback_reason is None, trainer.graph_fallback_reason
             assert modes == [False, False] + [True] * 6, modes
+            # a one-off short minibatch (the last batch of an epoch) runs eagerly and keeps the graph; the same new
+            # shape twice in a row is captured again
+            first = trainer._graph_state
             feats, labels = batch(gen)
+            half = ({k: v[: B // 2].contiguous() for k, v in feats.items()}, labels[: B // 2].contiguous())
+            assert trainer.train_minibatch(*half)[:2] == (True, 9) and trainer._graph_state is first
+            assert trainer.train_minibatch(feats, labels)[:2] == (True, 10) and trainer._graph_state is first
+            assert trainer.train_minibatch(*half)[:2] == (True, 11) and trainer._graph_state is first
+            assert trainer.train_minibatch(*half)[:2] == (True, 12)
+            assert isinstance(trainer._graph_state, dict) and trainer._graph_state is not first
+            assert trainer._graph_state["recaptures"] == 1 and trainer.graph_fallback_reason is None
+            feats, labels = batch(gen)
+            feats = {k: v[: B // 2].contiguous() for k, v in feats.items()}
+            labels = labels[: B // 2].contiguous()
             feats["ids_1"] = feats["ids_1"] + 10 ** 6  # outside table 1: flagged by the kernels, read after the replay
             with pytest.raises(_lib.PSError):
                 trainer.train_minibatch(feats, labels)
