@@ -145,6 +145,13 @@ def cpu_reference(batch, steps, warmup, dist_kind, threads=None):
     gRPC/protobuf and the TF tower are NOT included, which flatters the reference.  The
     thread count is swept (lock contention on Zipf-hot rows can make fewer threads faster)
     and the best is reported.  Returns (samples_per_sec, threads, description)."""
+    import ctypes
+
+    from oracle import ps_oracle as O
+    from oracle import ref_kernels
+
+    ref = ref_kernels.lib()  # oracle/_ref: the reference's own kernel_api.cc, compiled unmodified (None if not built)
+    O.lib.oracle_set_ref_adam(ctypes.cast(ref.Adam, ctypes.c_void_p) if ref is not None else None)
     ncpu = os.cpu_count() or 1
     cands = [threads] if threads else sorted({min(c, ncpu) for c in (8, 16, 32, 64, ncpu)})
     cands = [c for c in cands if c <= 128] or [min(ncpu, 128)]
@@ -157,9 +164,13 @@ def cpu_reference(batch, steps, warmup, dist_kind, threads=None):
                 best = (sps, T)
     T = best[1]
     sps = wl.run(T, steps, warmup)
+    O.lib.oracle_set_ref_adam(None)
     return sps, T, ("C restatement of the Go PS path (unique+pull+dedup+SparseAdam, 76 tables, no gRPC/protobuf, "
-                    "no tower): best of thread counts %s = %d threads x batch %d x %d steps, %s ids, %d host cores"
-                    % (cands, T, batch, steps, dist_kind, ncpu))
+                    "no tower), row update by %s: best of thread counts %s = %d threads x batch %d x %d steps, %s ids, "
+                    "%d host cores"
+                    % ("the reference's own compiled Adam (oracle/_ref = kernel_api.cc built unmodified), one call per row "
+                       "as kernel.go:119-138 does" if ref is not None else "the restated Adam (oracle/_ref not built)",
+                       cands, T, batch, steps, dist_kind, ncpu))
 
 
 def parity_check_multi(engine, group, rank, world, dev, lr=1e-3):

@@ -287,16 +287,28 @@ void oracle_sparse_momentum(otable_t* p, otable_t* vel, const int64_t* ids, cons
     oracle_momentum(grads + i * p->dim, otable_get_row(p, ids[i]), otable_get_row(vel, ids[i]),
                     mu, nesterov, lr, p->dim);
 }
+/* Optional: the reference's OWN compiled Adam (kernel_api.h:20-30, from oracle/_ref/libkernel_api_ref.so =
+ * kernel_api.cc built unmodified) for the per-row update, exactly as kernel.go:119-138 calls it through cgo.
+ * Set by bench.py's CPU arm when oracle/_ref is present; NULL = the restatement above (bit-identical,
+ * tests/test_oracle_vs_ref.py). */
+typedef void (*ref_adam_fn)(float*, float*, float*, float*, float, long long, long long, float, float, float, float*);
+static ref_adam_fn g_ref_adam = NULL;
+void oracle_set_ref_adam(void* fn) { g_ref_adam = (ref_adam_fn)fn; }
+
 /* kernel.go:119-138 */
 void oracle_sparse_adam(otable_t* p, otable_t* m, otable_t* v, otable_t* ms, const int64_t* ids,
                         const float* grads, int64_t n, float lr, long long step, float beta1,
                         float beta2, float epsilon) {
+  const ref_adam_fn ref = g_ref_adam;
   for (int64_t i = 0; i < n; ++i) {
     float* sp = otable_get_row(p, ids[i]);
     float* sm = otable_get_row(m, ids[i]);
     float* sv = otable_get_row(v, ids[i]);
     float* sms = ms ? otable_get_row(ms, ids[i]) : NULL;
-    oracle_adam(grads + i * p->dim, sp, sm, sv, lr, p->dim, step, beta1, beta2, epsilon, sms);
+    if (ref)
+      ref((float*)(grads + i * p->dim), sp, sm, sv, lr, p->dim, step, beta1, beta2, epsilon, sms);
+    else
+      oracle_adam(grads + i * p->dim, sp, sm, sv, lr, p->dim, step, beta1, beta2, epsilon, sms);
   }
 }
 /* kernel.go:172-184 */

@@ -67,6 +67,7 @@ def _load():
         "oracle_sparse_sgd": (None, [vp, i64p, f32p, ctypes.c_int64, f]),
         "oracle_sparse_momentum": (None, [vp, vp, i64p, f32p, ctypes.c_int64, f, ctypes.c_int, f]),
         "oracle_sparse_adam": (None, [vp, vp, vp, vp, i64p, f32p, ctypes.c_int64, f, ll, f, f, f]),
+        "oracle_set_ref_adam": (None, [vp]),
         "oracle_sparse_adagrad": (None, [vp, vp, i64p, f32p, ctypes.c_int64, f, f]),
         "oracle_sparse_ftrl": (None, [vp, vp, vp, i64p, f32p, ctypes.c_int64, f, f, f, f]),
         "oracle_indexed_apply": (None, [ctypes.c_int, f32p, f32p, f32p, f32p, ctypes.c_int64, i64p,

@@ -108,3 +108,30 @@ def test_ref_replays_kernel_test_go_vectors():
     ev = 0.999 * v0.astype(np.float64) + 0.001 * g.astype(np.float64) ** 2
     ep = p0 - 0.1 * np.sqrt(1 - 0.999 ** 5) / (1 - 0.9 ** 5) * em / (np.sqrt(ev) + 1e-8)
     assert np.allclose(m, em, rtol=1e-6) and np.allclose(v, ev, rtol=1e-6) and np.allclose(p, ep, rtol=1e-5, atol=1e-6)
+
+
+@needs_ref
+@pytest.mark.parametrize("dim", [1, 8])
+def test_sparse_adam_rows_through_the_reference_kernel(dim):
+    """The CPU arm of bench.py updates table rows with the reference's own compiled Adam (one call per row, as
+    kernel.go:119-138 does through cgo): with and without the hook the tables end up bit-identical, duplicates
+    applied sequentially, AMSGrad slot included."""
+    import ctypes
+
+    rng = np.random.default_rng(dim)
+    ids = rng.integers(0, 50, 400).astype(np.int64)  # many duplicates: sequential application
+    grads = (rng.standard_normal((400, dim)) * 0.1).astype(F)
+
+    def run(hook):
+        O.lib.oracle_set_ref_adam(ctypes.cast(R.lib().Adam, ctypes.c_void_p) if hook else None)
+        try:
+            tabs = [O.OracleTable(dim, "uniform", seed=3)] + [O.OracleTable(dim, "zero") for _ in range(3)]
+            for step in (1, 2, 7):
+                O.lib.oracle_sparse_adam(tabs[0]._h, tabs[1]._h, tabs[2]._h, tabs[3]._h, O._i64(ids), O._f32(grads),
+                                         ids.size, 0.01, step, 0.9, 0.999, 1e-7)
+            return [t.get(np.arange(50)) for t in tabs]
+        finally:
+            O.lib.oracle_set_ref_adam(None)
+
+    for a, b in zip(run(True), run(False)):
+        assert np.array_equal(bits(a), bits(b))
