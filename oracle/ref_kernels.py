@@ -34,10 +34,13 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        so = build()
-        if so is None:
+        try:
+            so = build()
+            if so is None:
+                return None
+            L = ctypes.CDLL(so)
+        except (OSError, subprocess.CalledProcessError):  # no compiler / an unloadable prebuilt file: run without it
             return None
-        L = ctypes.CDLL(so)
         f32p = ctypes.POINTER(ctypes.c_float)
         f, ll, b = ctypes.c_float, ctypes.c_longlong, ctypes.c_bool
         L.SGD.argtypes = [f32p, f32p, f, ll]  # kernel_api.h:10
