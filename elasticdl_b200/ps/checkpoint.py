@@ -88,7 +88,7 @@ def _fields(buf):
 def encode_tensor(array):
     """tensorflow.TensorProto{dtype=1, tensor_shape=2{dim=2{size=1}}, tensor_content=4}: raw
     little-endian bytes (python/common/tensor_utils.py:63-71, go/pkg/common/tensor.go:185-200)."""
-    array = np.ascontiguousarray(array)
+    array = np.asarray(array, order="C")  # (np.ascontiguousarray would turn a 0-d parameter into shape [1])
     dt = _DT_OF_NP[array.dtype]
     shape = b"".join(_ld(2, _tag(1, 0) + _varint(int(d))) for d in array.shape)
     return _tag(1, 0) + _varint(dt) + _ld(2, shape) + _ld(4, array.astype(array.dtype.newbyteorder("<"), copy=False).tobytes())
@@ -110,7 +110,8 @@ def decode_tensor(buf):
         elif f == 4:
             content = v
     arr = np.frombuffer(content, dtype=np.dtype(_NP_OF_DT[dt]).newbyteorder("<")).astype(_NP_OF_DT[dt])
-    return arr.reshape(dims) if dims else arr
+    # no dims + one element = a scalar (pb_to_ndarray, tensor_utils.py:80-95, builds shape [] from it)
+    return arr.reshape(dims) if (dims or arr.size == 1) else arr
 
 
 # ----------------------------------------------------------------------------- Model
