@@ -90,8 +90,12 @@ def encode_tensor(array):
     little-endian bytes (python/common/tensor_utils.py:63-71, go/pkg/common/tensor.go:185-200)."""
     array = np.asarray(array, order="C")  # (np.ascontiguousarray would turn a 0-d parameter into shape [1])
     dt = _DT_OF_NP[array.dtype]
-    shape = b"".join(_ld(2, _tag(1, 0) + _varint(int(d))) for d in array.shape)
-    return _tag(1, 0) + _varint(dt) + _ld(2, shape) + _ld(4, array.astype(array.dtype.newbyteorder("<"), copy=False).tobytes())
+    # canonical proto3, byte for byte what serialize_ndarray + SerializeToString give (tests/golden "wire" vectors,
+    # produced by executing them): zero-valued scalars and empty bytes are not written -- a dim of size 0 is an empty
+    # Dim message, a 0-d tensor has no tensor_shape field, an empty tensor no tensor_content field
+    shape = b"".join(_ld(2, (_tag(1, 0) + _varint(int(d))) if d else b"") for d in array.shape)
+    content = array.astype(array.dtype.newbyteorder("<"), copy=False).tobytes()
+    return _tag(1, 0) + _varint(dt) + (_ld(2, shape) if array.ndim else b"") + (_ld(4, content) if content else b"")
 
 
 def decode_tensor(buf):

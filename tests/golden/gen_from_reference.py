@@ -13,6 +13,13 @@ What is executed, unmodified, from /root/reference:
     only (the two functions use numpy alone).  `np.stack(dict_values)` worked on
     the numpy the reference pins; numpy 2.x wants a sequence, so np.stack is
     wrapped to list() its argument -- same values, same order.
+  * elasticdl/python/common/tensor_utils.py serializers (ndarray_to_pb, indexed_slices_to_pb, pb_to_ndarray,
+    pb_to_indexed_slices) and elasticdl/python/common/dtypes.py -- executed in a SECOND import of both files
+    (ref_wire_vectors()) with `tensor_pb2.TensorProto` / `elasticdl_pb2.IndexedSlicesProto` bound to message
+    classes built at runtime by google.protobuf from the field numbers of TensorFlow's tensor.proto /
+    tensor_shape.proto and elasticdl/proto/elasticdl.proto:12-15 (protoc is not installed), `odps.types` stubbed
+    (three attribute reads at import) and `np.bool` aliased to np.bool_ (removed in numpy 2).  The bytes those
+    functions serialise are what a reference worker puts on the wire and into checkpoint files.
 """
 import json
 import os
@@ -95,6 +102,84 @@ m = tensor_utils.merge_indexed_slices(a, b)
 out["merge_indexed_slices"] = {"a": [a.values.tolist(), a.indices.tolist()],
                                "b": [b.values.tolist(), b.indices.tolist()],
                                "values": m.values.tolist(), "indices": m.indices.tolist()}
+
+
+
+def ref_wire_vectors():
+    """Bytes produced by the reference's own proto serialisers (see the module docstring)."""
+    import importlib
+
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+
+    fd = descriptor_pb2.FileDescriptorProto()
+    fd.name, fd.package, fd.syntax = "edl_golden_wire.proto", "edlgolden", "proto3"
+    F = descriptor_pb2.FieldDescriptorProto
+
+    def msg(name, fields):
+        m = fd.message_type.add()
+        m.name = name
+        for fname, num, typ, label, tname in fields:
+            f = m.field.add()
+            f.name, f.number, f.type, f.label = fname, num, typ, label
+            if tname:
+                f.type_name = tname
+
+    O, R = F.LABEL_OPTIONAL, F.LABEL_REPEATED
+    msg("Dim", [("size", 1, F.TYPE_INT64, O, None), ("name", 2, F.TYPE_STRING, O, None)])     # tensor_shape.proto
+    msg("TensorShapeProto", [("dim", 2, F.TYPE_MESSAGE, R, ".edlgolden.Dim"), ("unknown_rank", 3, F.TYPE_BOOL, O, None)])
+    msg("TensorProto", [("dtype", 1, F.TYPE_INT32, O, None),                                 # tensor.proto
+                        ("tensor_shape", 2, F.TYPE_MESSAGE, O, ".edlgolden.TensorShapeProto"),
+                        ("version_number", 3, F.TYPE_INT32, O, None), ("tensor_content", 4, F.TYPE_BYTES, O, None)])
+    msg("IndexedSlicesProto", [("concat_tensors", 1, F.TYPE_MESSAGE, O, ".edlgolden.TensorProto"),  # elasticdl.proto:12-15
+                               ("ids", 2, F.TYPE_INT64, R, None)])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    cls = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName("edlgolden." + n))  # noqa: E731
+    sys.modules["tensorflow.core.framework.tensor_pb2"].TensorProto = cls("TensorProto")
+    sys.modules["elasticdl.proto.elasticdl_pb2"].IndexedSlicesProto = cls("IndexedSlicesProto")
+    odps = types.ModuleType("odps")
+    odps.types = types.SimpleNamespace(bigint="bigint", double="double", string="string")
+    sys.modules["odps"] = odps
+    had_bool = hasattr(np, "bool")
+    if not had_bool:
+        np.bool = np.bool_
+    try:
+        del sys.modules["elasticdl.python.common.dtypes"]
+        import elasticdl.python.common as common_pkg
+
+        if hasattr(common_pkg, "dtypes"):
+            delattr(common_pkg, "dtypes")
+        real_dtypes = importlib.import_module("elasticdl.python.common.dtypes")  # the real file, unmodified
+        tu = importlib.reload(tensor_utils)                                      # binds the real dtype functions
+        assert tu.dtype_numpy_to_tensor is real_dtypes.dtype_numpy_to_tensor
+        rng = np.random.RandomState(11)
+        tensors = [np.float32(2.5).reshape(()), rng.randn(5).astype(np.float32), rng.randn(3, 4).astype(np.float32),
+                   np.zeros((0, 8), np.float32), np.arange(6, dtype=np.int64).reshape(2, 3),
+                   rng.randn(2, 1, 3).astype(np.float64)]
+        out_t = []
+        for a in tensors:
+            pb = tu.ndarray_to_pb(a)
+            back = tu.pb_to_ndarray(pb)
+            assert back.shape == a.shape and np.array_equal(back, a)
+            out_t.append({"dtype": a.dtype.name, "shape": list(a.shape), "data": a.reshape(-1).tolist(),
+                          "hex": pb.SerializeToString().hex()})
+        out_s = []
+        for ids, dim in [([1, 3, 3, 5], 2), ([0], 8), ([7, 2 ** 40 + 5, 123456789], 4), (list(range(130, 150)), 1)]:
+            vals = rng.randn(len(ids), dim).astype(np.float32)
+            for as_array in (True, False):
+                idx = np.asarray(ids, dtype=np.int64) if as_array else list(ids)
+                pb = tu.indexed_slices_to_pb(tu.Tensor(None, vals, idx))
+                back = tu.pb_to_indexed_slices(pb)
+                assert np.array_equal(back.values, vals) and back.indices.tolist() == list(ids)
+                out_s.append({"ids": list(ids), "values": vals.tolist(), "ids_as_array": as_array,
+                              "hex": pb.SerializeToString().hex()})
+        return {"tensor_proto": out_t, "indexed_slices_proto": out_s}
+    finally:
+        if not had_bool:
+            del np.bool
+
+
+out["wire"] = ref_wire_vectors()
 
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_python_vectors.json")
 with open(path, "w") as f:

@@ -118,3 +118,42 @@ def test_valid_version_dir(tmp_path):
     (d / "variables-1-of-2.ckpt").write_bytes(ck.encode_model(5, [], {}, {}))
     assert ck.is_valid_version_dir(str(d))
     assert ck.latest_version_dir(str(tmp_path)) == str(d)
+
+
+def _wire_vectors():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python_vectors.json")) as f:
+        return json.load(f)["wire"]
+
+
+def test_tensor_proto_bytes_equal_the_reference_serialiser():
+    """tests/golden `wire.tensor_proto`: bytes written by the reference's own ndarray_to_pb (tensor_utils.py:63-77,
+    executed by tests/golden/gen_from_reference.py) + SerializeToString.  encode_tensor reproduces them byte for byte
+    (0-d tensor: no tensor_shape; a dim of size 0: empty Dim; empty tensor: no tensor_content) and decode_tensor
+    reads them back -- so checkpoint files and wire messages are interchangeable with a reference worker's."""
+    vec = _wire_vectors()["tensor_proto"]
+    assert {tuple(v["shape"]) for v in vec} >= {(), (5,), (3, 4), (0, 8)}
+    for v in vec:
+        a = np.asarray(v["data"], dtype=v["dtype"]).reshape(v["shape"])
+        assert ck.encode_tensor(a).hex() == v["hex"], (v["dtype"], v["shape"])
+        b = ck.decode_tensor(bytes.fromhex(v["hex"]))
+        assert b.dtype == a.dtype and b.shape == a.shape and np.array_equal(a, b)
+
+
+def test_indexed_slices_proto_bytes_equal_the_reference_serialiser():
+    """`wire.indexed_slices_proto`: indexed_slices_to_pb (tensor_utils.py:103-122) with ids given as an array or a
+    list.  The IndexedSlicesProto inside encode_model's embedding_tables entry is the same bytes; decode_model returns
+    the same ids / values."""
+    for v in _wire_vectors()["indexed_slices_proto"]:
+        ids = np.asarray(v["ids"], dtype=np.int64)
+        vals = np.asarray(v["values"], dtype=np.float32)
+        model = ck.encode_model(0, [], {}, {"t": (ids, vals)})
+        (f, _, entry), = list(ck._fields(model))
+        assert f == 4
+        parts = {f2: v2 for f2, _, v2 in ck._fields(entry)}
+        assert parts[1] == b"t" and parts[2].hex() == v["hex"]
+        _, _, _, tables = ck.decode_model(model)
+        got_ids, got_vals = tables["t"]
+        assert got_ids.tolist() == v["ids"] and np.array_equal(got_vals, vals)
