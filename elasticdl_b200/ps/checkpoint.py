@@ -232,6 +232,8 @@ def save(group, checkpoint_dir, version=None, dense_names=None, keep_checkpoint_
 
 def is_valid_version_dir(path):
     """save_utils.py:212-227: all N shard files are present."""
+    if not os.path.isdir(path):
+        return False
     files = [f for f in os.listdir(path) if re.match(r"variables-\d+-of-\d+\.ckpt$", f)]
     if not files:
         return False
@@ -240,6 +242,10 @@ def is_valid_version_dir(path):
 
 
 def latest_version_dir(checkpoint_dir):
+    """CheckpointSaver.get_valid_lastest_version_dir (save_utils.py:192-209): the complete version directory with the
+    highest version NUMBER, None when there is none (or no such directory)."""
+    if not checkpoint_dir or not os.path.isdir(checkpoint_dir):
+        return None
     best = None
     for d in os.listdir(checkpoint_dir):
         m = re.match(r"version-(\d+)$", d)

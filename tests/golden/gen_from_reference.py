@@ -20,6 +20,8 @@ What is executed, unmodified, from /root/reference:
     tensor_shape.proto and elasticdl/proto/elasticdl.proto:12-15 (protoc is not installed), `odps.types` stubbed
     (three attribute reads at import) and `np.bool` aliased to np.bool_ (removed in numpy 2).  The bytes those
     functions serialise are what a reference worker puts on the wire and into checkpoint files.
+  * elasticdl/python/common/save_utils.py CheckpointSaver (file naming, complete / latest version directory) on real
+    temporary directory trees (ref_checkpoint_dir_vectors()).
 """
 import json
 import os
@@ -180,6 +182,53 @@ def ref_wire_vectors():
 
 
 out["wire"] = ref_wire_vectors()
+
+
+CKPT_SCENARIOS = [  # {version: [shard files]} under one checkpoint directory
+    {},
+    {"3": ["variables-0-of-1.ckpt"]},
+    {"3": ["variables-0-of-2.ckpt", "variables-1-of-2.ckpt"], "7": ["variables-0-of-2.ckpt"]},            # 7 incomplete
+    {"10": ["variables-%d-of-3.ckpt" % i for i in range(3)], "9": ["variables-%d-of-3.ckpt" % i for i in range(3)],
+     "100": ["variables-0-of-3.ckpt", "variables-2-of-3.ckpt"]},                                        # numeric, not lexical, order
+    {"5": []},                                                                                           # empty version dir
+    {"2": ["variables-0-of-1.ckpt"], "4": ["variables-0-of-2.ckpt", "variables-1-of-2.ckpt"]},
+]
+
+
+def ref_checkpoint_dir_vectors():
+    """CheckpointSaver's directory logic (save_utils.py:124-141,192-227) executed on real directory trees: file naming,
+    which version directories are complete, which is the latest complete one.  save_utils.py imports TensorFlow and the
+    Python PS (for restore_params_from_checkpoint, not used here): stub modules stand in at import."""
+    import tempfile
+
+    for name in ["elasticdl.python.ps", "elasticdl.python.ps.embedding_table", "elasticdl.python.ps.parameters"]:
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["elasticdl.python.ps.embedding_table"].create_embedding_table = None
+    sys.modules["elasticdl.python.ps.parameters"].Parameters = None
+    from elasticdl.python.common import save_utils
+
+    S = save_utils.CheckpointSaver
+    res = []
+    for sc in CKPT_SCENARIOS:
+        with tempfile.TemporaryDirectory() as root:
+            for v, files in sc.items():
+                d = os.path.join(root, "version-" + v)
+                os.makedirs(d)
+                for fn in files:
+                    open(os.path.join(d, fn), "wb").close()
+            latest = S.get_valid_lastest_version_dir(root)
+            res.append({"tree": sc,
+                        "valid": {v: bool(S.check_checkpoint_valid(os.path.join(root, "version-" + v))) for v in sc},
+                        "latest": None if latest is None else os.path.basename(latest)})
+    with tempfile.TemporaryDirectory() as root:
+        saver = S(root, 1, 0, False)
+        names = [os.path.relpath(saver._get_checkpoint_file(v, False, i, n), root) for v, i, n in [(7, 0, 1), (120, 2, 3)]]
+        missing = S.get_valid_lastest_version_dir(os.path.join(root, "nope"))
+        missing_valid = bool(S.check_checkpoint_valid(os.path.join(root, "nope")))
+    return {"scenarios": res, "file_names": names, "missing_dir_latest": missing, "missing_dir_valid": missing_valid}
+
+
+out["checkpoint_dirs"] = ref_checkpoint_dir_vectors()
 
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_python_vectors.json")
 with open(path, "w") as f:

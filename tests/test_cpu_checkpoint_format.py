@@ -157,3 +157,30 @@ def test_indexed_slices_proto_bytes_equal_the_reference_serialiser():
         _, _, _, tables = ck.decode_model(model)
         got_ids, got_vals = tables["t"]
         assert got_ids.tolist() == v["ids"] and np.array_equal(got_vals, vals)
+
+
+def test_checkpoint_directory_logic_equals_the_reference(tmp_path):
+    """tests/golden `checkpoint_dirs`: CheckpointSaver's directory logic (save_utils.py:124-141,192-227) executed by
+    tests/golden/gen_from_reference.py on real directory trees -- same file names, same verdict on which version
+    directories are complete, same latest complete version (numeric order), None for a missing directory."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python_vectors.json")) as f:
+        vec = json.load(f)["checkpoint_dirs"]
+    for n, sc in enumerate(vec["scenarios"]):
+        root = tmp_path / ("case%d" % n)
+        root.mkdir()
+        for v, files in sc["tree"].items():
+            d = root / ("version-" + v)
+            d.mkdir()
+            for fn in files:
+                (d / fn).write_bytes(b"")
+        for v, want in sc["valid"].items():
+            assert ck.is_valid_version_dir(str(root / ("version-" + v))) == want, (n, v)
+        latest = ck.latest_version_dir(str(root))
+        assert (None if latest is None else os.path.basename(latest)) == sc["latest"], n
+    got = [os.path.relpath(ck._file(str(tmp_path), v, i, k), str(tmp_path)) for v, i, k in [(7, 0, 1), (120, 2, 3)]]
+    assert got == vec["file_names"]
+    assert ck.latest_version_dir(str(tmp_path / "nope")) is vec["missing_dir_latest"] is None
+    assert ck.is_valid_version_dir(str(tmp_path / "nope")) == vec["missing_dir_valid"]
