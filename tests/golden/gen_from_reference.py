@@ -22,6 +22,8 @@ What is executed, unmodified, from /root/reference:
     functions serialise are what a reference worker puts on the wire and into checkpoint files.
   * elasticdl/python/common/save_utils.py CheckpointSaver (file naming, complete / latest version directory) on real
     temporary directory trees (ref_checkpoint_dir_vectors()).
+  * elasticdl/python/worker/ps_client.py PSClient -- the worker-side boundary itself -- against recording fake stubs
+    (ref_ps_client_vectors()): every request each PS receives, every value the client returns.
 """
 import json
 import os
@@ -229,6 +231,194 @@ def ref_checkpoint_dir_vectors():
 
 
 out["checkpoint_dirs"] = ref_checkpoint_dir_vectors()
+
+
+
+def ref_ps_client_vectors():
+    """The reference's worker-side client, elasticdl/python/worker/ps_client.py:87-301, EXECUTED unmodified against
+    recording fake stubs: which request reaches which PS (ids grouping and order, dedup / merge of gradients, versions,
+    learning rate), what the client returns.  Message classes are built at runtime from elasticdl.proto:12-76;
+    `elasticdl_pb2_grpc.PserverStub(channel)` is stubbed to return the "channel" itself (a fake stub object); the
+    serialisers are the reference's (ref_wire_vectors() must have run: tensor_utils is already bound to real dtypes)."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+
+    fd = descriptor_pb2.FileDescriptorProto()
+    fd.name, fd.package, fd.syntax = "edl_golden_client.proto", "edlclient", "proto3"
+    F = descriptor_pb2.FieldDescriptorProto
+    O, R = F.LABEL_OPTIONAL, F.LABEL_REPEATED
+
+    def msg(name, fields, nested=()):
+        m = fd.message_type.add()
+        m.name = name
+        for n in nested:
+            m.nested_type.add().CopyFrom(n)
+        for fname, num, typ, label, tname in fields:
+            f = m.field.add()
+            f.name, f.number, f.type, f.label = fname, num, typ, label
+            if tname:
+                f.type_name = tname
+
+    def entry(name, vtype):
+        e = descriptor_pb2.DescriptorProto()
+        e.name = name
+        e.options.map_entry = True
+        k = e.field.add()
+        k.name, k.number, k.type, k.label = "key", 1, F.TYPE_STRING, O
+        v = e.field.add()
+        v.name, v.number, v.type, v.label, v.type_name = "value", 2, F.TYPE_MESSAGE, O, vtype
+        return e
+
+    P = ".edlclient."
+    msg("Dim", [("size", 1, F.TYPE_INT64, O, None)])
+    msg("TensorShapeProto", [("dim", 2, F.TYPE_MESSAGE, R, P + "Dim")])
+    msg("TensorProto", [("dtype", 1, F.TYPE_INT32, O, None), ("tensor_shape", 2, F.TYPE_MESSAGE, O, P + "TensorShapeProto"),
+                        ("tensor_content", 4, F.TYPE_BYTES, O, None)])
+    msg("IndexedSlicesProto", [("concat_tensors", 1, F.TYPE_MESSAGE, O, P + "TensorProto"), ("ids", 2, F.TYPE_INT64, R, None)])
+    msg("EmbeddingTableInfo", [("name", 1, F.TYPE_STRING, O, None), ("dim", 2, F.TYPE_INT64, O, None),
+                               ("initializer", 3, F.TYPE_STRING, O, None), ("dtype", 4, F.TYPE_INT32, O, None)])
+    msg("Model", [("version", 1, F.TYPE_INT32, O, None),
+                  ("embedding_table_infos", 2, F.TYPE_MESSAGE, R, P + "EmbeddingTableInfo"),
+                  ("dense_parameters", 3, F.TYPE_MESSAGE, R, P + "Model.DenseParametersEntry"),
+                  ("embedding_tables", 4, F.TYPE_MESSAGE, R, P + "Model.EmbeddingTablesEntry")],
+        nested=[entry("DenseParametersEntry", P + "TensorProto"), entry("EmbeddingTablesEntry", P + "IndexedSlicesProto")])
+    msg("PullEmbeddingVectorRequest", [("name", 1, F.TYPE_STRING, O, None), ("ids", 2, F.TYPE_INT64, R, None)])
+    msg("PullDenseParametersRequest", [("version", 1, F.TYPE_INT32, O, None)])
+    msg("PullDenseParametersResponse",
+        [("initialized", 1, F.TYPE_BOOL, O, None), ("version", 2, F.TYPE_INT32, O, None),
+         ("dense_parameters", 3, F.TYPE_MESSAGE, R, P + "PullDenseParametersResponse.DenseParametersEntry")],
+        nested=[entry("DenseParametersEntry", P + "TensorProto")])
+    msg("PushGradientsRequest", [("gradients", 1, F.TYPE_MESSAGE, O, P + "Model"), ("learning_rate", 2, F.TYPE_FLOAT, O, None)])
+    msg("PushGradientsResponse", [("accepted", 1, F.TYPE_BOOL, O, None), ("version", 2, F.TYPE_INT32, O, None)])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    pb2 = sys.modules["elasticdl.proto.elasticdl_pb2"]
+    for n in ("TensorProto", "IndexedSlicesProto", "EmbeddingTableInfo", "Model", "PullEmbeddingVectorRequest",
+              "PullDenseParametersRequest", "PullDenseParametersResponse", "PushGradientsRequest", "PushGradientsResponse"):
+        setattr(pb2, n, message_factory.GetMessageClass(pool.FindMessageTypeByName("edlclient." + n)))
+    sys.modules["tensorflow.core.framework.tensor_pb2"].TensorProto = pb2.TensorProto
+    grpc_mod = types.ModuleType("elasticdl.proto.elasticdl_pb2_grpc")
+    grpc_mod.PserverStub = lambda channel: channel
+    sys.modules["elasticdl.proto.elasticdl_pb2_grpc"] = grpc_mod
+    sys.modules["elasticdl.proto"].elasticdl_pb2_grpc = grpc_mod
+    import importlib
+
+    tu = importlib.reload(tensor_utils)  # rebinds tensor_pb2.TensorProto to the class Model's maps use
+    from elasticdl.python.worker import ps_client as ref_client
+
+    def tensor_dict(pb):
+        a = tu.pb_to_ndarray(pb)
+        return {"shape": list(a.shape), "data": np.asarray(a, dtype=np.float32).reshape(-1).tolist()}
+
+    def model_dict(m):
+        return {"version": m.version,
+                "infos": [[i.name, i.dim, i.initializer, i.dtype] for i in m.embedding_table_infos],
+                "dense": {k: tensor_dict(v) for k, v in m.dense_parameters.items()},
+                "tables": {k: {"ids": [int(i) for i in v.ids], **tensor_dict(v.concat_tensors)}
+                           for k, v in m.embedding_tables.items()}}
+
+    class Future(object):
+        def __init__(self, value):
+            self._v = value
+
+        def result(self):
+            return self._v
+
+    class Method(object):
+        def __init__(self, fn):
+            self._fn = fn
+
+        def __call__(self, req):
+            return self._fn(req)
+
+        def future(self, req):
+            return Future(self._fn(req))
+
+    class FakeStub(object):
+        """One PS: records every request, answers from a script."""
+
+        def __init__(self, ps_id, log, initialized=True, version=5, accept=True, dense=None):
+            self.ps_id, self.log = ps_id, log
+            self.initialized, self.version, self.accept, self.dense = initialized, version, accept, dense or {}
+            self.push_model = Method(lambda m: self.log.append(["push_model", ps_id, model_dict(m)]))
+            self.push_embedding_table_infos = Method(
+                lambda m: self.log.append(["push_embedding_table_infos", ps_id, model_dict(m)]))
+            self.pull_dense_parameters = Method(self._pull_dense)
+            self.pull_embedding_vectors = Method(self._pull_rows)
+            self.push_gradients = Method(self._push_gradients)
+
+        def _pull_dense(self, req):
+            self.log.append(["pull_dense_parameters", self.ps_id, {"version": req.version}])
+            res = pb2.PullDenseParametersResponse(initialized=self.initialized, version=self.version)
+            if self.initialized:
+                for k, a in self.dense.items():
+                    tu.serialize_ndarray(a, res.dense_parameters[k])
+            return res
+
+        def _pull_rows(self, req):
+            ids = [int(i) for i in req.ids]
+            self.log.append(["pull_embedding_vectors", self.ps_id, {"name": req.name, "ids": ids}])
+            rows = np.asarray([[i + 0.25 * c for c in range(4)] for i in ids], dtype=np.float32)
+            return tu.ndarray_to_pb(rows)
+
+        def _push_gradients(self, req):
+            self.log.append(["push_gradients", self.ps_id,
+                             {"learning_rate": req.learning_rate, "gradients": model_dict(req.gradients)}])
+            self.version += 1
+            return pb2.PushGradientsResponse(accepted=self.accept, version=self.version)
+
+    T = tu.Tensor
+    rng = np.random.RandomState(21)
+    f32 = lambda *s: np.asarray(rng.randn(*s), dtype=np.float32)  # noqa: E731
+    cases = []
+    for ps_num in (1, 2, 3):
+        log = []
+        stubs = [FakeStub(p, log, initialized=(p != 1), version=5 + p, accept=(p != 0 or ps_num == 1),
+                          dense={"from_ps_%d/kernel:0" % p: f32(2, 3)}) for p in range(ps_num)]
+        client = ref_client.PSClient(stubs)
+        names = ["dense/kernel:0", "dense/bias:0", "dense_1/kernel:0", "emb_keras/embeddings:0", "scalar:0"]
+        client.partition_dense_parameters(names)
+        infos = [tu.EmbeddingTableInfo("edl_emb", 4, "uniform", 1), tu.EmbeddingTableInfo("edl_emb2", 2, "zeros", 1)]
+        client.push_embedding_table_infos(infos)
+        params = [T(n, f32(3, 2) if "kernel" in n else f32(3), None) for n in names[:3]]
+        for p in range(ps_num):
+            client.push_dense_parameters(params, p, 3)
+        versions = [1] * ps_num
+        dense, uninit = client.pull_dense_parameters(list(range(ps_num)), versions)
+        pull_ids = [3, 5, 1, 6, 10, 2, 1, 2, 4, 7, 9]
+        rows = client.pull_embedding_vectors("edl_emb", pull_ids)
+        grads = [T("dense/kernel:0", f32(3, 2), None), T("dense/bias:0", f32(3), None), T("scalar:0", f32(), None),
+                 T("emb_keras/embeddings:0", f32(5, 2), np.array([4, 1, 4, 0, 1])),           # IndexedSlices of a dense param
+                 T("emb_keras/embeddings:0", f32(2, 2), np.array([7, 4]))]                    # same name: merged, then dedup
+        edl = [T("edl_emb", f32(6, 4), np.array([3, 1, 3, 8, 1, 6])), T("edl_emb2", f32(3, 2), np.array([5, 5, 2])),
+               T("edl_emb", f32(2, 4), np.array([1, 9]))]
+        g_in = [[g.name, g.values.tolist(), None if g.indices is None else g.indices.tolist()] for g in grads]
+        e_in = [[g.name, g.values.tolist(), g.indices.tolist()] for g in edl]
+        push_versions = [7 + p for p in range(ps_num)]
+        accepted, max_version = client.push_gradients(grads, edl, 0.125, push_versions)
+        # two DENSE gradients with one name: ps_client.py:217 does `namedtuple.values += ...` -- what happens is recorded
+        try:
+            n_before = len(log)
+            client.push_gradients([T("dense/bias:0", f32(3), None), T("dense/bias:0", f32(3), None)], [], 0.5,
+                                  list(push_versions))
+            dup_dense = "ok"
+        except Exception as err:  # noqa: BLE001
+            dup_dense = type(err).__name__
+        del log[n_before:]
+        cases.append({"ps_num": ps_num, "param_names": names, "parameter_to_ps": client.parameter_to_ps,
+                      "ps_to_parameter": {str(k): v for k, v in client.ps_to_parameter.items()},
+                      "infos": [list(i) for i in infos],
+                      "params": [[p.name, p.values.tolist()] for p in params],
+                      "fake": [{"initialized": s.initialized, "version0": 5 + s.ps_id, "accept": s.accept,
+                                "dense": {k: v.tolist() for k, v in s.dense.items()}} for s in stubs],
+                      "pull_dense": {"versions_in": [1] * ps_num, "versions_out": versions, "uninit": uninit,
+                                     "dense": {k: np.asarray(v).tolist() for k, v in dense.items()}},
+                      "pull_ids": pull_ids, "pull_rows": rows.tolist(),
+                      "grads": g_in, "edl_grads": e_in, "learning_rate": 0.125, "push_versions": push_versions,
+                      "push_result": [bool(accepted), int(max_version)], "duplicate_dense_name": dup_dense, "log": log})
+    return cases
+
+
+out["ps_client"] = ref_ps_client_vectors()
 
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_python_vectors.json")
 with open(path, "w") as f:

@@ -358,3 +358,84 @@ def test_amsgrad_dense_q1_flag():
         s.push_model(dense={"w": np.ones(4, dtype=F)})
         s.push_gradients({"w": np.ones(4, dtype=F)}, {}, 0.1, 0)
     assert not np.allclose(a.dense["w"], b.dense["w"])  # the reference applies twice
+
+
+# --------------------------------------------------------------- the reference's PSClient, executed
+class _RecordingServer:
+    """Stands where an OracleServer stands; mirrors the FakeStub script of tests/golden/gen_from_reference.py."""
+
+    def __init__(self, ps_id, log, fake):
+        self.ps_id, self.log = ps_id, log
+        self.initialized, self.version, self.accept = fake["initialized"], fake["version0"], fake["accept"]
+        self.dense = {k: np.asarray(v, dtype=F) for k, v in fake["dense"].items()}
+
+    @staticmethod
+    def _t(a):
+        a = np.asarray(a, dtype=F)
+        return {"shape": list(a.shape), "data": a.reshape(-1).tolist()}
+
+    def _model(self, version=0, infos=(), dense=None, tables=None):
+        return {"version": version, "infos": [list(i)[:4] for i in infos],
+                "dense": {k: self._t(v) for k, v in (dense or {}).items()},
+                "tables": {k: {"ids": [int(i) for i in ids], **self._t(v)} for k, (ids, v) in (tables or {}).items()}}
+
+    def push_embedding_table_infos(self, infos):
+        self.log.append(["push_embedding_table_infos", self.ps_id, self._model(infos=infos)])
+
+    def push_model(self, dense=None, infos=(), tables=None, version=0):
+        self.log.append(["push_model", self.ps_id, self._model(version, infos, dense, tables)])
+
+    def pull_dense_parameters(self, version):
+        self.log.append(["pull_dense_parameters", self.ps_id, {"version": version}])
+        return self.initialized, self.version, (dict(self.dense) if self.initialized else {})
+
+    def pull_embedding_vectors(self, name, ids):
+        ids = [int(i) for i in ids]
+        self.log.append(["pull_embedding_vectors", self.ps_id, {"name": name, "ids": ids}])
+        return np.asarray([[i + 0.25 * c for c in range(4)] for i in ids], dtype=F)
+
+    def push_gradients(self, dense_grads, sparse_grads, learning_rate, version):
+        self.log.append(["push_gradients", self.ps_id,
+                         {"learning_rate": learning_rate, "gradients": self._model(version, (), dense_grads, sparse_grads)}])
+        self.version += 1
+        return self.accept, self.version
+
+
+def test_oracle_ps_client_equals_the_executed_reference_ps_client():
+    """tests/golden `ps_client`: /root/reference's elasticdl/python/worker/ps_client.py (class PSClient, :87-301) was
+    EXECUTED unmodified against recording fake stubs (tests/golden/gen_from_reference.py::ref_ps_client_vectors) for
+    1, 2 and 3 PS.  The oracle's client -- what every GPU parity test compares the CUDA path with -- must send every PS
+    exactly the same requests in the same order (id grouping of a pull, merge + dedup + scatter of gradients incl.
+    IndexedSlices of a dense parameter and a 0-d gradient, versions, learning rate, an empty push to a PS that owns
+    nothing: quirk Q7) and return the same values (row order of a pull, uninitialised PS list, versions written back,
+    accepted = any, version = max)."""
+    gold = json.load(open(GOLD))["ps_client"]
+    assert [c["ps_num"] for c in gold] == [1, 2, 3]
+    for c in gold:
+        n = c["ps_num"]
+        log = []
+        client = O.OraclePSClient([_RecordingServer(p, log, c["fake"][p]) for p in range(n)])
+        client.partition_dense_parameters(c["param_names"])
+        assert client.parameter_to_ps == c["parameter_to_ps"]
+        assert {str(k): v for k, v in client.ps_to_parameter.items()} == c["ps_to_parameter"]
+        client.push_embedding_table_infos([O.EmbeddingTableInfo(*i) for i in c["infos"]])
+        params = [O.Tensor(name, np.asarray(v, dtype=F), None) for name, v in c["params"]]
+        for p in range(n):
+            client.push_dense_parameters(params, p, 3)
+        versions = list(c["pull_dense"]["versions_in"])
+        dense, uninit = client.pull_dense_parameters(list(range(n)), versions)
+        assert versions == c["pull_dense"]["versions_out"] and uninit == c["pull_dense"]["uninit"]
+        assert {k: np.asarray(v).tolist() for k, v in dense.items()} == c["pull_dense"]["dense"]
+        rows = client.pull_embedding_vectors("edl_emb", c["pull_ids"])
+        assert rows.tolist() == c["pull_rows"]
+        grads = [O.Tensor(name, np.asarray(v, dtype=F), None if i is None else np.asarray(i)) for name, v, i in c["grads"]]
+        edl = [O.Tensor(name, np.asarray(v, dtype=F), np.asarray(i)) for name, v, i in c["edl_grads"]]
+        result = client.push_gradients(grads, edl, c["learning_rate"], list(c["push_versions"]))
+        assert [bool(result[0]), int(result[1])] == c["push_result"]
+        assert len(log) == len(c["log"])
+        for got, want in zip(log, c["log"]):
+            assert got == want, (n, got[0], got[1])
+        # the reference cannot push two DENSE gradients under one name (ps_client.py:217 assigns to a namedtuple
+        # field): that branch is unreachable there, so summing them (the evident intent, what this repo does) is
+        # not a deviation from anything the reference can do
+        assert c["duplicate_dense_name"] == "AttributeError"
