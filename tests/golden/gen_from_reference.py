@@ -24,6 +24,7 @@ What is executed, unmodified, from /root/reference:
     temporary directory trees (ref_checkpoint_dir_vectors()).
   * elasticdl/python/worker/ps_client.py PSClient -- the worker-side boundary itself -- against recording fake stubs
     (ref_ps_client_vectors()): every request each PS receives, every value the client returns.
+  * get_optimizer_info of elasticdl/python/common/model_utils.py (ref_optimizer_info_vectors()): the optimizer strings.
 """
 import json
 import os
@@ -419,6 +420,45 @@ def ref_ps_client_vectors():
 
 
 out["ps_client"] = ref_ps_client_vectors()
+
+
+
+def ref_optimizer_info_vectors():
+    """get_optimizer_info (elasticdl/python/common/model_utils.py:227-254): the (opt_type, opt_args) strings a job hands
+    the PS (`-opt_type=... -opt_args=...`).  model_utils.py imports TensorFlow, odps and the worker package at module
+    level, so only THIS function is executed: its source segment is cut out of the file with `ast` and exec'd, unmodified,
+    in a namespace whose `tf.keras.optimizers.{SGD,Adam,Adagrad}` are stand-in classes with the Keras `get_config()`
+    contract (python floats / bools, or a callable for a schedule)."""
+    import ast
+
+    path = os.path.join(REF, "elasticdl/python/common/model_utils.py")
+    src = open(path).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_optimizer_info")
+    code = ast.get_source_segment(src, fn)
+
+    class _Opt(object):
+        def __init__(self, **cfg):
+            self._cfg = cfg
+
+        def get_config(self):
+            return dict(self._cfg)
+
+    SGD, Adam, Adagrad = (type(n, (_Opt,), {}) for n in ("SGD", "Adam", "Adagrad"))
+    ns = {"tf": types.SimpleNamespace(keras=types.SimpleNamespace(
+        optimizers=types.SimpleNamespace(SGD=SGD, Adam=Adam, Adagrad=Adagrad)))}
+    exec(compile(code, path, "exec"), ns)
+    f = ns["get_optimizer_info"]
+    opts = [SGD(learning_rate=0.01, momentum=0.0, nesterov=False, decay=0.0, name="SGD"),
+            SGD(learning_rate=0.1, momentum=0.9, nesterov=True, decay=0.0, name="SGD"),
+            SGD(learning_rate=(lambda: 0.05), momentum=0.5, nesterov=False),
+            Adam(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-07, amsgrad=False, decay=0.0, name="Adam"),
+            Adam(learning_rate=3e-4, beta_1=0.8, beta_2=0.99, epsilon=1e-08, amsgrad=True),
+            Adagrad(learning_rate=0.001, initial_accumulator_value=0.1, epsilon=1e-07),
+            Adagrad(learning_rate=0.5, epsilon=1e-10)]
+    return [{"opt_type": t, "opt_args": a} for t, a in (f(o) for o in opts)]
+
+
+out["optimizer_info"] = ref_optimizer_info_vectors()
 
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_python_vectors.json")
 with open(path, "w") as f:

@@ -215,3 +215,33 @@ def test_trainer_graph_input_staging_helpers():
     fake = types.SimpleNamespace(_feature_items=T._feature_items,
                                  _optimizer=types.SimpleNamespace(param_groups=[{"lr": 0.1}]))
     assert T._graph_signature(fake, feats, labels) is None
+
+
+def test_optimizer_strings_of_the_reference_parse_here():
+    """tests/golden `optimizer_info`: the (opt_type, opt_args) strings written by the reference's own
+    get_optimizer_info (common/model_utils.py:227-254, executed by tests/golden/gen_from_reference.py) for SGD /
+    Nesterov / a callable learning rate / Adam / AMSGrad / Adagrad -- Python's str(float) and str(bool) spellings.
+    The C-ABI parser takes every one of them past the grammar (without a device: up to the CUDA error, loudly), and
+    the oracle's parser reads the same values."""
+    import json
+
+    from elasticdl_b200 import _lib
+    from oracle import ps_oracle as O
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python_vectors.json")) as f:
+        vec = json.load(f)["optimizer_info"]
+    assert {v["opt_type"] for v in vec} == {"SGD", "Adam", "Adagrad"}
+    lib = _lib.lib()
+    for v in vec:
+        h = ctypes.c_void_p()
+        rc = lib.b200ps_create(1, 0, v["opt_type"].encode(), v["opt_args"].encode(), 0, 0, ctypes.byref(h))
+        assert rc in (_lib.OK, _lib.ECUDA), (v, rc)  # never EINVAL: the grammar is accepted
+        if rc == _lib.OK:
+            lib.b200ps_destroy(h)
+        args = O.parse_opt_args(v["opt_type"], v["opt_args"])
+        assert float(args["learning_rate"]) > 0
+        for k in ("nesterov", "amsgrad"):
+            if k in args:
+                assert O.parse_bool(args[k]) in (True, False)
+    want = {"learning_rate": "0.001", "beta_1": "0.9", "beta_2": "0.999", "epsilon": "1e-07", "amsgrad": "False"}
+    assert O.parse_opt_args("Adam", vec[3]["opt_args"]) == want
