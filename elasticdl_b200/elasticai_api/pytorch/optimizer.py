@@ -159,9 +159,10 @@ class _FusedPSBackend(object):
 class _DistributedOptimizer(torch.optim.Optimizer):
     def __init__(self, params, named_parameters=None, compression=Compression.none, backward_passes_per_step=1,
                  op=Average, gradient_predivide_factor=1.0, global_batch_num_per_step=None,
-                 fixed_global_batch_size=False, fused=False):
+                 fixed_global_batch_size=False, fused=False, reproduce_q10=False):
         super(self.__class__, self).__init__(params)
         self._fused_requested = fused
+        self._reproduce_q10 = bool(reproduce_q10)
         self._ps = None
         self._compression = compression
         if named_parameters is not None:
@@ -265,7 +266,14 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         if self.op == Average:
             if self.fixed_global_batch_size:
                 return 1.0 / self._global_batch_num_per_step
-            return 1.0 / comm_size()
+            # Quirk Q10.  Horovod's Average = sum * postscale / size, and its own optimizer passes postscale =
+            # predivide (-> the mean).  The reference passes postscale = predivide * size() in BOTH branches
+            # (optimizer.py:154,157: "Set size() to the multiplier because C++ backend ... will apply additional
+            # 1 / size() factor"), which is what makes the fixed-global-batch mean come out right -- and makes the
+            # plain mode return the SUM over ranks (executing the file shows it: tests/golden/gen_allreduce_reference.py).
+            # Default here: the mean (Horovod's documented Average, what `op=Average` says); reproduce_q10=True gives
+            # the reference's literal result.  The reference itself only ever runs the fixed-global-batch mode.
+            return 1.0 if self._reproduce_q10 else 1.0 / comm_size()
         return 1.0
 
     def synchronize(self):
@@ -328,11 +336,11 @@ class _DistributedOptimizer(torch.optim.Optimizer):
 
 def DistributedOptimizer(optimizer, named_parameters=None, compression=Compression.none, backward_passes_per_step=1,
                          op=Average, gradient_predivide_factor=1.0, global_batch_num_per_step=None,
-                         fixed_global_batch_size=False, fused=False):
+                         fixed_global_batch_size=False, fused=False, reproduce_q10=False):
     """optimizer.py:266-296: returns an instance of a dynamically created subclass of the
     wrapped optimizer's class, sharing its param_groups."""
     global_batch_num_per_step = global_batch_num_per_step if global_batch_num_per_step else int(
         os.getenv("WORKER_NUM", 1))
     cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedOptimizer.__dict__))
     return cls(optimizer.param_groups, named_parameters, compression, backward_passes_per_step, op,
-               gradient_predivide_factor, global_batch_num_per_step, fixed_global_batch_size, fused)
+               gradient_predivide_factor, global_batch_num_per_step, fixed_global_batch_size, fused, reproduce_q10)
