@@ -622,6 +622,17 @@ def main():
                             "note": "achieved = algorithmic bytes (SURVEY 8d) / CUDA-event time of the launch (eager pass, GPU kept "
                                     "busy so that the event pairs bracket device time); "
                                     "step_frac = sum of the step's algorithmic bytes / graph ms_per_step / peak"}
+        # NOT measured in this run (labelled as such): where the row kernels sit once the launch is big enough to be
+        # bandwidth-bound, and the roof a bare random-row gather / read-modify-write reaches on the same memory system
+        line["roofline"]["row_kernels_at_scale"] = {
+            "not_measured_in_this_run": True,
+            "source": "profiles/r2_13_kernel_roofline_sweep_rows_final.jsonl (bench_kernels.py, graph-timed, 4 M unique "
+                      "random rows, table >> L2) and profiles/r2_01_gather_roof.jsonl (tools/probes/gather_roof.cu)",
+            "frac_of_copy_peak": {"pull_dim8": 0.376, "push_adam_dim8": 0.385, "pull_dim64": 0.675, "push_adam_dim64": 0.533,
+                                  "pull_dim1": 0.131, "push_adam_dim1": 0.154},
+            "bare_probe_frac_of_copy_peak": {"gather_dim8": 0.374, "rmw_adam_dim8": 0.465, "gather_dim64": 0.954,
+                                             "gather_dim1": 0.108},
+        }
         pk = "pull" if "pull" in kern else ("pull_deep" if "pull_deep" in kern else None)
         if pk:
             line["pull_gbs"] = kern[pk]["gbs"]
