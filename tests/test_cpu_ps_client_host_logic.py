@@ -149,6 +149,9 @@ class HostGroup(PSGroup):
             self.calls.append(["push_rows", self._name_of(tid),
                                {int(i): row.tolist() for i, row in zip(ids[:live].tolist(), g)}])
 
+    def push_dense_reduce(self, name, grads, scale=1.0):
+        self.calls.append(["push_dense_reduce", name, [g.reshape(-1).tolist() for g in grads], float(scale)])
+
     def push_end(self, sync=True):
         self.versions = [v + 1 for v in self.versions]  # every shard, every push (quirk Q7)
         self.calls.append(["push_end"])
@@ -259,3 +262,42 @@ def test_product_ps_client_errors_before_any_update():
     assert [c[0] for c in group.calls] == ["bump_step"]
     with pytest.raises(ValueError):  # the reference np.concatenate()s an empty list (ps_client.py:123)
         client.pull_embedding_vectors("e", [])
+
+
+def test_product_sync_sgd_host_logic_pserver_servicer_test_py_366():
+    """Sync-SGD as the Python PS does it (python/ps/servicer.py:168-238; vector of pserver_servicer_test.py:366-432):
+    grads_to_wait = 2 -> the first push is buffered (accepted, version unchanged), the second applies ONE update with
+    the dense gradients averaged (the fused reduce kernel gets both parts and scale 1/2) and the sparse gradients
+    concatenated then summed per id, version 0 -> 1; a third push that still carries version 0 is rejected."""
+    import threading
+
+    fake = [{"initialized": True, "version0": 0, "accept": True, "dense": {}}]
+    group = HostGroup(1, fake)
+    group.use_async, group.grads_to_wait, group.sync_version_tolerance = False, 2, 0
+    group._sync_lock, group._sync_buffer = threading.Lock(), {"n": 0, "dense": {}, "sparse": {}}
+    client = PSClient(group)
+    rng = np.random.RandomState(3)
+    g0 = {"v0": rng.rand(3, 2).astype(F), "v1": rng.rand(3).astype(F)}
+    g1 = {"v0": rng.rand(3, 2).astype(F), "v1": rng.rand(3).astype(F)}
+    client.partition_dense_parameters(["v0", "v1"], shapes={"v0": (3, 2), "v1": (3,)})
+    client.push_embedding_table_infos([EmbeddingTableInfo("emb", 8, "zeros", 1, 16)])
+    e0 = (rng.rand(3, 8).astype(F), np.array([3, 1, 3]))
+    e1 = (rng.rand(2, 8).astype(F), np.array([1, 9]))
+    group.calls.clear()
+    assert client.push_gradients([Tensor(n, v, None) for n, v in g0.items()], [Tensor("emb", *e0)], 0.1, [0]) == (True, 0)
+    assert [c[0] for c in group.calls] == []  # buffered: nothing reaches the tables
+    assert client.push_gradients([Tensor(n, v, None) for n, v in g1.items()], [Tensor("emb", *e1)], 0.1, [0]) == (True, 1)
+    kinds = [c[0] for c in group.calls]
+    assert kinds == ["push_begin", "push_dense_reduce", "push_dense_reduce", "push_rows", "push_end"]
+    assert group.calls[0][1:] == [0.1, [0]]
+    for c in group.calls[1:3]:
+        name, parts, scale = c[1], c[2], c[3]
+        assert scale == 0.5 and parts == [g0[name].reshape(-1).tolist(), g1[name].reshape(-1).tolist()]
+    rows = group.calls[3][2]
+    assert group.calls[3][1] == "emb" and list(rows) == [3, 1, 9]  # first-occurrence order over e0 ++ e1
+    assert np.array_equal(np.asarray(rows[3], F), e0[0][0] + e0[0][2])
+    assert np.array_equal(np.asarray(rows[1], F), e0[0][1] + e1[0][0])
+    assert np.array_equal(np.asarray(rows[9], F), e1[0][1])
+    group.calls.clear()
+    assert client.push_gradients([Tensor(n, v, None) for n, v in g1.items()], [], 0.1, [0]) == (False, 1)
+    assert group.calls == []
