@@ -301,3 +301,95 @@ def test_product_sync_sgd_host_logic_pserver_servicer_test_py_366():
     group.calls.clear()
     assert client.push_gradients([Tensor(n, v, None) for n, v in g1.items()], [], 0.1, [0]) == (False, 1)
     assert group.calls == []
+
+
+class StoreGroup(HostGroup):
+    """HostGroup that keeps table rows, dense values and per-shard state: enough for ps/checkpoint.py save / load."""
+
+    def __init__(self, n_shards, opt_type="Adam", opt_args=""):
+        super().__init__(n_shards, [{"initialized": False, "version0": 0} for _ in range(n_shards)])
+        self.opt_type, self.opt_args = opt_type, opt_args
+        self.rows, self.dense_store, self.slot_writes = {}, {}, []
+
+    def set_rows(self, requests):
+        for name, ids, values in requests:
+            dim = self.lookup(name)[1]
+            vals = np.asarray(values, F).reshape(len(np.asarray(ids).reshape(-1)), dim)
+            for i, v in zip(np.asarray(ids).reshape(-1).tolist(), vals):
+                self.rows.setdefault(name, {})[int(i)] = v.copy()
+
+    def slot_rows(self, name, ids, slot, values=None):
+        if slot > 2:
+            raise ValueError("Adam has two slots")
+        self.slot_writes.append((name, sorted(np.asarray(ids).tolist()), slot, float(np.asarray(values).max())))
+
+    def table_ids(self, name, shard):
+        return torch.tensor(sorted(i for i in self.rows.get(name, {}) if i % self.n_shards == shard), dtype=torch.int64)
+
+    def pull_rows(self, requests):
+        return [torch.from_numpy(np.stack([self.rows[name][int(i)] for i in self._ids(ids).tolist()]))
+                for name, ids in requests]
+
+    def set_dense(self, named_values):
+        for name, v in named_values:
+            t = self._f32(v)
+            assert tuple(t.shape) == tuple(self.lookup(name)[3]), name
+            self.dense_store[name] = t.numpy().copy()
+
+    def pull_dense(self, names, into=None):
+        return {n: torch.from_numpy(self.dense_store[n]) for n in names}
+
+    def set_shard_state(self, shard, version=-1, step=-1, initialized=-1):
+        if version >= 0:
+            self.versions[shard] = version
+        if initialized >= 0:
+            self.initialized[shard] = bool(initialized)
+
+
+def test_checkpoint_save_load_resharding_host_logic_checkpoint_test_go_25(tmp_path):
+    """ps/checkpoint.py save -> load over host memory: 2 shards saved, 3 shards restored -- ids {0,2,4} U {1,3,5} land
+    on {0,3} {1,4} {2,5} (checkpoint_test.go:25-82), dense parameters re-hash by name, the version is adopted, the
+    optimizer slots of restored rows are reset (quirk Q9), and the files are proto.Model messages the protobuf library
+    reads (elasticdl.proto:24-29)."""
+    import sys
+
+    from elasticdl_b200.common.hash_utils import string_to_id
+    from elasticdl_b200.ps import checkpoint as ck
+
+    g2 = StoreGroup(2)
+    c2 = PSClient(g2)
+    c2.push_embedding_table_infos([EmbeddingTableInfo("e1", 2, "uniform", 1, 64)])
+    ids = np.array([0, 2, 4, 1, 3, 5], dtype=np.int64)
+    vals = np.arange(12, dtype=F).reshape(6, 2)
+    g2.set_rows([("e1", ids, vals)])
+    dense = {"dense/kernel:0": np.arange(6, dtype=F).reshape(2, 3), "dense/bias:0": np.array([9, 8, 7], dtype=F)}
+    c2.partition_dense_parameters(dense.keys(), shapes={k: v.shape for k, v in dense.items()})
+    g2.set_dense(list(dense.items()))
+    g2.versions = [3, 3]
+    vdir = ck.save(g2, str(tmp_path))
+    assert vdir.endswith("version-3") and sorted(os.listdir(vdir)) == ["variables-0-of-2.ckpt", "variables-1-of-2.ckpt"]
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_cpu_checkpoint_format import _pb_classes  # Model built at runtime from the .proto field numbers
+
+    Model, _ = _pb_classes()
+    seen_dense = {}
+    for shard in range(2):
+        m = Model()
+        m.ParseFromString(open(os.path.join(vdir, "variables-%d-of-2.ckpt" % shard), "rb").read())
+        assert m.version == 3 and [(i.name, i.dim, i.initializer) for i in m.embedding_table_infos] == [("e1", 2, "uniform")]
+        assert sorted(m.embedding_tables["e1"].ids) == [i for i in range(6) if i % 2 == shard]
+        for name in m.dense_parameters:
+            assert string_to_id(name, 2) == shard  # a dense parameter is saved by the shard that owns it
+            seen_dense[name] = np.frombuffer(m.dense_parameters[name].tensor_content, "<f4")
+    assert set(seen_dense) == set(dense) and all(np.array_equal(seen_dense[k], dense[k].reshape(-1)) for k in dense)
+
+    g3 = StoreGroup(3)
+    c3 = PSClient(g3)
+    assert ck.load(g3, c3, ck.latest_version_dir(str(tmp_path))) == 3
+    assert [g3.table_ids("e1", s).tolist() for s in range(3)] == [[0, 3], [1, 4], [2, 5]]
+    assert np.array_equal(c3.pull_embedding_vectors("e1", ids), vals)
+    assert g3.versions == [3, 3, 3] and g3.initialized == [True, True, True]
+    assert {k: c3.parameter_to_ps[k] for k in dense} == {k: string_to_id(k, 3) for k in dense}
+    assert all(np.array_equal(g3.dense_store[k], dense[k]) for k in dense)
+    assert [(w[0], w[1], w[2], w[3]) for w in g3.slot_writes] == [("e1", [0, 1, 2, 3, 4, 5], 1, 0.0), ("e1", [0, 1, 2, 3, 4, 5], 2, 0.0)]
