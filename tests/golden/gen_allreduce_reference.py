@@ -101,7 +101,7 @@ def run(mode, world, root):
         script = os.path.join(tmp, "w.py")
         open(script, "w").write(WORKER)
         out = os.path.join(tmp, "out.json")
-        port = str(32000 + os.getpid() % 2000 + world + (7 if mode == "reference" else 0))
+        port = str(32000 + os.getpid() % 2000 + world + {"reference": 7, "ours": 0, "ours_q10": 14}[mode])
         procs = []
         for r in range(world):
             env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=port,
